@@ -1,0 +1,32 @@
+"""eegan_b200 — B200 (sm_100a) word-region attention + DAMSM losses + SyncBatchNorm for
+qikizh/EE-GAN, behind the reference's own Python signatures.
+
+    import eegan_b200
+    eegan_b200.install()          # miscc.DAMSM_losses / sync_batchnorm now resolve here
+    from miscc.DAMSM_losses import words_loss, sent_loss      # train.py:24, unchanged
+
+Hot path: hand-written CUDA in eegan_b200/csrc -> libeegan_b200.so (C ABI:
+include/eegan_b200.h), loaded with ctypes.  No CPU path, no other backend.
+"""
+from __future__ import annotations
+
+import sys
+
+from . import damsm_losses  # noqa: F401
+from .damsm_losses import (GlobalAttentionGeneral, cosine_similarity, func_attention, sent_loss,  # noqa: F401
+                           sent_similarity, words_loss, words_similarity)
+
+__version__ = "0.1.0"
+
+
+def install(losses: bool = True, sync_batchnorm: bool = True) -> None:
+    """Route the reference's import names to this package (drop-in boundary):
+    ``miscc.DAMSM_losses`` (train.py:24) and ``sync_batchnorm`` (models.py:8-10, train.py:25)."""
+    if losses:
+        sys.modules["miscc.DAMSM_losses"] = damsm_losses
+        parent = sys.modules.get("miscc")
+        if parent is not None:
+            setattr(parent, "DAMSM_losses", damsm_losses)
+    if sync_batchnorm:
+        from . import sync_batchnorm as sbn
+        sys.modules["sync_batchnorm"] = sbn

@@ -1,0 +1,73 @@
+// Shared helpers for libeegan_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/eegan_b200.h"
+
+namespace eegan {
+
+// thread-local error text returned by eegan_last_error()
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return EEGAN_ERR_CUDA;
+    }
+    return EEGAN_OK;
+}
+
+#define EEGAN_REQUIRE(cond, ...)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            ::eegan::set_error(__VA_ARGS__); \
+            return EEGAN_ERR_INVALID;       \
+        }                                   \
+    } while (0)
+
+#define EEGAN_LAUNCH_CHECK(what)                       \
+    do {                                               \
+        int _rc = ::eegan::check_launch(what);         \
+        if (_rc != EEGAN_OK) return _rc;               \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32).  `red` is >= 32 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float t = (lane < nw) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float t = (lane < nw) ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    return t;
+}
+
+}  // namespace eegan

@@ -1,0 +1,652 @@
+// DAMSM pair grid: every caption against every image (miscc/DAMSM_losses.py:272-342 — the
+// caption loop :281-321 over func_attention :25-63 and cosine_similarity :17-23), forward
+// and backward, as a pipeline of GEMM-shaped contractions over *packed* word columns
+// (n = (caption i, word t), only t < cap_lens[i]) with small fused row/column kernels
+// between them.  Math: SURVEY.md App. A.
+//
+//   fwd:  S[j][n][r] = sum_d Wp[n][d] C[j][d][r]                (GEMM1, K = D)
+//         P = softmax over the words of a caption; A = softmax over regions of g1*P
+//         U[j][n][d] = sum_r A[j][n][r] C[j][d][r]              (GEMM2, K = R)
+//         cos, m[j][i] = log sum_t exp(g2 cos)
+//   bwd:  DU = a1 w - a2 u ; dA = DU . C (GEMM3) ; softmax backwards -> DS
+//         dC[j] = DU^T A + Wp^T DS (GEMM4a/b, K = packed columns)
+//         dWp   = sum_j DS C^T (GEMM5, split over j) + cosine term
+//
+// The forward stashes P, A, U, cos, |u| in the caller's workspace; the backward consumes
+// them (no recompute).  Nothing here synchronises the device or allocates memory.
+#include "common.cuh"
+#include "gemm_ffma.cuh"
+
+namespace eegan {
+
+struct PairWs {
+    int* col_start;  // [Bc+1] exclusive prefix of clamp(cap_lens)
+    int* ntot;       // [1]    = col_start[Bc]
+    int* col_cap;    // [NtM]  caption of packed column n
+    float* Wp;       // [NtM][D] packed words, d contiguous
+    float* wn;       // [NtM]  |w_n|
+    float* SP;       // [Bi][NtM][R]  S, then P in place
+    float* A;        // [Bi][NtM][R]
+    float* U;        // [Bi][NtM][D]  U, then DU in place (bwd)
+    float* cosv;     // [Bi][NtM]
+    float* un;       // [Bi][NtM]
+    float* alpha;    // [3][Bi][NtM]
+    float* DA;       // [Bi][NtM][R]  dA, then DS in place
+    float* dWpart;   // [nsplit][NtM][D]
+    float* dwcos;    // [NtM][D]
+    int nsplit;
+    size_t bytes;
+};
+
+static int pick_nsplit(int Bi, int NtM, int D) {
+    const int tiles = ((NtM + 127) / 128) * ((D + 127) / 128);
+    int ns = (2 * 148 + tiles - 1) / tiles;
+    if (ns > Bi) ns = Bi;
+    if (ns < 1) ns = 1;
+    return ns;
+}
+
+static PairWs carve(void* base, int Bi, int Bc, int D, int R, int Tm) {
+    PairWs w;
+    const size_t NtM = (size_t)Bc * Tm;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* q = p ? p + off : nullptr;
+        off += align_up(bytes, 256);
+        return q;
+    };
+    w.nsplit = pick_nsplit(Bi, (int)NtM, D);
+    w.col_start = (int*)take((Bc + 1) * sizeof(int));
+    w.ntot = (int*)take(sizeof(int));
+    w.col_cap = (int*)take(NtM * sizeof(int));
+    w.Wp = (float*)take(NtM * D * sizeof(float));
+    w.wn = (float*)take(NtM * sizeof(float));
+    w.SP = (float*)take((size_t)Bi * NtM * R * sizeof(float));
+    w.A = (float*)take((size_t)Bi * NtM * R * sizeof(float));
+    w.U = (float*)take((size_t)Bi * NtM * D * sizeof(float));
+    w.cosv = (float*)take((size_t)Bi * NtM * sizeof(float));
+    w.un = (float*)take((size_t)Bi * NtM * sizeof(float));
+    w.alpha = (float*)take((size_t)3 * Bi * NtM * sizeof(float));
+    w.DA = (float*)take((size_t)Bi * NtM * R * sizeof(float));
+    w.dWpart = (float*)take((size_t)w.nsplit * NtM * D * sizeof(float));
+    w.dwcos = (float*)take(NtM * D * sizeof(float));
+    w.bytes = off;
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------
+// prologue: column packing
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) pair_scan_kernel(const int32_t* __restrict__ cap_lens, int Bc, int Tm,
+                                                         int* __restrict__ col_start, int* __restrict__ ntot,
+                                                         int* __restrict__ col_cap) {
+    __shared__ int s[1024];
+    __shared__ int carry;
+    const int tid = threadIdx.x;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < Bc; base += 1024) {
+        const int i = base + tid;
+        int v = (i < Bc) ? min(max(cap_lens[i], 0), Tm) : 0;
+        s[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int t = (tid >= o) ? s[tid - o] : 0;
+            __syncthreads();
+            s[tid] += t;
+            __syncthreads();
+        }
+        const int excl = carry + s[tid] - v;
+        if (i < Bc) {
+            col_start[i] = excl;
+            for (int t = 0; t < v; ++t) col_cap[excl + t] = i;
+        }
+        __syncthreads();
+        if (tid == 1023) carry += s[1023];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        col_start[Bc] = carry;
+        *ntot = carry;
+    }
+}
+
+__global__ void __launch_bounds__(128) pair_pack_words_kernel(const float* __restrict__ words, const int* __restrict__ col_start,
+                                                              const int* __restrict__ col_cap, const int* __restrict__ ntot,
+                                                              int D, int Tm, float* __restrict__ Wp, float* __restrict__ wn) {
+    __shared__ float red[32];
+    const int n = blockIdx.x;
+    if (n >= *ntot) return;
+    const int i = col_cap[n];
+    const int t = n - col_start[i];
+    float ss = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float v = __ldg(words + ((size_t)i * D + d) * Tm + t);
+        Wp[(size_t)n * D + d] = v;
+        ss = fmaf(v, v, ss);
+    }
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) wn[n] = sqrtf(ss);
+}
+
+// ---------------------------------------------------------------------------------------
+// forward row/column kernels
+// ---------------------------------------------------------------------------------------
+// One CTA per (caption i, image j): P = softmax_words(S) (:44-45), A = softmax_regions(g1 P)
+// (:53-54).  P overwrites S.  Dynamic smem: T_max * R floats.
+__global__ void __launch_bounds__(256) pair_attn_softmax_kernel(float* __restrict__ SP, float* __restrict__ A,
+                                                                const int* __restrict__ col_start, int NtM, int R,
+                                                                float g1, float* __restrict__ att, int diag_offset,
+                                                                int Tm) {
+    extern __shared__ float p[];
+    const int i = blockIdx.x, j = blockIdx.y;
+    const int cs = col_start[i], T = col_start[i + 1] - cs;
+    float* Sj = SP + ((size_t)j * NtM + cs) * R;
+    float* Aj = A + ((size_t)j * NtM + cs) * R;
+    const bool diag = (att != nullptr) && (j == i + diag_offset);
+    float* attp = diag ? att + (size_t)i * Tm * R : nullptr;
+
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        float mx = -INFINITY;
+        for (int t = 0; t < T; ++t) mx = fmaxf(mx, Sj[(size_t)t * R + r]);
+        float sum = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float e = expf(Sj[(size_t)t * R + r] - mx);
+            p[t * R + r] = e;
+            sum += e;
+        }
+        for (int t = 0; t < T; ++t) {
+            const float pv = p[t * R + r] / sum;
+            p[t * R + r] = pv;
+            Sj[(size_t)t * R + r] = pv;
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int t = w; t < T; t += nw) {
+        float mx = -INFINITY;
+        for (int r = lane; r < R; r += 32) mx = fmaxf(mx, g1 * p[t * R + r]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int r = lane; r < R; r += 32) {
+            const float e = expf(g1 * p[t * R + r] - mx);
+            p[t * R + r] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        for (int r = lane; r < R; r += 32) {
+            const float a = p[t * R + r] / sum;
+            Aj[(size_t)t * R + r] = a;
+            if (diag) attp[(size_t)t * R + r] = a;
+        }
+    }
+    if (diag) {
+        for (int idx = T * R + threadIdx.x; idx < Tm * R; idx += blockDim.x) attp[idx] = 0.f;
+    }
+}
+
+// One CTA per (caption i, image j): cos_t (:17-23) and m = log sum_t exp(g2 cos_t) (:315-317).
+__global__ void __launch_bounds__(256) pair_cos_lse_kernel(const float* __restrict__ U, const float* __restrict__ Wp,
+                                                           const float* __restrict__ wn, const int* __restrict__ col_start,
+                                                           int NtM, int D, int Bc, float g2, float* __restrict__ cosv,
+                                                           float* __restrict__ un, float* __restrict__ m) {
+    __shared__ float ex[32];
+    const int i = blockIdx.x, j = blockIdx.y;
+    const int cs = col_start[i], T = col_start[i + 1] - cs;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int t = w; t < T; t += nw) {
+        const int n = cs + t;
+        const float4* u4 = reinterpret_cast<const float4*>(U + ((size_t)j * NtM + n) * D);
+        const float4* w4 = reinterpret_cast<const float4*>(Wp + (size_t)n * D);
+        float dot = 0.f, uu = 0.f;
+        for (int q = lane; q < D / 4; q += 32) {
+            const float4 a = u4[q], b = __ldg(w4 + q);
+            dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+            uu = fmaf(a.x, a.x, uu); uu = fmaf(a.y, a.y, uu); uu = fmaf(a.z, a.z, uu); uu = fmaf(a.w, a.w, uu);
+        }
+        dot = warp_sum(dot);
+        uu = warp_sum(uu);
+        if (lane == 0) {
+            const float unv = sqrtf(uu);
+            const float c = dot / fmaxf(wn[n] * unv, 1e-8f);
+            cosv[(size_t)j * NtM + n] = c;
+            un[(size_t)j * NtM + n] = unv;
+            ex[t] = expf(g2 * c);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int t = 0; t < T; ++t) s += ex[t];
+        m[(size_t)j * Bc + i] = logf(s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward row/column kernels
+// ---------------------------------------------------------------------------------------
+// One warp per (caption i, image j): dcos_t and the three per-column coefficients
+//   a1 = dcos / max(|w||u|, eps);  a2 = dcos cos / |u|^2;  a3 = dcos cos / |w|^2  (0 when clamped)
+// so that dU = a1 w - a2 u and the cosine part of dW is a1 u - a3 w.
+__global__ void __launch_bounds__(32) pair_bwd_scalars_kernel(const float* __restrict__ dm, const float* __restrict__ cosv,
+                                                              const float* __restrict__ un, const float* __restrict__ wn,
+                                                              const int* __restrict__ col_start, int NtM, int Bi, int Bc,
+                                                              float g2, float* __restrict__ alpha) {
+    const int i = blockIdx.x, j = blockIdx.y, t = threadIdx.x;
+    const int cs = col_start[i], T = col_start[i + 1] - cs;
+    const bool on = t < T;
+    const size_t idx = (size_t)j * NtM + cs + t;
+    const float c = on ? cosv[idx] : 0.f;
+    const float e = on ? expf(g2 * c) : 0.f;
+    const float s = warp_sum(e);
+    if (!on) return;
+    const float dcos = dm[(size_t)j * Bc + i] * g2 * e / s;
+    const float wv = wn[cs + t], uv = un[idx];
+    const float nn = wv * uv;
+    const bool live = nn > 1e-8f;
+    const size_t plane = (size_t)Bi * NtM;
+    alpha[idx] = dcos / fmaxf(nn, 1e-8f);
+    alpha[plane + idx] = live ? dcos * c / (uv * uv) : 0.f;
+    alpha[2 * plane + idx] = live ? dcos * c / (wv * wv) : 0.f;
+}
+
+// One CTA per packed column n: U -> DU in place, and the cosine part of dW summed over j.
+__global__ void __launch_bounds__(256) pair_du_dwcos_kernel(float* __restrict__ U, const float* __restrict__ Wp,
+                                                            const float* __restrict__ alpha, const int* __restrict__ ntot,
+                                                            int NtM, int Bi, int D, float* __restrict__ dwcos) {
+    const int n = blockIdx.x;
+    if (n >= *ntot) return;
+    const size_t plane = (size_t)Bi * NtM;
+    float wv[4], acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int d = threadIdx.x + q * 256;
+        wv[q] = (d < D) ? Wp[(size_t)n * D + d] : 0.f;
+        acc[q] = 0.f;
+    }
+    float a3s = 0.f;
+    for (int j = 0; j < Bi; ++j) {
+        const size_t idx = (size_t)j * NtM + n;
+        const float a1 = alpha[idx], a2 = alpha[plane + idx];
+        a3s += alpha[2 * plane + idx];
+        float* u = U + idx * D;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int d = threadIdx.x + q * 256;
+            if (d < D) {
+                const float uv = u[d];
+                acc[q] = fmaf(a1, uv, acc[q]);
+                u[d] = a1 * wv[q] - a2 * uv;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int d = threadIdx.x + q * 256;
+        if (d < D) dwcos[(size_t)n * D + d] = acc[q] - a3s * wv[q];
+    }
+}
+
+// One CTA per (caption i, image j): dA -> DS in place.
+//   dz = a (dA - sum_r a dA);  v = g1 p dz;  ds = v - p sum_t v
+__global__ void __launch_bounds__(256) pair_softmax_bwd_kernel(float* __restrict__ DA, const float* __restrict__ A,
+                                                               const float* __restrict__ P, const int* __restrict__ col_start,
+                                                               int NtM, int R, float g1) {
+    __shared__ float csum[32];
+    const int i = blockIdx.x, j = blockIdx.y;
+    const int cs = col_start[i], T = col_start[i + 1] - cs;
+    const size_t base = ((size_t)j * NtM + cs) * R;
+    float* dA = DA + base;
+    const float* a = A + base;
+    const float* p = P + base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int t = w; t < T; t += nw) {
+        float s = 0.f;
+        for (int r = lane; r < R; r += 32) s = fmaf(a[(size_t)t * R + r], dA[(size_t)t * R + r], s);
+        s = warp_sum(s);
+        if (lane == 0) csum[t] = s;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        float q = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const size_t k = (size_t)t * R + r;
+            q += g1 * p[k] * a[k] * (dA[k] - csum[t]);
+        }
+        for (int t = 0; t < T; ++t) {
+            const size_t k = (size_t)t * R + r;
+            const float pv = p[k];
+            dA[k] = g1 * pv * a[k] * (dA[k] - csum[t]) - pv * q;
+        }
+    }
+}
+
+// d_words[i][d][t] = dwcos + sum of the split-j partials; zero for padded words.
+__global__ void __launch_bounds__(256) pair_unpack_dw_kernel(const float* __restrict__ dWpart, const float* __restrict__ dwcos,
+                                                             const int* __restrict__ col_start, int nsplit, int NtM, int D,
+                                                             int Tm, float* __restrict__ d_words) {
+    const int i = blockIdx.x;
+    const int cs = col_start[i], T = col_start[i + 1] - cs;
+    for (int idx = threadIdx.x; idx < D * Tm; idx += blockDim.x) {
+        const int t = idx / D, d = idx - t * D;  // d fastest: coalesced reads of the packed grads
+        float v = 0.f;
+        if (t < T) {
+            const size_t k = (size_t)(cs + t) * D + d;
+            v = dwcos[k];
+            for (int s = 0; s < nsplit; ++s) v += dWpart[(size_t)s * NtM * D + k];
+        }
+        d_words[((size_t)i * D + d) * Tm + t] = v;
+    }
+}
+
+static int validate(int Bi, int Bc, int D, int R, int Tm) {
+    EEGAN_REQUIRE(Bi > 0 && Bc > 0, "pair grid: empty batch (B_img=%d B_cap=%d)", Bi, Bc);
+    EEGAN_REQUIRE(D > 0 && D % 4 == 0 && D <= 1024, "pair grid: D=%d must be a multiple of 4 and <= 1024", D);
+    EEGAN_REQUIRE(R > 0 && R <= 1024, "pair grid: R=%d must be in [1,1024]", R);
+    EEGAN_REQUIRE(Tm > 0 && Tm <= 32, "pair grid: T_max=%d must be in [1,32]", Tm);
+    EEGAN_REQUIRE((size_t)Tm * R * sizeof(float) <= 200 * 1024, "pair grid: T_max*R too large for shared memory");
+    return EEGAN_OK;
+}
+
+}  // namespace eegan
+
+using namespace eegan;
+
+extern "C" size_t eegan_damsm_pair_workspace_bytes(int B_img, int B_cap, int D, int R, int T_max) {
+    if (B_img <= 0 || B_cap <= 0 || D <= 0 || R <= 0 || T_max <= 0) return 0;
+    return carve(nullptr, B_img, B_cap, D, R, T_max).bytes;
+}
+
+extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const int32_t* cap_lens, int Bi, int Bc,
+                                    int D, int R, int Tm, float g1, float g2, float* m, float* att, int diag_offset,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = validate(Bi, Bc, D, R, Tm);
+    if (rc) return rc;
+    EEGAN_REQUIRE(img && words && cap_lens && m && workspace, "pair fwd: null pointer");
+    PairWs w = carve(workspace, Bi, Bc, D, R, Tm);
+    if (workspace_bytes < w.bytes) {
+        set_error("pair fwd: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return EEGAN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NtM = Bc * Tm;
+
+    pair_scan_kernel<<<1, 1024, 0, st>>>(cap_lens, Bc, Tm, w.col_start, w.ntot, w.col_cap);
+    pair_pack_words_kernel<<<NtM, 128, 0, st>>>(words, w.col_start, w.col_cap, w.ntot, D, Tm, w.Wp, w.wn);
+    EEGAN_LAUNCH_CHECK("pair prologue");
+
+    GemmArgs g{};
+    // GEMM1: S[j][n][r] = sum_d Wp[n][d] img[j][d][r]
+    g.A = w.Wp; g.B = img; g.C = w.SP;
+    g.M = NtM; g.N = R; g.K = D; g.dynM = w.ntot; g.dynK = nullptr;
+    g.sAm = D; g.sAk = 1; g.sBk = R; g.sBn = 1; g.sCm = R; g.sCn = 1;
+    g.bA = 0; g.bB = (long long)D * R; g.bC = (long long)NtM * R;
+    g.nred = 1; g.red_total = 0; g.rA = g.rB = 0; g.accumulate = 0;
+    launch_gemm_ffma<128, 64, 8, 4, true, true>(g, Bi, st);
+    EEGAN_LAUNCH_CHECK("pair GEMM1");
+
+    const size_t smem = (size_t)Tm * R * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pair_attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+    }
+    pair_attn_softmax_kernel<<<dim3(Bc, Bi), 256, smem, st>>>(w.SP, w.A, w.col_start, NtM, R, g1, att, diag_offset, Tm);
+    EEGAN_LAUNCH_CHECK("pair softmax");
+
+    // GEMM2: U[j][n][d] = sum_r A[j][n][r] img[j][d][r]
+    g = GemmArgs{};
+    g.A = w.A; g.B = img; g.C = w.U;
+    g.M = NtM; g.N = D; g.K = R; g.dynM = w.ntot;
+    g.sAm = R; g.sAk = 1; g.sBk = 1; g.sBn = R; g.sCm = D; g.sCn = 1;
+    g.bA = (long long)NtM * R; g.bB = (long long)D * R; g.bC = (long long)NtM * D;
+    g.nred = 1;
+    launch_gemm_ffma<128, 128, 8, 8, true, false>(g, Bi, st);
+    EEGAN_LAUNCH_CHECK("pair GEMM2");
+
+    pair_cos_lse_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.U, w.Wp, w.wn, w.col_start, NtM, D, Bc, g2, w.cosv, w.un, m);
+    EEGAN_LAUNCH_CHECK("pair cos/lse");
+    return EEGAN_OK;
+}
+
+extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const int32_t* cap_lens, int Bi, int Bc,
+                                    int D, int R, int Tm, float g1, float g2, const float* dm, float* d_img,
+                                    float* d_words, void* workspace, size_t workspace_bytes, void* stream) {
+    (void)words; (void)cap_lens;
+    int rc = validate(Bi, Bc, D, R, Tm);
+    if (rc) return rc;
+    EEGAN_REQUIRE(img && dm && workspace, "pair bwd: null pointer");
+    PairWs w = carve(workspace, Bi, Bc, D, R, Tm);
+    if (workspace_bytes < w.bytes) {
+        set_error("pair bwd: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return EEGAN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NtM = Bc * Tm;
+
+    pair_bwd_scalars_kernel<<<dim3(Bc, Bi), 32, 0, st>>>(dm, w.cosv, w.un, w.wn, w.col_start, NtM, Bi, Bc, g2, w.alpha);
+    pair_du_dwcos_kernel<<<NtM, 256, 0, st>>>(w.U, w.Wp, w.alpha, w.ntot, NtM, Bi, D, w.dwcos);
+    EEGAN_LAUNCH_CHECK("pair bwd scalars");
+
+    GemmArgs g{};
+    // GEMM3: dA[j][n][r] = sum_d DU[j][n][d] img[j][d][r]
+    g.A = w.U; g.B = img; g.C = w.DA;
+    g.M = NtM; g.N = R; g.K = D; g.dynM = w.ntot;
+    g.sAm = D; g.sAk = 1; g.sBk = R; g.sBn = 1; g.sCm = R; g.sCn = 1;
+    g.bA = (long long)NtM * D; g.bB = (long long)D * R; g.bC = (long long)NtM * R;
+    g.nred = 1;
+    launch_gemm_ffma<128, 64, 8, 4, true, true>(g, Bi, st);
+    EEGAN_LAUNCH_CHECK("pair GEMM3");
+
+    pair_softmax_bwd_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.DA, w.A, w.SP, w.col_start, NtM, R, g1);
+    EEGAN_LAUNCH_CHECK("pair softmax bwd");
+
+    if (d_img) {
+        // GEMM4a: dC[j][d][r] = sum_n DU[j][n][d] A[j][n][r]
+        g = GemmArgs{};
+        g.A = w.U; g.B = w.A; g.C = d_img;
+        g.M = D; g.N = R; g.K = NtM; g.dynK = w.ntot;
+        g.sAm = 1; g.sAk = D; g.sBk = R; g.sBn = 1; g.sCm = R; g.sCn = 1;
+        g.bA = (long long)NtM * D; g.bB = (long long)NtM * R; g.bC = (long long)D * R;
+        g.nred = 1;
+        launch_gemm_ffma<128, 64, 8, 4, false, true>(g, Bi, st);
+        // GEMM4b: dC[j][d][r] += sum_n Wp[n][d] DS[j][n][r]
+        g.A = w.Wp; g.B = w.DA; g.bA = 0; g.accumulate = 1;
+        launch_gemm_ffma<128, 64, 8, 4, false, true>(g, Bi, st);
+        EEGAN_LAUNCH_CHECK("pair GEMM4");
+    }
+    if (d_words) {
+        // GEMM5: dWpart[s][n][d] = sum_{j in split s} sum_r DS[j][n][r] img[j][d][r]
+        g = GemmArgs{};
+        const int nred = (Bi + w.nsplit - 1) / w.nsplit;
+        g.A = w.DA; g.B = img; g.C = w.dWpart;
+        g.M = NtM; g.N = D; g.K = R; g.dynM = w.ntot;
+        g.sAm = R; g.sAk = 1; g.sBk = 1; g.sBn = R; g.sCm = D; g.sCn = 1;
+        g.rA = (long long)NtM * R; g.rB = (long long)D * R;
+        g.bA = g.rA * nred; g.bB = g.rB * nred; g.bC = (long long)NtM * D;
+        g.nred = nred; g.red_total = Bi;
+        launch_gemm_ffma<128, 128, 8, 8, true, false>(g, w.nsplit, st);
+        pair_unpack_dw_kernel<<<Bc, 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.nsplit, NtM, D, Tm, d_words);
+        EEGAN_LAUNCH_CHECK("pair GEMM5");
+    }
+    return EEGAN_OK;
+}
+
+// =======================================================================================
+// func_attention (miscc/DAMSM_losses.py:25-63) as a stand-alone op: sample b's query against
+// sample b's context (the pair grid above is the all-pairs form of the same attention).
+// Re-uses the grid's softmax kernels with a single "caption" of T words per sample.
+// =======================================================================================
+namespace eegan {
+
+struct FaWs {
+    int* col_start;  // {0, T}
+    float* P;        // [B][T][R]
+    float* DA;       // [B][T][R]
+    size_t bytes;
+};
+static FaWs carve_fa(void* base, int B, int R, int T) {
+    FaWs w;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* q = p ? p + off : nullptr;
+        off += align_up(bytes, 256);
+        return q;
+    };
+    w.col_start = (int*)take(2 * sizeof(int));
+    w.P = (float*)take((size_t)B * T * R * sizeof(float));
+    w.DA = (float*)take((size_t)B * T * R * sizeof(float));
+    w.bytes = off;
+    return w;
+}
+__global__ void fa_init_kernel(int* col_start, int T) {
+    col_start[0] = 0;
+    col_start[1] = T;
+}
+
+// one warp per row: cos = <a,b> / max(|a||b|, eps)   (DAMSM_losses.py:17-23)
+__global__ void __launch_bounds__(256) cosine_rows_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                              long long rows, int D, float eps, float* __restrict__ out,
+                                                              float* __restrict__ norms) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* a = x1 + row * D;
+    const float* b = x2 + row * D;
+    float ab = 0.f, aa = 0.f, bb = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float av = a[d], bv = b[d];
+        ab = fmaf(av, bv, ab); aa = fmaf(av, av, aa); bb = fmaf(bv, bv, bb);
+    }
+    ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
+    if (lane == 0) {
+        const float na = sqrtf(aa), nb = sqrtf(bb);
+        out[row] = ab / fmaxf(na * nb, eps);
+        norms[2 * row] = na;
+        norms[2 * row + 1] = nb;
+    }
+}
+__global__ void __launch_bounds__(256) cosine_rows_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                              const float* __restrict__ out, const float* __restrict__ norms,
+                                                              const float* __restrict__ g, long long rows, int D, float eps,
+                                                              float* __restrict__ d1, float* __restrict__ d2) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float na = norms[2 * row], nb = norms[2 * row + 1], c = out[row], gv = g[row];
+    const float nn = na * nb;
+    const bool live = nn > eps;
+    const float k = gv / fmaxf(nn, eps);
+    const float ka = live ? gv * c / (na * na) : 0.f, kb = live ? gv * c / (nb * nb) : 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float av = x1[row * D + d], bv = x2[row * D + d];
+        d1[row * D + d] = k * bv - ka * av;
+        d2[row * D + d] = k * av - kb * bv;
+    }
+}
+
+}  // namespace eegan
+
+extern "C" size_t eegan_func_attention_workspace_bytes(int B, int D, int R, int T) {
+    (void)D;
+    if (B <= 0 || R <= 0 || T <= 0) return 0;
+    return carve_fa(nullptr, B, R, T).bytes;
+}
+
+extern "C" int eegan_func_attention_fwd(const float* query, const float* context, int B, int D, int R, int T,
+                                        float gamma1, float* u, float* attn, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+    int rc = validate(B, B, D, R, T);
+    if (rc) return rc;
+    EEGAN_REQUIRE(query && context && u && attn && workspace, "func_attention fwd: null pointer");
+    FaWs w = carve_fa(workspace, B, R, T);
+    if (workspace_bytes < w.bytes) { set_error("func_attention: workspace too small"); return EEGAN_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    fa_init_kernel<<<1, 1, 0, st>>>(w.col_start, T);
+    GemmArgs g{};
+    // S[b][t][r] = sum_d q[b][d][t] c[b][d][r]      (:42)
+    g.A = query; g.B = context; g.C = w.P;
+    g.M = T; g.N = R; g.K = D;
+    g.sAm = 1; g.sAk = T; g.sBk = R; g.sBn = 1; g.sCm = R; g.sCn = 1;
+    g.bA = (long long)D * T; g.bB = (long long)D * R; g.bC = (long long)T * R;
+    g.nred = 1;
+    launch_gemm_ffma<128, 64, 8, 4, false, true>(g, B, st);
+    const size_t smem = (size_t)T * R * sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(pair_attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pair_attn_softmax_kernel<<<dim3(1, B), 256, smem, st>>>(w.P, attn, w.col_start, T, R, gamma1, nullptr, 0, T);
+    // u[b][d][t] = sum_r c[b][d][r] a[b][t][r]      (:61)
+    g = GemmArgs{};
+    g.A = context; g.B = attn; g.C = u;
+    g.M = D; g.N = T; g.K = R;
+    g.sAm = R; g.sAk = 1; g.sBk = 1; g.sBn = R; g.sCm = T; g.sCn = 1;
+    g.bA = (long long)D * R; g.bB = (long long)T * R; g.bC = (long long)D * T;
+    g.nred = 1;
+    launch_gemm_ffma<128, 64, 8, 4, true, false>(g, B, st);
+    EEGAN_LAUNCH_CHECK("func_attention fwd");
+    return EEGAN_OK;
+}
+
+extern "C" int eegan_func_attention_bwd(const float* query, const float* context, const float* attn, const float* d_u,
+                                        const float* d_attn, int B, int D, int R, int T, float gamma1, float* d_query,
+                                        float* d_context, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = validate(B, B, D, R, T);
+    if (rc) return rc;
+    EEGAN_REQUIRE(query && context && attn && d_query && d_context && workspace, "func_attention bwd: null pointer");
+    FaWs w = carve_fa(workspace, B, R, T);
+    if (workspace_bytes < w.bytes) { set_error("func_attention: workspace too small"); return EEGAN_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nTR = (size_t)B * T * R * sizeof(float);
+    if (d_attn) cudaMemcpyAsync(w.DA, d_attn, nTR, cudaMemcpyDeviceToDevice, st);
+    else cudaMemsetAsync(w.DA, 0, nTR, st);
+    GemmArgs g{};
+    if (d_u) {  // dA[b][t][r] += sum_d d_u[b][d][t] c[b][d][r]
+        g.A = d_u; g.B = context; g.C = w.DA;
+        g.M = T; g.N = R; g.K = D;
+        g.sAm = 1; g.sAk = T; g.sBk = R; g.sBn = 1; g.sCm = R; g.sCn = 1;
+        g.bA = (long long)D * T; g.bB = (long long)D * R; g.bC = (long long)T * R;
+        g.nred = 1; g.accumulate = 1;
+        launch_gemm_ffma<128, 64, 8, 4, false, true>(g, B, st);
+    }
+    pair_softmax_bwd_kernel<<<dim3(1, B), 256, 0, st>>>(w.DA, attn, w.P, w.col_start, T, R, gamma1);
+    // d_context[b][d][r] = sum_t d_u[b][d][t] a[b][t][r] + q[b][d][t] ds[b][t][r]
+    g = GemmArgs{};
+    g.B = attn; g.C = d_context;
+    g.M = D; g.N = R; g.K = T;
+    g.sAm = T; g.sAk = 1; g.sBk = R; g.sBn = 1; g.sCm = R; g.sCn = 1;
+    g.bA = (long long)D * T; g.bB = (long long)T * R; g.bC = (long long)D * R;
+    g.nred = 1;
+    if (d_u) {
+        g.A = d_u;
+        launch_gemm_ffma<128, 64, 8, 4, true, true>(g, B, st);
+    }
+    g.A = query; g.B = w.DA; g.accumulate = d_u ? 1 : 0;
+    launch_gemm_ffma<128, 64, 8, 4, true, true>(g, B, st);
+    // d_query[b][d][t] = sum_r c[b][d][r] ds[b][t][r]
+    g = GemmArgs{};
+    g.A = context; g.B = w.DA; g.C = d_query;
+    g.M = D; g.N = T; g.K = R;
+    g.sAm = R; g.sAk = 1; g.sBk = 1; g.sBn = R; g.sCm = T; g.sCn = 1;
+    g.bA = (long long)D * R; g.bB = (long long)T * R; g.bC = (long long)D * T;
+    g.nred = 1;
+    launch_gemm_ffma<128, 64, 8, 4, true, false>(g, B, st);
+    EEGAN_LAUNCH_CHECK("func_attention bwd");
+    return EEGAN_OK;
+}
+
+extern "C" int eegan_cosine_rows_fwd(const float* x1, const float* x2, long long rows, int D, float eps, float* out,
+                                     float* norms, void* stream) {
+    EEGAN_REQUIRE(rows > 0 && D > 0 && x1 && x2 && out && norms, "cosine_rows fwd: bad arguments");
+    cosine_rows_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x1, x2, rows, D, eps, out, norms);
+    EEGAN_LAUNCH_CHECK("cosine_rows fwd");
+    return EEGAN_OK;
+}
+extern "C" int eegan_cosine_rows_bwd(const float* x1, const float* x2, const float* out, const float* norms,
+                                     const float* g, long long rows, int D, float eps, float* d_x1, float* d_x2,
+                                     void* stream) {
+    EEGAN_REQUIRE(rows > 0 && D > 0 && x1 && x2 && out && norms && g && d_x1 && d_x2, "cosine_rows bwd: bad arguments");
+    cosine_rows_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x1, x2, out, norms, g, rows, D,
+                                                                                         eps, d_x1, d_x2);
+    EEGAN_LAUNCH_CHECK("cosine_rows bwd");
+    return EEGAN_OK;
+}

@@ -1,0 +1,225 @@
+// SyncBatchNorm device side (sync_batchnorm/batchnorm.py:48-78, 113-125).  The reference
+// makes two extra full passes over x for sum and sum(x**2) (:60-62, the latter materialising
+// x**2) and a third to normalise; here the statistics are one fused pass, the cross-replica
+// reduction is an NCCL all-reduce of the 2*C floats issued by the host between these calls,
+// and normalise / backward are single streaming passes.  x is [N, C, HW] contiguous.
+#include "common.cuh"
+
+namespace eegan {
+
+constexpr int BN_THREADS = 256;
+
+// grid (C, S): block (c, s) reduces a strided share of the N*HW elements of channel c.
+// MODE 0: {sum x, sum x^2};  MODE 1: {sum dy, sum dy*xhat}
+template <int MODE>
+__global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ inv_std, int N, int C, int HW,
+                                                               float* __restrict__ out) {
+    __shared__ float red[32];
+    const int c = blockIdx.x;
+    const float mu = MODE ? mean[c] : 0.f, is = MODE ? inv_std[c] : 0.f;
+    float a = 0.f, b = 0.f;
+    const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                     (MODE == 0 || (reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+    if (vec) {
+        const int hw4 = HW / 4;
+        const long long total = (long long)N * hw4;
+        for (long long e = (long long)blockIdx.y * BN_THREADS + threadIdx.x; e < total;
+             e += (long long)gridDim.y * BN_THREADS) {
+            const int n = (int)(e / hw4), k = (int)(e - (long long)n * hw4);
+            const size_t off = ((size_t)n * C + c) * HW + (size_t)k * 4;
+            const float4 xv = *reinterpret_cast<const float4*>(x + off);
+            if (MODE == 0) {
+                a += (xv.x + xv.y) + (xv.z + xv.w);
+                b = fmaf(xv.x, xv.x, b); b = fmaf(xv.y, xv.y, b); b = fmaf(xv.z, xv.z, b); b = fmaf(xv.w, xv.w, b);
+            } else {
+                const float4 g = *reinterpret_cast<const float4*>(dy + off);
+                a += (g.x + g.y) + (g.z + g.w);
+                b = fmaf(g.x, (xv.x - mu) * is, b); b = fmaf(g.y, (xv.y - mu) * is, b);
+                b = fmaf(g.z, (xv.z - mu) * is, b); b = fmaf(g.w, (xv.w - mu) * is, b);
+            }
+        }
+    } else {
+        const long long total = (long long)N * HW;
+        for (long long e = (long long)blockIdx.y * BN_THREADS + threadIdx.x; e < total;
+             e += (long long)gridDim.y * BN_THREADS) {
+            const int n = (int)(e / HW), k = (int)(e - (long long)n * HW);
+            const size_t off = ((size_t)n * C + c) * HW + k;
+            const float xv = x[off];
+            if (MODE == 0) {
+                a += xv;
+                b = fmaf(xv, xv, b);
+            } else {
+                const float g = dy[off];
+                a += g;
+                b = fmaf(g, (xv - mu) * is, b);
+            }
+        }
+    }
+    a = block_sum(a, red);
+    b = block_sum(b, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(out + c, a);
+        atomicAdd(out + C + c, b);
+    }
+}
+
+__device__ __forceinline__ float dev_count(const float* count_dev, float host_count) {
+    // element counts cross the all-reduce as {count / 4096, count % 4096} so the fp32 sum stays exact
+    return count_dev ? count_dev[0] * 4096.f + count_dev[1] : host_count;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float count, const float* __restrict__ count_dev,
+                                   float eps, float momentum,
+                                   int clamp_mode, float* __restrict__ mean, float* __restrict__ inv_std,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float size = dev_count(count_dev, count);
+    const float s = stats[c], ss = stats[C + c];
+    const float mu = s / size;                 // batchnorm.py:116
+    const float sumvar = ss - s * mu;          // :117
+    const float bias_var = sumvar / size;      // :119
+    mean[c] = mu;
+    inv_std[c] = clamp_mode ? 1.0f / sqrtf(fmaxf(bias_var, eps))   // clamp(eps) ** -0.5, :125
+                            : 1.0f / sqrtf(bias_var + eps);        // F.batch_norm, :50-53
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;  // :122
+    if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (sumvar / (size - 1.f));  // :118,123
+}
+
+// y = (x - mean) * (inv_std * w) + b ;  MODE 1: dx = w*inv_std*(dy - r0/count - xhat*r1/count)
+template <int MODE>
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              const float* __restrict__ mean,
+                                                              const float* __restrict__ inv_std,
+                                                              const float* __restrict__ weight,
+                                                              const float* __restrict__ bias,
+                                                              const float* __restrict__ red, float host_count,
+                                                              const float* __restrict__ count_dev,
+                                                              int kill_var_term, float clamp_inv_std, int C, int HW,
+                                                              float* __restrict__ out) {
+    const int nc = blockIdx.y;  // n*C + c
+    const int c = nc % C;
+    const float mu = mean[c], is = inv_std[c];
+    const float w = weight ? weight[c] : 1.f;
+    const float scale = is * w;
+    const float shift = (MODE == 0 && bias) ? bias[c] : 0.f;
+    float r0 = 0.f, r1 = 0.f;
+    if (MODE == 1) {
+        const float inv_count = 1.0f / dev_count(count_dev, host_count);
+        r0 = red[c] * inv_count;
+        // when the variance was clamped (N-replica formula) inv_std is a constant: no var term
+        r1 = (kill_var_term && is >= clamp_inv_std) ? 0.f : red[C + c] * inv_count;
+    }
+    const size_t base = (size_t)nc * HW;
+    const bool vec = (HW % 4 == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                                         (MODE == 1 ? reinterpret_cast<uintptr_t>(dy) : 0)) & 15) == 0);
+    if (vec) {
+        const int hw4 = HW / 4;
+        for (int k = blockIdx.x * BN_THREADS + threadIdx.x; k < hw4; k += gridDim.x * BN_THREADS) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + base + (size_t)k * 4);
+            float4 o;
+            if (MODE == 0) {
+                o.x = (xv.x - mu) * scale + shift; o.y = (xv.y - mu) * scale + shift;
+                o.z = (xv.z - mu) * scale + shift; o.w = (xv.w - mu) * scale + shift;
+            } else {
+                const float4 g = *reinterpret_cast<const float4*>(dy + base + (size_t)k * 4);
+                o.x = scale * (g.x - r0 - (xv.x - mu) * is * r1); o.y = scale * (g.y - r0 - (xv.y - mu) * is * r1);
+                o.z = scale * (g.z - r0 - (xv.z - mu) * is * r1); o.w = scale * (g.w - r0 - (xv.w - mu) * is * r1);
+            }
+            *reinterpret_cast<float4*>(out + base + (size_t)k * 4) = o;
+        }
+    } else {
+        for (int k = blockIdx.x * BN_THREADS + threadIdx.x; k < HW; k += gridDim.x * BN_THREADS) {
+            const float xv = x[base + k];
+            out[base + k] = (MODE == 0) ? (xv - mu) * scale + shift
+                                        : scale * (dy[base + k] - r0 - (xv - mu) * is * r1);
+        }
+    }
+}
+
+static int reduce_splits(int N, int C, int HW) {
+    const long long per_c = (long long)N * HW;
+    long long want = (4LL * 148 + C - 1) / C;             // ~4 CTAs per SM in total
+    long long maxs = (per_c + 4 * BN_THREADS - 1) / (4 * BN_THREADS);  // >= 4 elements per thread
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    return (int)want;
+}
+
+static int validate_bn(int N, int C, int HW) {
+    EEGAN_REQUIRE(N > 0 && C > 0 && HW > 0, "syncbn: empty shape N=%d C=%d HW=%d", N, C, HW);
+    EEGAN_REQUIRE((long long)N * C <= 0x7fffffffLL, "syncbn: N*C too large");
+    return EEGAN_OK;
+}
+
+}  // namespace eegan
+
+using namespace eegan;
+
+extern "C" int eegan_syncbn_stats(const float* x, int N, int C, int HW, float* stats, void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && stats, "syncbn stats: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(stats, 0, 2 * (size_t)C * sizeof(float), st);
+    bn_reduce_kernel<0><<<dim3(C, reduce_splits(N, C, HW)), BN_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, N, C, HW, stats);
+    EEGAN_LAUNCH_CHECK("syncbn stats");
+    return EEGAN_OK;
+}
+
+extern "C" int eegan_syncbn_finalize(const float* stats, int C, double count, const float* count_dev, float eps, float momentum,
+                                     int clamp_mode, float* mean, float* inv_std, float* running_mean,
+                                     float* running_var, void* stream) {
+    EEGAN_REQUIRE(C > 0 && stats && mean && inv_std, "syncbn finalize: bad arguments");
+    EEGAN_REQUIRE(count_dev || count > 1.0, "BatchNorm computes unbiased standard-deviation, which requires size > 1.");  // batchnorm.py:115
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, C, (float)count, count_dev, eps, momentum, clamp_mode,
+                                                                          mean, inv_std, running_mean, running_var);
+    EEGAN_LAUNCH_CHECK("syncbn finalize");
+    return EEGAN_OK;
+}
+
+static dim3 apply_grid(int N, int C, int HW) {
+    int per = (HW / 4 + BN_THREADS - 1) / BN_THREADS;
+    if (per < 1) per = 1;
+    if (per > 64) per = 64;
+    return dim3(per, N * C);
+}
+
+extern "C" int eegan_syncbn_apply(const float* x, const float* mean, const float* inv_std, const float* weight,
+                                  const float* bias, int N, int C, int HW, float* y, void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && mean && inv_std && y, "syncbn apply: null pointer");
+    bn_apply_kernel<0><<<apply_grid(N, C, HW), BN_THREADS, 0, (cudaStream_t)stream>>>(
+        x, nullptr, mean, inv_std, weight, bias, nullptr, 1.f, nullptr, 0, 0.f, C, HW, y);
+    EEGAN_LAUNCH_CHECK("syncbn apply");
+    return EEGAN_OK;
+}
+
+extern "C" int eegan_syncbn_bwd_reduce(const float* x, const float* dy, const float* mean, const float* inv_std, int N,
+                                       int C, int HW, float* red, void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && dy && mean && inv_std && red, "syncbn bwd_reduce: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(red, 0, 2 * (size_t)C * sizeof(float), st);
+    bn_reduce_kernel<1><<<dim3(C, reduce_splits(N, C, HW)), BN_THREADS, 0, st>>>(x, dy, mean, inv_std, N, C, HW, red);
+    EEGAN_LAUNCH_CHECK("syncbn bwd_reduce");
+    return EEGAN_OK;
+}
+
+extern "C" int eegan_syncbn_bwd_apply(const float* x, const float* dy, const float* mean, const float* inv_std,
+                                      const float* weight, const float* red, double count, const float* count_dev,
+                                      float eps, int clamp_mode,
+                                      int N, int C, int HW, float* dx, void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && dy && mean && inv_std && red && dx && (count_dev || count > 0), "syncbn bwd_apply: bad arguments");
+    bn_apply_kernel<1><<<apply_grid(N, C, HW), BN_THREADS, 0, (cudaStream_t)stream>>>(
+        x, dy, mean, inv_std, weight, nullptr, red, (float)count, count_dev, clamp_mode, 1.0f / sqrtf(eps), C, HW, dx);
+    EEGAN_LAUNCH_CHECK("syncbn bwd_apply");
+    return EEGAN_OK;
+}

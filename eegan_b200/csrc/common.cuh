@@ -35,6 +35,9 @@ inline int check_launch(const char* what) {
         if (_rc != EEGAN_OK) return _rc;               \
     } while (0)
 
+// bench-only stage timing (profile.cu); a no-op unless eegan_profile_enable(1) was called
+void prof_mark(int stage, cudaStream_t st);
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __device__ __forceinline__ float warp_sum(float v) {

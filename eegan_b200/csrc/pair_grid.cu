@@ -372,9 +372,11 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
     cudaStream_t st = (cudaStream_t)stream;
     const int NtM = Bc * Tm;
 
+    prof_mark(-1, st);
     pair_scan_kernel<<<1, 1024, 0, st>>>(cap_lens, Bc, Tm, w.col_start, w.ntot, w.col_cap);
     pair_pack_words_kernel<<<NtM, 128, 0, st>>>(words, w.col_start, w.col_cap, w.ntot, D, Tm, w.Wp, w.wn);
     EEGAN_LAUNCH_CHECK("pair prologue");
+    prof_mark(0, st);
 
     GemmArgs g{};
     // GEMM1: S[j][n][r] = sum_d Wp[n][d] img[j][d][r]
@@ -385,6 +387,7 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
     g.nred = 1; g.red_total = 0; g.rA = g.rB = 0; g.accumulate = 0;
     launch_gemm_ffma<128, 64, 8, 4, true, true>(g, Bi, st);
     EEGAN_LAUNCH_CHECK("pair GEMM1");
+    prof_mark(1, st);
 
     const size_t smem = (size_t)Tm * R * sizeof(float);
     if (smem > 48 * 1024) {
@@ -393,6 +396,7 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
     }
     pair_attn_softmax_kernel<<<dim3(Bc, Bi), 256, smem, st>>>(w.SP, w.A, w.col_start, NtM, R, g1, att, diag_offset, Tm);
     EEGAN_LAUNCH_CHECK("pair softmax");
+    prof_mark(2, st);
 
     // GEMM2: U[j][n][d] = sum_r A[j][n][r] img[j][d][r]
     g = GemmArgs{};
@@ -403,9 +407,11 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
     g.nred = 1;
     launch_gemm_ffma<128, 128, 8, 8, true, false>(g, Bi, st);
     EEGAN_LAUNCH_CHECK("pair GEMM2");
+    prof_mark(3, st);
 
     pair_cos_lse_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.U, w.Wp, w.wn, w.col_start, NtM, D, Bc, g2, w.cosv, w.un, m);
     EEGAN_LAUNCH_CHECK("pair cos/lse");
+    prof_mark(4, st);
     return EEGAN_OK;
 }
 
@@ -424,9 +430,11 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
     cudaStream_t st = (cudaStream_t)stream;
     const int NtM = Bc * Tm;
 
+    prof_mark(-1, st);
     pair_bwd_scalars_kernel<<<dim3(Bc, Bi), 32, 0, st>>>(dm, w.cosv, w.un, w.wn, w.col_start, NtM, Bi, Bc, g2, w.alpha);
     pair_du_dwcos_kernel<<<NtM, 256, 0, st>>>(w.U, w.Wp, w.alpha, w.ntot, NtM, Bi, D, w.dwcos);
     EEGAN_LAUNCH_CHECK("pair bwd scalars");
+    prof_mark(5, st);
 
     GemmArgs g{};
     // GEMM3: dA[j][n][r] = sum_d DU[j][n][d] img[j][d][r]
@@ -437,9 +445,11 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
     g.nred = 1;
     launch_gemm_ffma<128, 64, 8, 4, true, true>(g, Bi, st);
     EEGAN_LAUNCH_CHECK("pair GEMM3");
+    prof_mark(6, st);
 
     pair_softmax_bwd_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.DA, w.A, w.SP, w.col_start, NtM, R, g1);
     EEGAN_LAUNCH_CHECK("pair softmax bwd");
+    prof_mark(7, st);
 
     if (d_img) {
         // GEMM4a: dC[j][d][r] = sum_n DU[j][n][d] A[j][n][r]
@@ -454,6 +464,7 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
         g.A = w.Wp; g.B = w.DA; g.bA = 0; g.accumulate = 1;
         launch_gemm_ffma<128, 64, 8, 4, false, true>(g, Bi, st);
         EEGAN_LAUNCH_CHECK("pair GEMM4");
+        prof_mark(8, st);
     }
     if (d_words) {
         // GEMM5: dWpart[s][n][d] = sum_{j in split s} sum_r DS[j][n][r] img[j][d][r]
@@ -468,6 +479,7 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
         launch_gemm_ffma<128, 128, 8, 8, true, false>(g, w.nsplit, st);
         pair_unpack_dw_kernel<<<Bc, 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.nsplit, NtM, D, Tm, d_words);
         EEGAN_LAUNCH_CHECK("pair GEMM5");
+        prof_mark(9, st);
     }
     return EEGAN_OK;
 }

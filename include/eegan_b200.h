@@ -182,6 +182,19 @@ int eegan_syncbn_bwd_apply(const float* x, const float* dy, const float* mean,
                            int N, int C, int HW,
                            float* dx, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Bench-only stage timing of the multi-kernel entry points (eegan_damsm_pair_fwd/_bwd).
+ * Thread-local and off by default.  While enabled, each call records a cudaEvent after every
+ * stage on the caller's stream; eegan_profile_collect synchronises those events (the only
+ * synchronising entry point of the library) and returns, per stage, the summed device time
+ * in ms and the number of times the stage ran since the previous collect.
+ * ---------------------------------------------------------------------------------- */
+#define EEGAN_PROF_NSTAGES 10
+int eegan_profile_enable(int on);
+int eegan_profile_nstages(void);
+const char* eegan_profile_stage_name(int stage);
+int eegan_profile_collect(double* stage_ms /*[NSTAGES], host*/, int* stage_launches /*[NSTAGES], host*/);
+
 #ifdef __cplusplus
 }
 #endif

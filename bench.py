@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — EE-GAN DAMSM hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one synthetic CUB-shaped batch: words_loss
+(miscc/DAMSM_losses.py:272-342) forward + backward with BOTH input gradients, i.e. the
+B x B grid of 289-region x <=18-word attentions, the gamma-LSE aggregation and the two
+cross-entropies.  Metric: attention pairs/s (one pair = one (caption, image) cell, fwd+bwd).
+
+ * value      — device-resident inputs, CUDA events around each step (L2 flushed between
+                steps, outside the timed spans), max over ranks.
+ * e2e        — same step through the public API from pinned HOST buffers: H2D of the
+                inputs and D2H of the two losses inside the timed span.
+ * roofline   — the dominant kernel's algorithmic FLOP/s from stage events recorded inside
+                the timed steps (eegan_profile_*), against MEASURED_PEAKS.json.
+ * cpu_baseline — the oracle's loop-structured fp32 port (the reference's algorithm and op
+                mix) timed on this host's cores on a bounded sample (rank 0, N=1 only).
+ * --impl reference — that same CPU arm as its own JSON line (the reference is pure Python
+                on torch CPU ops; /root/reference does not exist on the GPU box, so the port
+                under oracle/ that was validated bit-exact against it is what runs).
+N>1 (torchrun, one rank per GPU): each rank keeps B=48 captions + their images, the grid is
+caption-row-sharded (eegan_b200/sharded.py): all-gather of region features, local column
+block, all-gather of the blocks, redundant CE, reduce-scatter of d_img.  "weak": per-GPU
+caption rows fixed.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+B_PER_GPU, T_MAX, D, HW = 48, 18, 256, 17
+R = HW * HW
+METRIC = "attn+DAMSM fwd/bwd pairs/s at CUB shape"
+UNIT = "pairs/s"
+# kernels launched per step by OUR library (pair fwd 6 + CE fwd 2 + CE bwd 1 + pair bwd 8)
+LAUNCHES_PER_STEP = 17
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15] or self.rows[-3:]
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(B, seed):
+    from oracle import cases
+    c = cases.words_case(B, T_MAX, seed=seed, kind="realistic", class_mode="cub")
+    return c
+
+
+def algorithmic_flops(cap_lens_sum, B_img):
+    """12*R*D*sum(T_i) per image row of the grid: fwd 4RDT + bwd 8RDT."""
+    return 12.0 * R * D * float(cap_lens_sum) * B_img
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores
+# ---------------------------------------------------------------------------------------
+def cpu_step(c, B):
+    from oracle import damsm_oracle as O
+    img = c["img"].clone().requires_grad_()
+    words = c["words"].clone().requires_grad_()
+    l0, l1, _ = O.port_words_loss(img, words, c["labels"], c["cap_lens"], c["class_ids"], B)
+    (l0 + l1).backward()
+    return float((l0 + l1).detach())
+
+
+def cpu_arm(steps, warmup, budget_s=25.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = B_PER_GPU
+    c = make_inputs(B, 3407)
+    for _ in range(max(1, min(warmup, 2))):
+        cpu_step(c, B)
+    times, t_begin = [], time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(c, B)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    return dict(value=B * B / (ms / 1e3), unit=UNIT, cores=cores, kind="port",
+                sample="%d full steps of the B=%d batch (fwd+bwd, both grads), oracle/damsm_oracle.py port_words_loss, "
+                       "torch %s CPU, %d threads" % (len(times), B, torch.__version__, cores)), ms, len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, ms, n = cpu_arm(args.steps, args.warmup, budget_s=120.0)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": n, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CUB bird DAMSM words_loss fwd+bwd, B=%d, T<=%d ragged, D=%d, %dx%d regions, CPU host cores"
+                                   % (B_PER_GPU, T_MAX, D, HW, HW)},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def run_ours(args):
+    import eegan_b200 as E
+    from eegan_b200 import _lib
+    from eegan_b200.sharded import sharded_words_loss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    B = B_PER_GPU
+    Btot = B * world
+    c = make_inputs(B, 3407 + rank)
+    img_h = c["img"].pin_memory()
+    words_h = c["words"].pin_memory()
+    lens_h = c["cap_lens"].pin_memory()
+    cls = c["class_ids"]  # CPU LongTensor as in train.py:423
+    labels = c["labels"].to(dev)
+    img_d = img_h.to(dev).requires_grad_()
+    words_d = words_h.to(dev).requires_grad_()
+    lens_d = lens_h.to(dev)
+    lens_sum = torch.tensor([float(lens_h.sum())], device=dev)
+    if world > 1:
+        dist.all_reduce(lens_sum)
+    # per-rank algorithmic work: its column block = B_tot images x local captions
+    flops_rank = algorithmic_flops(float(lens_h.sum()), Btot)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step(img, words, lens):
+        img.grad = None
+        words.grad = None
+        if world > 1:
+            l0, l1, _ = sharded_words_loss(img, words, labels, lens, cls, B)
+        else:
+            l0, l1, _ = E.words_loss(img, words, labels, lens, cls, B)
+        (l0 + l1).backward()
+        return l0, l1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------
+    for _ in range(args.warmup):
+        step(img_d, words_d, lens_d)
+        flush.fill_(1.0)
+    L.eegan_profile_enable(1 if world == 1 else 0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    t_wall0 = time.time()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1.0)  # evict L2 (126 MB) between timed steps; outside the timed span
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(img_d, words_d, lens_d)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    stage = None
+    if world == 1:
+        n = L.eegan_profile_nstages()
+        ms_arr, cnt_arr = (ctypes.c_double * n)(), (ctypes.c_int * n)()
+        _lib.check(L.eegan_profile_collect(ms_arr, cnt_arr), "profile_collect")
+        L.eegan_profile_enable(0)
+        stage = [(L.eegan_profile_stage_name(i).decode(), ms_arr[i], cnt_arr[i]) for i in range(n)]
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    pairs_per_step = float(Btot) * Btot
+    value = pairs_per_step / (ms_step / 1e3)
+
+    # ---- end-to-end from pinned host buffers ---------------------------------------
+    h2d = img_h.numel() * 4 + words_h.numel() * 4 + lens_h.numel() * 8
+    loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
+    barrier()
+    e2e_evs = []
+    for k in range(args.warmup + args.steps):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        img = img_h.to(dev, non_blocking=True).requires_grad_()
+        words = words_h.to(dev, non_blocking=True).requires_grad_()
+        lens = lens_h.to(dev, non_blocking=True)
+        l0, l1 = step(img, words, lens)
+        loss_h.copy_(torch.stack([l0.detach(), l1.detach()]), non_blocking=True)
+        e1.record()
+        e1.synchronize()  # the caller sees the loss on the host
+        if k >= args.warmup:
+            e2e_evs.append(e0.elapsed_time(e1))
+    barrier()
+    t = torch.tensor([sum(e2e_evs)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+    e2e = {"value": pairs_per_step / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+           "d2h_bytes_per_step": 8 * world, "ms_per_step": e2e_ms}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "CUB bird (cfg/bird.yml shape) DAMSM words_loss fwd+bwd, both grads: B=%d per GPU "
+                                   "(global %d), T<=%d ragged (sum=%d), D=%d, %dx%d regions; caption-row-sharded for N>1"
+                                   % (B, Btot, T_MAX, int(lens_sum.item()), D, HW, HW),
+                       "l2": "256 MB fill between timed steps (outside the timed spans)",
+                       "pairs_per_step": pairs_per_step},
+            "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks}
+    if stage is not None:
+        gemm = [s for s in stage if s[0].startswith("gemm")]
+        gemm_ms = sum(s[1] for s in gemm)
+        gemm_launch_count = args.steps * 6  # gemm1, gemm2, gemm3, gemm4a, gemm4b, gemm5
+        achieved = flops_rank * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "gemm_ffma_kernel (6 launches/step: S, U, dA, dC x2, dW)",
+            "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_tflops"] if achieved else None, "traffic": None,
+            "peak_source": pk["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
+            "note": "fp32-exact contraction on the CUDA-core FMA pipe (SURVEY D7); fp32 FMA peak is 74.4 TFLOP/s "
+                    "(148 SM x 128 lanes x 2 x 1.965 GHz) -> frac_of_fp32_fma = %.3f; avg launch %.1f us"
+                    % ((achieved / 74.4) if achieved else 0.0, 1e3 * gemm_ms / max(1, gemm_launch_count)),
+            "stage_ms_per_step": {s[0]: s[1] / args.steps for s in stage},
+            "hbm_equiv": {"algorithmic_bytes_per_step": 3 * B * D * (R + T_MAX) * 4 + 3 * B * B * 4,
+                          "achieved_gbs": (3 * B * D * (R + T_MAX) * 4 + 3 * B * B * 4) / (ms_step / 1e3) / 1e9,
+                          "peak_gbs": pk["hbm_gbs"]}}
+    if world == 1:
+        base, _, _ = cpu_arm(args.steps, 1)
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,8 +46,10 @@ B_PER_GPU, T_MAX, D, HW = 48, 18, 256, 17
 R = HW * HW
 METRIC = "attn+DAMSM fwd/bwd pairs/s at CUB shape"
 UNIT = "pairs/s"
-# kernels launched per step by OUR library (pair fwd 6 + CE fwd 2 + CE bwd 1 + pair bwd 8)
-LAUNCHES_PER_STEP = 17
+# kernels launched per step by OUR library with the tcgen05 engine:
+#   pair fwd 7 (scan, pack, repitch, gemm S, softmax, gemm U, cos/lse) + CE fwd 2 + CE bwd 1
+#   + pair bwd 8 (scalars, dU, gemm dA, softmax bwd, zero-tail, gemm dC, gemm dW, unpack)
+LAUNCHES_PER_STEP = 18
 
 
 def peaks():
@@ -65,15 +67,18 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.err = [], None, ""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0 and self.proc.poll() is None:
+                time.sleep(0.02)  # nvidia-smi needs a few hundred ms before its first sample
+        except OSError as e:
+            self.proc, self.err = None, str(e)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -81,8 +86,15 @@ class ClockSampler:
 
     def summary(self, t0, t1):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable: " + self.err]}
+        time.sleep(0.06)
         self.proc.terminate()
+        if not self.rows:
+            try:
+                self.err = (self.proc.stderr.read() or "")[:200]
+            except Exception:
+                pass
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi gave no samples: " + self.err]}
         sm, mx, reasons = [], None, set()
         rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15] or self.rows[-3:]
         for _, line in rows:
@@ -288,16 +300,18 @@ def run_ours(args):
     if stage is not None:
         gemm = [s for s in stage if s[0].startswith("gemm")]
         gemm_ms = sum(s[1] for s in gemm)
-        gemm_launch_count = args.steps * 6  # gemm1, gemm2, gemm3, gemm4a, gemm4b, gemm5
+        gemm_launch_count = args.steps * 5  # S, U, dA, dC, dW
         achieved = flops_rank * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         line["roofline"] = {
-            "bound": "tensor", "kernel": "gemm_ffma_kernel (6 launches/step: S, U, dA, dC x2, dW)",
+            "bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 3xTF32; 5 launches/step: S, U, dA, dC, dW)",
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops"] if achieved else None, "traffic": None,
             "peak_source": pk["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
-            "note": "fp32-exact contraction on the CUDA-core FMA pipe (SURVEY D7); fp32 FMA peak is 74.4 TFLOP/s "
-                    "(148 SM x 128 lanes x 2 x 1.965 GHz) -> frac_of_fp32_fma = %.3f; avg launch %.1f us"
-                    % ((achieved / 74.4) if achieved else 0.0, 1e3 * gemm_ms / max(1, gemm_launch_count)),
+            "note": "fp32-accurate 3xTF32 (SURVEY D7): 3 tcgen05.mma.kind::tf32 per K-step at half the bf16 rate, so the "
+                    "engine's own ceiling is peak/6 = %.0f TFLOP/s -> frac_of_3xtf32_ceiling = %.3f; avg launch %.1f us; "
+                    "the fp32 FFMA engine it replaced ran at 58 TFLOP/s"
+                    % (pk["bf16_tflops"] / 6.0, (achieved / (pk["bf16_tflops"] / 6.0)) if achieved else 0.0,
+                       1e3 * gemm_ms / max(1, gemm_launch_count)),
             "stage_ms_per_step": {s[0]: s[1] / args.steps for s in stage},
             "hbm_equiv": {"algorithmic_bytes_per_step": 3 * B * D * (R + T_MAX) * 4 + 3 * B * B * 4,
                           "achieved_gbs": (3 * B * D * (R + T_MAX) * 4 + 3 * B * B * 4) / (ms_step / 1e3) / 1e9,
@@ -313,8 +327,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

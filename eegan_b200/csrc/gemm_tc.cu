@@ -1,0 +1,384 @@
+// tcgen05 3xTF32 GEMM engine — see gemm_tc.cuh for the design.
+#include <stdlib.h>
+
+#include "gemm_tc.cuh"
+
+namespace eegan {
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// Canonical 128B-swizzle UMMA shared-memory descriptor (version 1 = Blackwell).
+//   K-major : rows at 128 B, 8-row groups at SBO = 1024 B; a K-step of 8 fp32 advances the start by 32 B.
+//   MN-major: 32-bit operands only exist in the "128B swizzle, 32B atomicity" layout (descriptor
+//             layout type 1, TMA SWIZZLE_128B_ATOM_32B): [k][32 fp32] rows of 128 B, atoms of 4
+//             k-rows (SBO = 512 B between 4-row groups), 32-wide MN chunks LBO = 4096 B apart
+//             (one TMA box of 32 k-rows each); a K-step of 8 advances the start by 1024 B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t tile, bool kmajor, int kstep, uint32_t mn_lbo, uint32_t mn_sbo) {
+    const uint32_t start = tile + (kmajor ? kstep * 32 : kstep * 1024);
+    const uint64_t lbo = kmajor ? 1 : mn_lbo;
+    const uint64_t sbo = kmajor ? (1024 >> 4) : mn_sbo;
+    uint64_t d = (uint64_t)((start & 0x3FFFF) >> 4);
+    d |= lbo << 16;
+    d |= sbo << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version
+    d |= (uint64_t)(kmajor ? 2 : 1) << 61;  // SWIZZLE_128B (K-major) / SWIZZLE_128B_BASE32B (MN-major tf32)
+    return d;
+}
+
+struct TcArgs {
+    float* C;
+    long long ldc, bC;
+    int M, N;
+    const int* dynM;
+    const int* dynK;
+    int K[2];
+    int nseg, nred, red_total;
+    int a_batched[2], b_batched[2];
+    uint32_t mn_lbo, mn_sbo;  // debug-overridable descriptor fields of MN-major tiles (16-byte units)
+};
+
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const TcArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int z = blockIdx.z;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+    const int Mlive = p.dynM ? min(*p.dynM, p.M) : p.M;
+    if (m0 >= Mlive) return;  // uniform: before any barrier / TMEM state exists
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto conv = [&](int s) { return bars + 8u * (TC_STAGES + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };
+    const uint32_t tmem_full = bars + 8u * (3 * TC_STAGES);
+    const uint32_t tmem_slot = bars + 8u * (3 * TC_STAGES + 1);
+
+    int kb[2] = {0, 0};
+    for (int s = 0; s < p.nseg; ++s) {
+        const int Ks = p.dynK ? min(*p.dynK, p.K[s]) : p.K[s];
+        kb[s] = (Ks + TC_BK - 1) / TC_BK;
+    }
+    const int kbt = kb[0] + kb[1];
+    int nred = p.nred;
+    if (p.red_total > 0) nred = max(0, min(p.nred, p.red_total - z * p.nred));
+    const int total = nred * kbt;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(conv(s), 4);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_d;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int it = 0; it < total; ++it) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                const int red = it / kbt, rem = it - red * kbt;
+                const int seg = rem >= kb[0] ? 1 : 0;
+                const int k0 = (seg ? rem - kb[0] : rem) * TC_BK;
+                const CUtensorMap* ta = seg ? &tmA1 : &tmA0;
+                const CUtensorMap* tb = seg ? &tmB1 : &tmB0;
+                const int zr = z * p.nred + red;
+                const int zA = p.a_batched[seg] ? zr : 0, zB = p.b_batched[seg] ? zr : 0;
+                mbar_wait(empty(s), ph ^ 1);
+                mbar_arrive_expect_tx(full(s), 2 * TC_TILE_BYTES);
+                const uint32_t sA = base + s * TC_STAGE_BYTES, sB = sA + TC_TILE_BYTES;
+                if (A_K) {
+                    tma_load_3d(sA, ta, full(s), k0, m0, zA);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tma_load_3d(sA + c * 4096, ta, full(s), m0 + 32 * c, k0, zA);
+                }
+                if (B_K) {
+                    tma_load_3d(sB, tb, full(s), k0, n0, zB);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tma_load_3d(sB + c * 4096, tb, full(s), n0 + 32 * c, k0, zB);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) /*D=f32*/ | (2u << 7) /*A=tf32*/ | (2u << 10) /*B=tf32*/ |
+                                       ((A_K ? 0u : 1u) << 15) | ((B_K ? 0u : 1u) << 16) |
+                                       ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int it = 0; it < total; ++it) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                mbar_wait(conv(s), ph);
+                tc_fence_after();
+                const uint32_t a_hi = base + s * TC_STAGE_BYTES, b_hi = a_hi + TC_TILE_BYTES;
+                const uint32_t a_lo = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                    const uint64_t dah = umma_desc(a_hi, A_K, ks, p.mn_lbo, p.mn_sbo), dal = umma_desc(a_lo, A_K, ks, p.mn_lbo, p.mn_sbo);
+                    const uint64_t dbh = umma_desc(b_hi, B_K, ks, p.mn_lbo, p.mn_sbo), dbl = umma_desc(b_lo, B_K, ks, p.mn_lbo, p.mn_sbo);
+                    tc_mma_tf32(tmem_d, dal, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    tc_mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                    tc_mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                }
+                tc_commit(empty(s));  // implies tcgen05.fence::before_thread_sync
+            }
+            tc_commit(tmem_full);
+        }
+    } else {
+        // ===== splitters (warps 2..5), then epilogue =====
+        const int ctid = threadIdx.x - 64;
+        for (int it = 0; it < total; ++it) {
+            const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+            mbar_wait(full(s), ph);
+            const uint32_t hi = base + s * TC_STAGE_BYTES, lo = hi + 2 * TC_TILE_BYTES;
+#pragma unroll 4
+            for (int i = 0; i < (2 * TC_TILE_BYTES / 16) / 128; ++i) {
+                const uint32_t off = (uint32_t)(i * 128 + ctid) * 16u;
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + off));
+                float4 h, l;
+                h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(conv(s));
+        }
+        // ----- epilogue: TMEM -> registers -> shared (row-major, padded) -> coalesced global -----
+        constexpr int PITCH = TC_BN + 4;
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        if (total > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        const uint32_t stg = base;  // the pipeline stages are dead now (all MMAs committed)
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; ++c) {
+            uint32_t v[32];
+            if (total > 0) {
+                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t addr = stg + (uint32_t)(row * PITCH + c * 32 + q * 4) * 4u;
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[4 * q]), "r"(v[4 * q + 1]),
+                             "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                             : "memory");
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        float* Cz = p.C + (long long)z * p.bC;
+        const int ew = warp - 2;
+        for (int rr = 0; rr < 32; ++rr) {
+            const int r = ew * 32 + rr, gm = m0 + r;
+            if (gm >= Mlive) break;
+#pragma unroll
+            for (int i = 0; i < TC_BN / 32; ++i) {
+                const int col = lane + 32 * i, gn = n0 + col;
+                if (gn < p.N) {
+                    float val;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(stg + (uint32_t)(r * PITCH + col) * 4u));
+                    Cz[(long long)gm * p.ldc + gn] = val;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TC_BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static int make_map(CUtensorMap* m, const TcOperand& o, int box_rows_kmajor) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("tc gemm: cuTensorMapEncodeTiled unavailable"); return EEGAN_ERR_CUDA; }
+    if ((reinterpret_cast<uintptr_t>(o.ptr) & 15) || (o.ld % 4) || (o.bstride % 4)) {
+        set_error("tc gemm: operand base/pitch must be 16-byte aligned (ptr=%p ld=%lld bstride=%lld)", (const void*)o.ptr, o.ld, o.bstride);
+        return EEGAN_ERR_INVALID;
+    }
+    cuuint64_t dims[3], strides[2];
+    cuuint32_t box[3], estr[3] = {1, 1, 1};
+    if (o.kmajor) {  // [rows][K]
+        dims[0] = (cuuint64_t)o.K; dims[1] = (cuuint64_t)o.rows;
+        box[0] = TC_BK; box[1] = (cuuint32_t)box_rows_kmajor;
+    } else {         // [K][rows]
+        dims[0] = (cuuint64_t)o.rows; dims[1] = (cuuint64_t)o.K;
+        box[0] = 32; box[1] = TC_BK;
+    }
+    dims[2] = (cuuint64_t)(o.nbatch > 0 ? o.nbatch : 1);
+    box[2] = 1;
+    strides[0] = (cuuint64_t)o.ld * 4;
+    strides[1] = (cuuint64_t)(o.bstride > 0 ? o.bstride : (long long)dims[1] * o.ld) * 4;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(o.ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, o.kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tc gemm: cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu ld=%lld", (int)r, (unsigned long long)dims[0],
+                  (unsigned long long)dims[1], (unsigned long long)dims[2], o.ld);
+        return EEGAN_ERR_CUDA;
+    }
+    return EEGAN_OK;
+}
+
+template <bool A_K, bool B_K>
+static int launch_t(const CUtensorMap* maps, const TcArgs& a, dim3 grid, cudaStream_t st) {
+    static bool attr_set = false;  // idempotent; a race only repeats the call
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("tc gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+        attr_set = true;
+    }
+    tc_gemm_kernel<A_K, B_K><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], a);
+    return check_launch("tc gemm");
+}
+
+int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
+    EEGAN_REQUIRE(g.nseg == 1 || g.nseg == 2, "tc gemm: nseg=%d", g.nseg);
+    EEGAN_REQUIRE(g.M > 0 && g.N > 0 && g.batch > 0 && g.C, "tc gemm: empty problem");
+    for (int s = 1; s < g.nseg; ++s)
+        EEGAN_REQUIRE(g.A[s].kmajor == g.A[0].kmajor && g.B[s].kmajor == g.B[0].kmajor, "tc gemm: segments must share majorness");
+    CUtensorMap maps[4];
+    TcArgs a{};
+    for (int s = 0; s < 2; ++s) {
+        const int src = s < g.nseg ? s : 0;
+        int rc = make_map(&maps[2 * s], g.A[src], TC_BM);
+        if (rc) return rc;
+        rc = make_map(&maps[2 * s + 1], g.B[src], TC_BN);
+        if (rc) return rc;
+        a.K[s] = s < g.nseg ? g.A[src].K : 0;
+        a.a_batched[s] = g.A[src].bstride > 0;
+        a.b_batched[s] = g.B[src].bstride > 0;
+    }
+    a.C = g.C; a.ldc = g.ldc; a.bC = g.bC; a.M = g.M; a.N = g.N; a.dynM = g.dynM; a.dynK = g.dynK;
+    a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total;
+    a.mn_lbo = 4096 >> 4; a.mn_sbo = 512 >> 4;
+    if (const char* e = getenv("EEGAN_TC_MN_LBO")) a.mn_lbo = (uint32_t)atoi(e);
+    if (const char* e = getenv("EEGAN_TC_MN_SBO")) a.mn_sbo = (uint32_t)atoi(e);
+    dim3 grid((g.N + TC_BN - 1) / TC_BN, (g.M + TC_BM - 1) / TC_BM, g.batch);
+    const bool ak = g.A[0].kmajor, bk = g.B[0].kmajor;
+    if (ak && bk) return launch_t<true, true>(maps, a, grid, st);
+    if (ak && !bk) return launch_t<true, false>(maps, a, grid, st);
+    if (!ak && bk) return launch_t<false, true>(maps, a, grid, st);
+    return launch_t<false, false>(maps, a, grid, st);
+}
+
+}  // namespace eegan
+
+using namespace eegan;
+
+// Stand-alone entry point (tests / microbench): C[z] = A[z] * B[z]^T in 3xTF32.
+//   a_kmajor: A is [M][K] (ld = lda) else [K][M];  b_kmajor: B is [N][K] else [K][N].
+extern "C" int eegan_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, int a_kmajor, int b_kmajor,
+                                 long long lda, long long ldb, long long ldc, long long bsA, long long bsB, long long bsC,
+                                 int batch, void* stream) {
+    EEGAN_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tf32x3: bad arguments");
+    TcGemm g{};
+    g.nseg = 1;
+    g.A[0] = TcOperand{A, a_kmajor, lda, bsA, batch, M, K};
+    g.B[0] = TcOperand{B, b_kmajor, ldb, bsB, batch, N, K};
+    g.C = C; g.ldc = ldc; g.bC = bsC; g.M = M; g.N = N; g.batch = batch; g.nred = 1; g.red_total = 0;
+    return tc_gemm_launch(g, (cudaStream_t)stream);
+}

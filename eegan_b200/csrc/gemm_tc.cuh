@@ -1,0 +1,55 @@
+// tcgen05 (5th-gen tensor core) contraction engine for the pair-grid pipeline, sm_100a only.
+//
+//   C[z][m][n] = sum over segments s, reduction batches red, k of  A_s(m,k) * B_s(n,k)
+//
+// fp32-accurate "3xTF32": every fp32 operand element x is split in shared memory into
+// hi = tf32(x) and lo = tf32(x - hi) and each K-step issues three tcgen05.mma.kind::tf32
+// (lo*hi, hi*lo, hi*hi) into one fp32 accumulator tile in TMEM.  Single-pass TF32/BF16 flips
+// argmax word indices; the split keeps ~2^-21 relative error.
+//
+// Per CTA (192 threads, one 128 x 128 output tile, BK = 32 fp32 = one 128-byte swizzle row):
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of the raw fp32 A/B boxes
+//   warp 1      TMEM allocator + single-thread MMA issuer; tcgen05.commit frees the stage
+//   warps 2-5   hi/lo splitters (in place, layout-agnostic) during the main loop, then the
+//               epilogue: tcgen05.ld -> registers -> shared -> coalesced global stores
+// mbarrier pipeline per stage: full (TMA landed) -> conv (split done) -> empty (MMAs done).
+// Operands may be K-major ([rows][K], K contiguous) or MN-major ([K][rows], rows contiguous);
+// both use the canonical 128B-swizzle UMMA layouts, so no transposed copies are needed.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace eegan {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per operand tile
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi B_hi A_lo B_lo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+
+struct TcOperand {
+    const float* ptr;    // base
+    int kmajor;          // 1: [rows][K] (K contiguous); 0: [K][rows] (rows contiguous)
+    long long ld;        // pitch in elements of the non-contiguous index (multiple of 4)
+    long long bstride;   // elements between batches (multiple of 4); 0 = not batched
+    int nbatch;          // number of batches addressable (>= 1)
+    int rows, K;         // logical extents (TMA zero-fills beyond them)
+};
+
+struct TcGemm {
+    TcOperand A[2], B[2];   // up to two K-concatenated segments (segment 1 unused if nseg == 1)
+    int nseg;
+    float* C;
+    long long ldc, bC;
+    int M, N;               // output extents (static upper bounds)
+    const int* dynM;        // optional device int: live rows of C / A
+    const int* dynK;        // optional device int: live K extent (all segments)
+    int batch;              // grid.z
+    int nred, red_total;    // reduction batches per z: operand batch index = z*nred + red
+};
+
+// Enqueue the GEMM.  Returns EEGAN_OK or an error code (message via set_error).
+int tc_gemm_launch(const TcGemm& g, cudaStream_t st);
+
+}  // namespace eegan

@@ -15,9 +15,16 @@
 // The forward stashes P, A, U, cos, |u| in the caller's workspace; the backward consumes
 // them (no recompute).  Nothing here synchronises the device or allocates memory.
 #include "common.cuh"
+#include <atomic>
+
 #include "gemm_ffma.cuh"
+#include "gemm_tc.cuh"
 
 namespace eegan {
+
+// contraction engine: 1 = tcgen05 3xTF32 (default), 0 = CUDA-core fp32 FFMA.  Process-wide
+// (the backward runs on autograd's thread); set via eegan_set_contraction_engine().
+static std::atomic<int> g_engine{1};
 
 struct PairWs {
     int* col_start;  // [Bc+1] exclusive prefix of clamp(cap_lens)
@@ -25,15 +32,17 @@ struct PairWs {
     int* col_cap;    // [NtM]  caption of packed column n
     float* Wp;       // [NtM][D] packed words, d contiguous
     float* wn;       // [NtM]  |w_n|
-    float* SP;       // [Bi][NtM][R]  S, then P in place
-    float* A;        // [Bi][NtM][R]
+    float* SP;       // [Bi][NtM][Rp] S, then P in place
+    float* A;        // [Bi][NtM][Rp]
     float* U;        // [Bi][NtM][D]  U, then DU in place (bwd)
     float* cosv;     // [Bi][NtM]
     float* un;       // [Bi][NtM]
     float* alpha;    // [3][Bi][NtM]
-    float* DA;       // [Bi][NtM][R]  dA, then DS in place
+    float* DA;       // [Bi][NtM][Rp] dA, then DS in place
     float* dWpart;   // [nsplit][NtM][D]
     float* dwcos;    // [NtM][D]
+    float* Cp;       // [Bi][D][Rp] image features re-pitched for TMA (only if Rp != R)
+    int Rp;          // stash pitch of the region index: R rounded up to 4 floats (16 B)
     int nsplit;
     size_t bytes;
 };
@@ -56,21 +65,24 @@ static PairWs carve(void* base, int Bi, int Bc, int D, int R, int Tm) {
         off += align_up(bytes, 256);
         return q;
     };
+    const size_t Rp = (size_t)(R + 3) / 4 * 4;
+    w.Rp = (int)Rp;
     w.nsplit = pick_nsplit(Bi, (int)NtM, D);
     w.col_start = (int*)take((Bc + 1) * sizeof(int));
     w.ntot = (int*)take(sizeof(int));
     w.col_cap = (int*)take(NtM * sizeof(int));
     w.Wp = (float*)take(NtM * D * sizeof(float));
     w.wn = (float*)take(NtM * sizeof(float));
-    w.SP = (float*)take((size_t)Bi * NtM * R * sizeof(float));
-    w.A = (float*)take((size_t)Bi * NtM * R * sizeof(float));
+    w.SP = (float*)take((size_t)Bi * NtM * Rp * sizeof(float));
+    w.A = (float*)take((size_t)Bi * NtM * Rp * sizeof(float));
     w.U = (float*)take((size_t)Bi * NtM * D * sizeof(float));
     w.cosv = (float*)take((size_t)Bi * NtM * sizeof(float));
     w.un = (float*)take((size_t)Bi * NtM * sizeof(float));
     w.alpha = (float*)take((size_t)3 * Bi * NtM * sizeof(float));
-    w.DA = (float*)take((size_t)Bi * NtM * R * sizeof(float));
+    w.DA = (float*)take((size_t)Bi * NtM * Rp * sizeof(float));
     w.dWpart = (float*)take((size_t)w.nsplit * NtM * D * sizeof(float));
     w.dwcos = (float*)take(NtM * D * sizeof(float));
+    w.Cp = (float*)take(Rp != (size_t)R ? (size_t)Bi * D * Rp * sizeof(float) : 0);
     w.bytes = off;
     return w;
 }
@@ -136,30 +148,30 @@ __global__ void __launch_bounds__(128) pair_pack_words_kernel(const float* __res
 // One CTA per (caption i, image j): P = softmax_words(S) (:44-45), A = softmax_regions(g1 P)
 // (:53-54).  P overwrites S.  Dynamic smem: T_max * R floats.
 __global__ void __launch_bounds__(256) pair_attn_softmax_kernel(float* __restrict__ SP, float* __restrict__ A,
-                                                                const int* __restrict__ col_start, int NtM, int R,
+                                                                const int* __restrict__ col_start, int NtM, int R, int Rp,
                                                                 float g1, float* __restrict__ att, int diag_offset,
                                                                 int Tm) {
     extern __shared__ float p[];
     const int i = blockIdx.x, j = blockIdx.y;
     const int cs = col_start[i], T = col_start[i + 1] - cs;
-    float* Sj = SP + ((size_t)j * NtM + cs) * R;
-    float* Aj = A + ((size_t)j * NtM + cs) * R;
+    float* Sj = SP + ((size_t)j * NtM + cs) * Rp;
+    float* Aj = A + ((size_t)j * NtM + cs) * Rp;
     const bool diag = (att != nullptr) && (j == i + diag_offset);
     float* attp = diag ? att + (size_t)i * Tm * R : nullptr;
 
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         float mx = -INFINITY;
-        for (int t = 0; t < T; ++t) mx = fmaxf(mx, Sj[(size_t)t * R + r]);
+        for (int t = 0; t < T; ++t) mx = fmaxf(mx, Sj[(size_t)t * Rp + r]);
         float sum = 0.f;
         for (int t = 0; t < T; ++t) {
-            const float e = expf(Sj[(size_t)t * R + r] - mx);
+            const float e = expf(Sj[(size_t)t * Rp + r] - mx);
             p[t * R + r] = e;
             sum += e;
         }
         for (int t = 0; t < T; ++t) {
             const float pv = p[t * R + r] / sum;
             p[t * R + r] = pv;
-            Sj[(size_t)t * R + r] = pv;
+            Sj[(size_t)t * Rp + r] = pv;
         }
     }
     __syncthreads();
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(256) pair_attn_softmax_kernel(float* __restric
         sum = warp_sum(sum);
         for (int r = lane; r < R; r += 32) {
             const float a = p[t * R + r] / sum;
-            Aj[(size_t)t * R + r] = a;
+            Aj[(size_t)t * Rp + r] = a;
             if (diag) attp[(size_t)t * R + r] = a;
         }
     }
@@ -292,18 +304,18 @@ __global__ void __launch_bounds__(256) pair_du_dwcos_kernel(float* __restrict__ 
 //   dz = a (dA - sum_r a dA);  v = g1 p dz;  ds = v - p sum_t v
 __global__ void __launch_bounds__(256) pair_softmax_bwd_kernel(float* __restrict__ DA, const float* __restrict__ A,
                                                                const float* __restrict__ P, const int* __restrict__ col_start,
-                                                               int NtM, int R, float g1) {
+                                                               int NtM, int R, int Rp, float g1) {
     __shared__ float csum[32];
     const int i = blockIdx.x, j = blockIdx.y;
     const int cs = col_start[i], T = col_start[i + 1] - cs;
-    const size_t base = ((size_t)j * NtM + cs) * R;
+    const size_t base = ((size_t)j * NtM + cs) * Rp;
     float* dA = DA + base;
     const float* a = A + base;
     const float* p = P + base;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int t = w; t < T; t += nw) {
         float s = 0.f;
-        for (int r = lane; r < R; r += 32) s = fmaf(a[(size_t)t * R + r], dA[(size_t)t * R + r], s);
+        for (int r = lane; r < R; r += 32) s = fmaf(a[(size_t)t * Rp + r], dA[(size_t)t * Rp + r], s);
         s = warp_sum(s);
         if (lane == 0) csum[t] = s;
     }
@@ -311,11 +323,11 @@ __global__ void __launch_bounds__(256) pair_softmax_bwd_kernel(float* __restrict
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         float q = 0.f;
         for (int t = 0; t < T; ++t) {
-            const size_t k = (size_t)t * R + r;
+            const size_t k = (size_t)t * Rp + r;
             q += g1 * p[k] * a[k] * (dA[k] - csum[t]);
         }
         for (int t = 0; t < T; ++t) {
-            const size_t k = (size_t)t * R + r;
+            const size_t k = (size_t)t * Rp + r;
             const float pv = p[k];
             dA[k] = g1 * pv * a[k] * (dA[k] - csum[t]) - pv * q;
         }
@@ -323,21 +335,57 @@ __global__ void __launch_bounds__(256) pair_softmax_bwd_kernel(float* __restrict
 }
 
 // d_words[i][d][t] = dwcos + sum of the split-j partials; zero for padded words.
+// grid (Bc, D/32): a 32(d) x T_max tile goes through shared memory so that both the packed
+// reads (d contiguous) and the d_words writes (t contiguous) are coalesced.
 __global__ void __launch_bounds__(256) pair_unpack_dw_kernel(const float* __restrict__ dWpart, const float* __restrict__ dwcos,
                                                              const int* __restrict__ col_start, int nsplit, int NtM, int D,
                                                              int Tm, float* __restrict__ d_words) {
-    const int i = blockIdx.x;
+    __shared__ float tile[32][33];
+    const int i = blockIdx.x, d0 = blockIdx.y * 32;
     const int cs = col_start[i], T = col_start[i + 1] - cs;
-    for (int idx = threadIdx.x; idx < D * Tm; idx += blockDim.x) {
-        const int t = idx / D, d = idx - t * D;  // d fastest: coalesced reads of the packed grads
+    for (int idx = threadIdx.x; idx < 32 * Tm; idx += blockDim.x) {
+        const int t = idx / 32, dd = idx % 32;
         float v = 0.f;
-        if (t < T) {
-            const size_t k = (size_t)(cs + t) * D + d;
+        if (t < T && d0 + dd < D) {
+            const size_t k = (size_t)(cs + t) * D + d0 + dd;
             v = dwcos[k];
             for (int s = 0; s < nsplit; ++s) v += dWpart[(size_t)s * NtM * D + k];
         }
-        d_words[((size_t)i * D + d) * Tm + t] = v;
+        tile[dd][t] = v;
     }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * Tm; idx += blockDim.x) {
+        const int dd = idx / Tm, t = idx % Tm;
+        if (d0 + dd < D) d_words[((size_t)i * D + d0 + dd) * Tm + t] = tile[dd][t];
+    }
+}
+
+// img [Bi*D][R] -> Cp [Bi*D][Rp] (TMA needs 16-byte row pitches; R = 289 is odd)
+__global__ void __launch_bounds__(256) pair_repitch_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           long long rows, int R, int Rp) {
+    const long long total = rows * Rp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / Rp;
+        const int r = (int)(e - row * Rp);
+        dst[e] = r < R ? __ldg(src + row * R + r) : 0.f;
+    }
+}
+
+// The K = packed-column contraction (dC) runs in blocks of 32 rows: rows [ntot, roundup32(ntot)) of
+// the four operands must be zero, not stale.  grid (32, Bi, 4).
+__global__ void __launch_bounds__(128) pair_zero_tail_kernel(float* __restrict__ DU, float* __restrict__ A,
+                                                             float* __restrict__ DS, float* __restrict__ Wp,
+                                                             const int* __restrict__ ntot, int NtM, int D, int Rp) {
+    const int n = *ntot + blockIdx.x;
+    if (n >= NtM || n >= (*ntot + 31) / 32 * 32) return;
+    const int j = blockIdx.y, which = blockIdx.z;
+    float* row;
+    int len;
+    if (which == 0) { row = DU + ((size_t)j * NtM + n) * D; len = D; }
+    else if (which == 1) { row = A + ((size_t)j * NtM + n) * Rp; len = Rp; }
+    else if (which == 2) { row = DS + ((size_t)j * NtM + n) * Rp; len = Rp; }
+    else { if (j) return; row = Wp + (size_t)n * D; len = D; }
+    for (int k = threadIdx.x; k < len; k += blockDim.x) row[k] = 0.f;
 }
 
 static int validate(int Bi, int Bc, int D, int R, int Tm) {
@@ -358,6 +406,87 @@ extern "C" size_t eegan_damsm_pair_workspace_bytes(int B_img, int B_cap, int D, 
     return carve(nullptr, B_img, B_cap, D, R, T_max).bytes;
 }
 
+// ---- the six contractions, on either engine -------------------------------------------
+static const float* image_operand(const PairWs& w, const float* img) { return w.Cp ? w.Cp : img; }
+
+// S / dA [j][n][Rp] = X[n][d] . img[j][d][r]   (X = Wp unbatched, or DU batched)
+static int gemm_nd_dr(const PairWs& w, const float* X, bool x_batched, const float* img, float* out, int Bi, int NtM, int D,
+                      int R, cudaStream_t st) {
+    if (g_engine.load()) {
+        TcGemm g{};
+        g.nseg = 1;
+        g.A[0] = TcOperand{X, 1, D, x_batched ? (long long)NtM * D : 0, x_batched ? Bi : 1, NtM, D};
+        g.B[0] = TcOperand{image_operand(w, img), 0, w.Rp, (long long)D * w.Rp, Bi, R, D};
+        g.C = out; g.ldc = w.Rp; g.bC = (long long)NtM * w.Rp; g.M = NtM; g.N = R; g.dynM = w.ntot; g.batch = Bi; g.nred = 1;
+        return tc_gemm_launch(g, st);
+    }
+    GemmArgs g{};
+    g.A = X; g.B = img; g.C = out;
+    g.M = NtM; g.N = R; g.K = D; g.dynM = w.ntot;
+    g.sAm = D; g.sAk = 1; g.sBk = R; g.sBn = 1; g.sCm = w.Rp; g.sCn = 1;
+    g.bA = x_batched ? (long long)NtM * D : 0; g.bB = (long long)D * R; g.bC = (long long)NtM * w.Rp;
+    g.nred = 1;
+    launch_gemm_ffma<128, 64, 8, 4, true, true>(g, Bi, st);
+    return check_launch("pair gemm (n,d)x(d,r)");
+}
+
+// U [j][n][D] / dWpart[s][n][D] = X[j][n][r] . img[j][d][r], optionally reduced over j in nsplit groups
+static int gemm_nr_dr(const PairWs& w, const float* X, const float* img, float* out, int Bi, int NtM, int D, int R,
+                      int nsplit, cudaStream_t st) {
+    const int nred = nsplit ? (Bi + nsplit - 1) / nsplit : 1;
+    const int batch = nsplit ? nsplit : Bi;
+    if (g_engine.load()) {
+        TcGemm g{};
+        g.nseg = 1;
+        g.A[0] = TcOperand{X, 1, w.Rp, (long long)NtM * w.Rp, Bi, NtM, R};
+        g.B[0] = TcOperand{image_operand(w, img), 1, w.Rp, (long long)D * w.Rp, Bi, D, R};
+        g.C = out; g.ldc = D; g.bC = (long long)NtM * D; g.M = NtM; g.N = D; g.dynM = w.ntot; g.batch = batch;
+        g.nred = nred; g.red_total = nsplit ? Bi : 0;
+        return tc_gemm_launch(g, st);
+    }
+    GemmArgs g{};
+    g.A = X; g.B = img; g.C = out;
+    g.M = NtM; g.N = D; g.K = R; g.dynM = w.ntot;
+    g.sAm = w.Rp; g.sAk = 1; g.sBk = 1; g.sBn = R; g.sCm = D; g.sCn = 1;
+    g.rA = (long long)NtM * w.Rp; g.rB = (long long)D * R;
+    g.bA = g.rA * nred; g.bB = g.rB * nred; g.bC = (long long)NtM * D;
+    g.nred = nred; g.red_total = nsplit ? Bi : 0;
+    launch_gemm_ffma<128, 128, 8, 8, true, false>(g, batch, st);
+    return check_launch("pair gemm (n,r)x(d,r)");
+}
+
+// d_img[j][d][r] = sum_n DU[j][n][d] A[j][n][r] + Wp[n][d] DS[j][n][r]
+static int gemm_dc(const PairWs& w, float* d_img, int Bi, int NtM, int D, int R, cudaStream_t st) {
+    if (g_engine.load()) {
+        pair_zero_tail_kernel<<<dim3(32, Bi, 4), 128, 0, st>>>(w.U, w.A, w.DA, w.Wp, w.ntot, NtM, D, w.Rp);
+        TcGemm g{};
+        g.nseg = 2;
+        g.A[0] = TcOperand{w.U, 0, D, (long long)NtM * D, Bi, D, NtM};
+        g.B[0] = TcOperand{w.A, 0, w.Rp, (long long)NtM * w.Rp, Bi, R, NtM};
+        g.A[1] = TcOperand{w.Wp, 0, D, 0, 1, D, NtM};
+        g.B[1] = TcOperand{w.DA, 0, w.Rp, (long long)NtM * w.Rp, Bi, R, NtM};
+        g.C = d_img; g.ldc = R; g.bC = (long long)D * R; g.M = D; g.N = R; g.dynK = w.ntot; g.batch = Bi; g.nred = 1;
+        return tc_gemm_launch(g, st);
+    }
+    GemmArgs g{};
+    g.A = w.U; g.B = w.A; g.C = d_img;
+    g.M = D; g.N = R; g.K = NtM; g.dynK = w.ntot;
+    g.sAm = 1; g.sAk = D; g.sBk = w.Rp; g.sBn = 1; g.sCm = R; g.sCn = 1;
+    g.bA = (long long)NtM * D; g.bB = (long long)NtM * w.Rp; g.bC = (long long)D * R;
+    g.nred = 1;
+    launch_gemm_ffma<128, 64, 8, 4, false, true>(g, Bi, st);
+    g.A = w.Wp; g.B = w.DA; g.bA = 0; g.accumulate = 1;
+    launch_gemm_ffma<128, 64, 8, 4, false, true>(g, Bi, st);
+    return check_launch("pair gemm dC");
+}
+
+extern "C" int eegan_set_contraction_engine(int engine) {
+    EEGAN_REQUIRE(engine == 0 || engine == 1, "contraction engine must be 0 (fp32 FFMA) or 1 (tcgen05 3xTF32)");
+    g_engine.store(engine);
+    return EEGAN_OK;
+}
+extern "C" int eegan_get_contraction_engine(void) { return g_engine.load(); }
+
 extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const int32_t* cap_lens, int Bi, int Bc,
                                     int D, int R, int Tm, float g1, float g2, float* m, float* att, int diag_offset,
                                     void* workspace, size_t workspace_bytes, void* stream) {
@@ -369,24 +498,20 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
         set_error("pair fwd: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
         return EEGAN_ERR_WORKSPACE;
     }
+    if (w.Rp == R) w.Cp = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     const int NtM = Bc * Tm;
 
     prof_mark(-1, st);
     pair_scan_kernel<<<1, 1024, 0, st>>>(cap_lens, Bc, Tm, w.col_start, w.ntot, w.col_cap);
     pair_pack_words_kernel<<<NtM, 128, 0, st>>>(words, w.col_start, w.col_cap, w.ntot, D, Tm, w.Wp, w.wn);
+    if (w.Cp && g_engine.load())
+        pair_repitch_kernel<<<148 * 4, 256, 0, st>>>(img, w.Cp, (long long)Bi * D, R, w.Rp);
     EEGAN_LAUNCH_CHECK("pair prologue");
     prof_mark(0, st);
 
-    GemmArgs g{};
-    // GEMM1: S[j][n][r] = sum_d Wp[n][d] img[j][d][r]
-    g.A = w.Wp; g.B = img; g.C = w.SP;
-    g.M = NtM; g.N = R; g.K = D; g.dynM = w.ntot; g.dynK = nullptr;
-    g.sAm = D; g.sAk = 1; g.sBk = R; g.sBn = 1; g.sCm = R; g.sCn = 1;
-    g.bA = 0; g.bB = (long long)D * R; g.bC = (long long)NtM * R;
-    g.nred = 1; g.red_total = 0; g.rA = g.rB = 0; g.accumulate = 0;
-    launch_gemm_ffma<128, 64, 8, 4, true, true>(g, Bi, st);
-    EEGAN_LAUNCH_CHECK("pair GEMM1");
+    rc = gemm_nd_dr(w, w.Wp, false, img, w.SP, Bi, NtM, D, R, st);  // GEMM1: S = Wp . C
+    if (rc) return rc;
     prof_mark(1, st);
 
     const size_t smem = (size_t)Tm * R * sizeof(float);
@@ -394,19 +519,12 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
         cudaError_t e = cudaFuncSetAttribute(pair_attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
     }
-    pair_attn_softmax_kernel<<<dim3(Bc, Bi), 256, smem, st>>>(w.SP, w.A, w.col_start, NtM, R, g1, att, diag_offset, Tm);
+    pair_attn_softmax_kernel<<<dim3(Bc, Bi), 256, smem, st>>>(w.SP, w.A, w.col_start, NtM, R, w.Rp, g1, att, diag_offset, Tm);
     EEGAN_LAUNCH_CHECK("pair softmax");
     prof_mark(2, st);
 
-    // GEMM2: U[j][n][d] = sum_r A[j][n][r] img[j][d][r]
-    g = GemmArgs{};
-    g.A = w.A; g.B = img; g.C = w.U;
-    g.M = NtM; g.N = D; g.K = R; g.dynM = w.ntot;
-    g.sAm = R; g.sAk = 1; g.sBk = 1; g.sBn = R; g.sCm = D; g.sCn = 1;
-    g.bA = (long long)NtM * R; g.bB = (long long)D * R; g.bC = (long long)NtM * D;
-    g.nred = 1;
-    launch_gemm_ffma<128, 128, 8, 8, true, false>(g, Bi, st);
-    EEGAN_LAUNCH_CHECK("pair GEMM2");
+    rc = gemm_nr_dr(w, w.A, img, w.U, Bi, NtM, D, R, 0, st);  // GEMM2: U = A . C^T
+    if (rc) return rc;
     prof_mark(3, st);
 
     pair_cos_lse_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.U, w.Wp, w.wn, w.col_start, NtM, D, Bc, g2, w.cosv, w.un, m);
@@ -427,6 +545,7 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
         set_error("pair bwd: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
         return EEGAN_ERR_WORKSPACE;
     }
+    if (w.Rp == R) w.Cp = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     const int NtM = Bc * Tm;
 
@@ -436,48 +555,23 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
     EEGAN_LAUNCH_CHECK("pair bwd scalars");
     prof_mark(5, st);
 
-    GemmArgs g{};
-    // GEMM3: dA[j][n][r] = sum_d DU[j][n][d] img[j][d][r]
-    g.A = w.U; g.B = img; g.C = w.DA;
-    g.M = NtM; g.N = R; g.K = D; g.dynM = w.ntot;
-    g.sAm = D; g.sAk = 1; g.sBk = R; g.sBn = 1; g.sCm = R; g.sCn = 1;
-    g.bA = (long long)NtM * D; g.bB = (long long)D * R; g.bC = (long long)NtM * R;
-    g.nred = 1;
-    launch_gemm_ffma<128, 64, 8, 4, true, true>(g, Bi, st);
-    EEGAN_LAUNCH_CHECK("pair GEMM3");
+    rc = gemm_nd_dr(w, w.U, true, img, w.DA, Bi, NtM, D, R, st);  // GEMM3: dA = DU . C
+    if (rc) return rc;
     prof_mark(6, st);
 
-    pair_softmax_bwd_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.DA, w.A, w.SP, w.col_start, NtM, R, g1);
+    pair_softmax_bwd_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.DA, w.A, w.SP, w.col_start, NtM, R, w.Rp, g1);
     EEGAN_LAUNCH_CHECK("pair softmax bwd");
     prof_mark(7, st);
 
     if (d_img) {
-        // GEMM4a: dC[j][d][r] = sum_n DU[j][n][d] A[j][n][r]
-        g = GemmArgs{};
-        g.A = w.U; g.B = w.A; g.C = d_img;
-        g.M = D; g.N = R; g.K = NtM; g.dynK = w.ntot;
-        g.sAm = 1; g.sAk = D; g.sBk = R; g.sBn = 1; g.sCm = R; g.sCn = 1;
-        g.bA = (long long)NtM * D; g.bB = (long long)NtM * R; g.bC = (long long)D * R;
-        g.nred = 1;
-        launch_gemm_ffma<128, 64, 8, 4, false, true>(g, Bi, st);
-        // GEMM4b: dC[j][d][r] += sum_n Wp[n][d] DS[j][n][r]
-        g.A = w.Wp; g.B = w.DA; g.bA = 0; g.accumulate = 1;
-        launch_gemm_ffma<128, 64, 8, 4, false, true>(g, Bi, st);
-        EEGAN_LAUNCH_CHECK("pair GEMM4");
+        rc = gemm_dc(w, d_img, Bi, NtM, D, R, st);  // GEMM4: dC = DU^T A + Wp^T DS
+        if (rc) return rc;
         prof_mark(8, st);
     }
     if (d_words) {
-        // GEMM5: dWpart[s][n][d] = sum_{j in split s} sum_r DS[j][n][r] img[j][d][r]
-        g = GemmArgs{};
-        const int nred = (Bi + w.nsplit - 1) / w.nsplit;
-        g.A = w.DA; g.B = img; g.C = w.dWpart;
-        g.M = NtM; g.N = D; g.K = R; g.dynM = w.ntot;
-        g.sAm = R; g.sAk = 1; g.sBk = 1; g.sBn = R; g.sCm = D; g.sCn = 1;
-        g.rA = (long long)NtM * R; g.rB = (long long)D * R;
-        g.bA = g.rA * nred; g.bB = g.rB * nred; g.bC = (long long)NtM * D;
-        g.nred = nred; g.red_total = Bi;
-        launch_gemm_ffma<128, 128, 8, 8, true, false>(g, w.nsplit, st);
-        pair_unpack_dw_kernel<<<Bc, 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.nsplit, NtM, D, Tm, d_words);
+        rc = gemm_nr_dr(w, w.DA, img, w.dWpart, Bi, NtM, D, R, w.nsplit, st);  // GEMM5: dWp = sum_j DS . C^T
+        if (rc) return rc;
+        pair_unpack_dw_kernel<<<dim3(Bc, (D + 31) / 32), 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.nsplit, NtM, D, Tm, d_words);
         EEGAN_LAUNCH_CHECK("pair GEMM5");
         prof_mark(9, st);
     }
@@ -586,7 +680,7 @@ extern "C" int eegan_func_attention_fwd(const float* query, const float* context
     launch_gemm_ffma<128, 64, 8, 4, false, true>(g, B, st);
     const size_t smem = (size_t)T * R * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(pair_attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pair_attn_softmax_kernel<<<dim3(1, B), 256, smem, st>>>(w.P, attn, w.col_start, T, R, gamma1, nullptr, 0, T);
+    pair_attn_softmax_kernel<<<dim3(1, B), 256, smem, st>>>(w.P, attn, w.col_start, T, R, R, gamma1, nullptr, 0, T);
     // u[b][d][t] = sum_r c[b][d][r] a[b][t][r]      (:61)
     g = GemmArgs{};
     g.A = context; g.B = attn; g.C = u;
@@ -620,7 +714,7 @@ extern "C" int eegan_func_attention_bwd(const float* query, const float* context
         g.nred = 1; g.accumulate = 1;
         launch_gemm_ffma<128, 64, 8, 4, false, true>(g, B, st);
     }
-    pair_softmax_bwd_kernel<<<dim3(1, B), 256, 0, st>>>(w.DA, attn, w.P, w.col_start, T, R, gamma1);
+    pair_softmax_bwd_kernel<<<dim3(1, B), 256, 0, st>>>(w.DA, attn, w.P, w.col_start, T, R, R, gamma1);
     // d_context[b][d][r] = sum_t d_u[b][d][t] a[b][t][r] + q[b][d][t] ds[b][t][r]
     g = GemmArgs{};
     g.B = attn; g.C = d_context;

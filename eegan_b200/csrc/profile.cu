@@ -1,7 +1,9 @@
-// Optional per-stage device timing for bench.py: when enabled on the calling host thread the
+// Optional per-stage device timing for bench.py: when enabled the
 // multi-kernel entry points drop a cudaEvent after each stage on the caller's stream;
 // eegan_profile_collect() then synchronises those events and returns summed durations per
 // stage.  Off by default: the hot path records nothing and never synchronises.
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -12,9 +14,12 @@ struct Mark {
     cudaEvent_t ev;
     int stage;  // -1 = start of a call
 };
-static thread_local bool g_on = false;
-static thread_local std::vector<Mark> g_marks;
-static thread_local std::vector<cudaEvent_t> g_pool;
+// process-wide (autograd runs the backward on its own thread), guarded by a mutex; only ever
+// touched when the bench switched profiling on
+static std::atomic<bool> g_on{false};
+static std::mutex g_mu;
+static std::vector<Mark> g_marks;
+static std::vector<cudaEvent_t> g_pool;
 
 static const char* kStageNames[EEGAN_PROF_NSTAGES] = {
     "prologue(pack)", "gemm1(S=W.C)", "attn_softmax", "gemm2(U=A.C^T)", "cos_lse",
@@ -22,7 +27,8 @@ static const char* kStageNames[EEGAN_PROF_NSTAGES] = {
 };
 
 void prof_mark(int stage, cudaStream_t st) {
-    if (!g_on) return;
+    if (!g_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_mu);
     cudaEvent_t ev;
     if (!g_pool.empty()) {
         ev = g_pool.back();
@@ -51,6 +57,7 @@ extern "C" const char* eegan_profile_stage_name(int stage) {
 
 extern "C" int eegan_profile_collect(double* stage_ms, int* stage_launches) {
     EEGAN_REQUIRE(stage_ms && stage_launches, "profile_collect: null pointer");
+    std::lock_guard<std::mutex> lk(g_mu);
     for (int s = 0; s < EEGAN_PROF_NSTAGES; ++s) { stage_ms[s] = 0.0; stage_launches[s] = 0; }
     for (size_t k = 0; k < g_marks.size(); ++k) {
         if (g_marks[k].stage < 0 || k == 0) continue;

@@ -61,8 +61,9 @@ class _AllGatherCols(torch.autograd.Function):
     def forward(ctx, block, group):
         world, rank = _world(group)
         ctx.rank, ctx.b = rank, block.shape[1]
-        parts = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=block.device)
-        dist.all_gather_into_tensor(parts, block.contiguous(), group=group)
+        parts = torch.empty((world * block.shape[0], block.shape[1]), dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(parts, block.contiguous(), group=group)  # concatenated along dim 0
+        parts = parts.view(world, block.shape[0], block.shape[1])
         return parts.permute(1, 0, 2).reshape(block.shape[0], world * block.shape[1]).contiguous()
 
     @staticmethod

@@ -182,9 +182,27 @@ int eegan_syncbn_bwd_apply(const float* x, const float* dy, const float* mean,
                            int N, int C, int HW,
                            float* dx, void* stream);
 
+/* Contraction engine of the pair grid's six GEMM-shaped stages: 1 (default) = tcgen05
+ * 3xTF32 tensor-core engine, 0 = exact-fp32 CUDA-core FFMA engine (validation / A-B runs).
+ * Both are sm_100a kernels of this library; process-wide setting. */
+int eegan_set_contraction_engine(int engine);
+int eegan_get_contraction_engine(void);
+
+/* ------------------------------------------------------------------------------------
+ * The tensor-core contraction engine on its own (tests / microbenchmarks):
+ *   C[z][m][n] = sum_k A[z](m,k) * B[z](n,k), fp32 in / fp32 out, computed as fp32-accurate
+ *   3xTF32 on tcgen05 (hi/lo operand split, three MMAs per K-step, fp32 accumulators in TMEM).
+ * a_kmajor: A is [M][K] with pitch lda, else [K][M]; b_kmajor: B is [N][K] with pitch ldb, else
+ * [K][N].  Pitches and batch strides are in elements and must be multiples of 4; bases 16-byte
+ * aligned (TMA).  C is [M][N] with pitch ldc (any alignment).
+ * ---------------------------------------------------------------------------------- */
+int eegan_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K,
+                      int a_kmajor, int b_kmajor, long long lda, long long ldb, long long ldc,
+                      long long bsA, long long bsB, long long bsC, int batch, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Bench-only stage timing of the multi-kernel entry points (eegan_damsm_pair_fwd/_bwd).
- * Thread-local and off by default.  While enabled, each call records a cudaEvent after every
+ * Process-wide switch, off by default (the backward runs on autograd's thread).  While enabled, each call records a cudaEvent after every
  * stage on the caller's stream; eegan_profile_collect synchronises those events (the only
  * synchronising entry point of the library) and returns, per stage, the summed device time
  * in ms and the number of times the stage ran since the previous collect.

@@ -17,6 +17,10 @@ from oracle.make_golden import IMG_GRAD_STRIDE, W0, W1
 pytestmark = pytest.mark.gpu
 
 TOL_SIM, TOL_LOSS, TOL_GRAD, TOL_ATT = 1e-4, 1e-5, 1e-4, 1e-6
+# The "stress" inputs (randn x randn, score std ~16, near-one-hot softmaxes) amplify the 2^-21
+# relative error of the 3xTF32 contraction: attention maps are held to 2.5e-6 there (the fp32
+# reference itself sits ~1e-6 from float64 on that set).
+TOL_ATT_STRESS = 2.5e-6
 
 
 def dev(t):
@@ -40,7 +44,7 @@ def test_words_loss_vs_reference_fixture(cuda_lib, name):
     finite_close(sim.cpu(), g["sim"], TOL_SIM)
     assert isinstance(att, list) and len(att) == B
     got = np.concatenate([a.detach().cpu().numpy().reshape(-1) for a in att])
-    np.testing.assert_allclose(got, g["att"], atol=TOL_ATT)
+    np.testing.assert_allclose(got, g["att"], atol=TOL_ATT_STRESS if kw["kind"] == "stress" else TOL_ATT)
     off = 0
     for i, T in enumerate(g["cap_lens"]):  # argmax word per region: bit-exact
         R = att[i].shape[2] * att[i].shape[3]
@@ -76,7 +80,7 @@ def test_words_loss_vs_oracle(cuda_lib, kind, cls, B, T):
     assert relmax(words.grad.cpu(), words_o.grad) <= TOL_GRAD
     flips = 0
     for a, b in zip(att, oatt):
-        assert float((a.cpu().double() - b.detach()).abs().max()) <= TOL_ATT
+        assert float((a.cpu().double() - b.detach()).abs().max()) <= (TOL_ATT_STRESS if kind == "stress" else TOL_ATT)
         flips += int((a.cpu().reshape(a.shape[1], -1).argmax(0) != b.detach().reshape(b.shape[1], -1).argmax(0)).sum())
     if kind == "realistic":
         assert flips == 0
@@ -209,3 +213,23 @@ def test_full_size_properties(cuda_lib):
         assert torch.equal(sim_j, sim)
         for a in att:
             assert float((a.sum(dim=(2, 3)) - 1).abs().max()) <= 1e-5
+
+
+def test_ffma_engine_still_matches(cuda_lib):
+    """The exact-fp32 CUDA-core engine stays selectable for A/B validation of the tensor-core
+    engine: both must agree with the float64 oracle, and with each other to fp32 noise."""
+    import eegan_b200 as E
+    c = cases.words_case(12, 18, seed=5)
+    res = {}
+    try:
+        for eng in (0, 1):
+            assert cuda_lib.eegan_set_contraction_engine(eng) == 0
+            img = c["img"].cuda().requires_grad_()
+            words = c["words"].cuda().requires_grad_()
+            l0, l1, _ = E.words_loss(img, words, c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], 12)
+            (l0 + l1).backward()
+            res[eng] = (l0.item(), l1.item(), img.grad.clone(), words.grad.clone())
+    finally:
+        cuda_lib.eegan_set_contraction_engine(1)
+    assert abs(res[0][0] - res[1][0]) <= 2e-5 and abs(res[0][1] - res[1][1]) <= 2e-5
+    assert relmax(res[1][2], res[0][2]) <= TOL_GRAD and relmax(res[1][3], res[0][3]) <= TOL_GRAD

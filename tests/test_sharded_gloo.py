@@ -1,0 +1,156 @@
+"""CPU, world_size = 2 over gloo: the host-side sharding / collective logic of the N > 1 path
+(eegan_b200/sharded.py and the SyncBN module) with the ORACLE standing in for the CUDA kernels.
+The sharded result must equal the single-process full-batch result (the reference computes
+the full-batch grid on GPU 0 after DataParallel gathers, train.py:195,419-435)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_grid(img_all, words, cap_lens, diag_offset=0, want_att=True):
+    from oracle import damsm_oracle as O
+    t = O.dense_pair_terms(img_all, words, cap_lens)
+    b = words.shape[0]
+    att = torch.stack([t["a"][diag_offset + i, i] for i in range(b)])  # [b, T, R]
+    return t["m"], att.detach()
+
+
+def _oracle_ce(m_all, g3, cls_all, lab_all):
+    from oracle import damsm_oracle as O
+    sim = m_all * g3
+    mask = O.class_mask(cls_all, sim.shape[0])
+    if mask is not None:
+        sim = sim.masked_fill(mask, float("-inf"))
+    return O._two_way_ce(sim, lab_all)
+
+
+class OracleBNOps:
+    """CPU stand-in for the SyncBN kernels (same five steps, torch ops)."""
+
+    @staticmethod
+    def stats(x3, out):
+        C = x3.shape[1]
+        out[:C] = x3.sum(dim=(0, 2))
+        out[C:2 * C] = (x3 * x3).sum(dim=(0, 2))
+
+    @staticmethod
+    def finalize(stats, C, count, count_dev, eps, momentum, clamp_mode, mean, inv_std, rm, rv):
+        n = float(count_dev[0] * 4096 + count_dev[1]) if count_dev is not None else float(count)
+        s, ss = stats[:C], stats[C:2 * C]
+        mu = s / n
+        sumvar = ss - s * mu
+        mean.copy_(mu)
+        inv_std.copy_((sumvar / n).clamp(min=eps) ** -0.5 if clamp_mode else 1.0 / torch.sqrt(sumvar / n + eps))
+        if rm is not None:
+            rm.mul_(1 - momentum).add_(momentum * mu)
+            rv.mul_(1 - momentum).add_(momentum * sumvar / (n - 1))
+
+    @staticmethod
+    def apply(x3, mean, inv_std, w, b, y):
+        scale = inv_std * (w if w is not None else 1.0)
+        y.copy_((x3 - mean.view(1, -1, 1)) * scale.view(1, -1, 1) + (b.view(1, -1, 1) if b is not None else 0.0))
+
+    @staticmethod
+    def bwd_reduce(x3, dy3, mean, inv_std, red):
+        C = x3.shape[1]
+        xh = (x3 - mean.view(1, -1, 1)) * inv_std.view(1, -1, 1)
+        red[:C] = dy3.sum(dim=(0, 2))
+        red[C:] = (dy3 * xh).sum(dim=(0, 2))
+
+    @staticmethod
+    def bwd_apply(x3, dy3, mean, inv_std, w, red, count, count_dev, eps, clamp_mode, dx):
+        n = float(count_dev[0] * 4096 + count_dev[1]) if count_dev is not None else float(count)
+        C = x3.shape[1]
+        xh = (x3 - mean.view(1, -1, 1)) * inv_std.view(1, -1, 1)
+        scale = (inv_std * (w if w is not None else 1.0)).view(1, -1, 1)
+        dx.copy_(scale * (dy3 - red[:C].view(1, -1, 1) / n - xh * red[C:].view(1, -1, 1) / n))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    try:
+        from eegan_b200 import sharded
+        from eegan_b200.sync_batchnorm import SynchronizedBatchNorm2d
+        from oracle import cases
+        from oracle import damsm_oracle as O
+        B, T, b = 8, 7, 4
+        c = cases.words_case(B, T, D=16, H=3, seed=21, min_len=2)
+        sl = slice(rank * b, (rank + 1) * b)
+        img = c["img"][sl].double().requires_grad_()
+        words = c["words"][sl].double().requires_grad_()
+        l0, l1, att = sharded.sharded_words_loss(img, words, torch.arange(b), c["cap_lens"][sl], c["class_ids"][sl], b,
+                                                 grid_fn=_oracle_grid, ce_fn=_oracle_ce)
+        (l0 + 2 * l1).backward()
+        # single-process full batch
+        fi = c["img"].double().requires_grad_()
+        fw = c["words"].double().requires_grad_()
+        f0, f1, fatt, _ = O.dense_words_loss(fi, fw, c["labels"], c["cap_lens"], c["class_ids"])
+        (f0 + 2 * f1).backward()
+        res = dict(
+            loss=abs(float(l0.detach() - f0.detach())) + abs(float(l1.detach() - f1.detach())),
+            dimg=float((img.grad - fi.grad[sl]).abs().max()), dwords=float((words.grad - fw.grad[sl]).abs().max()),
+            att=max(float((a - fa.detach()).abs().max()) for a, fa in zip(att, fatt[sl])), natt=len(att))
+        # sentence loss
+        s = cases.sent_case(B, D=16, seed=4)
+        cn = s["cnn"][sl].double().requires_grad_()
+        rn = s["rnn"][sl].double().requires_grad_()
+        s0, s1 = sharded.sharded_sent_loss(cn, rn, torch.arange(b), s["class_ids"][sl], b, loss_fn=O.port_sent_loss)
+        (s0 + s1).backward()
+        fc = s["cnn"].double().requires_grad_()
+        fr = s["rnn"].double().requires_grad_()
+        g0, g1 = O.port_sent_loss(fc, fr, s["labels"], s["class_ids"], B)
+        (g0 + g1).backward()
+        res.update(sent=abs(float(s0.detach() - g0.detach())) + abs(float(s1.detach() - g1.detach())),
+                   dcnn=float((cn.grad - fc.grad[sl]).abs().max()), drnn=float((rn.grad - fr.grad[sl]).abs().max()))
+        # SyncBN: 2 ranks x 3 samples == the N-replica formula on the 6-sample batch
+        bc = cases.bn_case(6, 8, 5)
+        bn = SynchronizedBatchNorm2d(8)
+        bn._ops = OracleBNOps
+        with torch.no_grad():
+            bn.weight.copy_(bc["weight"]); bn.bias.copy_(bc["bias"])
+        xs = bc["x"][rank * 3:(rank + 1) * 3].clone().requires_grad_()
+        y = bn(xs)
+        gy = torch.randn(6, 8, 5, 5, generator=cases._gen(1))
+        (y * gy[rank * 3:(rank + 1) * 3]).sum().backward()
+        xf = bc["x"].clone().requires_grad_()
+        outs, mean, inv_std, unb = O.syncbn_forward([xf], bc["weight"], bc["bias"])
+        (outs[0] * gy).sum().backward()
+        res.update(bn_y=float((y.detach() - outs[0].detach()[rank * 3:(rank + 1) * 3]).abs().max()),
+                   bn_dx=float((xs.grad - xf.grad[rank * 3:(rank + 1) * 3]).abs().max()),
+                   bn_rm=float((bn.running_mean - 0.1 * mean.detach()).abs().max()),
+                   bn_rv=float((bn.running_var - (0.9 + 0.1 * unb.detach())).abs().max()))
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_sharded_equals_full_batch():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        r = out[rank]
+        assert r["natt"] == 4
+        assert r["loss"] < 1e-12 and r["dimg"] < 1e-12 and r["dwords"] < 1e-12 and r["att"] < 1e-14, r
+        assert r["sent"] < 1e-12 and r["dcnn"] < 1e-12 and r["drnn"] < 1e-12, r
+        assert r["bn_y"] < 1e-5 and r["bn_dx"] < 1e-4 and r["bn_rm"] < 1e-6 and r["bn_rv"] < 1e-5, r

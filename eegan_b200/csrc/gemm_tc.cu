@@ -2,43 +2,10 @@
 #include <stdlib.h>
 
 #include "gemm_tc.cuh"
+#include "ptx.cuh"
 
 namespace eegan {
 
-// ---------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -54,11 +21,9 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t da, uint64
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
+// round-to-nearest (ties away) to the 10-bit tf32 mantissa with two integer ops; same result as
+// cvt.rna.tf32.f32 for finite inputs (inf/nan inputs poison the output either way)
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // Canonical 128B-swizzle UMMA shared-memory descriptor (version 1 = Blackwell).
 //   K-major : rows at 128 B, 8-row groups at SBO = 1024 B; a K-step of 8 fp32 advances the start by 32 B.
@@ -85,85 +50,109 @@ struct TcArgs {
     const int* dynM;
     const int* dynK;
     int K[2];
-    int nseg, nred, red_total;
+    int nseg, nred, red_total, batch;
     int a_batched[2], b_batched[2];
     uint32_t mn_lbo, mn_sbo;  // debug-overridable descriptor fields of MN-major tiles (16-byte units)
 };
 
+// Persistent, warp-specialised kernel: grid = min(#live tiles, #SMs); every CTA walks tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, then m, then batch z).
+//   warp 0      TMA producer            warp 1      TMEM alloc + MMA issuer
+//   warps 2-9   hi/lo splitters         warps 10-13 epilogue (TMEM lane quarter = warp & 3)
+// The smem stage ring runs continuously across tiles; two TMEM accumulators (2 x 128 columns)
+// let the epilogue of tile i overlap the main loop of tile i+1.
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const TcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int z = blockIdx.z;
-    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
     const int Mlive = p.dynM ? min(*p.dynM, p.M) : p.M;
-    if (m0 >= Mlive) return;  // uniform: before any barrier / TMEM state exists
+    const int mt = (Mlive + TC_BM - 1) / TC_BM, nt = (p.N + TC_BN - 1) / TC_BN;
+    const int ntiles = mt * nt * p.batch;
+    if ((int)blockIdx.x >= ntiles) return;  // uniform: before any barrier / TMEM state exists
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t epi_stage = base + TC_STAGES * TC_STAGE_BYTES;       // 4 warps x [32][33] floats
+    const uint32_t bars = epi_stage + 4 * 32 * 33 * 4;
     auto full = [&](int s) { return bars + 8u * s; };
     auto conv = [&](int s) { return bars + 8u * (TC_STAGES + s); };
     auto empty = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };
-    const uint32_t tmem_full = bars + 8u * (3 * TC_STAGES);
-    const uint32_t tmem_slot = bars + 8u * (3 * TC_STAGES + 1);
+    auto tmem_full = [&](int a) { return bars + 8u * (3 * TC_STAGES + a); };
+    auto tmem_empty = [&](int a) { return bars + 8u * (3 * TC_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (3 * TC_STAGES + 4);
 
-    int kb[2] = {0, 0};
-    for (int s = 0; s < p.nseg; ++s) {
-        const int Ks = p.dynK ? min(*p.dynK, p.K[s]) : p.K[s];
-        kb[s] = (Ks + TC_BK - 1) / TC_BK;
+    int kb0 = 0, kb1 = 0;
+    {
+        const int K0 = p.dynK ? min(*p.dynK, p.K[0]) : p.K[0];
+        kb0 = (K0 + TC_BK - 1) / TC_BK;
+        if (p.nseg > 1) {
+            const int K1 = p.dynK ? min(*p.dynK, p.K[1]) : p.K[1];
+            kb1 = (K1 + TC_BK - 1) / TC_BK;
+        }
     }
-    const int kbt = kb[0] + kb[1];
-    int nred = p.nred;
-    if (p.red_total > 0) nred = max(0, min(p.nred, p.red_total - z * p.nred));
-    const int total = nred * kbt;
+    const int kbt = kb0 + kb1;
+    // k-blocks of the tile whose batch index is z
+    auto tile_total = [&](int z) {
+        int nred = p.nred;
+        if (p.red_total > 0) nred = max(0, min(p.nred, p.red_total - z * p.nred));
+        return nred * kbt;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(full(s), 1);
-            mbar_init(conv(s), 4);
+            mbar_init(conv(s), TC_SPLIT_WARPS);
             mbar_init(empty(s), 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * TC_BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    uint32_t tmem_d;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot) : "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int it = 0; it < total; ++it) {
-                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
-                const int red = it / kbt, rem = it - red * kbt;
-                const int seg = rem >= kb[0] ? 1 : 0;
-                const int k0 = (seg ? rem - kb[0] : rem) * TC_BK;
-                const CUtensorMap* ta = seg ? &tmA1 : &tmA0;
-                const CUtensorMap* tb = seg ? &tmB1 : &tmB0;
-                const int zr = z * p.nred + red;
-                const int zA = p.a_batched[seg] ? zr : 0, zB = p.b_batched[seg] ? zr : 0;
-                mbar_wait(empty(s), ph ^ 1);
-                mbar_arrive_expect_tx(full(s), 2 * TC_TILE_BYTES);
-                const uint32_t sA = base + s * TC_STAGE_BYTES, sB = sA + TC_TILE_BYTES;
-                if (A_K) {
-                    tma_load_3d(sA, ta, full(s), k0, m0, zA);
-                } else {
+            int it = 0;  // running k-block counter across tiles: stage ring position
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int z = t / (mt * nt), rem_t = t - z * (mt * nt);
+                const int m0 = (rem_t / nt) * TC_BM, n0 = (rem_t % nt) * TC_BN;
+                const int total = tile_total(z);
+                for (int k = 0; k < total; ++k, ++it) {
+                    const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                    const int red = k / kbt, rem = k - red * kbt;
+                    const int seg = rem >= kb0 ? 1 : 0;
+                    const int k0 = (seg ? rem - kb0 : rem) * TC_BK;
+                    const CUtensorMap* ta = seg ? &tmA1 : &tmA0;
+                    const CUtensorMap* tb = seg ? &tmB1 : &tmB0;
+                    const int zr = z * p.nred + red;
+                    const int zA = p.a_batched[seg] ? zr : 0, zB = p.b_batched[seg] ? zr : 0;
+                    mbar_wait(empty(s), ph ^ 1);
+                    mbar_arrive_expect_tx(full(s), 2 * TC_TILE_BYTES);
+                    const uint32_t sA = base + s * TC_STAGE_BYTES, sB = sA + TC_TILE_BYTES;
+                    if (A_K) {
+                        tma_load_3d(sA, ta, full(s), k0, m0, zA);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) tma_load_3d(sA + c * 4096, ta, full(s), m0 + 32 * c, k0, zA);
-                }
-                if (B_K) {
-                    tma_load_3d(sB, tb, full(s), k0, n0, zB);
-                } else {
+                        for (int c = 0; c < 4; ++c) tma_load_3d(sA + c * 4096, ta, full(s), m0 + 32 * c, k0, zA);
+                    }
+                    if (B_K) {
+                        tma_load_3d(sB, tb, full(s), k0, n0, zB);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) tma_load_3d(sB + c * 4096, tb, full(s), n0 + 32 * c, k0, zB);
+                        for (int c = 0; c < 4; ++c) tma_load_3d(sB + c * 4096, tb, full(s), n0 + 32 * c, k0, zB);
+                    }
                 }
             }
         }
@@ -173,95 +162,110 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             constexpr uint32_t idesc = (1u << 4) /*D=f32*/ | (2u << 7) /*A=tf32*/ | (2u << 10) /*B=tf32*/ |
                                        ((A_K ? 0u : 1u) << 15) | ((B_K ? 0u : 1u) << 16) |
                                        ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            for (int it = 0; it < total; ++it) {
-                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
-                mbar_wait(conv(s), ph);
+            int it = 0, ti = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+                const int z = t / (mt * nt);
+                const int total = tile_total(z);
+                const int acc = ti & 1;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BN);
+                mbar_wait(tmem_empty(acc), ((ti >> 1) & 1) ^ 1);  // the epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t a_hi = base + s * TC_STAGE_BYTES, b_hi = a_hi + TC_TILE_BYTES;
-                const uint32_t a_lo = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+                for (int k = 0; k < total; ++k, ++it) {
+                    const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                    mbar_wait(conv(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + s * TC_STAGE_BYTES, b_hi = a_hi + TC_TILE_BYTES;
+                    const uint32_t a_lo = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                    const uint64_t dah = umma_desc(a_hi, A_K, ks, p.mn_lbo, p.mn_sbo), dal = umma_desc(a_lo, A_K, ks, p.mn_lbo, p.mn_sbo);
-                    const uint64_t dbh = umma_desc(b_hi, B_K, ks, p.mn_lbo, p.mn_sbo), dbl = umma_desc(b_lo, B_K, ks, p.mn_lbo, p.mn_sbo);
-                    tc_mma_tf32(tmem_d, dal, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                    tc_mma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                    tc_mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        const uint64_t dah = umma_desc(a_hi, A_K, ks, p.mn_lbo, p.mn_sbo), dal = umma_desc(a_lo, A_K, ks, p.mn_lbo, p.mn_sbo);
+                        const uint64_t dbh = umma_desc(b_hi, B_K, ks, p.mn_lbo, p.mn_sbo), dbl = umma_desc(b_lo, B_K, ks, p.mn_lbo, p.mn_sbo);
+                        tc_mma_tf32(tmem_d, dal, dbh, idesc, (k > 0 || ks > 0) ? 1u : 0u);
+                        tc_mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                        tc_mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                    }
+                    tc_commit(empty(s));  // implies tcgen05.fence::before_thread_sync
                 }
-                tc_commit(empty(s));  // implies tcgen05.fence::before_thread_sync
+                tc_commit(tmem_full(acc));
             }
-            tc_commit(tmem_full);
+        }
+    } else if (warp < 2 + TC_SPLIT_WARPS) {
+        // ===== hi/lo splitters =====
+        const int ctid = threadIdx.x - 64;
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int total = tile_total(t / (mt * nt));
+            for (int k = 0; k < total; ++k, ++it) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                mbar_wait(full(s), ph);
+                const uint32_t hi = base + s * TC_STAGE_BYTES, lo = hi + 2 * TC_TILE_BYTES;
+#pragma unroll 4
+                for (int i = 0; i < (2 * TC_TILE_BYTES / 16) / (32 * TC_SPLIT_WARPS); ++i) {
+                    const uint32_t off = (uint32_t)(i * (32 * TC_SPLIT_WARPS) + ctid) * 16u;
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + off));
+                    float4 h, l;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+                __syncwarp();
+                if (lane == 0) mbar_arrive(conv(s));
+            }
         }
     } else {
-        // ===== splitters (warps 2..5), then epilogue =====
-        const int ctid = threadIdx.x - 64;
-        for (int it = 0; it < total; ++it) {
-            const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
-            mbar_wait(full(s), ph);
-            const uint32_t hi = base + s * TC_STAGE_BYTES, lo = hi + 2 * TC_TILE_BYTES;
-#pragma unroll 4
-            for (int i = 0; i < (2 * TC_TILE_BYTES / 16) / 128; ++i) {
-                const uint32_t off = (uint32_t)(i * 128 + ctid) * 16u;
-                float4 v;
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + off));
-                float4 h, l;
-                h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-                l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
-            __syncwarp();
-            if (lane == 0) mbar_arrive(conv(s));
-        }
-        // ----- epilogue: TMEM -> registers -> shared (row-major, padded) -> coalesced global -----
-        constexpr int PITCH = TC_BN + 4;
+        // ===== epilogue (last four warps): TMEM -> registers -> per-warp smem transpose -> coalesced global =====
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int row = quarter * 32 + lane;
-        if (total > 0) {
-            mbar_wait(tmem_full, 0);
+        const uint32_t my_stage = epi_stage + (uint32_t)(warp - 2 - TC_SPLIT_WARPS) * (32 * 33 * 4);
+        int ti = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+            const int z = t / (mt * nt), rem_t = t - z * (mt * nt);
+            const int m0 = (rem_t / nt) * TC_BM, n0 = (rem_t % nt) * TC_BN;
+            const int total = tile_total(z);
+            const int acc = ti & 1;
+            mbar_wait(tmem_full(acc), (ti >> 1) & 1);
             tc_fence_after();
-        }
-        const uint32_t stg = base;  // the pipeline stages are dead now (all MMAs committed)
+            float* Cz = p.C + (long long)z * p.bC;
+            const int rows_live = min(32, Mlive - (m0 + quarter * 32));  // rows of this warp that exist
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; ++c) {
+                uint32_t v[32];
+                if (total > 0) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
 #pragma unroll
-        for (int c = 0; c < TC_BN / 32; ++c) {
-            uint32_t v[32];
-            if (total > 0) {
-                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
+                    for (int q = 0; q < 32; ++q) v[q] = 0u;
+                }
+                if (c == TC_BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty(acc));
+                }
+                __syncwarp();  // previous chunk's readers are done with the staging buffer
 #pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = 0u;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint32_t addr = stg + (uint32_t)(row * PITCH + c * 32 + q * 4) * 4u;
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[4 * q]), "r"(v[4 * q + 1]),
-                             "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
-                             : "memory");
-            }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-        float* Cz = p.C + (long long)z * p.bC;
-        const int ew = warp - 2;
-        for (int rr = 0; rr < 32; ++rr) {
-            const int r = ew * 32 + rr, gm = m0 + r;
-            if (gm >= Mlive) break;
-#pragma unroll
-            for (int i = 0; i < TC_BN / 32; ++i) {
-                const int col = lane + 32 * i, gn = n0 + col;
+                for (int q = 0; q < 32; ++q)
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(my_stage + (uint32_t)(lane * 33 + q) * 4u), "r"(v[q]) : "memory");
+                __syncwarp();
+                const int gn = n0 + c * 32 + lane;
                 if (gn < p.N) {
-                    float val;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(stg + (uint32_t)(r * PITCH + col) * 4u));
-                    Cz[(long long)gm * p.ldc + gn] = val;
+                    float* dst = Cz + (long long)(m0 + quarter * 32) * p.ldc + gn;
+                    for (int rr = 0; rr < rows_live; ++rr) {
+                        float val;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(my_stage + (uint32_t)(rr * 33 + lane) * 4u));
+                        dst[(long long)rr * p.ldc] = val;
+                    }
                 }
             }
         }
@@ -270,7 +274,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TC_BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_BN) : "memory");
     }
 }
 
@@ -323,6 +327,15 @@ static int make_map(CUtensorMap* m, const TcOperand& o, int box_rows_kmajor) {
     return EEGAN_OK;
 }
 
+static int num_sms() {
+    static int n = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    return n;
+}
+
 template <bool A_K, bool B_K>
 static int launch_t(const CUtensorMap* maps, const TcArgs& a, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;  // idempotent; a race only repeats the call
@@ -353,11 +366,12 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
         a.b_batched[s] = g.B[src].bstride > 0;
     }
     a.C = g.C; a.ldc = g.ldc; a.bC = g.bC; a.M = g.M; a.N = g.N; a.dynM = g.dynM; a.dynK = g.dynK;
-    a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total;
+    a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total; a.batch = g.batch;
     a.mn_lbo = 4096 >> 4; a.mn_sbo = 512 >> 4;
     if (const char* e = getenv("EEGAN_TC_MN_LBO")) a.mn_lbo = (uint32_t)atoi(e);
     if (const char* e = getenv("EEGAN_TC_MN_SBO")) a.mn_sbo = (uint32_t)atoi(e);
-    dim3 grid((g.N + TC_BN - 1) / TC_BN, (g.M + TC_BM - 1) / TC_BM, g.batch);
+    const long long tiles = (long long)((g.N + TC_BN - 1) / TC_BN) * ((g.M + TC_BM - 1) / TC_BM) * g.batch;
+    dim3 grid((unsigned)(tiles < num_sms() ? tiles : num_sms()));
     const bool ak = g.A[0].kmajor, bk = g.B[0].kmajor;
     if (ak && bk) return launch_t<true, true>(maps, a, grid, st);
     if (ak && !bk) return launch_t<true, false>(maps, a, grid, st);

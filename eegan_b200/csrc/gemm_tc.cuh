@@ -7,12 +7,14 @@
 // (lo*hi, hi*lo, hi*hi) into one fp32 accumulator tile in TMEM.  Single-pass TF32/BF16 flips
 // argmax word indices; the split keeps ~2^-21 relative error.
 //
-// Per CTA (192 threads, one 128 x 128 output tile, BK = 32 fp32 = one 128-byte swizzle row):
+// Persistent CTAs (one per SM, 448 threads) walk 128 x 128 output tiles, BK = 32 fp32 = one
+// 128-byte swizzle row:
 //   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) of the raw fp32 A/B boxes
 //   warp 1      TMEM allocator + single-thread MMA issuer; tcgen05.commit frees the stage
-//   warps 2-5   hi/lo splitters (in place, layout-agnostic) during the main loop, then the
-//               epilogue: tcgen05.ld -> registers -> shared -> coalesced global stores
-// mbarrier pipeline per stage: full (TMA landed) -> conv (split done) -> empty (MMAs done).
+//   warps 2-9   hi/lo splitters (in place, layout-agnostic)
+//   warps 10-13 epilogue: tcgen05.ld -> registers -> per-warp smem transpose -> coalesced stores
+// mbarrier pipeline per stage: full (TMA landed) -> conv (split done) -> empty (MMAs done);
+// two TMEM accumulators (tmem_full / tmem_empty) overlap a tile's epilogue with the next main loop.
 // Operands may be K-major ([rows][K], K contiguous) or MN-major ([K][rows], rows contiguous);
 // both use the canonical 128B-swizzle UMMA layouts, so no transposed copies are needed.
 #pragma once
@@ -25,8 +27,9 @@ namespace eegan {
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi B_hi A_lo B_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 4 * 32 * 33 * 4 /*epilogue staging*/ + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + 4);
 
 struct TcOperand {
     const float* ptr;    // base

@@ -19,12 +19,15 @@
 
 #include "gemm_ffma.cuh"
 #include "gemm_tc.cuh"
+#include "ptx.cuh"
 
 namespace eegan {
 
 // contraction engine: 1 = tcgen05 3xTF32 (default), 0 = CUDA-core fp32 FFMA.  Process-wide
 // (the backward runs on autograd's thread); set via eegan_set_contraction_engine().
 static std::atomic<int> g_engine{1};
+
+constexpr int PAIR_DU_JG = 8;  // images per CTA of the dU kernel
 
 struct PairWs {
     int* col_start;  // [Bc+1] exclusive prefix of clamp(cap_lens)
@@ -40,7 +43,7 @@ struct PairWs {
     float* alpha;    // [3][Bi][NtM]
     float* DA;       // [Bi][NtM][Rp] dA, then DS in place
     float* dWpart;   // [nsplit][NtM][D]
-    float* dwcos;    // [NtM][D]
+    float* dwcos;    // [ceil(Bi/8)][NtM][D] per-image-group cosine part of dW
     float* Cp;       // [Bi][D][Rp] image features re-pitched for TMA (only if Rp != R)
     int Rp;          // stash pitch of the region index: R rounded up to 4 floats (16 B)
     int nsplit;
@@ -81,7 +84,7 @@ static PairWs carve(void* base, int Bi, int Bc, int D, int R, int Tm) {
     w.alpha = (float*)take((size_t)3 * Bi * NtM * sizeof(float));
     w.DA = (float*)take((size_t)Bi * NtM * Rp * sizeof(float));
     w.dWpart = (float*)take((size_t)w.nsplit * NtM * D * sizeof(float));
-    w.dwcos = (float*)take(NtM * D * sizeof(float));
+    w.dwcos = (float*)take((size_t)((Bi + PAIR_DU_JG - 1) / PAIR_DU_JG) * NtM * D * sizeof(float));
     w.Cp = (float*)take(Rp != (size_t)R ? (size_t)Bi * D * Rp * sizeof(float) : 0);
     w.bytes = off;
     return w;
@@ -147,29 +150,102 @@ __global__ void __launch_bounds__(128) pair_pack_words_kernel(const float* __res
 // ---------------------------------------------------------------------------------------
 // One CTA per (caption i, image j): P = softmax_words(S) (:44-45), A = softmax_regions(g1 P)
 // (:53-54).  P overwrites S.  Dynamic smem: T_max * R floats.
+// TMA-staged version: the caption's [T][Rp] score block is ONE contiguous chunk, so a single
+// cp.async.bulk pulls it into shared memory (all bytes in flight at once, no registers), both
+// softmaxes run out of shared memory, and P / A leave through two bulk stores.
 __global__ void __launch_bounds__(256) pair_attn_softmax_kernel(float* __restrict__ SP, float* __restrict__ A,
                                                                 const int* __restrict__ col_start, int NtM, int R, int Rp,
                                                                 float g1, float* __restrict__ att, int diag_offset,
                                                                 int Tm) {
-    extern __shared__ float p[];
+    extern __shared__ __align__(128) float smf[];
+    float* ps = smf;                       // [T][Rp]  S -> P
+    float* as = smf + (size_t)Tm * Rp;     // [T][Rp]  A
+    __shared__ __align__(8) unsigned long long bar_storage;
+    const uint32_t bar = smem_u32(&bar_storage);
+    const int i = blockIdx.x, j = blockIdx.y;
+    const int cs = col_start[i], T = col_start[i + 1] - cs;
+    if (T <= 0) return;
+    float* Sj = SP + ((size_t)j * NtM + cs) * Rp;
+    float* Aj = A + ((size_t)j * NtM + cs) * Rp;
+    const uint32_t bytes = (uint32_t)T * Rp * 4u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_load(smem_u32(ps), Sj, bytes, bar);
+    }
+    mbar_wait(bar, 0);
+    // softmax over the caption's words, per region (:44-45)
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        float mx = -INFINITY;
+        for (int t = 0; t < T; ++t) mx = fmaxf(mx, ps[t * Rp + r]);
+        float sum = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float e = __expf(ps[t * Rp + r] - mx);
+            ps[t * Rp + r] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / sum;
+        for (int t = 0; t < T; ++t) ps[t * Rp + r] *= inv;
+    }
+    __syncthreads();
+    // softmax over regions of gamma1 * P, per word (:53-54)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int t = w; t < T; t += nw) {
+        const float* pr = ps + t * Rp;
+        float* ar = as + t * Rp;
+        float mx = -INFINITY;
+        for (int r = lane; r < R; r += 32) mx = fmaxf(mx, pr[r]);
+        mx = warp_max(mx) * g1;
+        float sum = 0.f;
+        for (int r = lane; r < R; r += 32) {
+            const float e = __expf(fmaf(g1, pr[r], -mx));
+            ar[r] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / warp_sum(sum);
+        for (int r = lane; r < Rp; r += 32) ar[r] = (r < R) ? ar[r] * inv : 0.f;
+    }
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the bulk-store engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bulk_store(Sj, smem_u32(ps), bytes);
+        bulk_store(Aj, smem_u32(as), bytes);
+        bulk_store_commit_wait();
+    }
+    if ((att != nullptr) && (j == i + diag_offset)) {  // the caption's own image: att_maps (:301)
+        float* attp = att + (size_t)i * Tm * R;
+        for (int idx = threadIdx.x; idx < Tm * R; idx += blockDim.x) {
+            const int t = idx / R, r = idx - t * R;
+            attp[idx] = t < T ? as[t * Rp + r] : 0.f;
+        }
+    }
+}
+
+// Pitch-agnostic fallback (func_attention's unpadded buffers): same math, plain loads/stores.
+__global__ void __launch_bounds__(256) pair_attn_softmax_generic_kernel(float* __restrict__ SP, float* __restrict__ A,
+                                                                        const int* __restrict__ col_start, int NtM, int R,
+                                                                        int Rp, float g1) {
+    extern __shared__ float p[];  // [T][R]
     const int i = blockIdx.x, j = blockIdx.y;
     const int cs = col_start[i], T = col_start[i + 1] - cs;
     float* Sj = SP + ((size_t)j * NtM + cs) * Rp;
     float* Aj = A + ((size_t)j * NtM + cs) * Rp;
-    const bool diag = (att != nullptr) && (j == i + diag_offset);
-    float* attp = diag ? att + (size_t)i * Tm * R : nullptr;
-
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         float mx = -INFINITY;
         for (int t = 0; t < T; ++t) mx = fmaxf(mx, Sj[(size_t)t * Rp + r]);
         float sum = 0.f;
         for (int t = 0; t < T; ++t) {
-            const float e = expf(Sj[(size_t)t * Rp + r] - mx);
+            const float e = __expf(Sj[(size_t)t * Rp + r] - mx);
             p[t * R + r] = e;
             sum += e;
         }
+        const float inv = 1.0f / sum;
         for (int t = 0; t < T; ++t) {
-            const float pv = p[t * R + r] / sum;
+            const float pv = p[t * R + r] * inv;
             p[t * R + r] = pv;
             Sj[(size_t)t * Rp + r] = pv;
         }
@@ -178,23 +254,16 @@ __global__ void __launch_bounds__(256) pair_attn_softmax_kernel(float* __restric
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int t = w; t < T; t += nw) {
         float mx = -INFINITY;
-        for (int r = lane; r < R; r += 32) mx = fmaxf(mx, g1 * p[t * R + r]);
-        mx = warp_max(mx);
+        for (int r = lane; r < R; r += 32) mx = fmaxf(mx, p[t * R + r]);
+        mx = warp_max(mx) * g1;
         float sum = 0.f;
         for (int r = lane; r < R; r += 32) {
-            const float e = expf(g1 * p[t * R + r] - mx);
+            const float e = __expf(fmaf(g1, p[t * R + r], -mx));
             p[t * R + r] = e;
             sum += e;
         }
-        sum = warp_sum(sum);
-        for (int r = lane; r < R; r += 32) {
-            const float a = p[t * R + r] / sum;
-            Aj[(size_t)t * Rp + r] = a;
-            if (diag) attp[(size_t)t * R + r] = a;
-        }
-    }
-    if (diag) {
-        for (int idx = T * R + threadIdx.x; idx < Tm * R; idx += blockDim.x) attp[idx] = 0.f;
+        const float inv = 1.0f / warp_sum(sum);
+        for (int r = lane; r < R; r += 32) Aj[(size_t)t * Rp + r] = p[t * R + r] * inv;
     }
 }
 
@@ -263,48 +332,103 @@ __global__ void __launch_bounds__(32) pair_bwd_scalars_kernel(const float* __res
     alpha[2 * plane + idx] = live ? dcos * c / (wv * wv) : 0.f;
 }
 
-// One CTA per packed column n: U -> DU in place, and the cosine part of dW summed over j.
+// Thread = (packed column n, 4 channels), blockIdx.y = image group jg (PAIR_DU_JG images):
+// U -> DU in place and the group's share of the cosine part of dW:
+//   dwcos[jg][n][d] = sum_{j in jg} a1 u - (sum_{j in jg} a3) w        (summed over jg by unpack)
 __global__ void __launch_bounds__(256) pair_du_dwcos_kernel(float* __restrict__ U, const float* __restrict__ Wp,
                                                             const float* __restrict__ alpha, const int* __restrict__ ntot,
                                                             int NtM, int Bi, int D, float* __restrict__ dwcos) {
-    const int n = blockIdx.x;
-    if (n >= *ntot) return;
+    const int d4 = D >> 2;                               // float4 per column
+    const int per_cta = blockDim.x / d4;                 // columns per CTA (D <= 1024 -> >= 1)
+    const int n = blockIdx.x * per_cta + threadIdx.x / d4, q4 = threadIdx.x % d4;
+    if (threadIdx.x >= per_cta * d4 || n >= *ntot) return;
+    const int jg = blockIdx.y, j0 = jg * PAIR_DU_JG;
     const size_t plane = (size_t)Bi * NtM;
-    float wv[4], acc[4];
+    const float4 wv = reinterpret_cast<const float4*>(Wp + (size_t)n * D)[q4];
+    float4 uv[PAIR_DU_JG];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int d = threadIdx.x + q * 256;
-        wv[q] = (d < D) ? Wp[(size_t)n * D + d] : 0.f;
-        acc[q] = 0.f;
-    }
+    for (int q = 0; q < PAIR_DU_JG; ++q)  // all loads first: 8 independent 16-byte requests in flight
+        if (j0 + q < Bi) uv[q] = reinterpret_cast<const float4*>(U + ((size_t)(j0 + q) * NtM + n) * D)[q4];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float a3s = 0.f;
-    for (int j = 0; j < Bi; ++j) {
-        const size_t idx = (size_t)j * NtM + n;
-        const float a1 = alpha[idx], a2 = alpha[plane + idx];
-        a3s += alpha[2 * plane + idx];
-        float* u = U + idx * D;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int d = threadIdx.x + q * 256;
-            if (d < D) {
-                const float uv = u[d];
-                acc[q] = fmaf(a1, uv, acc[q]);
-                u[d] = a1 * wv[q] - a2 * uv;
-            }
+    for (int q = 0; q < PAIR_DU_JG; ++q) {
+        if (j0 + q < Bi) {
+            const size_t idx = (size_t)(j0 + q) * NtM + n;
+            const float a1 = alpha[idx], a2 = alpha[plane + idx];
+            a3s += alpha[2 * plane + idx];
+            acc.x = fmaf(a1, uv[q].x, acc.x); acc.y = fmaf(a1, uv[q].y, acc.y);
+            acc.z = fmaf(a1, uv[q].z, acc.z); acc.w = fmaf(a1, uv[q].w, acc.w);
+            float4 o;
+            o.x = a1 * wv.x - a2 * uv[q].x; o.y = a1 * wv.y - a2 * uv[q].y;
+            o.z = a1 * wv.z - a2 * uv[q].z; o.w = a1 * wv.w - a2 * uv[q].w;
+            reinterpret_cast<float4*>(U + idx * D)[q4] = o;
         }
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int d = threadIdx.x + q * 256;
-        if (d < D) dwcos[(size_t)n * D + d] = acc[q] - a3s * wv[q];
-    }
+    float4 o;
+    o.x = acc.x - a3s * wv.x; o.y = acc.y - a3s * wv.y; o.z = acc.z - a3s * wv.z; o.w = acc.w - a3s * wv.w;
+    reinterpret_cast<float4*>(dwcos + ((size_t)jg * NtM + n) * D)[q4] = o;
 }
 
 // One CTA per (caption i, image j): dA -> DS in place.
 //   dz = a (dA - sum_r a dA);  v = g1 p dz;  ds = v - p sum_t v
 __global__ void __launch_bounds__(256) pair_softmax_bwd_kernel(float* __restrict__ DA, const float* __restrict__ A,
                                                                const float* __restrict__ P, const int* __restrict__ col_start,
-                                                               int NtM, int R, int Rp, float g1) {
+                                                               int NtM, int R, int Rp, float g1, int Tm) {
+    extern __shared__ __align__(128) float smf[];
+    float* g = smf;                          // [T][Rp] dA -> v -> dS
+    float* a = smf + (size_t)Tm * Rp;        // [T][Rp]
+    float* p = smf + (size_t)2 * Tm * Rp;    // [T][Rp]
+    __shared__ float csum[32];
+    __shared__ __align__(8) unsigned long long bar_storage;
+    const uint32_t bar = smem_u32(&bar_storage);
+    const int i = blockIdx.x, j = blockIdx.y;
+    const int cs = col_start[i], T = col_start[i + 1] - cs;
+    if (T <= 0) return;
+    const size_t base = ((size_t)j * NtM + cs) * Rp;
+    const uint32_t bytes = (uint32_t)T * Rp * 4u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // the three [T][Rp] blocks are contiguous: three bulk copies, all in flight
+        mbar_arrive_expect_tx(bar, 3 * bytes);
+        bulk_load(smem_u32(g), DA + base, bytes, bar);
+        bulk_load(smem_u32(a), A + base, bytes, bar);
+        bulk_load(smem_u32(p), P + base, bytes, bar);
+    }
+    mbar_wait(bar, 0);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int t = w; t < T; t += nw) {  // csum[t] = sum_r a dA
+        float s = 0.f;
+        for (int r = lane; r < R; r += 32) s = fmaf(a[t * Rp + r], g[t * Rp + r], s);
+        s = warp_sum(s);
+        if (lane == 0) csum[t] = s;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        float q = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float v = g1 * p[t * Rp + r] * a[t * Rp + r] * (g[t * Rp + r] - csum[t]);  // g1 p dz
+            g[t * Rp + r] = v;
+            q += v;
+        }
+        for (int t = 0; t < T; ++t) g[t * Rp + r] -= p[t * Rp + r] * q;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bulk_store(DA + base, smem_u32(g), bytes);
+        bulk_store_commit_wait();
+    }
+}
+
+// Pitch-agnostic fallback (func_attention's unpadded buffers).
+__global__ void __launch_bounds__(256) pair_softmax_bwd_generic_kernel(float* __restrict__ DA, const float* __restrict__ A,
+                                                                       const float* __restrict__ P,
+                                                                       const int* __restrict__ col_start, int NtM, int R,
+                                                                       int Rp, float g1) {
     __shared__ float csum[32];
     const int i = blockIdx.x, j = blockIdx.y;
     const int cs = col_start[i], T = col_start[i + 1] - cs;
@@ -338,8 +462,8 @@ __global__ void __launch_bounds__(256) pair_softmax_bwd_kernel(float* __restrict
 // grid (Bc, D/32): a 32(d) x T_max tile goes through shared memory so that both the packed
 // reads (d contiguous) and the d_words writes (t contiguous) are coalesced.
 __global__ void __launch_bounds__(256) pair_unpack_dw_kernel(const float* __restrict__ dWpart, const float* __restrict__ dwcos,
-                                                             const int* __restrict__ col_start, int nsplit, int NtM, int D,
-                                                             int Tm, float* __restrict__ d_words) {
+                                                             const int* __restrict__ col_start, int nsplit, int ngroups,
+                                                             int NtM, int D, int Tm, float* __restrict__ d_words) {
     __shared__ float tile[32][33];
     const int i = blockIdx.x, d0 = blockIdx.y * 32;
     const int cs = col_start[i], T = col_start[i + 1] - cs;
@@ -348,7 +472,7 @@ __global__ void __launch_bounds__(256) pair_unpack_dw_kernel(const float* __rest
         float v = 0.f;
         if (t < T && d0 + dd < D) {
             const size_t k = (size_t)(cs + t) * D + d0 + dd;
-            v = dwcos[k];
+            for (int s = 0; s < ngroups; ++s) v += dwcos[(size_t)s * NtM * D + k];
             for (int s = 0; s < nsplit; ++s) v += dWpart[(size_t)s * NtM * D + k];
         }
         tile[dd][t] = v;
@@ -363,11 +487,12 @@ __global__ void __launch_bounds__(256) pair_unpack_dw_kernel(const float* __rest
 // img [Bi*D][R] -> Cp [Bi*D][Rp] (TMA needs 16-byte row pitches; R = 289 is odd)
 __global__ void __launch_bounds__(256) pair_repitch_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                            long long rows, int R, int Rp) {
-    const long long total = rows * Rp;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long row = e / Rp;
-        const int r = (int)(e - row * Rp);
-        dst[e] = r < R ? __ldg(src + row * R + r) : 0.f;
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+        const float* s = src + row * R;
+        float* d = dst + row * Rp;
+        for (int r = lane; r < Rp; r += 32) d[r] = r < R ? __ldg(s + r) : 0.f;
     }
 }
 
@@ -386,6 +511,47 @@ __global__ void __launch_bounds__(128) pair_zero_tail_kernel(float* __restrict__
     else if (which == 2) { row = DS + ((size_t)j * NtM + n) * Rp; len = Rp; }
     else { if (j) return; row = Wp + (size_t)n * D; len = D; }
     for (int k = threadIdx.x; k < len; k += blockDim.x) row[k] = 0.f;
+}
+
+static bool bulk_ok(const void* p, int Rp) { return (Rp % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0); }
+
+static int softmax_fwd_launch(dim3 grid, cudaStream_t st, float* SP, float* A, const int* col_start, int NtM, int R, int Rp,
+                              float g1, float* att, int diag_offset, int Tm) {
+    if (bulk_ok(SP, Rp) && bulk_ok(A, Rp)) {
+        const size_t smem = (size_t)2 * Tm * Rp * sizeof(float);
+        static std::atomic<size_t> granted{48 * 1024};
+        if (smem > granted.load()) {
+            cudaError_t e = cudaFuncSetAttribute(pair_attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+            granted.store(smem);
+        }
+        pair_attn_softmax_kernel<<<grid, 256, smem, st>>>(SP, A, col_start, NtM, R, Rp, g1, att, diag_offset, Tm);
+    } else {
+        EEGAN_REQUIRE(att == nullptr, "softmax: att output needs the padded pitch");
+        const size_t smem = (size_t)Tm * R * sizeof(float);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(pair_attn_softmax_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+        }
+        pair_attn_softmax_generic_kernel<<<grid, 256, smem, st>>>(SP, A, col_start, NtM, R, Rp, g1);
+    }
+    return check_launch("pair softmax");
+}
+static int softmax_bwd_launch(dim3 grid, cudaStream_t st, float* DA, const float* A, const float* P, const int* col_start,
+                              int NtM, int R, int Rp, float g1, int Tm) {
+    if (bulk_ok(DA, Rp) && bulk_ok(A, Rp) && bulk_ok(P, Rp)) {
+        const size_t smem = (size_t)3 * Tm * Rp * sizeof(float);
+        static std::atomic<size_t> granted{48 * 1024};
+        if (smem > granted.load()) {
+            cudaError_t e = cudaFuncSetAttribute(pair_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+            granted.store(smem);
+        }
+        pair_softmax_bwd_kernel<<<grid, 256, smem, st>>>(DA, A, P, col_start, NtM, R, Rp, g1, Tm);
+    } else {
+        pair_softmax_bwd_generic_kernel<<<grid, 256, 0, st>>>(DA, A, P, col_start, NtM, R, Rp, g1);
+    }
+    return check_launch("pair softmax bwd");
 }
 
 static int validate(int Bi, int Bc, int D, int R, int Tm) {
@@ -506,7 +672,7 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
     pair_scan_kernel<<<1, 1024, 0, st>>>(cap_lens, Bc, Tm, w.col_start, w.ntot, w.col_cap);
     pair_pack_words_kernel<<<NtM, 128, 0, st>>>(words, w.col_start, w.col_cap, w.ntot, D, Tm, w.Wp, w.wn);
     if (w.Cp && g_engine.load())
-        pair_repitch_kernel<<<148 * 4, 256, 0, st>>>(img, w.Cp, (long long)Bi * D, R, w.Rp);
+        pair_repitch_kernel<<<148 * 8, 256, 0, st>>>(img, w.Cp, (long long)Bi * D, R, w.Rp);
     EEGAN_LAUNCH_CHECK("pair prologue");
     prof_mark(0, st);
 
@@ -514,13 +680,8 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
     if (rc) return rc;
     prof_mark(1, st);
 
-    const size_t smem = (size_t)Tm * R * sizeof(float);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(pair_attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-    }
-    pair_attn_softmax_kernel<<<dim3(Bc, Bi), 256, smem, st>>>(w.SP, w.A, w.col_start, NtM, R, w.Rp, g1, att, diag_offset, Tm);
-    EEGAN_LAUNCH_CHECK("pair softmax");
+    rc = softmax_fwd_launch(dim3(Bc, Bi), st, w.SP, w.A, w.col_start, NtM, R, w.Rp, g1, att, diag_offset, Tm);
+    if (rc) return rc;
     prof_mark(2, st);
 
     rc = gemm_nr_dr(w, w.A, img, w.U, Bi, NtM, D, R, 0, st);  // GEMM2: U = A . C^T
@@ -551,7 +712,11 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
 
     prof_mark(-1, st);
     pair_bwd_scalars_kernel<<<dim3(Bc, Bi), 32, 0, st>>>(dm, w.cosv, w.un, w.wn, w.col_start, NtM, Bi, Bc, g2, w.alpha);
-    pair_du_dwcos_kernel<<<NtM, 256, 0, st>>>(w.U, w.Wp, w.alpha, w.ntot, NtM, Bi, D, w.dwcos);
+    {
+        const int per_cta = 256 / (D / 4) > 0 ? 256 / (D / 4) : 1;
+        pair_du_dwcos_kernel<<<dim3((NtM + per_cta - 1) / per_cta, (Bi + PAIR_DU_JG - 1) / PAIR_DU_JG), D / 4 > 256 ? D / 4 : 256, 0, st>>>(
+            w.U, w.Wp, w.alpha, w.ntot, NtM, Bi, D, w.dwcos);
+    }
     EEGAN_LAUNCH_CHECK("pair bwd scalars");
     prof_mark(5, st);
 
@@ -559,8 +724,8 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
     if (rc) return rc;
     prof_mark(6, st);
 
-    pair_softmax_bwd_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.DA, w.A, w.SP, w.col_start, NtM, R, w.Rp, g1);
-    EEGAN_LAUNCH_CHECK("pair softmax bwd");
+    rc = softmax_bwd_launch(dim3(Bc, Bi), st, w.DA, w.A, w.SP, w.col_start, NtM, R, w.Rp, g1, Tm);
+    if (rc) return rc;
     prof_mark(7, st);
 
     if (d_img) {
@@ -571,7 +736,7 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
     if (d_words) {
         rc = gemm_nr_dr(w, w.DA, img, w.dWpart, Bi, NtM, D, R, w.nsplit, st);  // GEMM5: dWp = sum_j DS . C^T
         if (rc) return rc;
-        pair_unpack_dw_kernel<<<dim3(Bc, (D + 31) / 32), 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.nsplit, NtM, D, Tm, d_words);
+        pair_unpack_dw_kernel<<<dim3(Bc, (D + 31) / 32), 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.nsplit, (Bi + PAIR_DU_JG - 1) / PAIR_DU_JG, NtM, D, Tm, d_words);
         EEGAN_LAUNCH_CHECK("pair GEMM5");
         prof_mark(9, st);
     }
@@ -678,9 +843,8 @@ extern "C" int eegan_func_attention_fwd(const float* query, const float* context
     g.bA = (long long)D * T; g.bB = (long long)D * R; g.bC = (long long)T * R;
     g.nred = 1;
     launch_gemm_ffma<128, 64, 8, 4, false, true>(g, B, st);
-    const size_t smem = (size_t)T * R * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(pair_attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pair_attn_softmax_kernel<<<dim3(1, B), 256, smem, st>>>(w.P, attn, w.col_start, T, R, R, gamma1, nullptr, 0, T);
+    rc = softmax_fwd_launch(dim3(1, B), st, w.P, attn, w.col_start, T, R, R, gamma1, nullptr, 0, T);
+    if (rc) return rc;
     // u[b][d][t] = sum_r c[b][d][r] a[b][t][r]      (:61)
     g = GemmArgs{};
     g.A = context; g.B = attn; g.C = u;
@@ -714,7 +878,8 @@ extern "C" int eegan_func_attention_bwd(const float* query, const float* context
         g.nred = 1; g.accumulate = 1;
         launch_gemm_ffma<128, 64, 8, 4, false, true>(g, B, st);
     }
-    pair_softmax_bwd_kernel<<<dim3(1, B), 256, 0, st>>>(w.DA, attn, w.P, w.col_start, T, R, R, gamma1);
+    rc = softmax_bwd_launch(dim3(1, B), st, w.DA, attn, w.P, w.col_start, T, R, R, gamma1, T);
+    if (rc) return rc;
     // d_context[b][d][r] = sum_t d_u[b][d][t] a[b][t][r] + q[b][d][t] ds[b][t][r]
     g = GemmArgs{};
     g.B = attn; g.C = d_context;

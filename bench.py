@@ -170,6 +170,89 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------
+# secondary kernels of the path (reported under "extra"; N=1 only)
+# ---------------------------------------------------------------------------------------
+def _time_cuda(fn, iters, flush):
+    ms = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ms += e0.elapsed_time(e1)
+    return ms / iters
+
+
+def gag_extra(dev, flush, hbm_gbs):
+    """GlobalAttentionGeneral fwd+bwd (grads on both outputs) at the synthetic generator shapes of
+    SURVEY.md §8a-a7: B=48, T=18, (64^2,128ch) (128^2,64ch) (256^2,32ch).  HBM-bound: algorithmic
+    bytes per (sample, pixel) row fwd+bwd = (5*idf + 2*T)*4."""
+    import eegan_b200 as E
+    out = []
+    g = torch.Generator(device="cpu").manual_seed(7)
+    Bq, T = 48, 18
+    lens = torch.randint(5, T + 1, (Bq,), generator=g)
+    mask = (torch.arange(T)[None, :] >= lens[:, None]).to(dev)
+    for res, idf in ((64, 128), (128, 64), (256, 32)):
+        x = torch.randn(Bq, idf, res, res, device=dev).requires_grad_()
+        key = (torch.randn(Bq, idf, T, device=dev) * idf ** -0.5).requires_grad_()
+        val = torch.randn(Bq, idf, T, device=dev).requires_grad_()
+        mod = E.GlobalAttentionGeneral(idf, 256)
+        mod.applyMask(mask)
+        go = torch.randn(Bq, idf, res, res, device=dev)
+        ga = torch.randn(Bq, T, res, res, device=dev)
+
+        def fwd_bwd():
+            x.grad = key.grad = val.grad = None
+            o, a = mod(x, key, val)
+            torch.autograd.backward([o, a], [go, ga])
+
+        def fwd_only():
+            with torch.no_grad():
+                mod(x, key, val)
+
+        for _ in range(3):
+            fwd_bwd()
+        ms = _time_cuda(fwd_bwd, 10, flush)
+        ms_f = _time_cuda(fwd_only, 10, flush)
+        rows = Bq * res * res
+        by = (5 * idf + 2 * T) * 4 * rows
+        by_f = (2 * idf + T) * 4 * rows
+        out.append({"res": res, "idf": idf, "rows_per_s": rows / (ms / 1e3), "ms_fwd_bwd": ms, "ms_fwd": ms_f,
+                    "hbm_gbs_fwd_bwd": by / (ms / 1e3) / 1e9, "hbm_frac_fwd_bwd": by / (ms / 1e3) / 1e9 / hbm_gbs,
+                    "hbm_gbs_fwd": by_f / (ms_f / 1e3) / 1e9, "hbm_frac_fwd": by_f / (ms_f / 1e3) / 1e9 / hbm_gbs})
+        del x, key, val, go, ga
+    return out
+
+
+def syncbn_extra(dev, flush, hbm_gbs):
+    """SynchronizedBatchNorm2d fwd+bwd, single replica, at generator shapes (SURVEY App. C, B=32).
+    Algorithmic bytes: fwd read x twice + write y; bwd read x, dy twice + write dx = 8 passes."""
+    from eegan_b200.sync_batchnorm import SynchronizedBatchNorm2d
+    out = []
+    for C, hw in ((256, 16), (64, 128), (32, 256)):
+        x = torch.randn(32, C, hw, hw, device=dev).requires_grad_()
+        bn = SynchronizedBatchNorm2d(C).to(dev)
+        gy = torch.randn_like(x)
+
+        def fwd_bwd():
+            x.grad = None
+            bn(x).backward(gy)
+
+        for _ in range(3):
+            fwd_bwd()
+        ms = _time_cuda(fwd_bwd, 10, flush)
+        by = 8 * x.numel() * 4
+        out.append({"shape": [32, C, hw, hw], "ms_fwd_bwd": ms, "hbm_gbs": by / (ms / 1e3) / 1e9,
+                    "hbm_frac": by / (ms / 1e3) / 1e9 / hbm_gbs})
+        del x, gy
+    return out
+
+
+# ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
 def run_ours(args):
@@ -390,6 +473,9 @@ def run_ours(args):
                           "achieved_gbs": (3 * B * D * (R + T_MAX) * 4 + 3 * B * B * 4) / (ms_step / 1e3) / 1e9,
                           "peak_gbs": pk["hbm_gbs"]}}
     if world == 1:
+        if not args.no_extra:
+            line["extra"] = {"global_attention_general": gag_extra(dev, flush, pk["hbm_gbs"]),
+                             "sync_batchnorm_1replica": syncbn_extra(dev, flush, pk["hbm_gbs"])}
         base, _, _ = cpu_arm(args.steps, 1)
         line["cpu_baseline"] = base
     print(json.dumps(line))
@@ -403,6 +489,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the GlobalAttentionGeneral / SyncBN side measurements")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of the CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -233,3 +233,20 @@ def test_ffma_engine_still_matches(cuda_lib):
         cuda_lib.eegan_set_contraction_engine(1)
     assert abs(res[0][0] - res[1][0]) <= 2e-5 and abs(res[0][1] - res[1][1]) <= 2e-5
     assert relmax(res[1][2], res[0][2]) <= TOL_GRAD and relmax(res[1][3], res[0][3]) <= TOL_GRAD
+
+
+def test_graphed_words_loss_matches_eager(cuda_lib):
+    """The CUDA-graph step API replays exactly the kernels of the eager call."""
+    import eegan_b200 as E
+    from eegan_b200.graphed import GraphedWordsLoss
+    B, T = 10, 18
+    gw = GraphedWordsLoss(B, 256, 17, 17, T, "cuda", use_class_ids=True, words_grad=True, w0=1.0, w1=2.0)
+    for seed in (31, 32):  # second call exercises replay with new data and new ragged lengths
+        c = cases.words_case(B, T, seed=seed)
+        l0, l1, d_img, d_words = gw(c["img"].cuda(), c["words"].cuda(), c["cap_lens"].cuda(), c["class_ids"].cuda())
+        img = c["img"].cuda().requires_grad_()
+        words = c["words"].cuda().requires_grad_()
+        e0, e1, _ = E.words_loss(img, words, c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], B)
+        (e0 + 2.0 * e1).backward()
+        assert abs(l0.item() - e0.item()) <= 1e-6 and abs(l1.item() - e1.item()) <= 1e-6
+        assert relmax(d_img, img.grad) <= 1e-6 and relmax(d_words, words.grad) <= 1e-6

@@ -304,11 +304,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N>1 stays eager: capturing the NCCL collectives of the sharded path into the graph hung on
+    # this stack (torch 2.11 / NCCL 2.28.9); at N>=4 the per-rank GPU work exceeds the host time anyway
     use_graph = (world == 1) and not args.eager
     graphed = None
     if use_graph:
         from eegan_b200.graphed import GraphedWordsLoss
-        graphed = GraphedWordsLoss(B, D, HW, HW, T_MAX, dev, use_class_ids=True, words_grad=True)
+        graphed = GraphedWordsLoss(B, D, HW, HW, T_MAX, dev, use_class_ids=True, words_grad=True, sharded=world > 1)
         cls_d = cls.to(dev)
         graphed(img_d.detach(), words_d.detach(), lens_d, cls_d)  # capture
 

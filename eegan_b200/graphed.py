@@ -22,7 +22,7 @@ class GraphedWordsLoss:
     int64 values per call (or None at construction for "no class mask")."""
 
     def __init__(self, batch_size, D, H, W, T_max, device, use_class_ids=True, words_grad=True, w0=1.0, w1=1.0,
-                 warmup=3):
+                 warmup=3, sharded=False, group=None):
         self.B = batch_size
         dev = torch.device(device)
         self.img = torch.zeros(batch_size, D, H, W, device=dev).requires_grad_()
@@ -33,12 +33,20 @@ class GraphedWordsLoss:
         self.w0, self.w1 = float(w0), float(w1)
         self.graph = None
         self._warmup = warmup
+        # sharded=True: batch_size is the rank's local batch; the loss is the global-batch loss of
+        # eegan_b200.sharded.sharded_words_loss (NCCL collectives are captured into the graph)
+        self.sharded, self.group = sharded, group
         self.loss0 = self.loss1 = None
 
     def _step(self):
         self.img.grad = None
         self.words.grad = None
-        l0, l1, _ = dl.words_loss(self.img, self.words, self.labels, self.cap_lens, self.class_ids, self.B)
+        if self.sharded:
+            from .sharded import sharded_words_loss
+            l0, l1, _ = sharded_words_loss(self.img, self.words, self.labels, self.cap_lens, self.class_ids, self.B,
+                                           group=self.group)
+        else:
+            l0, l1, _ = dl.words_loss(self.img, self.words, self.labels, self.cap_lens, self.class_ids, self.B)
         (self.w0 * l0 + self.w1 * l1).backward()
         return l0.detach(), l1.detach()
 

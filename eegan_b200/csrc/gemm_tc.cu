@@ -295,7 +295,33 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// Encoding a tensor map is pure host work (a few microseconds); the same handful of operands
+// recurs every step (the workspace comes back at the same address from the caching allocator),
+// so the last encodes are memoised per host thread.
+struct MapKey {
+    const float* ptr;
+    long long ld, bstride;
+    int kmajor, nbatch, rows, K, box_rows;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && ld == o.ld && bstride == o.bstride && kmajor == o.kmajor && nbatch == o.nbatch &&
+               rows == o.rows && K == o.K && box_rows == o.box_rows;
+    }
+};
+struct MapSlot {
+    MapKey key;
+    CUtensorMap map;
+    bool used;
+};
+static thread_local MapSlot g_map_cache[32];
+static thread_local int g_map_next = 0;
+
 static int make_map(CUtensorMap* m, const TcOperand& o, int box_rows_kmajor) {
+    const MapKey key{o.ptr, o.ld, o.bstride, o.kmajor, o.nbatch, o.rows, o.K, box_rows_kmajor};
+    for (int i = 0; i < 32; ++i)
+        if (g_map_cache[i].used && g_map_cache[i].key == key) {
+            *m = g_map_cache[i].map;
+            return EEGAN_OK;
+        }
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("tc gemm: cuTensorMapEncodeTiled unavailable"); return EEGAN_ERR_CUDA; }
     if ((reinterpret_cast<uintptr_t>(o.ptr) & 15) || (o.ld % 4) || (o.bstride % 4)) {
@@ -317,13 +343,17 @@ static int make_map(CUtensorMap* m, const TcOperand& o, int box_rows_kmajor) {
     strides[1] = (cuuint64_t)(o.bstride > 0 ? o.bstride : (long long)dims[1] * o.ld) * 4;
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(o.ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, o.kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("tc gemm: cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu ld=%lld", (int)r, (unsigned long long)dims[0],
                   (unsigned long long)dims[1], (unsigned long long)dims[2], o.ld);
         return EEGAN_ERR_CUDA;
     }
+    MapSlot& slot = g_map_cache[g_map_next];
+    g_map_next = (g_map_next + 1) % 32;
+    slot.key = key;
+    slot.map = *m;
+    slot.used = true;
     return EEGAN_OK;
 }
 

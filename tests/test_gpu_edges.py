@@ -1,0 +1,93 @@
+"""GPU: edge cases of the pair grid the reference's semantics define — single pair, one-word
+captions, T_max = 32, non-CUB shapes, all-same-class batches (every off-diagonal cell -inf),
+and a batch larger than one GEMM tile in every dimension."""
+import pytest
+import torch
+
+from helpers import finite_close, relmax
+from oracle import cases
+from oracle import damsm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(c, B, w0=1.0, w1=1.0, use_port=False):
+    import eegan_b200 as E
+    img = c["img"].cuda().requires_grad_()
+    words = c["words"].cuda().requires_grad_()
+    l0, l1, att = E.words_loss(img, words, c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], B)
+    (w0 * l0 + w1 * l1).backward()
+    if use_port:
+        io, wo = c["img"].clone().requires_grad_(), c["words"].clone().requires_grad_()
+        o0, o1, oatt = O.port_words_loss(io, wo, c["labels"], c["cap_lens"], c["class_ids"], B)
+    else:
+        io, wo = c["img"].double().requires_grad_(), c["words"].double().requires_grad_()
+        o0, o1, oatt, _ = O.dense_words_loss(io, wo, c["labels"], c["cap_lens"], c["class_ids"])
+    (w0 * o0 + w1 * o1).backward()
+    return (l0, l1, att, img.grad, words.grad), (o0, o1, oatt, io.grad, wo.grad)
+
+
+@pytest.mark.parametrize("B,T,D,H,lens", [
+    (1, 18, 256, 17, [7]),                 # a single pair: CE over one cell is exactly 0
+    (2, 18, 256, 17, [1, 18]),             # one-word caption: softmax over a single word is 1
+    (3, 32, 64, 10, [32, 5, 17]),          # T_max = 32 (lane-per-word limit), non-CUB D / R
+    (5, 9, 128, 4, [9, 9, 9, 9, 9]),       # no ragged captions, R = 16 < one TMA box
+])
+def test_small_and_odd_shapes(cuda_lib, B, T, D, H, lens):
+    c = cases.words_case(B, T, D=D, H=H, seed=B * 100 + T, class_mode="none", min_len=1)
+    c["cap_lens"] = torch.tensor(lens)
+    got, ref = _run_both(c, B)
+    assert abs(got[0].item() - ref[0].item()) <= 2e-5 and abs(got[1].item() - ref[1].item()) <= 2e-5
+    for a, b in zip(got[2], ref[2]):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert float((a.cpu().double() - b.detach()).abs().max()) <= 2e-6
+    if B > 1:
+        assert relmax(got[3].cpu(), ref[3]) <= 1e-4 and relmax(got[4].cpu(), ref[4]) <= 1e-4
+    else:
+        assert float(got[3].abs().max()) <= 1e-7 and float(got[4].abs().max()) <= 1e-7
+
+
+def test_all_same_class_masks_every_off_diagonal(cuda_lib):
+    """class_ids all equal: every off-diagonal cell is -inf (DAMSM_losses.py:282-285,331-333), each
+    CE row has one finite logit, both losses are exactly 0 and no gradient flows."""
+    import eegan_b200 as E
+    B = 6
+    c = cases.words_case(B, 12, seed=9)
+    c["class_ids"] = torch.full((B,), 7)
+    img = c["img"].cuda().requires_grad_()
+    words = c["words"].cuda().requires_grad_()
+    l0, l1, _ = E.words_loss(img, words, c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], B)
+    (l0 + l1).backward()
+    assert l0.item() == 0.0 and l1.item() == 0.0
+    assert float(img.grad.abs().max()) == 0.0 and float(words.grad.abs().max()) == 0.0
+    sim, _ = E.words_similarity(img.detach(), words.detach(), c["cap_lens"].cuda(), c["class_ids"], B)
+    off = ~torch.eye(B, dtype=torch.bool, device="cuda")
+    assert torch.isinf(sim[off]).all() and torch.isfinite(sim.diagonal()).all()
+
+
+def test_batch_larger_than_one_tile_everywhere(cuda_lib):
+    """B = 130: > 128 images, sum(cap_lens) spans many 128-row tiles, GEMM5 splits images unevenly.
+    Checked against the fp32 loop port (the float64 dense oracle would need > 10 GB here)."""
+    B, T = 130, 18
+    c = cases.words_case(B, T, seed=4, class_mode="cub")
+    got, ref = _run_both(c, B, 1.0, 2.0, use_port=True)
+    assert abs(got[0].item() - ref[0].item()) <= 5e-5 * abs(ref[0].item())
+    assert abs(got[1].item() - ref[1].item()) <= 5e-5 * abs(ref[1].item())
+    assert relmax(got[3].cpu(), ref[3]) <= 1e-4 and relmax(got[4].cpu(), ref[4]) <= 1e-4
+    for a, b in zip(got[2][:8], ref[2][:8]):
+        assert float((a.cpu() - b.detach()).abs().max()) <= 1e-6
+
+
+def test_sharded_block_equals_columns_of_full_grid(cuda_lib):
+    """The caption-row-sharded building block on ONE GPU: a rank's [B, b] column block with
+    diag_offset must equal the same columns of the full grid, and its att maps the matching rows."""
+    from eegan_b200.damsm_losses import pair_grid
+    B, b = 12, 4
+    c = cases.words_case(B, 18, seed=2)
+    img, words, lens = c["img"].cuda(), c["words"].cuda(), c["cap_lens"].cuda()
+    full, att_full = pair_grid(img, words, lens)
+    for rank in range(B // b):
+        sl = slice(rank * b, (rank + 1) * b)
+        blk, att = pair_grid(img, words[sl], lens[sl], diag_offset=rank * b)
+        assert float((blk - full[:, sl]).abs().max()) <= 2e-6
+        assert float((att - att_full[sl]).abs().max()) <= 1e-7

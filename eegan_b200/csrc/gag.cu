@@ -4,7 +4,11 @@
 // HBM-bound streaming kernels: one thread owns PX pixels (coalesced along q for every d),
 // key/value (and the mask) live in shared memory and are read as broadcast float4.
 // Algorithmic bytes per pixel fwd+bwd: (5*idf + 2*T)*4.
+#include <atomic>
+
 #include "common.cuh"
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
 
 namespace eegan {
 
@@ -243,6 +247,381 @@ __global__ void __launch_bounds__(GAG_BT) gag_bwd_kernel(const float* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// TMA-fed forward: the x tile is streamed by the TMA engine in [16 channels][512 pixels] chunks
+// through a 4-stage mbarrier ring, so the compute threads never wait on a global load; key /
+// value stay in shared memory.  Needs Q % 4 == 0, idf % 16 == 0, 16-byte aligned x.
+// ---------------------------------------------------------------------------------------
+constexpr int GF_TILE = 512, GF_DC = 8, GF_NS = 3;
+constexpr int GF_STAGE_BYTES = GF_DC * GF_TILE * 4;  // 32 KB
+
+template <int TP>
+__global__ void __launch_bounds__(256, 2) gag_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ key,
+                                                             const float* __restrict__ value, const uint8_t* __restrict__ mask,
+                                                             int mask_mode, int B, int idf, int Q, int T, float* __restrict__ out,
+                                                             float* __restrict__ attn) {
+    extern __shared__ uint8_t gsm[];
+    const uint32_t base = (smem_u32(gsm) + 127u) & ~127u;
+    float* ks = reinterpret_cast<float*>(gsm + (base - smem_u32(gsm)) + GF_NS * GF_STAGE_BYTES);  // [idf][TP]
+    float* vs = ks + idf * TP;
+    __shared__ __align__(8) unsigned long long bars[2 * GF_NS];
+    __shared__ uint32_t mbits[1024];  // per mask row: bit t set = word t is padding
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (GF_NS + s); };
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int q0 = blockIdx.x * GF_TILE;
+    for (int idx = tid; idx < idf * TP; idx += 256) {
+        const int d = idx / TP, t = idx - d * TP;
+        ks[idx] = (t < T) ? key[((size_t)b * idf + d) * T + t] : 0.f;
+        vs[idx] = (t < T) ? value[((size_t)b * idf + d) * T + t] : 0.f;
+    }
+    if (mask)
+        for (int row = tid; row < B; row += 256) {
+            uint32_t bits = 0;
+            for (int t = 0; t < T; ++t) bits |= (mask[(size_t)row * T + t] ? 1u : 0u) << t;
+            mbits[row] = bits;
+        }
+    if (tid == 0) {
+        for (int s = 0; s < GF_NS; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 8);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int nchunks = idf / GF_DC;
+    auto issue = [&](int c) {
+        const int s = c % GF_NS;
+        mbar_arrive_expect_tx(full(s), GF_STAGE_BYTES);
+        tma_load_2d(base + s * GF_STAGE_BYTES, &tmx, full(s), q0, b * idf + c * GF_DC);
+        tma_load_2d(base + s * GF_STAGE_BYTES + GF_STAGE_BYTES / 2, &tmx, full(s), q0 + 256, b * idf + c * GF_DC);
+    };
+    if (tid == 0)
+        for (int c = 0; c < GF_NS - 1 && c < nchunks; ++c) issue(c);
+
+    float s[2][TP];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int t = 0; t < TP; ++t) s[u][t] = 0.f;
+
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0) {
+            const int cc = c + GF_NS - 1;
+            if (cc < nchunks) {
+                if (cc >= GF_NS) mbar_wait(empty(cc % GF_NS), ((cc / GF_NS) - 1) & 1);
+                issue(cc);
+            }
+        }
+        const int st = c % GF_NS;
+        mbar_wait(full(st), (c / GF_NS) & 1);
+        const float* xs = reinterpret_cast<const float*>(gsm + (base - smem_u32(gsm)) + st * GF_STAGE_BYTES);
+#pragma unroll 4
+        for (int dd = 0; dd < GF_DC; ++dd) {
+            const float x0 = xs[dd * 256 + tid], x1 = xs[GF_DC * 256 + dd * 256 + tid];
+            const float* kr = ks + (c * GF_DC + dd) * TP;
+#pragma unroll
+            for (int t = 0; t < TP; t += 4) {
+                const float4 k4 = *reinterpret_cast<const float4*>(kr + t);
+                s[0][t + 0] = fmaf(x0, k4.x, s[0][t + 0]); s[1][t + 0] = fmaf(x1, k4.x, s[1][t + 0]);
+                s[0][t + 1] = fmaf(x0, k4.y, s[0][t + 1]); s[1][t + 1] = fmaf(x1, k4.y, s[1][t + 1]);
+                s[0][t + 2] = fmaf(x0, k4.z, s[0][t + 2]); s[1][t + 2] = fmaf(x1, k4.z, s[1][t + 2]);
+                s[0][t + 3] = fmaf(x0, k4.w, s[0][t + 3]); s[1][t + 3] = fmaf(x1, k4.w, s[1][t + 3]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty(st));
+    }
+    bool ok[2];
+    const uint32_t tail = (T < 32) ? (0xffffffffu << T) : 0u;  // columns t >= T never exist
+    const uint32_t rowbase = (uint32_t)(((long long)b * Q) % B);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int q = q0 + u * 256 + tid;
+        ok[u] = q < Q;
+        if (!ok[u]) continue;
+        uint32_t dead = tail;
+        if (mask) dead |= mbits[mask_mode == 0 ? (rowbase + (uint32_t)q) % (uint32_t)B : (uint32_t)b];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            s[u][t] = ((dead >> t) & 1u) ? -INFINITY : s[u][t];
+            mx = fmaxf(mx, s[u][t]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            // a fully masked row gives exp(-inf - -inf) = NaN exactly like the reference's softmax
+            const float e = (t < T) ? __expf(s[u][t] - mx) : 0.f;
+            s[u][t] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            s[u][t] *= inv;
+            if (t < T) attn[((size_t)b * T + t) * Q + q] = s[u][t];
+        }
+    }
+    float* ob = out + (size_t)b * idf * Q;
+#pragma unroll 2
+    for (int d = 0; d < idf; ++d) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int t = 0; t < TP; t += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(vs + d * TP + t);
+            a0 = fmaf(v4.x, s[0][t + 0], a0); a1 = fmaf(v4.x, s[1][t + 0], a1);
+            a0 = fmaf(v4.y, s[0][t + 1], a0); a1 = fmaf(v4.y, s[1][t + 1], a1);
+            a0 = fmaf(v4.z, s[0][t + 2], a0); a1 = fmaf(v4.z, s[1][t + 2], a1);
+            a0 = fmaf(v4.w, s[0][t + 3], a0); a1 = fmaf(v4.w, s[1][t + 3], a1);
+        }
+        if (ok[0]) ob[(size_t)d * Q + q0 + tid] = a0;
+        if (ok[1]) ob[(size_t)d * Q + q0 + 256 + tid] = a1;
+    }
+}
+
+template <int TP>
+static int gag_fwd_tma_launch(const float* x, const float* key, const float* value, const uint8_t* mask, int mask_mode,
+                              int B, int idf, int Q, int T, float* out, float* attn, cudaStream_t st) {
+    CUtensorMap tmx;
+    int rc = make_tmap_2d(&tmx, x, (unsigned long long)B * idf, (unsigned long long)Q, (unsigned long long)Q, 256, GF_DC);
+    if (rc) return rc;
+    const size_t smem = (size_t)GF_NS * GF_STAGE_BYTES + (size_t)2 * idf * TP * sizeof(float) + 128;
+    static std::atomic<size_t> granted{48 * 1024};
+    if (smem > granted.load()) {
+        cudaError_t e = cudaFuncSetAttribute(gag_fwd_tma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("gag fwd smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+        granted.store(smem);
+    }
+    gag_fwd_tma_kernel<TP><<<dim3((Q + GF_TILE - 1) / GF_TILE, B), 256, smem, st>>>(tmx, key, value, mask, mask_mode, B, idf, Q,
+                                                                                     T, out, attn);
+    return check_launch("gag fwd (tma)");
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA-fed backward.  CTA = 256 threads walking 256-pixel tiles of sample b.  Per tile:
+//   pass A  stream d_out in [8 ch][256 px] chunks: dp[t] += d_out[d,q] v[d,t]; then
+//           ds = p (dp + d_attn - sum_t p (dp + d_attn)), kept in registers and in smem [px][TP]
+//   pass B  stream x and d_out chunks again (L2 hits): dx[d,q] = sum_t ds[t] key[d,t] (thread = pixel)
+//           and dkey[d,:] += sum_q x[d,q] ds[q,:], dvalue[d,:] += sum_q d_out[d,q] p[q,:]
+//           with lanes = the 16 chunk rows (8 x + 8 d_out) and a broadcast read of ds / p rows.
+// Chunks arrive as 128B-swizzled TMA boxes of [8 rows][32 px] so that BOTH access patterns
+// (lanes = consecutive pixels, lanes = different rows of one pixel) are (nearly) conflict-free.
+// ---------------------------------------------------------------------------------------
+constexpr int GB_TILE = 256, GB_DC = 8, GB_NS = 3;
+constexpr int GB_BOX_BYTES = GB_DC * 128;                  // one [8][32 px] box = 1 KB
+constexpr int GB_OPER_BYTES = (GB_TILE / 32) * GB_BOX_BYTES;  // 8 KB per operand per chunk
+constexpr int GB_STAGE_BYTES = 2 * GB_OPER_BYTES;          // x then d_out
+
+__device__ __forceinline__ uint32_t gb_off(int row, int px) {  // byte offset of (row, px) inside an operand block
+    return (uint32_t)((px >> 5) * GB_BOX_BYTES + row * 128 + ((((px & 31) >> 2) ^ (row & 7)) << 4) + ((px & 3) << 2));
+}
+
+template <int TP>
+__global__ void __launch_bounds__(256, 2) gag_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                             const __grid_constant__ CUtensorMap tmg,
+                                                             const float* __restrict__ key, const float* __restrict__ value,
+                                                             const float* __restrict__ attn, const float* __restrict__ d_attn,
+                                                             int idf, int Q, int T, float* __restrict__ d_x,
+                                                             float* __restrict__ d_key, float* __restrict__ d_value) {
+    extern __shared__ uint8_t gsm[];
+    const uint32_t base = (smem_u32(gsm) + 1023u) & ~1023u;
+    uint8_t* gbase = gsm + (base - smem_u32(gsm));
+    float* ks = reinterpret_cast<float*>(gbase + GB_NS * GB_STAGE_BYTES);  // [idf][TP]
+    float* vs = ks + idf * TP;
+    float* dks = vs + idf * TP;   // accumulators
+    float* dvs = dks + idf * TP;
+    float* ds_s = dvs + idf * TP;  // [256][TP]
+    float* p_s = ds_s + GB_TILE * TP;
+    __shared__ __align__(8) unsigned long long bars[2 * GB_NS];
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (GB_NS + s); };
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < idf * TP; idx += 256) {
+        const int d = idx / TP, t = idx - d * TP;
+        ks[idx] = (t < T) ? key[((size_t)b * idf + d) * T + t] : 0.f;
+        vs[idx] = (t < T) ? value[((size_t)b * idf + d) * T + t] : 0.f;
+        dks[idx] = 0.f;
+        dvs[idx] = 0.f;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < GB_NS; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 8);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int nch = idf / GB_DC;
+    const int ntiles = (Q + GB_TILE - 1) / GB_TILE;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int per_tile = 2 * nch;             // pass A chunks then pass B chunks
+    const int total = my_tiles * per_tile;    // items of this CTA, ring position = item index
+    auto issue = [&](int it) {
+        const int s = it % GB_NS;
+        const int ti = it / per_tile, r = it - ti * per_tile;
+        const int q0 = ((int)blockIdx.x + ti * (int)gridDim.x) * GB_TILE;
+        const bool passB = r >= nch;
+        const int row0 = b * idf + (passB ? r - nch : r) * GB_DC;
+        const uint32_t dst = base + s * GB_STAGE_BYTES;
+        mbar_arrive_expect_tx(full(s), passB ? GB_STAGE_BYTES : GB_OPER_BYTES);
+#pragma unroll
+        for (int j = 0; j < GB_TILE / 32; ++j) {
+            tma_load_2d(dst + GB_OPER_BYTES + j * GB_BOX_BYTES, &tmg, full(s), q0 + 32 * j, row0);
+            if (passB) tma_load_2d(dst + j * GB_BOX_BYTES, &tmx, full(s), q0 + 32 * j, row0);
+        }
+    };
+    if (tid == 0)
+        for (int it = 0; it < GB_NS - 1 && it < total; ++it) issue(it);
+
+    // dk/dv phase mapping: lanes 0-7 = x rows, 8-15 = d_out rows; 16 pixel groups of 16 pixels
+    const int crow = lane & 15, cgrp = (warp << 1) | (lane >> 4);
+    const bool is_k = crow < GB_DC;
+    const int cr = is_k ? crow : crow - GB_DC;
+
+    int it = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+        const int q = ((int)blockIdx.x + ti * (int)gridDim.x) * GB_TILE + tid;
+        const bool ok = q < Q;
+        float dp[TP], p[TP];
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            const bool on = ok && t < T;
+            p[t] = on ? attn[((size_t)b * T + t) * Q + q] : 0.f;
+            dp[t] = (on && d_attn) ? d_attn[((size_t)b * T + t) * Q + q] : 0.f;
+        }
+        // ---------------- pass A ----------------
+        for (int c = 0; c < nch; ++c, ++it) {
+            if (tid == 0) {
+                const int nx = it + GB_NS - 1;
+                if (nx < total) {
+                    if (nx >= GB_NS) mbar_wait(empty(nx % GB_NS), ((nx / GB_NS) - 1) & 1);
+                    issue(nx);
+                }
+            }
+            const int st = it % GB_NS;
+            mbar_wait(full(st), (it / GB_NS) & 1);
+            const uint8_t* gch = gbase + st * GB_STAGE_BYTES + GB_OPER_BYTES;
+#pragma unroll
+            for (int dd = 0; dd < GB_DC; ++dd) {
+                const float gv = *reinterpret_cast<const float*>(gch + gb_off(dd, tid));
+                const float* vr = vs + (c * GB_DC + dd) * TP;
+#pragma unroll
+                for (int t = 0; t < TP; t += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(vr + t);
+                    dp[t + 0] = fmaf(gv, v4.x, dp[t + 0]);
+                    dp[t + 1] = fmaf(gv, v4.y, dp[t + 1]);
+                    dp[t + 2] = fmaf(gv, v4.z, dp[t + 2]);
+                    dp[t + 3] = fmaf(gv, v4.w, dp[t + 3]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty(st));
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int t = 0; t < TP; ++t) dot = fmaf(p[t], dp[t], dot);
+        float ds[TP];
+        __syncthreads();  // the previous tile's dk/dv readers are done with ds_s / p_s
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            ds[t] = p[t] * (dp[t] - dot);
+            ds_s[tid * TP + t] = ds[t];
+            p_s[tid * TP + t] = p[t];
+        }
+        __syncthreads();
+        // ---------------- pass B ----------------
+        for (int c = 0; c < nch; ++c, ++it) {
+            if (tid == 0) {
+                const int nx = it + GB_NS - 1;
+                if (nx < total) {
+                    if (nx >= GB_NS) mbar_wait(empty(nx % GB_NS), ((nx / GB_NS) - 1) & 1);
+                    issue(nx);
+                }
+            }
+            // dx needs no streamed data: do it while the chunk is in flight
+#pragma unroll
+            for (int dd = 0; dd < GB_DC; ++dd) {
+                const int d = c * GB_DC + dd;
+                const float* kr = ks + d * TP;
+                float acc = 0.f;
+#pragma unroll
+                for (int t = 0; t < TP; t += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(kr + t);
+                    acc = fmaf(ds[t + 0], k4.x, acc);
+                    acc = fmaf(ds[t + 1], k4.y, acc);
+                    acc = fmaf(ds[t + 2], k4.z, acc);
+                    acc = fmaf(ds[t + 3], k4.w, acc);
+                }
+                if (ok) d_x[((size_t)b * idf + d) * Q + q] = acc;
+            }
+            const int st = it % GB_NS;
+            mbar_wait(full(st), (it / GB_NS) & 1);
+            const uint8_t* src = gbase + st * GB_STAGE_BYTES + (is_k ? 0 : GB_OPER_BYTES);
+            const float* rhs = is_k ? ds_s : p_s;
+            float acc[TP];
+#pragma unroll
+            for (int t = 0; t < TP; ++t) acc[t] = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < GB_TILE / 16; ++k) {
+                const int px = cgrp * (GB_TILE / 16) + k;
+                const float sv = *reinterpret_cast<const float*>(src + gb_off(cr, px));
+                const float* rr = rhs + px * TP;
+#pragma unroll
+                for (int t = 0; t < TP; t += 4) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(rr + t);
+                    acc[t + 0] = fmaf(sv, r4.x, acc[t + 0]);
+                    acc[t + 1] = fmaf(sv, r4.y, acc[t + 1]);
+                    acc[t + 2] = fmaf(sv, r4.z, acc[t + 2]);
+                    acc[t + 3] = fmaf(sv, r4.w, acc[t + 3]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty(st));
+            float* dst = (is_k ? dks : dvs) + (c * GB_DC + cr) * TP;
+#pragma unroll
+            for (int t = 0; t < TP; ++t) atomicAdd(dst + t, acc[t]);
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < idf * TP; idx += 256) {
+        const int d = idx / TP, t = idx - d * TP;
+        if (t < T) {
+            atomicAdd(d_key + ((size_t)b * idf + d) * T + t, dks[idx]);
+            atomicAdd(d_value + ((size_t)b * idf + d) * T + t, dvs[idx]);
+        }
+    }
+}
+
+template <int TP>
+static int gag_bwd_tma_launch(const float* x, const float* key, const float* value, const float* attn, const float* d_out,
+                              const float* d_attn, int B, int idf, int Q, int T, float* d_x, float* d_key, float* d_value,
+                              cudaStream_t st) {
+    CUtensorMap tmx, tmg;
+    int rc = make_tmap_2d(&tmx, x, (unsigned long long)B * idf, (unsigned long long)Q, (unsigned long long)Q, 32, GB_DC, true);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmg, d_out, (unsigned long long)B * idf, (unsigned long long)Q, (unsigned long long)Q, 32, GB_DC, true);
+    if (rc) return rc;
+    const size_t smem = (size_t)GB_NS * GB_STAGE_BYTES + ((size_t)4 * idf * TP + 2 * GB_TILE * TP) * sizeof(float) + 1024;
+    static std::atomic<size_t> granted{48 * 1024};
+    if (smem > granted.load()) {
+        cudaError_t e = cudaFuncSetAttribute(gag_bwd_tma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("gag bwd smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+        granted.store(smem);
+    }
+    cudaMemsetAsync(d_key, 0, (size_t)B * idf * T * sizeof(float), st);
+    cudaMemsetAsync(d_value, 0, (size_t)B * idf * T * sizeof(float), st);
+    const int ntiles = (Q + GB_TILE - 1) / GB_TILE;
+    int per_sample = (2 * 148 + B - 1) / B;
+    if (per_sample > ntiles) per_sample = ntiles;
+    if (per_sample < 1) per_sample = 1;
+    gag_bwd_tma_kernel<TP><<<dim3(per_sample, B), 256, smem, st>>>(tmx, tmg, key, value, attn, d_attn, idf, Q, T, d_x, d_key,
+                                                                   d_value);
+    return check_launch("gag bwd (tma)");
+}
+
 template <int TP>
 static int gag_fwd_launch(const float* x, const float* key, const float* value, const uint8_t* mask, int mask_mode,
                           int B, int idf, int Q, int T, float* out, float* attn, cudaStream_t st) {
@@ -289,6 +668,9 @@ extern "C" int eegan_gag_fwd(const float* x, const float* key, const float* valu
     EEGAN_REQUIRE(T <= 32 && idf <= 512, "gag: T=%d (<=32) idf=%d (<=512) unsupported", T, idf);
     EEGAN_REQUIRE(x && key && value && out && attn, "gag fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t tma_smem = (size_t)GF_NS * GF_STAGE_BYTES + (size_t)2 * idf * 32 * sizeof(float) + 128;
+    if (Q % 4 == 0 && idf % GF_DC == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && tma_smem <= 100 * 1024 && B <= 1024)
+        return GAG_DISPATCH(T, gag_fwd_tma_launch)(x, key, value, mask, mask_mode, B, idf, Q, T, out, attn, st);
     return GAG_DISPATCH(T, gag_fwd_launch)(x, key, value, mask, mask_mode, B, idf, Q, T, out, attn, st);
 }
 
@@ -299,5 +681,9 @@ extern "C" int eegan_gag_bwd(const float* x, const float* key, const float* valu
     EEGAN_REQUIRE(T <= 32 && idf <= 256, "gag bwd: T=%d (<=32) idf=%d (<=256) unsupported", T, idf);
     EEGAN_REQUIRE(x && key && value && attn && d_x && d_key && d_value, "gag bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t tma_smem = (size_t)GB_NS * GB_STAGE_BYTES + ((size_t)4 * idf * 32 + 2 * GB_TILE * 32) * sizeof(float) + 1024;
+    if (d_out && Q % 4 == 0 && idf % GB_DC == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0 &&
+        tma_smem <= 220 * 1024)
+        return GAG_DISPATCH(T, gag_bwd_tma_launch)(x, key, value, attn, d_out, d_attn, B, idf, Q, T, d_x, d_key, d_value, st);
     return GAG_DISPATCH(T, gag_bwd_launch)(x, key, value, attn, d_out, d_attn, B, idf, Q, T, d_x, d_key, d_value, st);
 }

@@ -357,6 +357,23 @@ static int make_map(CUtensorMap* m, const TcOperand& o, int box_rows_kmajor) {
     return EEGAN_OK;
 }
 
+int make_tmap_2d(CUtensorMap* m, const float* ptr, unsigned long long rows, unsigned long long cols, unsigned long long pitch,
+                 unsigned box_cols, unsigned box_rows, bool swizzle128) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("tmap2d: cuTensorMapEncodeTiled unavailable"); return EEGAN_ERR_CUDA; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch % 4)) {
+        set_error("tmap2d: base/pitch must be 16-byte aligned");
+        return EEGAN_ERR_INVALID;
+    }
+    cuuint64_t dims[2] = {cols, rows}, strides[1] = {pitch * 4};
+    cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tmap2d: cuTensorMapEncodeTiled failed (%d)", (int)r); return EEGAN_ERR_CUDA; }
+    return EEGAN_OK;
+}
+
 static int num_sms() {
     static int n = [] {
         int dev = 0, v = 148;

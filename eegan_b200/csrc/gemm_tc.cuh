@@ -52,6 +52,11 @@ struct TcGemm {
     int nred, red_total;    // reduction batches per z: operand batch index = z*nred + red
 };
 
+// Plain (un-swizzled) 2-D fp32 tensor map over a row-major [rows][cols] array with row pitch
+// `pitch` elements (multiple of 4) and a [box_rows][box_cols] box; TMA zero-fills out of bounds.
+int make_tmap_2d(CUtensorMap* m, const float* ptr, unsigned long long rows, unsigned long long cols, unsigned long long pitch,
+                 unsigned box_cols, unsigned box_rows, bool swizzle128 = false);
+
 // Enqueue the GEMM.  Returns EEGAN_OK or an error code (message via set_error).
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st);
 

@@ -23,6 +23,7 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t da, uint64
 }
 // round-to-nearest (ties away) to the 10-bit tf32 mantissa with two integer ops; same result as
 // cvt.rna.tf32.f32 for finite inputs (inf/nan inputs poison the output either way)
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // Canonical 128B-swizzle UMMA shared-memory descriptor (version 1 = Blackwell).
@@ -43,6 +44,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t tile, bool kmajor, int ks
     return d;
 }
 
+// [segment][0 = A, 1 = B][0 = raw / hi, 1 = pre-split lo]
+struct TcMaps {
+    CUtensorMap m[2][2][2];
+};
+
 struct TcArgs {
     float* C;
     long long ldc, bC;
@@ -52,6 +58,9 @@ struct TcArgs {
     int K[2];
     int nseg, nred, red_total, batch;
     int a_batched[2], b_batched[2];
+    int a_pre[2], b_pre[2];   // operand arrives pre-split (raw + lo arrays): no in-kernel split for it
+    int dbg;                  // timing experiments only: 1 skip MMAs, 2 skip split math, 4 skip TMA
+    int trunc_hi;             // 1: leave the raw operand as hi (hardware truncation), write lo only
     uint32_t mn_lbo, mn_sbo;  // debug-overridable descriptor fields of MN-major tiles (16-byte units)
 };
 
@@ -63,8 +72,7 @@ struct TcArgs {
 // let the epilogue of tile i overlap the main loop of tile i+1.
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
-               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const TcArgs p) {
+tc_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Mlive = p.dynM ? min(*p.dynM, p.M) : p.M;
@@ -134,24 +142,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const int red = k / kbt, rem = k - red * kbt;
                     const int seg = rem >= kb0 ? 1 : 0;
                     const int k0 = (seg ? rem - kb0 : rem) * TC_BK;
-                    const CUtensorMap* ta = seg ? &tmA1 : &tmA0;
-                    const CUtensorMap* tb = seg ? &tmB1 : &tmB0;
                     const int zr = z * p.nred + red;
                     const int zA = p.a_batched[seg] ? zr : 0, zB = p.b_batched[seg] ? zr : 0;
+                    const bool apre = p.a_pre[seg], bpre = p.b_pre[seg];
                     mbar_wait(empty(s), ph ^ 1);
-                    mbar_arrive_expect_tx(full(s), 2 * TC_TILE_BYTES);
+                    if (p.dbg & 4) { mbar_arrive(full(s)); continue; }
+                    mbar_arrive_expect_tx(full(s), (uint32_t)((2 + (apre ? 1 : 0) + (bpre ? 1 : 0)) * TC_TILE_BYTES));
                     const uint32_t sA = base + s * TC_STAGE_BYTES, sB = sA + TC_TILE_BYTES;
-                    if (A_K) {
-                        tma_load_3d(sA, ta, full(s), k0, m0, zA);
-                    } else {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) tma_load_3d(sA + c * 4096, ta, full(s), m0 + 32 * c, k0, zA);
-                    }
-                    if (B_K) {
-                        tma_load_3d(sB, tb, full(s), k0, n0, zB);
-                    } else {
+                    for (int h = 0; h < 2; ++h) {  // h = 1: the pre-split lo arrays land directly in the lo tiles
+                        if (h == 0 || apre) {
+                            const CUtensorMap* ta = &tm.m[seg][0][h];
+                            const uint32_t dst = sA + h * 2 * TC_TILE_BYTES;
+                            if (A_K) {
+                                tma_load_3d(dst, ta, full(s), k0, m0, zA);
+                            } else {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) tma_load_3d(sB + c * 4096, tb, full(s), n0 + 32 * c, k0, zB);
+                                for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * 4096, ta, full(s), m0 + 32 * c, k0, zA);
+                            }
+                        }
+                        if (h == 0 || bpre) {
+                            const CUtensorMap* tb = &tm.m[seg][1][h];
+                            const uint32_t dst = sB + h * 2 * TC_TILE_BYTES;
+                            if (B_K) {
+                                tma_load_3d(dst, tb, full(s), k0, n0, zB);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * 4096, tb, full(s), n0 + 32 * c, k0, zB);
+                            }
+                        }
                     }
                 }
             }
@@ -178,6 +197,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const uint32_t a_lo = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        if (p.dbg & 1) break;
                         const uint64_t dah = umma_desc(a_hi, A_K, ks, p.mn_lbo, p.mn_sbo), dal = umma_desc(a_lo, A_K, ks, p.mn_lbo, p.mn_sbo);
                         const uint64_t dbh = umma_desc(b_hi, B_K, ks, p.mn_lbo, p.mn_sbo), dbl = umma_desc(b_lo, B_K, ks, p.mn_lbo, p.mn_sbo);
                         tc_mma_tf32(tmem_d, dal, dbh, idesc, (k > 0 || ks > 0) ? 1u : 0u);
@@ -197,20 +217,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int total = tile_total(t / (mt * nt));
             for (int k = 0; k < total; ++k, ++it) {
                 const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                const int seg = (k % kbt) >= kb0 ? 1 : 0;
+                // float4 range of the stage that still needs splitting: A tile = [0,1024), B tile = [1024,2048)
+                const int f0 = p.a_pre[seg] ? TC_TILE_BYTES / 16 : 0;
+                const int f1 = p.b_pre[seg] ? TC_TILE_BYTES / 16 : 2 * TC_TILE_BYTES / 16;
                 mbar_wait(full(s), ph);
                 const uint32_t hi = base + s * TC_STAGE_BYTES, lo = hi + 2 * TC_TILE_BYTES;
+                if (!(p.dbg & 2)) {
 #pragma unroll 4
-                for (int i = 0; i < (2 * TC_TILE_BYTES / 16) / (32 * TC_SPLIT_WARPS); ++i) {
-                    const uint32_t off = (uint32_t)(i * (32 * TC_SPLIT_WARPS) + ctid) * 16u;
-                    float4 v;
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + off));
-                    float4 h, l;
-                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-                    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                    for (int f = f0 + ctid; f < f1; f += 32 * TC_SPLIT_WARPS) {
+                        const uint32_t off = (uint32_t)f * 16u;
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + off));
+                        float4 h, l;
+                        if (p.trunc_hi) {
+                            // the tensor core reads only the top 19 bits of an fp32 operand: the raw tile IS hi = trunc(x);
+                            // only lo = tf32(x - trunc(x)) is written
+                            h.x = trunc_tf32(v.x); h.y = trunc_tf32(v.y); h.z = trunc_tf32(v.z); h.w = trunc_tf32(v.w);
+                        } else {
+                            h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                        }
+                        l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                    }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+                if (f0 < f1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
                 __syncwarp();
                 if (lane == 0) mbar_arrive(conv(s));
             }
@@ -384,14 +416,14 @@ static int num_sms() {
 }
 
 template <bool A_K, bool B_K>
-static int launch_t(const CUtensorMap* maps, const TcArgs& a, dim3 grid, cudaStream_t st) {
+static int launch_t(const TcMaps& maps, const TcArgs& a, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;  // idempotent; a race only repeats the call
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) { set_error("tc gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
         attr_set = true;
     }
-    tc_gemm_kernel<A_K, B_K><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], a);
+    tc_gemm_kernel<A_K, B_K><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, a);
     return check_launch("tc gemm");
 }
 
@@ -400,21 +432,37 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
     EEGAN_REQUIRE(g.M > 0 && g.N > 0 && g.batch > 0 && g.C, "tc gemm: empty problem");
     for (int s = 1; s < g.nseg; ++s)
         EEGAN_REQUIRE(g.A[s].kmajor == g.A[0].kmajor && g.B[s].kmajor == g.B[0].kmajor, "tc gemm: segments must share majorness");
-    CUtensorMap maps[4];
+
+    TcMaps maps;
     TcArgs a{};
     for (int s = 0; s < 2; ++s) {
         const int src = s < g.nseg ? s : 0;
-        int rc = make_map(&maps[2 * s], g.A[src], TC_BM);
-        if (rc) return rc;
-        rc = make_map(&maps[2 * s + 1], g.B[src], TC_BN);
-        if (rc) return rc;
+        const TcOperand* ops[2] = {&g.A[src], &g.B[src]};
+        for (int o = 0; o < 2; ++o) {
+            int rc = make_map(&maps.m[s][o][0], *ops[o], o == 0 ? TC_BM : TC_BN);
+            if (rc) return rc;
+            if (ops[o]->lo) {
+                TcOperand lo = *ops[o];
+                lo.ptr = ops[o]->lo;
+                rc = make_map(&maps.m[s][o][1], lo, o == 0 ? TC_BM : TC_BN);
+                if (rc) return rc;
+            } else {
+                maps.m[s][o][1] = maps.m[s][o][0];
+            }
+        }
         a.K[s] = s < g.nseg ? g.A[src].K : 0;
         a.a_batched[s] = g.A[src].bstride > 0;
         a.b_batched[s] = g.B[src].bstride > 0;
+        a.a_pre[s] = g.A[src].lo != nullptr;
+        a.b_pre[s] = g.B[src].lo != nullptr;
     }
     a.C = g.C; a.ldc = g.ldc; a.bC = g.bC; a.M = g.M; a.N = g.N; a.dynM = g.dynM; a.dynK = g.dynK;
     a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total; a.batch = g.batch;
     a.mn_lbo = 4096 >> 4; a.mn_sbo = 512 >> 4;
+    a.trunc_hi = 1;
+    a.dbg = 0;
+    if (const char* e = getenv("EEGAN_TC_DBG")) a.dbg = atoi(e);
+    if (const char* e = getenv("EEGAN_TC_TRUNC_HI")) a.trunc_hi = atoi(e);
     if (const char* e = getenv("EEGAN_TC_MN_LBO")) a.mn_lbo = (uint32_t)atoi(e);
     if (const char* e = getenv("EEGAN_TC_MN_SBO")) a.mn_sbo = (uint32_t)atoi(e);
     const long long tiles = (long long)((g.N + TC_BN - 1) / TC_BN) * ((g.M + TC_BM - 1) / TC_BM) * g.batch;
@@ -438,8 +486,8 @@ extern "C" int eegan_gemm_tf32x3(const float* A, const float* B, float* C, int M
     EEGAN_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tf32x3: bad arguments");
     TcGemm g{};
     g.nseg = 1;
-    g.A[0] = TcOperand{A, a_kmajor, lda, bsA, batch, M, K};
-    g.B[0] = TcOperand{B, b_kmajor, ldb, bsB, batch, N, K};
+    g.A[0] = TcOperand{A, nullptr, a_kmajor, lda, bsA, batch, M, K};
+    g.B[0] = TcOperand{B, nullptr, b_kmajor, ldb, bsB, batch, N, K};
     g.C = C; g.ldc = ldc; g.bC = bsC; g.M = M; g.N = N; g.batch = batch; g.nred = 1; g.red_total = 0;
     return tc_gemm_launch(g, (cudaStream_t)stream);
 }

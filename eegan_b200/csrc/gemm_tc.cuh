@@ -2,8 +2,10 @@
 //
 //   C[z][m][n] = sum over segments s, reduction batches red, k of  A_s(m,k) * B_s(n,k)
 //
-// fp32-accurate "3xTF32": every fp32 operand element x is split in shared memory into
-// hi = tf32(x) and lo = tf32(x - hi) and each K-step issues three tcgen05.mma.kind::tf32
+// fp32-accurate "3xTF32": every fp32 operand element x is used as hi = trunc_tf32(x) (the
+// tensor core reads only the top 19 bits of an fp32 operand, so the raw tile IS hi) plus
+// lo = tf32(x - hi), produced either by the splitter warps in shared memory or ahead of time by
+// the kernel that wrote the operand; each K-step issues three tcgen05.mma.kind::tf32
 // (lo*hi, hi*lo, hi*hi) into one fp32 accumulator tile in TMEM.  Single-pass TF32/BF16 flips
 // argmax word indices; the split keeps ~2^-21 relative error.
 //
@@ -32,7 +34,8 @@ constexpr int TC_SPLIT_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + 4);
 
 struct TcOperand {
-    const float* ptr;    // base
+    const float* ptr;    // base (raw fp32; the tensor core uses its top 19 bits = hi)
+    const float* lo;     // optional pre-split lo = tf32(x - trunc_tf32(x)), same layout; NULL = split in the kernel
     int kmajor;          // 1: [rows][K] (K contiguous); 0: [K][rows] (rows contiguous)
     long long ld;        // pitch in elements of the non-contiguous index (multiple of 4)
     long long bstride;   // elements between batches (multiple of 4); 0 = not batched

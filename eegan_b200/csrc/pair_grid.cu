@@ -588,8 +588,8 @@ static int gemm_nd_dr(const PairWs& w, const float* X, bool x_batched, const flo
     if (g_engine.load()) {
         TcGemm g{};
         g.nseg = 1;
-        g.A[0] = TcOperand{X, 1, D, x_batched ? (long long)NtM * D : 0, x_batched ? Bi : 1, NtM, D};
-        g.B[0] = TcOperand{image_operand(w, img), 0, w.Rp, (long long)D * w.Rp, Bi, R, D};
+        g.A[0] = TcOperand{X, nullptr, 1, D, x_batched ? (long long)NtM * D : 0, x_batched ? Bi : 1, NtM, D};
+        g.B[0] = TcOperand{image_operand(w, img), nullptr, 0, w.Rp, (long long)D * w.Rp, Bi, R, D};
         g.C = out; g.ldc = w.Rp; g.bC = (long long)NtM * w.Rp; g.M = NtM; g.N = R; g.dynM = w.ntot; g.batch = Bi; g.nred = 1;
         return tc_gemm_launch(g, st);
     }
@@ -611,8 +611,8 @@ static int gemm_nr_dr(const PairWs& w, const float* X, const float* img, float* 
     if (g_engine.load()) {
         TcGemm g{};
         g.nseg = 1;
-        g.A[0] = TcOperand{X, 1, w.Rp, (long long)NtM * w.Rp, Bi, NtM, R};
-        g.B[0] = TcOperand{image_operand(w, img), 1, w.Rp, (long long)D * w.Rp, Bi, D, R};
+        g.A[0] = TcOperand{X, nullptr, 1, w.Rp, (long long)NtM * w.Rp, Bi, NtM, R};
+        g.B[0] = TcOperand{image_operand(w, img), nullptr, 1, w.Rp, (long long)D * w.Rp, Bi, D, R};
         g.C = out; g.ldc = D; g.bC = (long long)NtM * D; g.M = NtM; g.N = D; g.dynM = w.ntot; g.batch = batch;
         g.nred = nred; g.red_total = nsplit ? Bi : 0;
         return tc_gemm_launch(g, st);
@@ -634,10 +634,10 @@ static int gemm_dc(const PairWs& w, float* d_img, int Bi, int NtM, int D, int R,
         pair_zero_tail_kernel<<<dim3(32, Bi, 4), 128, 0, st>>>(w.U, w.A, w.DA, w.Wp, w.ntot, NtM, D, w.Rp);
         TcGemm g{};
         g.nseg = 2;
-        g.A[0] = TcOperand{w.U, 0, D, (long long)NtM * D, Bi, D, NtM};
-        g.B[0] = TcOperand{w.A, 0, w.Rp, (long long)NtM * w.Rp, Bi, R, NtM};
-        g.A[1] = TcOperand{w.Wp, 0, D, 0, 1, D, NtM};
-        g.B[1] = TcOperand{w.DA, 0, w.Rp, (long long)NtM * w.Rp, Bi, R, NtM};
+        g.A[0] = TcOperand{w.U, nullptr, 0, D, (long long)NtM * D, Bi, D, NtM};
+        g.B[0] = TcOperand{w.A, nullptr, 0, w.Rp, (long long)NtM * w.Rp, Bi, R, NtM};
+        g.A[1] = TcOperand{w.Wp, nullptr, 0, D, 0, 1, D, NtM};
+        g.B[1] = TcOperand{w.DA, nullptr, 0, w.Rp, (long long)NtM * w.Rp, Bi, R, NtM};
         g.C = d_img; g.ldc = R; g.bC = (long long)D * R; g.M = D; g.N = R; g.dynK = w.ntot; g.batch = Bi; g.nred = 1;
         return tc_gemm_launch(g, st);
     }

@@ -3,66 +3,9 @@
 
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
+#include "tc_device.cuh"
 
 namespace eegan {
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// round-to-nearest (ties away) to the 10-bit tf32 mantissa with two integer ops; same result as
-// cvt.rna.tf32.f32 for finite inputs (inf/nan inputs poison the output either way)
-__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
-
-// Canonical 128B-swizzle UMMA shared-memory descriptor (version 1 = Blackwell).
-//   K-major : rows at 128 B, 8-row groups at SBO = 1024 B; a K-step of 8 fp32 advances the start by 32 B.
-//   MN-major: 32-bit operands only exist in the "128B swizzle, 32B atomicity" layout (descriptor
-//             layout type 1, TMA SWIZZLE_128B_ATOM_32B): [k][32 fp32] rows of 128 B, atoms of 4
-//             k-rows (SBO = 512 B between 4-row groups), 32-wide MN chunks LBO = 4096 B apart
-//             (one TMA box of 32 k-rows each); a K-step of 8 advances the start by 1024 B.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t tile, bool kmajor, int kstep, uint32_t mn_lbo, uint32_t mn_sbo) {
-    const uint32_t start = tile + (kmajor ? kstep * 32 : kstep * 1024);
-    const uint64_t lbo = kmajor ? 1 : mn_lbo;
-    const uint64_t sbo = kmajor ? (1024 >> 4) : mn_sbo;
-    uint64_t d = (uint64_t)((start & 0x3FFFF) >> 4);
-    d |= lbo << 16;
-    d |= sbo << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version
-    d |= (uint64_t)(kmajor ? 2 : 1) << 61;  // SWIZZLE_128B (K-major) / SWIZZLE_128B_BASE32B (MN-major tf32)
-    return d;
-}
-
-// [segment][0 = A, 1 = B][0 = raw / hi, 1 = pre-split lo]
-struct TcMaps {
-    CUtensorMap m[2][2][2];
-};
-
-struct TcArgs {
-    float* C;
-    long long ldc, bC;
-    int M, N;
-    const int* dynM;
-    const int* dynK;
-    int K[2];
-    int nseg, nred, red_total, batch;
-    int a_batched[2], b_batched[2];
-    int a_pre[2], b_pre[2];   // operand arrives pre-split (raw + lo arrays): no in-kernel split for it
-    int dbg;                  // timing experiments only: 1 skip MMAs, 2 skip split math, 4 skip TMA
-    int trunc_hi;             // 1: leave the raw operand as hi (hardware truncation), write lo only
-    uint32_t mn_lbo, mn_sbo;  // debug-overridable descriptor fields of MN-major tiles (16-byte units)
-};
 
 // Persistent, warp-specialised kernel: grid = min(#live tiles, #SMs); every CTA walks tiles
 // t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, then m, then batch z).
@@ -70,19 +13,21 @@ struct TcArgs {
 //   warps 2-9   hi/lo splitters         warps 10-13 epilogue (TMEM lane quarter = warp & 3)
 // The smem stage ring runs continuously across tiles; two TMEM accumulators (2 x 128 columns)
 // let the epilogue of tile i overlap the main loop of tile i+1.
-template <bool A_K, bool B_K>
+template <bool A_K, bool B_K, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Mlive = p.dynM ? min(*p.dynM, p.M) : p.M;
-    const int mt = (Mlive + TC_BM - 1) / TC_BM, nt = (p.N + TC_BN - 1) / TC_BN;
+    const int Nlive = p.dynN ? min(*p.dynN, p.N) : p.N;
+    const int mt = (Mlive + TC_BM - 1) / TC_BM, nt = (Nlive + TC_BN - 1) / TC_BN;
     const int ntiles = mt * nt * p.batch;
     if ((int)blockIdx.x >= ntiles) return;  // uniform: before any barrier / TMEM state exists
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t epi_stage = base + TC_STAGES * TC_STAGE_BYTES;       // 4 warps x [32][33] floats
-    const uint32_t bars = epi_stage + 4 * 32 * 33 * 4;
+    const uint32_t epi_stage = base + TC_STAGES * TC_STAGE_BYTES;       // 4 warps x [32][TC_EPI_PITCH] floats
+    const uint32_t epi_czs = epi_stage + TC_EPI_STAGE_BYTES;            // 4 warps x 64 floats
+    const uint32_t bars = epi_czs + 1024u;
     auto full = [&](int s) { return bars + 8u * s; };
     auto conv = [&](int s) { return bars + 8u * (TC_STAGES + s); };
     auto empty = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };
@@ -119,8 +64,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * TC_BN) : "memory");
+    if (warp == 1) {  // all 512 columns: the attention epilogues read 32-column windows that may overhang an accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -146,7 +91,6 @@ tc_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
                     const int zA = p.a_batched[seg] ? zr : 0, zB = p.b_batched[seg] ? zr : 0;
                     const bool apre = p.a_pre[seg], bpre = p.b_pre[seg];
                     mbar_wait(empty(s), ph ^ 1);
-                    if (p.dbg & 4) { mbar_arrive(full(s)); continue; }
                     mbar_arrive_expect_tx(full(s), (uint32_t)((2 + (apre ? 1 : 0) + (bpre ? 1 : 0)) * TC_TILE_BYTES));
                     const uint32_t sA = base + s * TC_STAGE_BYTES, sB = sA + TC_TILE_BYTES;
 #pragma unroll
@@ -197,7 +141,6 @@ tc_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
                     const uint32_t a_lo = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                        if (p.dbg & 1) break;
                         const uint64_t dah = umma_desc(a_hi, A_K, ks, p.mn_lbo, p.mn_sbo), dal = umma_desc(a_lo, A_K, ks, p.mn_lbo, p.mn_sbo);
                         const uint64_t dbh = umma_desc(b_hi, B_K, ks, p.mn_lbo, p.mn_sbo), dbl = umma_desc(b_lo, B_K, ks, p.mn_lbo, p.mn_sbo);
                         tc_mma_tf32(tmem_d, dal, dbh, idesc, (k > 0 || ks > 0) ? 1u : 0u);
@@ -223,24 +166,22 @@ tc_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
                 const int f1 = p.b_pre[seg] ? TC_TILE_BYTES / 16 : 2 * TC_TILE_BYTES / 16;
                 mbar_wait(full(s), ph);
                 const uint32_t hi = base + s * TC_STAGE_BYTES, lo = hi + 2 * TC_TILE_BYTES;
-                if (!(p.dbg & 2)) {
 #pragma unroll 4
-                    for (int f = f0 + ctid; f < f1; f += 32 * TC_SPLIT_WARPS) {
-                        const uint32_t off = (uint32_t)f * 16u;
-                        float4 v;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + off));
-                        float4 h, l;
-                        if (p.trunc_hi) {
-                            // the tensor core reads only the top 19 bits of an fp32 operand: the raw tile IS hi = trunc(x);
-                            // only lo = tf32(x - trunc(x)) is written
-                            h.x = trunc_tf32(v.x); h.y = trunc_tf32(v.y); h.z = trunc_tf32(v.z); h.w = trunc_tf32(v.w);
-                        } else {
-                            h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                        }
-                        l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                for (int f = f0 + ctid; f < f1; f += 32 * TC_SPLIT_WARPS) {
+                    const uint32_t off = (uint32_t)f * 16u;
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + off));
+                    float4 h, l;
+                    if (p.trunc_hi) {
+                        // the tensor core reads only the top 19 bits of an fp32 operand: the raw tile IS hi = trunc(x);
+                        // only lo = tf32(x - trunc(x)) is written
+                        h.x = trunc_tf32(v.x); h.y = trunc_tf32(v.y); h.z = trunc_tf32(v.z); h.w = trunc_tf32(v.w);
+                    } else {
+                        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
                     }
+                    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
                 }
                 if (f0 < f1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
                 __syncwarp();
@@ -248,65 +189,34 @@ tc_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
             }
         }
     } else {
-        // ===== epilogue (last four warps): TMEM -> registers -> per-warp smem transpose -> coalesced global =====
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const uint32_t my_stage = epi_stage + (uint32_t)(warp - 2 - TC_SPLIT_WARPS) * (32 * 33 * 4);
+        // ===== epilogue (last four warps) =====
+        EpiTile et;
+        et.quarter = warp & 3;  // TMEM lane quarter this warp may access
+        et.half = -1;
+        et.stage = epi_stage + (uint32_t)(warp - 2 - TC_SPLIT_WARPS) * (32 * TC_EPI_PITCH * 4);
+        et.czs = epi_czs + (uint32_t)(warp - 2 - TC_SPLIT_WARPS) * 256u;
+        et.Mlive = Mlive;
+        et.Nlive = Nlive;
         int ti = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
-            const int z = t / (mt * nt), rem_t = t - z * (mt * nt);
-            const int m0 = (rem_t / nt) * TC_BM, n0 = (rem_t % nt) * TC_BN;
-            const int total = tile_total(z);
+            const int rem_t = t % (mt * nt);
             const int acc = ti & 1;
-            mbar_wait(tmem_full(acc), (ti >> 1) & 1);
-            tc_fence_after();
-            float* Cz = p.C + (long long)z * p.bC;
-            const int rows_live = min(32, Mlive - (m0 + quarter * 32));  // rows of this warp that exist
-#pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
-                uint32_t v[32];
-                if (total > 0) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr)
-                        : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = 0u;
-                }
-                if (c == TC_BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty(acc));
-                }
-                __syncwarp();  // previous chunk's readers are done with the staging buffer
-#pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(my_stage + (uint32_t)(lane * 33 + q) * 4u), "r"(v[q]) : "memory");
-                __syncwarp();
-                const int gn = n0 + c * 32 + lane;
-                if (gn < p.N) {
-                    float* dst = Cz + (long long)(m0 + quarter * 32) * p.ldc + gn;
-                    for (int rr = 0; rr < rows_live; ++rr) {
-                        float val;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(my_stage + (uint32_t)(rr * 33 + lane) * 4u));
-                        dst[(long long)rr * p.ldc] = val;
-                    }
-                }
-            }
+            et.z = t / (mt * nt);
+            et.m0 = (rem_t / nt) * TC_BM;
+            et.n0 = (rem_t % nt) * TC_BN;
+            et.total = tile_total(et.z);
+            et.tacc = tmem_base + ((uint32_t)(et.quarter * 32) << 16) + (uint32_t)(acc * TC_BN);
+            et.full_bar = tmem_full(acc);
+            et.full_parity = (uint32_t)((ti >> 1) & 1);
+            et.empty_bar = tmem_empty(acc);
+            tc_epilogue_tile<EPI>(p, et, lane);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
     }
 }
 
@@ -333,10 +243,10 @@ static EncodeTiledFn get_encode() {
 struct MapKey {
     const float* ptr;
     long long ld, bstride;
-    int kmajor, nbatch, rows, K, box_rows;
+    int kmajor, nbatch, rows, K, box_rows, plain;
     bool operator==(const MapKey& o) const {
         return ptr == o.ptr && ld == o.ld && bstride == o.bstride && kmajor == o.kmajor && nbatch == o.nbatch &&
-               rows == o.rows && K == o.K && box_rows == o.box_rows;
+               rows == o.rows && K == o.K && box_rows == o.box_rows && plain == o.plain;
     }
 };
 struct MapSlot {
@@ -347,8 +257,9 @@ struct MapSlot {
 static thread_local MapSlot g_map_cache[32];
 static thread_local int g_map_next = 0;
 
-static int make_map(CUtensorMap* m, const TcOperand& o, int box_rows_kmajor) {
-    const MapKey key{o.ptr, o.ld, o.bstride, o.kmajor, o.nbatch, o.rows, o.K, box_rows_kmajor};
+// plain = true: un-swizzled [K][128 rows] box of an MN-major operand (read by threads, not by the tensor core: gemm_ts.cu)
+static int make_map(CUtensorMap* m, const TcOperand& o, int box_rows_kmajor, bool plain = false) {
+    const MapKey key{o.ptr, o.ld, o.bstride, o.kmajor, o.nbatch, o.rows, o.K, box_rows_kmajor, plain ? 1 : 0};
     for (int i = 0; i < 32; ++i)
         if (g_map_cache[i].used && g_map_cache[i].key == key) {
             *m = g_map_cache[i].map;
@@ -367,14 +278,15 @@ static int make_map(CUtensorMap* m, const TcOperand& o, int box_rows_kmajor) {
         box[0] = TC_BK; box[1] = (cuuint32_t)box_rows_kmajor;
     } else {         // [K][rows]
         dims[0] = (cuuint64_t)o.rows; dims[1] = (cuuint64_t)o.K;
-        box[0] = 32; box[1] = TC_BK;
+        box[0] = plain ? TC_BM : 32; box[1] = TC_BK;
     }
     dims[2] = (cuuint64_t)(o.nbatch > 0 ? o.nbatch : 1);
     box[2] = 1;
     strides[0] = (cuuint64_t)o.ld * 4;
     strides[1] = (cuuint64_t)(o.bstride > 0 ? o.bstride : (long long)dims[1] * o.ld) * 4;
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(o.ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, o.kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     plain ? CU_TENSOR_MAP_SWIZZLE_NONE : (o.kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("tc gemm: cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu ld=%lld", (int)r, (unsigned long long)dims[0],
@@ -415,15 +327,15 @@ static int num_sms() {
     return n;
 }
 
-template <bool A_K, bool B_K>
+template <bool A_K, bool B_K, int EPI>
 static int launch_t(const TcMaps& maps, const TcArgs& a, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;  // idempotent; a race only repeats the call
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<A_K, B_K, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) { set_error("tc gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
         attr_set = true;
     }
-    tc_gemm_kernel<A_K, B_K><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, a);
+    tc_gemm_kernel<A_K, B_K, EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, a);
     return check_launch("tc gemm");
 }
 
@@ -432,6 +344,7 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
     EEGAN_REQUIRE(g.M > 0 && g.N > 0 && g.batch > 0 && g.C, "tc gemm: empty problem");
     for (int s = 1; s < g.nseg; ++s)
         EEGAN_REQUIRE(g.A[s].kmajor == g.A[0].kmajor && g.B[s].kmajor == g.B[0].kmajor, "tc gemm: segments must share majorness");
+    if (g.ts) EEGAN_REQUIRE(!g.A[0].kmajor && g.B[0].kmajor, "tc gemm: the TMEM-staged kernel takes an MN-major A and a K-major B");
 
     TcMaps maps;
     TcArgs a{};
@@ -439,12 +352,13 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
         const int src = s < g.nseg ? s : 0;
         const TcOperand* ops[2] = {&g.A[src], &g.B[src]};
         for (int o = 0; o < 2; ++o) {
-            int rc = make_map(&maps.m[s][o][0], *ops[o], o == 0 ? TC_BM : TC_BN);
+            const bool plain = g.ts && o == 0;
+            int rc = make_map(&maps.m[s][o][0], *ops[o], o == 0 ? TC_BM : TC_BN, plain);
             if (rc) return rc;
             if (ops[o]->lo) {
                 TcOperand lo = *ops[o];
                 lo.ptr = ops[o]->lo;
-                rc = make_map(&maps.m[s][o][1], lo, o == 0 ? TC_BM : TC_BN);
+                rc = make_map(&maps.m[s][o][1], lo, o == 0 ? TC_BM : TC_BN, plain);
                 if (rc) return rc;
             } else {
                 maps.m[s][o][1] = maps.m[s][o][0];
@@ -456,22 +370,36 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
         a.a_pre[s] = g.A[src].lo != nullptr;
         a.b_pre[s] = g.B[src].lo != nullptr;
     }
-    a.C = g.C; a.ldc = g.ldc; a.bC = g.bC; a.M = g.M; a.N = g.N; a.dynM = g.dynM; a.dynK = g.dynK;
+    a.C = g.C; a.ldc = g.ldc; a.bC = g.bC; a.M = g.M; a.N = g.N; a.dynM = g.dynM; a.dynN = g.dynN; a.dynK = g.dynK;
+    a.attn = g.attn;
     a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total; a.batch = g.batch;
     a.mn_lbo = 4096 >> 4; a.mn_sbo = 512 >> 4;
     a.trunc_hi = 1;
-    a.dbg = 0;
-    if (const char* e = getenv("EEGAN_TC_DBG")) a.dbg = atoi(e);
     if (const char* e = getenv("EEGAN_TC_TRUNC_HI")) a.trunc_hi = atoi(e);
     if (const char* e = getenv("EEGAN_TC_MN_LBO")) a.mn_lbo = (uint32_t)atoi(e);
     if (const char* e = getenv("EEGAN_TC_MN_SBO")) a.mn_sbo = (uint32_t)atoi(e);
     const long long tiles = (long long)((g.N + TC_BN - 1) / TC_BN) * ((g.M + TC_BM - 1) / TC_BM) * g.batch;
     dim3 grid((unsigned)(tiles < num_sms() ? tiles : num_sms()));
     const bool ak = g.A[0].kmajor, bk = g.B[0].kmajor;
-    if (ak && bk) return launch_t<true, true>(maps, a, grid, st);
-    if (ak && !bk) return launch_t<true, false>(maps, a, grid, st);
-    if (!ak && bk) return launch_t<false, true>(maps, a, grid, st);
-    return launch_t<false, false>(maps, a, grid, st);
+    if (g.epi != TC_EPI_PLAIN) {
+        EEGAN_REQUIRE(!ak && bk && g.nseg == 1, "tc gemm: the attention epilogues take an MN-major A (regions) and a K-major B (packed words)");
+        EEGAN_REQUIRE(g.attn.nbins && g.attn.bin_cap && g.attn.bin_used && g.attn.col_start && g.attn.cap_len && g.attn.P,
+                      "tc gemm: attention epilogue arguments missing");
+        EEGAN_REQUIRE(g.ldc % 64 == 0, "tc gemm: attention epilogue needs a column pitch that is a multiple of 64");
+        if (g.epi == TC_EPI_ATTN_FWD) {
+            EEGAN_REQUIRE(g.attn.Zpart, "tc gemm: attention forward epilogue needs Zpart");
+            if (g.ts) return ts_gemm_dispatch(maps, a, grid.x, g.epi, st);
+            return launch_t<false, true, TC_EPI_ATTN_FWD>(maps, a, grid, st);
+        }
+        EEGAN_REQUIRE(g.epi == TC_EPI_ATTN_BWD && g.attn.csz, "tc gemm: attention backward epilogue needs csz");
+        if (g.ts) return ts_gemm_dispatch(maps, a, grid.x, g.epi, st);
+        return launch_t<false, true, TC_EPI_ATTN_BWD>(maps, a, grid, st);
+    }
+    if (g.ts) return ts_gemm_dispatch(maps, a, grid.x, g.epi, st);
+    if (ak && bk) return launch_t<true, true, TC_EPI_PLAIN>(maps, a, grid, st);
+    if (ak && !bk) return launch_t<true, false, TC_EPI_PLAIN>(maps, a, grid, st);
+    if (!ak && bk) return launch_t<false, true, TC_EPI_PLAIN>(maps, a, grid, st);
+    return launch_t<false, false, TC_EPI_PLAIN>(maps, a, grid, st);
 }
 
 }  // namespace eegan
@@ -480,12 +408,14 @@ using namespace eegan;
 
 // Stand-alone entry point (tests / microbench): C[z] = A[z] * B[z]^T in 3xTF32.
 //   a_kmajor: A is [M][K] (ld = lda) else [K][M];  b_kmajor: B is [N][K] else [K][N].
+//   staging: 0 = both operands read from shared memory; 1 = A staged in tensor memory (needs a_kmajor = 0, b_kmajor = 1).
 extern "C" int eegan_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K, int a_kmajor, int b_kmajor,
                                  long long lda, long long ldb, long long ldc, long long bsA, long long bsB, long long bsC,
-                                 int batch, void* stream) {
+                                 int batch, int staging, void* stream) {
     EEGAN_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tf32x3: bad arguments");
     TcGemm g{};
     g.nseg = 1;
+    g.ts = staging;
     g.A[0] = TcOperand{A, nullptr, a_kmajor, lda, bsA, batch, M, K};
     g.B[0] = TcOperand{B, nullptr, b_kmajor, ldb, bsB, batch, N, K};
     g.C = C; g.ldc = ldc; g.bC = bsC; g.M = M; g.N = N; g.batch = batch; g.nred = 1; g.red_total = 0;

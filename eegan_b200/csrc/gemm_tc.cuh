@@ -29,8 +29,11 @@ namespace eegan {
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi B_hi A_lo B_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 4 * 32 * 33 * 4 /*epilogue staging*/ + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_EPI_PITCH = 65;                            // staging row pitch (floats): odd => conflict-free both ways
+constexpr int TC_EPI_STAGE_BYTES = 4 * 32 * TC_EPI_PITCH * 4;  // 4 epilogue warps x [32 rows][64 (+1) columns]
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_EPI_STAGE_BYTES + 1024 /*epilogue scratch*/ + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_TMEM_COLS = 512;                           // 2 x 128 accumulator columns + read-window slack
 constexpr int TC_THREADS = 32 * (2 + TC_SPLIT_WARPS + 4);
 
 struct TcOperand {
@@ -43,6 +46,25 @@ struct TcOperand {
     int rows, K;         // logical extents (TMA zero-fills beyond them)
 };
 
+// Epilogues.  PLAIN stores the accumulator tile.  The two ATTN epilogues run the word-region
+// attention of the DAMSM pair grid (miscc/DAMSM_losses.py:44-54 and its backward) on the
+// accumulator while it is still in TMEM: the tile is [128 regions r (TMEM lanes)] x [128 packed word
+// columns n' (TMEM columns)], so one thread owns one region and a caption's words sit in its
+// registers.  Packed columns are grouped in 64-column bins that hold whole captions.
+enum TcEpilogue { TC_EPI_PLAIN = 0, TC_EPI_ATTN_FWD = 1, TC_EPI_ATTN_BWD = 2 };
+
+struct TcAttnEpi {
+    const int* nbins;      // device: live 64-column bins
+    const int* bin_cap;    // [nbins + 1] first caption of each bin
+    const int* bin_used;   // [nbins] columns of the bin that carry words
+    const int* col_start;  // [captions] first packed column of caption i
+    const int* cap_len;    // [captions] words of caption i (clamped)
+    float* P;              // [batch][M][ldc]  FWD: out, P = softmax_words(S);  BWD: in
+    float* Zpart;          // FWD: [batch][ceil(M/32)][ldc] per-32-region partial sums of E over regions
+    const float* csz;      // BWD: [batch][ldc]  (sum_r A dA) / Z per column
+    float g1;
+};
+
 struct TcGemm {
     TcOperand A[2], B[2];   // up to two K-concatenated segments (segment 1 unused if nseg == 1)
     int nseg;
@@ -50,7 +72,11 @@ struct TcGemm {
     long long ldc, bC;
     int M, N;               // output extents (static upper bounds)
     const int* dynM;        // optional device int: live rows of C / A
+    const int* dynN;        // optional device int: live columns of C / rows of B
     const int* dynK;        // optional device int: live K extent (all segments)
+    int ts;                 // 1: A operand staged in tensor memory (gemm_ts.cu; MN-major A, K-major B only)
+    int epi;                // TcEpilogue; ATTN_*: C = E (FWD) / dS (BWD), both [batch][M][ldc]
+    TcAttnEpi attn;
     int batch;              // grid.z
     int nred, red_total;    // reduction batches per z: operand batch index = z*nred + red
 };
@@ -59,6 +85,11 @@ struct TcGemm {
 // `pitch` elements (multiple of 4) and a [box_rows][box_cols] box; TMA zero-fills out of bounds.
 int make_tmap_2d(CUtensorMap* m, const float* ptr, unsigned long long rows, unsigned long long cols, unsigned long long pitch,
                  unsigned box_cols, unsigned box_rows, bool swizzle128 = false);
+
+struct TcMaps;
+struct TcArgs;
+// gemm_ts.cu: launch of the TMEM-staged kernel on prepared maps / arguments
+int ts_gemm_dispatch(const TcMaps& maps, const TcArgs& args, unsigned grid, int epi, cudaStream_t st);
 
 // Enqueue the GEMM.  Returns EEGAN_OK or an error code (message via set_error).
 int tc_gemm_launch(const TcGemm& g, cudaStream_t st);

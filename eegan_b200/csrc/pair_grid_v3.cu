@@ -1,0 +1,533 @@
+// DAMSM pair grid, region-major fused pipeline (contraction engine 2, the default).
+//
+// Same math as pair_grid.cu (miscc/DAMSM_losses.py:272-342) but the word-region
+// attention runs inside the tcgen05 GEMM epilogues, so the only kernels between the contractions
+// are two small per-column passes:
+//
+//   fwd  scan/pack                 packed word columns n' in 64-column bins of whole captions
+//        GEMM1 + attention fwd     S^T[j][r][n'] = C_j^T Wp^T in TMEM; per region thread: P = softmax_words(S),
+//                                  E = exp(g1 (P - 1)); stores P^T, E^T and per-32-region partial sums of E
+//        GEMM2                     U'[j][n'][d] = sum_r E^T[r][n'] C_j[d][r]      (u = U' / Z, Z = sum_r E)
+//        cos/lse                   cos, |u|, m[j][i] = log sum_t exp(g2 cos); att_maps from the diagonal
+//   bwd  dU                        DUz = (a1 w - a2 u) / Z, csz = <DU, u> / Z, cosine part of dW
+//        GEMM3 + attention bwd     acc = C_j^T DUz^T = dA / Z in TMEM; per region thread:
+//                                  v = g1 P E (acc - csz), dS = v - P sum_t v; stores dS^T
+//        GEMM4                     dC_j[d][r] = sum_n' DUz[n'][d] E^T[r][n'] + Wp[n'][d] dS^T[r][n']
+//        GEMM5 + unpack            dWp[n'][d] = sum_j sum_r dS^T[j][r][n'] C_j[d][r]
+//
+// sum_r A dA = <DU, u> (because u = A C^T), which is why the softmax backward needs no reduction
+// over regions.  All stash arrays are [image j][region r][packed column n'] with n' contiguous, so
+// every GEMM reads them through a legal K-major / MN-major tensor map without a transposed copy.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "pair_v3.cuh"
+
+namespace eegan {
+
+constexpr int V3_BIN = 64;     // packed columns per bin (captions never straddle a bin)
+constexpr int V3_DU_JG = 8;    // images per warp of the dU kernel
+
+struct V3Ws {
+    int* col_start;  // [Bc+1] first packed column of caption i (col_start[Bc] = live padded extent)
+    int* cap_len;    // [Bc]   clamped caption lengths
+    int* bin_cap;    // [maxbins+1]
+    int* bin_used;   // [maxbins]
+    int* meta;       // [0] = nbins, [1] = ntotp = nbins * 64
+    int* col_cap;    // [NtP] caption of packed column n' (-1 = padding)
+    float* Wp;       // [NtP][D]  packed words (zero rows for padding columns)
+    float* wn;       // [NtP]
+    float* Cp;       // [Bi][D][Rp] image features re-pitched for TMA (only if Rp != R)
+    float* P;        // [Bi][R][NtP]
+    float* E;        // [Bi][R][NtP]
+    float* Zpart;    // [Bi][ceil(R/32)][NtP]
+    float* Z;        // [Bi][NtP]
+    float* U;        // [Bi][NtP][D]  unnormalised word contexts U'
+    float* DUz;      // [Bi][NtP][D]
+    float* cosv;     // [Bi][NtP]
+    float* un;       // [Bi][NtP]  |u|
+    float* csz;      // [Bi][NtP]
+    float* mst;      // [Bi][Bc]   forward m (log-sum-exp), needed by the backward
+    float* dS;       // [Bi][R][NtP]
+    float* dWpart;   // [nsplit][NtP][D]
+    float* dwcos;    // [ngroups][NtP][D]
+    int Rp, NtP, maxbins, nsplit, ngroups, nz;
+    size_t bytes;
+};
+
+static int v3_nsplit(int Bi, int NtP, int D) {
+    // GEMM5 reduces over images inside its K loop; split so that about one wave of live tiles exists
+    const int live_m = ((int)(0.6f * NtP) + 127) / 128 > 0 ? ((int)(0.6f * NtP) + 127) / 128 : 1;
+    const int tiles = live_m * ((D + 127) / 128);
+    int ns = 148 / tiles;
+    if (ns < 1) ns = 1;
+    if (ns > Bi) ns = Bi;
+    const int nred = (Bi + ns - 1) / ns;
+    return (Bi + nred - 1) / nred;
+}
+
+static V3Ws v3_carve(void* base, int Bi, int Bc, int D, int R, int Tm) {
+    V3Ws w;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* q = p ? p + off : nullptr;
+        off += align_up(bytes, 256);
+        return q;
+    };
+    const int per_bin = V3_BIN / Tm;  // >= 2 because Tm <= 32
+    w.maxbins = (Bc + per_bin - 1) / per_bin;
+    w.NtP = w.maxbins * V3_BIN;
+    w.Rp = (R + 3) / 4 * 4;
+    w.nz = (R + 31) / 32;
+    w.nsplit = v3_nsplit(Bi, w.NtP, D);
+    w.ngroups = (Bi + V3_DU_JG - 1) / V3_DU_JG;
+    const size_t NtP = (size_t)w.NtP;
+    w.col_start = (int*)take((Bc + 1) * sizeof(int));
+    w.cap_len = (int*)take(Bc * sizeof(int));
+    w.bin_cap = (int*)take((w.maxbins + 1) * sizeof(int));
+    w.bin_used = (int*)take(w.maxbins * sizeof(int));
+    w.meta = (int*)take(4 * sizeof(int));
+    w.col_cap = (int*)take(NtP * sizeof(int));
+    w.Wp = (float*)take(NtP * D * sizeof(float));
+    w.wn = (float*)take(NtP * sizeof(float));
+    w.Cp = (float*)take(w.Rp != R ? (size_t)Bi * D * w.Rp * sizeof(float) : 0);
+    w.P = (float*)take((size_t)Bi * R * NtP * sizeof(float));
+    w.E = (float*)take((size_t)Bi * R * NtP * sizeof(float));
+    w.Zpart = (float*)take((size_t)Bi * w.nz * NtP * sizeof(float));
+    w.Z = (float*)take((size_t)Bi * NtP * sizeof(float));
+    w.U = (float*)take((size_t)Bi * NtP * D * sizeof(float));
+    w.DUz = (float*)take((size_t)Bi * NtP * D * sizeof(float));
+    w.cosv = (float*)take((size_t)Bi * NtP * sizeof(float));
+    w.un = (float*)take((size_t)Bi * NtP * sizeof(float));
+    w.csz = (float*)take((size_t)Bi * NtP * sizeof(float));
+    w.mst = (float*)take((size_t)Bi * Bc * sizeof(float));
+    w.dS = (float*)take((size_t)Bi * R * NtP * sizeof(float));
+    w.dWpart = (float*)take((size_t)w.nsplit * NtP * D * sizeof(float));
+    w.dwcos = (float*)take((size_t)w.ngroups * NtP * D * sizeof(float));
+    w.bytes = off;
+    if (w.Rp == R) w.Cp = nullptr;
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------
+// prologue
+// ---------------------------------------------------------------------------------------
+// Greedy, order-preserving packing of whole captions into 64-column bins, then the column ->
+// caption map.  The lengths are staged in shared memory so that the one sequential pass (thread
+// 0; B is at most a few thousand) never waits on global memory.
+__global__ void __launch_bounds__(256) v3_scan_kernel(const int32_t* __restrict__ cap_lens, int Bc, int Tm, int maxbins,
+                                                      int* __restrict__ col_start, int* __restrict__ cap_len,
+                                                      int* __restrict__ bin_cap, int* __restrict__ bin_used,
+                                                      int* __restrict__ meta, int* __restrict__ col_cap) {
+    extern __shared__ int s_buf[];  // [Bc] lengths, [Bc] first columns
+    int* s_len = s_buf;
+    int* s_cs = s_buf + Bc;
+    __shared__ int s_nbins;
+    for (int i = threadIdx.x; i < Bc; i += blockDim.x) s_len[i] = min(max(cap_lens[i], 0), Tm);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = 0, fill = 0;
+        bin_cap[0] = 0;
+        for (int i = 0; i < Bc; ++i) {
+            const int T = s_len[i];
+            if (fill + T > V3_BIN) {
+                bin_used[b] = fill;
+                ++b;
+                bin_cap[b] = i;
+                fill = 0;
+            }
+            s_cs[i] = b * V3_BIN + fill;
+            fill += T;
+        }
+        bin_used[b] = fill;
+        const int nbins = b + 1;  // <= maxbins by construction
+        bin_cap[nbins] = Bc;
+        for (int q = nbins + 1; q <= maxbins; ++q) bin_cap[q] = Bc;
+        for (int q = nbins; q < maxbins; ++q) bin_used[q] = 0;
+        col_start[Bc] = nbins * V3_BIN;
+        meta[0] = nbins;
+        meta[1] = nbins * V3_BIN;
+        s_nbins = nbins;
+    }
+    __syncthreads();
+    const int ntotp = s_nbins * V3_BIN;
+    for (int n = threadIdx.x; n < ntotp; n += blockDim.x) col_cap[n] = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < Bc; i += blockDim.x) {
+        const int cs = s_cs[i], T = s_len[i];
+        col_start[i] = cs;
+        cap_len[i] = T;
+        for (int t = 0; t < T; ++t) col_cap[cs + t] = i;
+    }
+}
+
+// one CTA per packed column: gather the word vector (words is [i][d][t]) and its norm
+__global__ void __launch_bounds__(64) v3_pack_words_kernel(const float* __restrict__ words, const int* __restrict__ col_start,
+                                                           const int* __restrict__ col_cap, const int* __restrict__ meta, int D,
+                                                           int Tm, float* __restrict__ Wp, float* __restrict__ wn) {
+    __shared__ float red[32];
+    const int n = blockIdx.x;
+    if (n >= meta[1]) return;
+    const int i = col_cap[n];
+    float ss = 0.f;
+    if (i < 0) {
+        for (int d = threadIdx.x; d < D; d += blockDim.x) Wp[(size_t)n * D + d] = 0.f;
+    } else {
+        const int t = n - col_start[i];
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const float v = __ldg(words + ((size_t)i * D + d) * Tm + t);
+            Wp[(size_t)n * D + d] = v;
+            ss = fmaf(v, v, ss);
+        }
+    }
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) wn[n] = sqrtf(ss);
+}
+
+// img [Bi*D][R] -> Cp [Bi*D][Rp] (TMA needs 16-byte row pitches; R = 289 is odd)
+__global__ void __launch_bounds__(256) v3_repitch_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows,
+                                                         int R, int Rp) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+        const float* s = src + row * R;
+        float* d = dst + row * Rp;
+        for (int r = lane; r < Rp; r += 32) d[r] = r < R ? __ldg(s + r) : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// forward: cosine + log-sum-exp per (caption i, image j)   (DAMSM_losses.py:17-23, :315-317)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) v3_cos_lse_kernel(const float* __restrict__ U, const float* __restrict__ Wp,
+                                                         const float* __restrict__ wn, const float* __restrict__ Zpart,
+                                                         const int* __restrict__ col_start, const int* __restrict__ cap_len,
+                                                         int NtP, int D, int Bc, int nz, float g2, float* __restrict__ Z,
+                                                         float* __restrict__ cosv, float* __restrict__ un,
+                                                         float* __restrict__ m, float* __restrict__ mst) {
+    __shared__ float ex[32];
+    const int i = blockIdx.x, j = blockIdx.y;
+    const int cs = col_start[i], T = cap_len[i];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int t = w; t < T; t += nw) {
+        const int n = cs + t;
+        const float4* u4 = reinterpret_cast<const float4*>(U + ((size_t)j * NtP + n) * D);
+        const float4* w4 = reinterpret_cast<const float4*>(Wp + (size_t)n * D);
+        float dot = 0.f, uu = 0.f;
+        for (int q = lane; q < D / 4; q += 32) {
+            const float4 a = u4[q], b = __ldg(w4 + q);
+            dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+            uu = fmaf(a.x, a.x, uu); uu = fmaf(a.y, a.y, uu); uu = fmaf(a.z, a.z, uu); uu = fmaf(a.w, a.w, uu);
+        }
+        dot = warp_sum(dot);
+        uu = warp_sum(uu);
+        if (lane == 0) {
+            float z = 0.f;  // fixed order: deterministic
+            for (int s = 0; s < nz; ++s) z += Zpart[((size_t)j * nz + s) * NtP + n];
+            const float unv = sqrtf(uu) / z;  // |u|, u = U' / Z
+            const float c = (dot / z) / fmaxf(wn[n] * unv, 1e-8f);
+            Z[(size_t)j * NtP + n] = z;
+            cosv[(size_t)j * NtP + n] = c;
+            un[(size_t)j * NtP + n] = unv;
+            ex[t] = expf(g2 * c);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int t = 0; t < T; ++t) s += ex[t];
+        const float v = logf(s);
+        m[(size_t)j * Bc + i] = v;
+        mst[(size_t)j * Bc + i] = v;
+    }
+}
+
+// att_maps[i][t][r] = E^T[j][r][cs+t] / Z[j][cs+t] for the caption's own image j = i + diag_offset (:301).
+// grid (captions, 32-region slabs): the slab goes through shared memory so that both the E^T reads
+// (words contiguous) and the att writes (regions contiguous) are coalesced.
+__global__ void __launch_bounds__(256) v3_att_diag_kernel(const float* __restrict__ E, const float* __restrict__ Z,
+                                                          const int* __restrict__ col_start, const int* __restrict__ cap_len,
+                                                          int NtP, int R, int Tm, int Bi, int diag_offset, float* __restrict__ att) {
+    __shared__ float tile[32][33];
+    const int i = blockIdx.x, j = i + diag_offset, r0 = blockIdx.y * 32;
+    float* out = att + (size_t)i * Tm * R;
+    const bool have = j >= 0 && j < Bi;
+    const int cs = col_start[i], T = have ? cap_len[i] : 0;
+    for (int idx = threadIdx.x; idx < 32 * Tm; idx += blockDim.x) {
+        const int rr = idx / Tm, t = idx - rr * Tm;
+        float v = 0.f;
+        if (t < T && r0 + rr < R) v = E[((size_t)j * R + r0 + rr) * NtP + cs + t] / Z[(size_t)j * NtP + cs + t];
+        tile[t][rr] = v;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * Tm; idx += blockDim.x) {
+        const int t = idx / 32, rr = idx - t * 32;
+        if (r0 + rr < R) out[(size_t)t * R + r0 + rr] = tile[t][rr];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward: per packed column
+// ---------------------------------------------------------------------------------------
+// One warp per (packed column n', group of V3_DU_JG images):
+//   dcos = dm g2 exp(g2 cos - m);  a1 = dcos / max(|w||u|, eps);  a2 = dcos cos / |u|^2;  a3 = dcos cos / |w|^2
+//   DU = a1 w - a2 u  (u = U'/Z);  DUz = DU / Z;  csz = <DU, u> / Z;  dwcos[g][n'] = sum_j a1 u - (sum_j a3) w
+template <int NQ>  // float4 per lane: D = 128 * NQ
+__global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U, const float* __restrict__ Wp,
+                                                    const float* __restrict__ wn, const float* __restrict__ Z,
+                                                    const float* __restrict__ cosv, const float* __restrict__ un,
+                                                    const float* __restrict__ dm, const float* __restrict__ mst,
+                                                    const int* __restrict__ col_cap, const int* __restrict__ meta, int NtP,
+                                                    int Bi, int Bc, int D, float g2, float* __restrict__ DUz,
+                                                    float* __restrict__ csz, float* __restrict__ dwcos) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= meta[1]) return;
+    const int g = blockIdx.y, j0 = g * V3_DU_JG;
+    const int i = col_cap[n];
+    float4* dwc = reinterpret_cast<float4*>(dwcos + ((size_t)g * NtP + n) * D);
+    if (i < 0) {  // padding column: zero operand rows so that GEMM4's K loop adds nothing
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < V3_DU_JG; ++q) {
+            const int j = j0 + q;
+            if (j >= Bi) break;
+            float4* o = reinterpret_cast<float4*>(DUz + ((size_t)j * NtP + n) * D);
+#pragma unroll
+            for (int c = 0; c < NQ; ++c) o[lane + 32 * c] = zero;
+            if (lane == 0) csz[(size_t)j * NtP + n] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < NQ; ++c) dwc[lane + 32 * c] = zero;
+        return;
+    }
+    float4 wv[NQ], acc[NQ];
+#pragma unroll
+    for (int c = 0; c < NQ; ++c) {
+        wv[c] = __ldg(reinterpret_cast<const float4*>(Wp + (size_t)n * D) + lane + 32 * c);
+        acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float wnv = wn[n];
+    float a3s = 0.f;
+    for (int q = 0; q < V3_DU_JG; ++q) {
+        const int j = j0 + q;
+        if (j >= Bi) break;
+        const size_t idx = (size_t)j * NtP + n;
+        const float z = Z[idx], c = cosv[idx], unv = un[idx];
+        const float dcos = dm[(size_t)j * Bc + i] * g2 * expf(g2 * c - mst[(size_t)j * Bc + i]);
+        const float nn = wnv * unv;
+        const bool live = nn > 1e-8f;
+        const float a1 = dcos / fmaxf(nn, 1e-8f);
+        const float a2 = live ? dcos * c / (unv * unv) : 0.f;
+        a3s += live ? dcos * c / (wnv * wnv) : 0.f;
+        const float iz = 1.0f / z;
+        const float a2z = a2 * iz, a1z = a1 * iz;
+        const float4* u4 = reinterpret_cast<const float4*>(U + idx * D);
+        float4* o4 = reinterpret_cast<float4*>(DUz + idx * D);
+        float cs = 0.f;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const float4 uv = u4[lane + 32 * k];
+            float4 du;
+            du.x = a1 * wv[k].x - a2z * uv.x; du.y = a1 * wv[k].y - a2z * uv.y;
+            du.z = a1 * wv[k].z - a2z * uv.z; du.w = a1 * wv[k].w - a2z * uv.w;
+            cs = fmaf(du.x, uv.x, cs); cs = fmaf(du.y, uv.y, cs); cs = fmaf(du.z, uv.z, cs); cs = fmaf(du.w, uv.w, cs);
+            acc[k].x = fmaf(a1z, uv.x, acc[k].x); acc[k].y = fmaf(a1z, uv.y, acc[k].y);
+            acc[k].z = fmaf(a1z, uv.z, acc[k].z); acc[k].w = fmaf(a1z, uv.w, acc[k].w);
+            du.x *= iz; du.y *= iz; du.z *= iz; du.w *= iz;
+            o4[lane + 32 * k] = du;
+        }
+        cs = warp_sum(cs);  // <DU, U'>
+        if (lane == 0) csz[idx] = cs * iz * iz;
+    }
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        float4 o;
+        o.x = acc[k].x - a3s * wv[k].x; o.y = acc[k].y - a3s * wv[k].y;
+        o.z = acc[k].z - a3s * wv[k].z; o.w = acc[k].w - a3s * wv[k].w;
+        dwc[lane + 32 * k] = o;
+    }
+}
+
+// d_words[i][d][t] = dwcos + sum of the split-j partials; zero for padded words.
+__global__ void __launch_bounds__(256) v3_unpack_dw_kernel(const float* __restrict__ dWpart, const float* __restrict__ dwcos,
+                                                           const int* __restrict__ col_start, const int* __restrict__ cap_len,
+                                                           int nsplit, int ngroups, int NtP, int D, int Tm,
+                                                           float* __restrict__ d_words) {
+    __shared__ float tile[32][33];
+    const int i = blockIdx.x, d0 = blockIdx.y * 32;
+    const int cs = col_start[i], T = cap_len[i];
+    for (int idx = threadIdx.x; idx < 32 * Tm; idx += blockDim.x) {
+        const int t = idx / 32, dd = idx % 32;
+        float v = 0.f;
+        if (t < T && d0 + dd < D) {
+            const size_t k = (size_t)(cs + t) * D + d0 + dd;
+            for (int s = 0; s < ngroups; ++s) v += dwcos[(size_t)s * NtP * D + k];
+            for (int s = 0; s < nsplit; ++s) v += dWpart[(size_t)s * NtP * D + k];
+        }
+        tile[dd][t] = v;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * Tm; idx += blockDim.x) {
+        const int dd = idx / Tm, t = idx % Tm;
+        if (d0 + dd < D) d_words[((size_t)i * D + d0 + dd) * Tm + t] = tile[dd][t];
+    }
+}
+
+// A operand staged in tensor memory (gemm_ts.cu) unless EEGAN_V3_TS=0 asks for the all-shared-memory kernel (A/B timing)
+static int use_ts() {
+    static int v = [] {
+        const char* e = getenv("EEGAN_V3_TS");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+
+static TcAttnEpi attn_args(const V3Ws& w, float g1) {
+    TcAttnEpi a{};
+    a.nbins = w.meta;
+    a.bin_cap = w.bin_cap;
+    a.bin_used = w.bin_used;
+    a.col_start = w.col_start;
+    a.cap_len = w.cap_len;
+    a.P = w.P;
+    a.Zpart = w.Zpart;
+    a.csz = w.csz;
+    a.g1 = g1;
+    return a;
+}
+
+size_t pair_v3_workspace_bytes(int Bi, int Bc, int D, int R, int Tm) { return v3_carve(nullptr, Bi, Bc, D, R, Tm).bytes; }
+
+int pair_v3_fwd(const float* img, const float* words, const int32_t* cap_lens, int Bi, int Bc, int D, int R, int Tm, float g1,
+                float g2, float* m, float* att, int diag_offset, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    EEGAN_REQUIRE(D % 128 == 0 && D <= 1024, "pair grid (fused engine): D=%d must be a multiple of 128 and <= 1024", D);
+    EEGAN_REQUIRE(Bc <= 4096, "pair grid (fused engine): at most 4096 captions per call (got %d)", Bc);
+    V3Ws w = v3_carve(workspace, Bi, Bc, D, R, Tm);
+    if (workspace_bytes < w.bytes) {
+        set_error("pair fwd: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return EEGAN_ERR_WORKSPACE;
+    }
+    const float* C = w.Cp ? w.Cp : img;
+    const int NtP = w.NtP;
+
+    prof_mark(-1, st);
+    v3_scan_kernel<<<1, 256, 2 * Bc * sizeof(int), st>>>(cap_lens, Bc, Tm, w.maxbins, w.col_start, w.cap_len, w.bin_cap, w.bin_used, w.meta, w.col_cap);
+    v3_pack_words_kernel<<<NtP, 64, 0, st>>>(words, w.col_start, w.col_cap, w.meta, D, Tm, w.Wp, w.wn);
+    if (w.Cp) v3_repitch_kernel<<<148 * 8, 256, 0, st>>>(img, w.Cp, (long long)Bi * D, R, w.Rp);
+    EEGAN_LAUNCH_CHECK("pair prologue");
+    prof_mark(0, st);
+
+    {  // GEMM1 + attention forward: S^T[j][r][n'] -> P^T, E^T, Zpart
+        TcGemm g{};
+        g.nseg = 1;
+        g.ts = use_ts();
+        g.A[0] = TcOperand{C, nullptr, 0, w.Rp, (long long)D * w.Rp, Bi, R, D};
+        g.B[0] = TcOperand{w.Wp, nullptr, 1, D, 0, 1, NtP, D};
+        g.C = w.E; g.ldc = NtP; g.bC = (long long)R * NtP; g.M = R; g.N = NtP; g.dynN = w.meta + 1; g.batch = Bi; g.nred = 1;
+        g.epi = TC_EPI_ATTN_FWD;
+        g.attn = attn_args(w, g1);
+        int rc = tc_gemm_launch(g, st);
+        if (rc) return rc;
+    }
+    prof_mark(1, st);
+
+    {  // GEMM2: U'[j][n'][d] = sum_r E^T[j][r][n'] C[j][d][r]
+        TcGemm g{};
+        g.nseg = 1;
+        g.ts = use_ts();
+        g.A[0] = TcOperand{w.E, nullptr, 0, NtP, (long long)R * NtP, Bi, NtP, R};
+        g.B[0] = TcOperand{C, nullptr, 1, w.Rp, (long long)D * w.Rp, Bi, D, R};
+        g.C = w.U; g.ldc = D; g.bC = (long long)NtP * D; g.M = NtP; g.N = D; g.dynM = w.meta + 1; g.batch = Bi; g.nred = 1;
+        int rc = tc_gemm_launch(g, st);
+        if (rc) return rc;
+    }
+    prof_mark(3, st);
+
+    v3_cos_lse_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.U, w.Wp, w.wn, w.Zpart, w.col_start, w.cap_len, NtP, D, Bc, w.nz, g2, w.Z,
+                                                    w.cosv, w.un, m, w.mst);
+    if (att) v3_att_diag_kernel<<<dim3(Bc, (R + 31) / 32), 256, 0, st>>>(w.E, w.Z, w.col_start, w.cap_len, NtP, R, Tm, Bi, diag_offset, att);
+    EEGAN_LAUNCH_CHECK("pair cos/lse");
+    prof_mark(4, st);
+    return EEGAN_OK;
+}
+
+int pair_v3_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1, float g2, const float* dm, float* d_img,
+                float* d_words, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    V3Ws w = v3_carve(workspace, Bi, Bc, D, R, Tm);
+    if (workspace_bytes < w.bytes) {
+        set_error("pair bwd: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return EEGAN_ERR_WORKSPACE;
+    }
+    const float* C = w.Cp ? w.Cp : img;
+    const int NtP = w.NtP;
+
+    prof_mark(-1, st);
+    {
+        dim3 grid((NtP + 7) / 8, w.ngroups);
+#define V3_DU(NQ)                                                                                                            \
+    v3_du_kernel<NQ><<<grid, 256, 0, st>>>(w.U, w.Wp, w.wn, w.Z, w.cosv, w.un, dm, w.mst, w.col_cap, w.meta, NtP, Bi, Bc, D, g2, \
+                                           w.DUz, w.csz, w.dwcos)
+        switch (D / 128) {
+            case 1: V3_DU(1); break;
+            case 2: V3_DU(2); break;
+            case 3: V3_DU(3); break;
+            case 4: V3_DU(4); break;
+            case 5: V3_DU(5); break;
+            case 6: V3_DU(6); break;
+            case 7: V3_DU(7); break;
+            default: V3_DU(8); break;
+        }
+#undef V3_DU
+    }
+    EEGAN_LAUNCH_CHECK("pair dU");
+    prof_mark(5, st);
+
+    {  // GEMM3 + attention backward: acc = C^T DUz^T -> dS^T
+        TcGemm g{};
+        g.nseg = 1;
+        g.ts = use_ts();
+        g.A[0] = TcOperand{C, nullptr, 0, w.Rp, (long long)D * w.Rp, Bi, R, D};
+        g.B[0] = TcOperand{w.DUz, nullptr, 1, D, (long long)NtP * D, Bi, NtP, D};
+        g.C = w.dS; g.ldc = NtP; g.bC = (long long)R * NtP; g.M = R; g.N = NtP; g.dynN = w.meta + 1; g.batch = Bi; g.nred = 1;
+        g.epi = TC_EPI_ATTN_BWD;
+        g.attn = attn_args(w, g1);
+        int rc = tc_gemm_launch(g, st);
+        if (rc) return rc;
+    }
+    prof_mark(6, st);
+
+    if (d_img) {  // GEMM4: dC[j][d][r] = sum_n' DUz[j][n'][d] E^T[j][r][n'] + Wp[n'][d] dS^T[j][r][n']
+        TcGemm g{};
+        g.nseg = 2;
+        g.ts = use_ts();
+        g.A[0] = TcOperand{w.DUz, nullptr, 0, D, (long long)NtP * D, Bi, D, NtP};
+        g.B[0] = TcOperand{w.E, nullptr, 1, NtP, (long long)R * NtP, Bi, R, NtP};
+        g.A[1] = TcOperand{w.Wp, nullptr, 0, D, 0, 1, D, NtP};
+        g.B[1] = TcOperand{w.dS, nullptr, 1, NtP, (long long)R * NtP, Bi, R, NtP};
+        g.C = d_img; g.ldc = R; g.bC = (long long)D * R; g.M = D; g.N = R; g.dynK = w.meta + 1; g.batch = Bi; g.nred = 1;
+        int rc = tc_gemm_launch(g, st);
+        if (rc) return rc;
+        prof_mark(8, st);
+    }
+    if (d_words) {  // GEMM5: dWp[n'][d] = sum_j sum_r dS^T[j][r][n'] C[j][d][r], images split in nsplit groups
+        const int nred = (Bi + w.nsplit - 1) / w.nsplit;
+        TcGemm g{};
+        g.nseg = 1;
+        g.ts = use_ts();
+        g.A[0] = TcOperand{w.dS, nullptr, 0, NtP, (long long)R * NtP, Bi, NtP, R};
+        g.B[0] = TcOperand{C, nullptr, 1, w.Rp, (long long)D * w.Rp, Bi, D, R};
+        g.C = w.dWpart; g.ldc = D; g.bC = (long long)NtP * D; g.M = NtP; g.N = D; g.dynM = w.meta + 1; g.batch = w.nsplit;
+        g.nred = nred; g.red_total = Bi;
+        int rc = tc_gemm_launch(g, st);
+        if (rc) return rc;
+        v3_unpack_dw_kernel<<<dim3(Bc, (D + 31) / 32), 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.cap_len, w.nsplit, w.ngroups,
+                                                                     NtP, D, Tm, d_words);
+        EEGAN_LAUNCH_CHECK("pair GEMM5");
+        prof_mark(9, st);
+    }
+    return EEGAN_OK;
+}
+
+}  // namespace eegan

@@ -195,10 +195,12 @@ int eegan_get_contraction_engine(void);
  * a_kmajor: A is [M][K] with pitch lda, else [K][M]; b_kmajor: B is [N][K] with pitch ldb, else
  * [K][N].  Pitches and batch strides are in elements and must be multiples of 4; bases 16-byte
  * aligned (TMA).  C is [M][N] with pitch ldc (any alignment).
+ * staging: 0 = both operands are read by the tensor core from shared memory; 1 = the A operand is
+ * staged in tensor memory (needs a_kmajor = 0 and b_kmajor = 1; the form the pair-grid pipeline uses).
  * ---------------------------------------------------------------------------------- */
 int eegan_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K,
                       int a_kmajor, int b_kmajor, long long lda, long long ldb, long long ldc,
-                      long long bsA, long long bsB, long long bsC, int batch, void* stream);
+                      long long bsA, long long bsB, long long bsC, int batch, int staging, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Bench-only stage timing of the multi-kernel entry points (eegan_damsm_pair_fwd/_bwd).

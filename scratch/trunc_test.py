@@ -9,7 +9,7 @@ def run(M, N, K, a_k, b_k):
     Bb = B.clone() if b_k else B.transpose(1, 2).contiguous()
     lda = K if a_k else M; ldb = K if b_k else N
     Ad, Bd = Ab.cuda(), Bb.cuda(); C = torch.zeros(1, M, N, device='cuda')
-    _lib.check(L.eegan_gemm_tf32x3(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(C), M, N, K, int(a_k), int(b_k), lda, ldb, N, Ad.stride(0), Bd.stride(0), C.stride(0), 1, _lib.stream_ptr()))
+    _lib.check(L.eegan_gemm_tf32x3(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(C), M, N, K, int(a_k), int(b_k), lda, ldb, N, Ad.stride(0), Bd.stride(0), C.stride(0), 1, 0, _lib.stream_ptr()))
     torch.cuda.synchronize()
     ref = torch.bmm(A.double(), B.double().transpose(1, 2))[0]
     return float((C[0].cpu().double() - ref).abs().max())

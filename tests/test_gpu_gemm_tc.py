@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def run_case(L, M, N, K, a_k, b_k, batch, seed=0):
+def run_case(L, M, N, K, a_k, b_k, batch, seed=0, staging=0):
     from eegan_b200 import _lib
     g = torch.Generator(device="cpu").manual_seed(seed)
     pad = lambda v: (v + 3) // 4 * 4
@@ -39,7 +39,7 @@ def run_case(L, M, N, K, a_k, b_k, batch, seed=0):
     ldc = N + 3
     C = torch.full((batch, M, ldc), -7.0, device="cuda")
     rc = L.eegan_gemm_tf32x3(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(C), M, N, K, int(a_k), int(b_k), lda, ldb, ldc,
-                             Ad.stride(0), Bd.stride(0), C.stride(0), batch, _lib.stream_ptr())
+                             Ad.stride(0), Bd.stride(0), C.stride(0), batch, staging, _lib.stream_ptr())
     _lib.check(rc, "gemm_tf32x3")
     torch.cuda.synchronize()
     ref = torch.bmm(A.double(), B.double().transpose(1, 2))
@@ -55,3 +55,10 @@ def run_case(L, M, N, K, a_k, b_k, batch, seed=0):
 def test_tf32x3_matches_fp64(cuda_lib, a_k, b_k, M, N, K, batch):
     err, scale = run_case(cuda_lib, M, N, K, a_k, b_k, batch, seed=M + N + K)
     assert err <= 4e-6 * scale, "max err %.3e vs scale %.3e (a_k=%s b_k=%s)" % (err, scale, a_k, b_k)
+
+
+@pytest.mark.parametrize("M,N,K,batch", [(128, 128, 32, 1), (289, 552, 256, 3), (256, 289, 540, 2), (100, 40, 289, 2), (640, 256, 289, 5)])
+def test_tf32x3_tmem_staged_a_matches_fp64(cuda_lib, M, N, K, batch):
+    """The TMEM-staged form (A: MN-major, split into tensor memory by tcgen05.st; B: K-major)."""
+    err, scale = run_case(cuda_lib, M, N, K, False, True, batch, seed=M + N + K, staging=1)
+    assert err <= 4e-6 * scale, "max err %.3e vs scale %.3e" % (err, scale)

@@ -216,13 +216,13 @@ def test_full_size_properties(cuda_lib):
 
 
 def test_ffma_engine_still_matches(cuda_lib):
-    """The exact-fp32 CUDA-core engine stays selectable for A/B validation of the tensor-core
-    engine: both must agree with the float64 oracle, and with each other to fp32 noise."""
+    """The exact-fp32 CUDA-core engine (0) and the unfused tensor-core pipeline (1) stay selectable
+    for A/B validation of the default fused engine (2): all agree to fp32 noise."""
     import eegan_b200 as E
     c = cases.words_case(12, 18, seed=5)
     res = {}
     try:
-        for eng in (0, 1):
+        for eng in (0, 1, 2):
             assert cuda_lib.eegan_set_contraction_engine(eng) == 0
             img = c["img"].cuda().requires_grad_()
             words = c["words"].cuda().requires_grad_()
@@ -230,9 +230,10 @@ def test_ffma_engine_still_matches(cuda_lib):
             (l0 + l1).backward()
             res[eng] = (l0.item(), l1.item(), img.grad.clone(), words.grad.clone())
     finally:
-        cuda_lib.eegan_set_contraction_engine(1)
-    assert abs(res[0][0] - res[1][0]) <= 2e-5 and abs(res[0][1] - res[1][1]) <= 2e-5
-    assert relmax(res[1][2], res[0][2]) <= TOL_GRAD and relmax(res[1][3], res[0][3]) <= TOL_GRAD
+        cuda_lib.eegan_set_contraction_engine(2)
+    for eng in (1, 2):
+        assert abs(res[0][0] - res[eng][0]) <= 2e-5 and abs(res[0][1] - res[eng][1]) <= 2e-5, eng
+        assert relmax(res[eng][2], res[0][2]) <= TOL_GRAD and relmax(res[eng][3], res[0][3]) <= TOL_GRAD, eng
 
 
 def test_graphed_words_loss_matches_eager(cuda_lib):

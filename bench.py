@@ -46,10 +46,10 @@ B_PER_GPU, T_MAX, D, HW = 48, 18, 256, 17
 R = HW * HW
 METRIC = "attn+DAMSM fwd/bwd pairs/s at CUB shape"
 UNIT = "pairs/s"
-# kernels launched per step by OUR library with the tcgen05 engine:
-#   pair fwd 7 (scan, pack, repitch, gemm S, softmax, gemm U, cos/lse) + CE fwd 2 + CE bwd 1
-#   + pair bwd 8 (scalars, dU, gemm dA, softmax bwd, zero-tail, gemm dC, gemm dW, unpack)
-LAUNCHES_PER_STEP = 18
+# kernels launched per step by OUR library with the fused tcgen05 engine:
+#   pair fwd 6 (scan, pack+repitch, gemm S + attention fwd, gemm U, cos/lse, att_maps) + CE fwd 2 + CE bwd 1
+#   + pair bwd 5 (dU, gemm dA + attention bwd, gemm dC, gemm dW, unpack)
+LAUNCHES_PER_STEP = 14
 
 
 def peaks():
@@ -461,13 +461,14 @@ def run_ours(args):
         gemm_launch_count = args.steps * 5  # S, U, dA, dC, dW
         achieved = flops_rank * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         line["roofline"] = {
-            "bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 3xTF32; 5 launches/step: S, U, dA, dC, dW)",
+            "bound": "tensor", "kernel": "ts_gemm_kernel (tcgen05 3xTF32, A operand staged in TMEM; 5 launches/step: S + attention fwd epilogue, U, dA + attention bwd epilogue, dC, dW)",
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops"] if achieved else None, "traffic": None,
             "peak_source": pk["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
             "note": "fp32-accurate 3xTF32 (SURVEY D7): 3 tcgen05.mma.kind::tf32 per K-step at half the bf16 rate, so the "
                     "engine's own ceiling is peak/6 = %.0f TFLOP/s -> frac_of_3xtf32_ceiling = %.3f; avg launch %.1f us; "
-                    "the fp32 FFMA engine it replaced ran at 58 TFLOP/s"
+                    "achieved = algorithmic 12*R*D*sum(T)*B FLOP per step / summed duration of the 5 GEMM launches "
+                    "(their epilogues carry the softmax work of the path)"
                     % (pk["bf16_tflops"] / 6.0, (achieved / (pk["bf16_tflops"] / 6.0)) if achieved else 0.0,
                        1e3 * gemm_ms / max(1, gemm_launch_count)),
             "stage_ms_per_step": {s[0]: s[1] / args.steps for s in stage},

@@ -375,6 +375,7 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
     a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total; a.batch = g.batch;
     a.mn_lbo = 4096 >> 4; a.mn_sbo = 512 >> 4;
     a.trunc_hi = 1;
+    if (const char* e = getenv("EEGAN_TS_DBG")) a.dbg = atoi(e);
     if (const char* e = getenv("EEGAN_TC_TRUNC_HI")) a.trunc_hi = atoi(e);
     if (const char* e = getenv("EEGAN_TC_MN_LBO")) a.mn_lbo = (uint32_t)atoi(e);
     if (const char* e = getenv("EEGAN_TC_MN_SBO")) a.mn_sbo = (uint32_t)atoi(e);

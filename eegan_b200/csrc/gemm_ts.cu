@@ -151,6 +151,7 @@ ts_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
                         const uint64_t dbh = umma_desc(b_hi, true, ks, 0, 0), dbl = umma_desc(b_lo, true, ks, 0, 0);
                         tc_mma_tf32_ts(tmem_d, a_lo + ks * 8, dbh, idesc, (k > 0 || ks > 0) ? 1u : 0u);
+                        if (p.dbg & 1) continue;
                         tc_mma_tf32_ts(tmem_d, a_hi + ks * 8, dbl, idesc, 1u);
                         tc_mma_tf32_ts(tmem_d, a_hi + ks * 8, dbh, idesc, 1u);
                     }
@@ -170,6 +171,11 @@ ts_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
                 const int s = it % TS_STAGES, ph = (it / TS_STAGES) & 1;
                 mbar_wait(full(s), ph);
                 const uint32_t sA = base + s * TS_STAGE_BYTES + my_m;
+                if (p.dbg & 2) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(conv(s));
+                    continue;
+                }
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
@@ -197,7 +203,7 @@ ts_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
                 const int s = it % TS_STAGES, ph = (it / TS_STAGES) & 1;
                 const int seg = (k % kbt) >= kb0 ? 1 : 0;
                 mbar_wait(full(s), ph);
-                if (!p.b_pre[seg]) {
+                if (!p.b_pre[seg] && !(p.dbg & 4)) {
                     const uint32_t hi = base + s * TS_STAGE_BYTES + TC_TILE_BYTES, lo = hi + TC_TILE_BYTES;
                     constexpr int NF = (TC_TILE_BYTES / 16) / (32 * Cfg::kBWarps);  // float4 per thread
                     float4 v[NF];

@@ -163,11 +163,25 @@ __global__ void __launch_bounds__(256) v3_scan_kernel(const int32_t* __restrict_
     }
 }
 
-// one CTA per packed column: gather the word vector (words is [i][d][t]) and its norm
-__global__ void __launch_bounds__(64) v3_pack_words_kernel(const float* __restrict__ words, const int* __restrict__ col_start,
-                                                           const int* __restrict__ col_cap, const int* __restrict__ meta, int D,
-                                                           int Tm, float* __restrict__ Wp, float* __restrict__ wn) {
+// One launch for the two independent input re-layouts:
+//   CTAs [0, NtP):   one packed column each: gather the word vector (words is [i][d][t]) and its norm
+//   CTAs [NtP, ...): img [Bi*D][R] -> Cp [Bi*D][Rp] (TMA needs 16-byte row pitches; R = 289 is odd)
+__global__ void __launch_bounds__(128) v3_pack_kernel(const float* __restrict__ words, const int* __restrict__ col_start,
+                                                      const int* __restrict__ col_cap, const int* __restrict__ meta, int D,
+                                                      int Tm, int NtP, float* __restrict__ Wp, float* __restrict__ wn,
+                                                      const float* __restrict__ img, float* __restrict__ Cp, long long rows,
+                                                      int R, int Rp) {
     __shared__ float red[32];
+    if ((int)blockIdx.x >= NtP) {
+        const int lane = threadIdx.x & 31;
+        const long long warps = (long long)(gridDim.x - NtP) * (blockDim.x >> 5);
+        for (long long row = (long long)(blockIdx.x - NtP) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+            const float* sp = img + row * R;
+            float* dp = Cp + row * Rp;
+            for (int r = lane; r < Rp; r += 32) dp[r] = r < R ? __ldg(sp + r) : 0.f;
+        }
+        return;
+    }
     const int n = blockIdx.x;
     if (n >= meta[1]) return;
     const int i = col_cap[n];
@@ -186,59 +200,65 @@ __global__ void __launch_bounds__(64) v3_pack_words_kernel(const float* __restri
     if (threadIdx.x == 0) wn[n] = sqrtf(ss);
 }
 
-// img [Bi*D][R] -> Cp [Bi*D][Rp] (TMA needs 16-byte row pitches; R = 289 is odd)
-__global__ void __launch_bounds__(256) v3_repitch_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows,
-                                                         int R, int Rp) {
-    const int lane = threadIdx.x & 31;
-    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
-        const float* s = src + row * R;
-        float* d = dst + row * Rp;
-        for (int r = lane; r < Rp; r += 32) d[r] = r < R ? __ldg(s + r) : 0.f;
-    }
-}
-
 // ---------------------------------------------------------------------------------------
-// forward: cosine + log-sum-exp per (caption i, image j)   (DAMSM_losses.py:17-23, :315-317)
+// forward: cosine + log-sum-exp   (DAMSM_losses.py:17-23, :315-317)
 // ---------------------------------------------------------------------------------------
+// One CTA per (64-column bin, image j), 8 warps x 8 packed columns, two columns in flight per warp:
+//   Z = sum of the per-32-region partials (fixed order: deterministic), u = U'/Z,
+//   cos = <w,u> / max(|w||u|, 1e-8);   then one thread per caption of the bin: m[j][i] = log sum_t exp(g2 cos_t).
 __global__ void __launch_bounds__(256) v3_cos_lse_kernel(const float* __restrict__ U, const float* __restrict__ Wp,
                                                          const float* __restrict__ wn, const float* __restrict__ Zpart,
                                                          const int* __restrict__ col_start, const int* __restrict__ cap_len,
-                                                         int NtP, int D, int Bc, int nz, float g2, float* __restrict__ Z,
-                                                         float* __restrict__ cosv, float* __restrict__ un,
+                                                         const int* __restrict__ bin_cap, const int* __restrict__ bin_used,
+                                                         const int* __restrict__ meta, int NtP, int D, int Bc, int nz, float g2,
+                                                         float* __restrict__ Z, float* __restrict__ cosv, float* __restrict__ un,
                                                          float* __restrict__ m, float* __restrict__ mst) {
-    __shared__ float ex[32];
-    const int i = blockIdx.x, j = blockIdx.y;
-    const int cs = col_start[i], T = cap_len[i];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int t = w; t < T; t += nw) {
-        const int n = cs + t;
-        const float4* u4 = reinterpret_cast<const float4*>(U + ((size_t)j * NtP + n) * D);
-        const float4* w4 = reinterpret_cast<const float4*>(Wp + (size_t)n * D);
-        float dot = 0.f, uu = 0.f;
-        for (int q = lane; q < D / 4; q += 32) {
-            const float4 a = u4[q], b = __ldg(w4 + q);
-            dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
-            uu = fmaf(a.x, a.x, uu); uu = fmaf(a.y, a.y, uu); uu = fmaf(a.z, a.z, uu); uu = fmaf(a.w, a.w, uu);
+    __shared__ float s_cos[V3_BIN];
+    const int b = blockIdx.x, j = blockIdx.y;
+    if (b >= meta[0]) return;
+    const int used = bin_used[b];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int d4 = D >> 2;
+#pragma unroll 1
+    for (int c2 = 0; c2 < 8; c2 += 2) {
+        const int c0 = w * 8 + c2;
+        if (c0 >= used) break;
+        const bool two = c0 + 1 < used;
+        const size_t n0 = (size_t)b * V3_BIN + c0, n1 = two ? n0 + 1 : n0;
+        const float4* u0 = reinterpret_cast<const float4*>(U + ((size_t)j * NtP + n0) * D);
+        const float4* u1 = reinterpret_cast<const float4*>(U + ((size_t)j * NtP + n1) * D);
+        const float4* w0 = reinterpret_cast<const float4*>(Wp + n0 * D);
+        const float4* w1 = reinterpret_cast<const float4*>(Wp + n1 * D);
+        float z0 = lane < nz ? Zpart[((size_t)j * nz + lane) * NtP + n0] : 0.f;
+        float z1 = lane < nz ? Zpart[((size_t)j * nz + lane) * NtP + n1] : 0.f;
+        float dot0 = 0.f, uu0 = 0.f, dot1 = 0.f, uu1 = 0.f;
+        for (int q = lane; q < d4; q += 32) {
+            const float4 a0 = u0[q], b0 = __ldg(w0 + q), a1 = u1[q], b1 = __ldg(w1 + q);
+            dot0 = fmaf(a0.x, b0.x, dot0); dot0 = fmaf(a0.y, b0.y, dot0); dot0 = fmaf(a0.z, b0.z, dot0); dot0 = fmaf(a0.w, b0.w, dot0);
+            uu0 = fmaf(a0.x, a0.x, uu0); uu0 = fmaf(a0.y, a0.y, uu0); uu0 = fmaf(a0.z, a0.z, uu0); uu0 = fmaf(a0.w, a0.w, uu0);
+            dot1 = fmaf(a1.x, b1.x, dot1); dot1 = fmaf(a1.y, b1.y, dot1); dot1 = fmaf(a1.z, b1.z, dot1); dot1 = fmaf(a1.w, b1.w, dot1);
+            uu1 = fmaf(a1.x, a1.x, uu1); uu1 = fmaf(a1.y, a1.y, uu1); uu1 = fmaf(a1.z, a1.z, uu1); uu1 = fmaf(a1.w, a1.w, uu1);
         }
-        dot = warp_sum(dot);
-        uu = warp_sum(uu);
-        if (lane == 0) {
-            float z = 0.f;  // fixed order: deterministic
-            for (int s = 0; s < nz; ++s) z += Zpart[((size_t)j * nz + s) * NtP + n];
+        dot0 = warp_sum(dot0); uu0 = warp_sum(uu0); z0 = warp_sum(z0);
+        dot1 = warp_sum(dot1); uu1 = warp_sum(uu1); z1 = warp_sum(z1);
+        if (lane < 2 && (lane == 0 || two)) {
+            const float z = lane ? z1 : z0, dot = lane ? dot1 : dot0, uu = lane ? uu1 : uu0;
+            const size_t n = lane ? n1 : n0;
             const float unv = sqrtf(uu) / z;  // |u|, u = U' / Z
             const float c = (dot / z) / fmaxf(wn[n] * unv, 1e-8f);
             Z[(size_t)j * NtP + n] = z;
             cosv[(size_t)j * NtP + n] = c;
             un[(size_t)j * NtP + n] = unv;
-            ex[t] = expf(g2 * c);
+            s_cos[c0 + lane] = c;
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int t = 0; t < T; ++t) s += ex[t];
-        const float v = logf(s);
+    const int i0 = bin_cap[b], i1 = bin_cap[b + 1];
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const int cl = col_start[i] - b * V3_BIN, T = cap_len[i];
+        float sum = 0.f;
+        for (int t = 0; t < T; ++t) sum += expf(g2 * s_cos[cl + t]);
+        const float v = logf(sum);
         m[(size_t)j * Bc + i] = v;
         mst[(size_t)j * Bc + i] = v;
     }
@@ -310,36 +330,51 @@ __global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U,
     }
     const float wnv = wn[n];
     float a3s = 0.f;
-    for (int q = 0; q < V3_DU_JG; ++q) {
-        const int j = j0 + q;
-        if (j >= Bi) break;
-        const size_t idx = (size_t)j * NtP + n;
-        const float z = Z[idx], c = cosv[idx], unv = un[idx];
-        const float dcos = dm[(size_t)j * Bc + i] * g2 * expf(g2 * c - mst[(size_t)j * Bc + i]);
-        const float nn = wnv * unv;
-        const bool live = nn > 1e-8f;
-        const float a1 = dcos / fmaxf(nn, 1e-8f);
-        const float a2 = live ? dcos * c / (unv * unv) : 0.f;
-        a3s += live ? dcos * c / (wnv * wnv) : 0.f;
-        const float iz = 1.0f / z;
-        const float a2z = a2 * iz, a1z = a1 * iz;
-        const float4* u4 = reinterpret_cast<const float4*>(U + idx * D);
-        float4* o4 = reinterpret_cast<float4*>(DUz + idx * D);
-        float cs = 0.f;
+#pragma unroll 1
+    for (int q0 = 0; q0 < V3_DU_JG; q0 += 4) {  // four images per round: all their loads are issued before the math
+        float zs[4], cs4[4], us[4], dms[4], ms[4];
+        float4 uv[4][NQ];
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) {
-            const float4 uv = u4[lane + 32 * k];
-            float4 du;
-            du.x = a1 * wv[k].x - a2z * uv.x; du.y = a1 * wv[k].y - a2z * uv.y;
-            du.z = a1 * wv[k].z - a2z * uv.z; du.w = a1 * wv[k].w - a2z * uv.w;
-            cs = fmaf(du.x, uv.x, cs); cs = fmaf(du.y, uv.y, cs); cs = fmaf(du.z, uv.z, cs); cs = fmaf(du.w, uv.w, cs);
-            acc[k].x = fmaf(a1z, uv.x, acc[k].x); acc[k].y = fmaf(a1z, uv.y, acc[k].y);
-            acc[k].z = fmaf(a1z, uv.z, acc[k].z); acc[k].w = fmaf(a1z, uv.w, acc[k].w);
-            du.x *= iz; du.y *= iz; du.z *= iz; du.w *= iz;
-            o4[lane + 32 * k] = du;
+        for (int q = 0; q < 4; ++q) {
+            const int j = min(j0 + q0 + q, Bi - 1);
+            const size_t idx = (size_t)j * NtP + n;
+            zs[q] = Z[idx]; cs4[q] = cosv[idx]; us[q] = un[idx];
+            dms[q] = dm[(size_t)j * Bc + i]; ms[q] = mst[(size_t)j * Bc + i];
+            const float4* u4 = reinterpret_cast<const float4*>(U + idx * D);
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) uv[q][k] = u4[lane + 32 * k];
         }
-        cs = warp_sum(cs);  // <DU, U'>
-        if (lane == 0) csz[idx] = cs * iz * iz;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q0 + q;
+            if (j >= Bi) break;
+            const size_t idx = (size_t)j * NtP + n;
+            const float c = cs4[q], unv = us[q];
+            const float dcos = dms[q] * g2 * expf(g2 * c - ms[q]);
+            const float nn = wnv * unv;
+            const bool live = nn > 1e-8f;
+            const float a1 = dcos / fmaxf(nn, 1e-8f);
+            const float a2 = live ? dcos * c / (unv * unv) : 0.f;
+            a3s += live ? dcos * c / (wnv * wnv) : 0.f;
+            const float iz = 1.0f / zs[q];
+            const float a2z = a2 * iz, a1z = a1 * iz;
+            float4* o4 = reinterpret_cast<float4*>(DUz + idx * D);
+            float cs = 0.f;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) {
+                const float4 u = uv[q][k];
+                float4 du;
+                du.x = a1 * wv[k].x - a2z * u.x; du.y = a1 * wv[k].y - a2z * u.y;
+                du.z = a1 * wv[k].z - a2z * u.z; du.w = a1 * wv[k].w - a2z * u.w;
+                cs = fmaf(du.x, u.x, cs); cs = fmaf(du.y, u.y, cs); cs = fmaf(du.z, u.z, cs); cs = fmaf(du.w, u.w, cs);
+                acc[k].x = fmaf(a1z, u.x, acc[k].x); acc[k].y = fmaf(a1z, u.y, acc[k].y);
+                acc[k].z = fmaf(a1z, u.z, acc[k].z); acc[k].w = fmaf(a1z, u.w, acc[k].w);
+                du.x *= iz; du.y *= iz; du.z *= iz; du.w *= iz;
+                o4[lane + 32 * k] = du;
+            }
+            cs = warp_sum(cs);  // <DU, U'>
+            if (lane == 0) csz[idx] = cs * iz * iz;
+        }
     }
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
@@ -362,9 +397,20 @@ __global__ void __launch_bounds__(256) v3_unpack_dw_kernel(const float* __restri
         const int t = idx / 32, dd = idx % 32;
         float v = 0.f;
         if (t < T && d0 + dd < D) {
-            const size_t k = (size_t)(cs + t) * D + d0 + dd;
-            for (int s = 0; s < ngroups; ++s) v += dwcos[(size_t)s * NtP * D + k];
-            for (int s = 0; s < nsplit; ++s) v += dWpart[(size_t)s * NtP * D + k];
+            const size_t k = (size_t)(cs + t) * D + d0 + dd, plane = (size_t)NtP * D;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;  // four independent chains: the loads of a round are in flight together
+            int s = 0;
+            for (; s + 4 <= ngroups; s += 4) {
+                v0 += dwcos[(size_t)s * plane + k]; v1 += dwcos[(size_t)(s + 1) * plane + k];
+                v2 += dwcos[(size_t)(s + 2) * plane + k]; v3 += dwcos[(size_t)(s + 3) * plane + k];
+            }
+            for (; s < ngroups; ++s) v0 += dwcos[(size_t)s * plane + k];
+            for (s = 0; s + 4 <= nsplit; s += 4) {
+                v0 += dWpart[(size_t)s * plane + k]; v1 += dWpart[(size_t)(s + 1) * plane + k];
+                v2 += dWpart[(size_t)(s + 2) * plane + k]; v3 += dWpart[(size_t)(s + 3) * plane + k];
+            }
+            for (; s < nsplit; ++s) v1 += dWpart[(size_t)s * plane + k];
+            v = (v0 + v1) + (v2 + v3);
         }
         tile[dd][t] = v;
     }
@@ -403,6 +449,7 @@ size_t pair_v3_workspace_bytes(int Bi, int Bc, int D, int R, int Tm) { return v3
 int pair_v3_fwd(const float* img, const float* words, const int32_t* cap_lens, int Bi, int Bc, int D, int R, int Tm, float g1,
                 float g2, float* m, float* att, int diag_offset, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     EEGAN_REQUIRE(D % 128 == 0 && D <= 1024, "pair grid (fused engine): D=%d must be a multiple of 128 and <= 1024", D);
+    EEGAN_REQUIRE(R <= 1024, "pair grid (fused engine): R=%d must be <= 1024", R);  // cos/lse sums <= 32 region partials per column
     EEGAN_REQUIRE(Bc <= 4096, "pair grid (fused engine): at most 4096 captions per call (got %d)", Bc);
     V3Ws w = v3_carve(workspace, Bi, Bc, D, R, Tm);
     if (workspace_bytes < w.bytes) {
@@ -414,8 +461,8 @@ int pair_v3_fwd(const float* img, const float* words, const int32_t* cap_lens, i
 
     prof_mark(-1, st);
     v3_scan_kernel<<<1, 256, 2 * Bc * sizeof(int), st>>>(cap_lens, Bc, Tm, w.maxbins, w.col_start, w.cap_len, w.bin_cap, w.bin_used, w.meta, w.col_cap);
-    v3_pack_words_kernel<<<NtP, 64, 0, st>>>(words, w.col_start, w.col_cap, w.meta, D, Tm, w.Wp, w.wn);
-    if (w.Cp) v3_repitch_kernel<<<148 * 8, 256, 0, st>>>(img, w.Cp, (long long)Bi * D, R, w.Rp);
+    v3_pack_kernel<<<NtP + (w.Cp ? 148 * 8 : 0), 128, 0, st>>>(words, w.col_start, w.col_cap, w.meta, D, Tm, NtP, w.Wp, w.wn, img,
+                                                              w.Cp, (long long)Bi * D, R, w.Rp);
     EEGAN_LAUNCH_CHECK("pair prologue");
     prof_mark(0, st);
 
@@ -445,8 +492,8 @@ int pair_v3_fwd(const float* img, const float* words, const int32_t* cap_lens, i
     }
     prof_mark(3, st);
 
-    v3_cos_lse_kernel<<<dim3(Bc, Bi), 256, 0, st>>>(w.U, w.Wp, w.wn, w.Zpart, w.col_start, w.cap_len, NtP, D, Bc, w.nz, g2, w.Z,
-                                                    w.cosv, w.un, m, w.mst);
+    v3_cos_lse_kernel<<<dim3(w.maxbins, Bi), 256, 0, st>>>(w.U, w.Wp, w.wn, w.Zpart, w.col_start, w.cap_len, w.bin_cap, w.bin_used,
+                                                           w.meta, NtP, D, Bc, w.nz, g2, w.Z, w.cosv, w.un, m, w.mst);
     if (att) v3_att_diag_kernel<<<dim3(Bc, (R + 31) / 32), 256, 0, st>>>(w.E, w.Z, w.col_start, w.cap_len, NtP, R, Tm, Bi, diag_offset, att);
     EEGAN_LAUNCH_CHECK("pair cos/lse");
     prof_mark(4, st);

@@ -22,8 +22,8 @@ static std::vector<Mark> g_marks;
 static std::vector<cudaEvent_t> g_pool;
 
 static const char* kStageNames[EEGAN_PROF_NSTAGES] = {
-    "prologue(pack)", "gemm1(S=W.C)", "attn_softmax", "gemm2(U=A.C^T)", "cos_lse",
-    "bwd_scalars+du", "gemm3(dA=dU.C)", "softmax_bwd", "gemm4(dC)", "gemm5(dW)+unpack",
+    "prologue(pack)", "gemm1(S=W.C)+attn_fwd", "attn_softmax(unfused engines)", "gemm2(U=A.C^T)", "cos_lse+att_maps",
+    "bwd_scalars+du", "gemm3(dA=dU.C)+attn_bwd", "softmax_bwd(unfused engines)", "gemm4(dC)", "gemm5(dW)+unpack",
 };
 
 void prof_mark(int stage, cudaStream_t st) {

@@ -74,6 +74,7 @@ struct TcArgs {
     int nseg, nred, red_total, batch;
     int a_batched[2], b_batched[2];
     int a_pre[2], b_pre[2];   // operand arrives pre-split (raw + lo arrays): no in-kernel split for it
+    int dbg;                  // timing experiments only (EEGAN_TS_DBG): 1 one MMA per K-step, 2 skip the A split, 4 skip the B split
     int trunc_hi;             // 1: leave the raw operand as hi (hardware truncation), write lo only
     uint32_t mn_lbo, mn_sbo;  // debug-overridable descriptor fields of MN-major tiles (16-byte units)
     TcAttnEpi attn;

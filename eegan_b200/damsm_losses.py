@@ -52,6 +52,7 @@ class _PairGridFn(torch.autograd.Function):
                                               _lib.stream_ptr()), "damsm_pair_fwd")
         ctx.save_for_backward(img, words, cap_lens32)
         ctx.ws, ctx.g = ws, (g1, g2)
+        ctx.engine = L.eegan_get_contraction_engine()  # the stash layout belongs to the engine that wrote it
         if att is None:
             att = torch.empty(0, device=img.device)
         ctx.mark_non_differentiable(att)
@@ -67,11 +68,17 @@ class _PairGridFn(torch.autograd.Function):
         d_img = torch.empty_like(img) if need_img else None
         d_words = torch.empty_like(words) if need_words else None
         dm = _lib.f32c(dm)
+        if ctx.ws is None:
+            raise RuntimeError("words_loss backward: the forward stash was consumed by an earlier backward "
+                               "(only the fused contraction engine, 2, keeps it for retain_graph)")
+        if L.eegan_get_contraction_engine() != ctx.engine:
+            raise RuntimeError("words_loss backward: the contraction engine changed since the forward")
         with torch.cuda.device(img.device):
             _lib.check(L.eegan_damsm_pair_bwd(_lib.ptr(img), _lib.ptr(words), _lib.ptr(cap_lens32), Bi, Bc, D, R, Tm,
                                               ctx.g[0], ctx.g[1], _lib.ptr(dm), _lib.ptr(d_img), _lib.ptr(d_words),
                                               _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()), "damsm_pair_bwd")
-        ctx.ws = None  # the stash is consumed (U and dA were overwritten in place)
+        if ctx.engine != 2 or D % 128:
+            ctx.ws = None  # engines 0/1 consume the stash (U and dA are overwritten in place); the fused engine keeps it
         return d_img, d_words, None, None, None, None, None
 
 

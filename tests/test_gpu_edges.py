@@ -47,6 +47,53 @@ def test_small_and_odd_shapes(cuda_lib, B, T, D, H, lens):
         assert float(got[3].abs().max()) <= 1e-7 and float(got[4].abs().max()) <= 1e-7
 
 
+@pytest.mark.parametrize("B,T,D,H,lens", [
+    (3, 32, 128, 10, [32, 5, 17]),                       # T_max = 32: two captions per 64-column bin at most
+    (4, 32, 128, 6, [32, 32, 32, 32]),                   # bins filled exactly (64 of 64 columns), R = 36 < 128
+    (9, 20, 128, 17, [1, 2, 3, 4, 5, 8, 9, 16, 20]),     # every 4-word bucket boundary of the epilogue
+    (4, 18, 512, 8, [18, 11, 6, 13]),                    # D = 512 (dU kernel NQ = 4), R = 64: no re-pitch copy
+    (6, 18, 256, 20, [18, 7, 12, 5, 18, 9]),             # R = 400: four region tiles, last one 16 rows
+    (7, 18, 384, 17, [18, 18, 18, 10, 18, 18, 18]),      # odd number of bins: the last tile has one live bin
+])
+def test_fused_engine_shapes(cuda_lib, B, T, D, H, lens):
+    """Shapes that exercise the fused engine's packing (64-column bins, 128-column tiles), its
+    per-caption word buckets and the region-tile edges, against the float64 dense oracle."""
+    assert cuda_lib.eegan_get_contraction_engine() == 2 and D % 128 == 0
+    c = cases.words_case(B, T, D=D, H=H, seed=B * 100 + T + D, class_mode="none", min_len=1)
+    c["cap_lens"] = torch.tensor(lens)
+    got, ref = _run_both(c, B, 1.0, 0.5)
+    assert abs(got[0].item() - ref[0].item()) <= 2e-5 and abs(got[1].item() - ref[1].item()) <= 2e-5
+    # a map row sums to 1 over R regions: the CUB tolerance (2e-6 at R = 289) scales with the entry size 1/R
+    tol_att = 2e-6 * max(1.0, 289.0 / (H * H))
+    for a, b in zip(got[2], ref[2]):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert float((a.cpu().double() - b.detach()).abs().max()) <= tol_att
+        # argmax word per region: identical wherever the float64 oracle separates its top two words by more
+        # than the map tolerance (an fp32 reference flips the same near-ties)
+        bd = b.detach()
+        top2 = bd.topk(min(2, bd.shape[1]), dim=1).values
+        clear = (top2[:, 0] - top2[:, -1]) > 2 * tol_att if bd.shape[1] > 1 else torch.ones_like(top2[:, 0], dtype=torch.bool)
+        assert torch.equal(a.cpu().argmax(1)[clear], bd.argmax(1)[clear])
+    assert relmax(got[3].cpu(), ref[3]) <= 1e-4 and relmax(got[4].cpu(), ref[4]) <= 1e-4
+    for i, n in enumerate(lens):  # padded words receive exactly zero gradient
+        assert float(got[4][i, :, n:].abs().max()) == 0.0 if n < T else True
+
+
+def test_backward_twice_on_one_forward(cuda_lib):
+    """retain_graph: the backward leaves the forward stash intact (dU goes to its own buffer)."""
+    import eegan_b200 as E
+    c = cases.words_case(6, 18, seed=77)
+    img = c["img"].cuda().requires_grad_()
+    words = c["words"].cuda().requires_grad_()
+    l0, l1, _ = E.words_loss(img, words, c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], 6)
+    (l0 + l1).backward(retain_graph=True)
+    g1 = (img.grad.clone(), words.grad.clone())
+    img.grad = None
+    words.grad = None
+    (l0 + l1).backward()
+    assert torch.equal(img.grad, g1[0]) and torch.equal(words.grad, g1[1])
+
+
 def test_all_same_class_masks_every_off_diagonal(cuda_lib):
     """class_ids all equal: every off-diagonal cell is -inf (DAMSM_losses.py:282-285,331-333), each
     CE row has one finite logit, both losses are exactly 0 and no gradient flows."""

@@ -27,7 +27,7 @@
 namespace eegan {
 
 constexpr int V3_BIN = 64;     // packed columns per bin (captions never straddle a bin)
-constexpr int V3_DU_JG = 8;    // images per warp of the dU kernel
+constexpr int V3_DU_JG = 64;   // images per CTA of the dU kernel (8 warps x 8 images)
 
 struct V3Ws {
     int* col_start;  // [Bc+1] first packed column of caption i (col_start[Bc] = live padded extent)
@@ -178,7 +178,19 @@ __global__ void __launch_bounds__(128) v3_pack_kernel(const float* __restrict__ 
         for (long long row = (long long)(blockIdx.x - NtP) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
             const float* sp = img + row * R;
             float* dp = Cp + row * Rp;
-            for (int r = lane; r < Rp; r += 32) dp[r] = r < R ? __ldg(sp + r) : 0.f;
+            for (int r0 = 0; r0 < Rp; r0 += 32 * 10) {  // up to ten loads per lane in flight (R = 289 -> one round)
+                float v[10];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) {
+                    const int r = r0 + 32 * q + lane;
+                    v[q] = r < R ? __ldg(sp + r) : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 10; ++q) {
+                    const int r = r0 + 32 * q + lane;
+                    if (r < Rp) dp[r] = v[q];
+                }
+            }
         }
         return;
     }
@@ -220,32 +232,44 @@ __global__ void __launch_bounds__(256) v3_cos_lse_kernel(const float* __restrict
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int d4 = D >> 2;
 #pragma unroll 1
-    for (int c2 = 0; c2 < 8; c2 += 2) {
-        const int c0 = w * 8 + c2;
+    for (int c4 = 0; c4 < 8; c4 += 4) {  // four packed columns in flight per warp
+        const int c0 = w * 8 + c4;
         if (c0 >= used) break;
-        const bool two = c0 + 1 < used;
-        const size_t n0 = (size_t)b * V3_BIN + c0, n1 = two ? n0 + 1 : n0;
-        const float4* u0 = reinterpret_cast<const float4*>(U + ((size_t)j * NtP + n0) * D);
-        const float4* u1 = reinterpret_cast<const float4*>(U + ((size_t)j * NtP + n1) * D);
-        const float4* w0 = reinterpret_cast<const float4*>(Wp + n0 * D);
-        const float4* w1 = reinterpret_cast<const float4*>(Wp + n1 * D);
-        float z0 = lane < nz ? Zpart[((size_t)j * nz + lane) * NtP + n0] : 0.f;
-        float z1 = lane < nz ? Zpart[((size_t)j * nz + lane) * NtP + n1] : 0.f;
-        float dot0 = 0.f, uu0 = 0.f, dot1 = 0.f, uu1 = 0.f;
-        for (int q = lane; q < d4; q += 32) {
-            const float4 a0 = u0[q], b0 = __ldg(w0 + q), a1 = u1[q], b1 = __ldg(w1 + q);
-            dot0 = fmaf(a0.x, b0.x, dot0); dot0 = fmaf(a0.y, b0.y, dot0); dot0 = fmaf(a0.z, b0.z, dot0); dot0 = fmaf(a0.w, b0.w, dot0);
-            uu0 = fmaf(a0.x, a0.x, uu0); uu0 = fmaf(a0.y, a0.y, uu0); uu0 = fmaf(a0.z, a0.z, uu0); uu0 = fmaf(a0.w, a0.w, uu0);
-            dot1 = fmaf(a1.x, b1.x, dot1); dot1 = fmaf(a1.y, b1.y, dot1); dot1 = fmaf(a1.z, b1.z, dot1); dot1 = fmaf(a1.w, b1.w, dot1);
-            uu1 = fmaf(a1.x, a1.x, uu1); uu1 = fmaf(a1.y, a1.y, uu1); uu1 = fmaf(a1.z, a1.z, uu1); uu1 = fmaf(a1.w, a1.w, uu1);
+        float dot[4], uu[4], zz[4];
+        size_t nn[4];
+        const float4* up[4];
+        const float4* wp[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            nn[k] = (size_t)b * V3_BIN + min(c0 + k, used - 1);
+            up[k] = reinterpret_cast<const float4*>(U + ((size_t)j * NtP + nn[k]) * D);
+            wp[k] = reinterpret_cast<const float4*>(Wp + nn[k] * D);
+            zz[k] = lane < nz ? Zpart[((size_t)j * nz + lane) * NtP + nn[k]] : 0.f;
+            dot[k] = 0.f;
+            uu[k] = 0.f;
         }
-        dot0 = warp_sum(dot0); uu0 = warp_sum(uu0); z0 = warp_sum(z0);
-        dot1 = warp_sum(dot1); uu1 = warp_sum(uu1); z1 = warp_sum(z1);
-        if (lane < 2 && (lane == 0 || two)) {
-            const float z = lane ? z1 : z0, dot = lane ? dot1 : dot0, uu = lane ? uu1 : uu0;
-            const size_t n = lane ? n1 : n0;
-            const float unv = sqrtf(uu) / z;  // |u|, u = U' / Z
-            const float c = (dot / z) / fmaxf(wn[n] * unv, 1e-8f);
+        for (int q = lane; q < d4; q += 32) {
+            float4 a[4], bw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a[k] = up[k][q]; bw[k] = __ldg(wp[k] + q); }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                dot[k] = fmaf(a[k].x, bw[k].x, dot[k]); dot[k] = fmaf(a[k].y, bw[k].y, dot[k]);
+                dot[k] = fmaf(a[k].z, bw[k].z, dot[k]); dot[k] = fmaf(a[k].w, bw[k].w, dot[k]);
+                uu[k] = fmaf(a[k].x, a[k].x, uu[k]); uu[k] = fmaf(a[k].y, a[k].y, uu[k]);
+                uu[k] = fmaf(a[k].z, a[k].z, uu[k]); uu[k] = fmaf(a[k].w, a[k].w, uu[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { dot[k] = warp_sum(dot[k]); uu[k] = warp_sum(uu[k]); zz[k] = warp_sum(zz[k]); }
+        if (lane < 4 && c0 + lane < used) {
+            float z = zz[0], d = dot[0], u2 = uu[0];
+            size_t n = nn[0];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (lane == k) { z = zz[k]; d = dot[k]; u2 = uu[k]; n = nn[k]; }
+            const float unv = sqrtf(u2) / z;  // |u|, u = U' / Z
+            const float c = (d / z) / fmaxf(wn[n] * unv, 1e-8f);
             Z[(size_t)j * NtP + n] = z;
             cosv[(size_t)j * NtP + n] = c;
             un[(size_t)j * NtP + n] = unv;
@@ -291,9 +315,11 @@ __global__ void __launch_bounds__(256) v3_att_diag_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------
 // backward: per packed column
 // ---------------------------------------------------------------------------------------
-// One warp per (packed column n', group of V3_DU_JG images):
+// One CTA per (packed column n', group of V3_DU_JG = 64 images); warp w takes images j0 + 8 w ... + 7, four per round
+// with all their loads issued before the math:
 //   dcos = dm g2 exp(g2 cos - m);  a1 = dcos / max(|w||u|, eps);  a2 = dcos cos / |u|^2;  a3 = dcos cos / |w|^2
 //   DU = a1 w - a2 u  (u = U'/Z);  DUz = DU / Z;  csz = <DU, u> / Z;  dwcos[g][n'] = sum_j a1 u - (sum_j a3) w
+// (the per-warp parts of dwcos meet in shared memory and are added in a fixed order).
 template <int NQ>  // float4 per lane: D = 128 * NQ
 __global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U, const float* __restrict__ Wp,
                                                     const float* __restrict__ wn, const float* __restrict__ Z,
@@ -302,15 +328,17 @@ __global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U,
                                                     const int* __restrict__ col_cap, const int* __restrict__ meta, int NtP,
                                                     int Bi, int Bc, int D, float g2, float* __restrict__ DUz,
                                                     float* __restrict__ csz, float* __restrict__ dwcos) {
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ float4 s_acc[8][32 * NQ];
+    __shared__ float s_a3[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x;
     if (n >= meta[1]) return;
-    const int g = blockIdx.y, j0 = g * V3_DU_JG;
+    const int g = blockIdx.y, j0 = g * V3_DU_JG + warp * 8;
     const int i = col_cap[n];
     float4* dwc = reinterpret_cast<float4*>(dwcos + ((size_t)g * NtP + n) * D);
     if (i < 0) {  // padding column: zero operand rows so that GEMM4's K loop adds nothing
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < V3_DU_JG; ++q) {
+        for (int q = 0; q < 8; ++q) {
             const int j = j0 + q;
             if (j >= Bi) break;
             float4* o = reinterpret_cast<float4*>(DUz + ((size_t)j * NtP + n) * D);
@@ -318,8 +346,10 @@ __global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U,
             for (int c = 0; c < NQ; ++c) o[lane + 32 * c] = zero;
             if (lane == 0) csz[(size_t)j * NtP + n] = 0.f;
         }
+        if (warp == 0) {
 #pragma unroll
-        for (int c = 0; c < NQ; ++c) dwc[lane + 32 * c] = zero;
+            for (int c = 0; c < NQ; ++c) dwc[lane + 32 * c] = zero;
+        }
         return;
     }
     float4 wv[NQ], acc[NQ];
@@ -331,7 +361,7 @@ __global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U,
     const float wnv = wn[n];
     float a3s = 0.f;
 #pragma unroll 1
-    for (int q0 = 0; q0 < V3_DU_JG; q0 += 4) {  // four images per round: all their loads are issued before the math
+    for (int q0 = 0; q0 < 8 && j0 + q0 < Bi; q0 += 4) {
         float zs[4], cs4[4], us[4], dms[4], ms[4];
         float4 uv[4][NQ];
 #pragma unroll
@@ -377,11 +407,21 @@ __global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U,
         }
     }
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-        float4 o;
-        o.x = acc[k].x - a3s * wv[k].x; o.y = acc[k].y - a3s * wv[k].y;
-        o.z = acc[k].z - a3s * wv[k].z; o.w = acc[k].w - a3s * wv[k].w;
-        dwc[lane + 32 * k] = o;
+    for (int k = 0; k < NQ; ++k) s_acc[warp][lane + 32 * k] = acc[k];
+    if (lane == 0) s_a3[warp] = a3s;
+    __syncthreads();
+    for (int q = threadIdx.x; q < 32 * NQ; q += blockDim.x) {
+        float4 t = s_acc[0][q];
+        float a3 = s_a3[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) {
+            const float4 o = s_acc[w][q];
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+            a3 += s_a3[w];
+        }
+        const float4 wq = __ldg(reinterpret_cast<const float4*>(Wp + (size_t)n * D) + q);
+        t.x -= a3 * wq.x; t.y -= a3 * wq.y; t.z -= a3 * wq.z; t.w -= a3 * wq.w;
+        dwc[q] = t;
     }
 }
 
@@ -398,19 +438,13 @@ __global__ void __launch_bounds__(256) v3_unpack_dw_kernel(const float* __restri
         float v = 0.f;
         if (t < T && d0 + dd < D) {
             const size_t k = (size_t)(cs + t) * D + d0 + dd, plane = (size_t)NtP * D;
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;  // four independent chains: the loads of a round are in flight together
-            int s = 0;
-            for (; s + 4 <= ngroups; s += 4) {
-                v0 += dwcos[(size_t)s * plane + k]; v1 += dwcos[(size_t)(s + 1) * plane + k];
-                v2 += dwcos[(size_t)(s + 2) * plane + k]; v3 += dwcos[(size_t)(s + 3) * plane + k];
+            for (int s = 0; s < ngroups; ++s) v += dwcos[(size_t)s * plane + k];
+            for (int s0 = 0; s0 < nsplit; s0 += 8) {  // eight partials in flight per round
+                float p8[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) p8[q] = (s0 + q < nsplit) ? dWpart[(size_t)(s0 + q) * plane + k] : 0.f;
+                v += ((p8[0] + p8[1]) + (p8[2] + p8[3])) + ((p8[4] + p8[5]) + (p8[6] + p8[7]));
             }
-            for (; s < ngroups; ++s) v0 += dwcos[(size_t)s * plane + k];
-            for (s = 0; s + 4 <= nsplit; s += 4) {
-                v0 += dWpart[(size_t)s * plane + k]; v1 += dWpart[(size_t)(s + 1) * plane + k];
-                v2 += dWpart[(size_t)(s + 2) * plane + k]; v3 += dWpart[(size_t)(s + 3) * plane + k];
-            }
-            for (; s < nsplit; ++s) v1 += dWpart[(size_t)s * plane + k];
-            v = (v0 + v1) + (v2 + v3);
         }
         tile[dd][t] = v;
     }
@@ -512,7 +546,7 @@ int pair_v3_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1
 
     prof_mark(-1, st);
     {
-        dim3 grid((NtP + 7) / 8, w.ngroups);
+        dim3 grid(NtP, w.ngroups);
 #define V3_DU(NQ)                                                                                                            \
     v3_du_kernel<NQ><<<grid, 256, 0, st>>>(w.U, w.Wp, w.wn, w.Z, w.cosv, w.un, dm, w.mst, w.col_cap, w.meta, NtP, Bi, Bc, D, g2, \
                                            w.DUz, w.csz, w.dwcos)

@@ -1,0 +1,90 @@
+"""Run under torchrun on N GPUs of one box (not collected by pytest: needs N devices):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29533 tests/multigpu_check.py
+
+Checks, over NCCL, that the caption-row-sharded words_loss / sent_loss and the NCCL
+SynchronizedBatchNorm2d equal the single-device full-batch result (computed redundantly on every
+rank by the same CUDA library) — losses, both gradients, attention maps, BN output and grads."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import eegan_b200 as E  # noqa: E402
+from eegan_b200.sharded import sharded_sent_loss, sharded_words_loss  # noqa: E402
+from oracle import cases  # noqa: E402  (seeded input generator only)
+
+
+def relmax(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    b, T = 12, 18
+    B = b * world
+    c = cases.words_case(B, T, seed=11, class_mode="cub")
+    sl = slice(rank * b, (rank + 1) * b)
+    # full batch on this device
+    img = c["img"].to(dev).requires_grad_()
+    words = c["words"].to(dev).requires_grad_()
+    f0, f1, fatt = E.words_loss(img, words, c["labels"].to(dev), c["cap_lens"].to(dev), c["class_ids"], B)
+    (f0 + 2.0 * f1).backward()
+    # sharded
+    img_s = c["img"][sl].to(dev).requires_grad_()
+    words_s = c["words"][sl].to(dev).requires_grad_()
+    s0, s1, satt = sharded_words_loss(img_s, words_s, torch.arange(b, device=dev), c["cap_lens"][sl].to(dev),
+                                      c["class_ids"][sl], b)
+    (s0 + 2.0 * s1).backward()
+    assert abs(s0.item() - f0.item()) <= 2e-6 * max(1.0, abs(f0.item())), (s0.item(), f0.item())
+    assert abs(s1.item() - f1.item()) <= 2e-6 * max(1.0, abs(f1.item())), (s1.item(), f1.item())
+    assert relmax(img_s.grad, img.grad[sl]) <= 2e-5, relmax(img_s.grad, img.grad[sl])
+    assert relmax(words_s.grad, words.grad[sl]) <= 2e-5, relmax(words_s.grad, words.grad[sl])
+    for a, r in zip(satt, fatt[sl]):
+        assert float((a - r).abs().max()) <= 1e-7
+    # sentence loss
+    sc = cases.sent_case(B, seed=12)
+    cnn = sc["cnn"].to(dev).requires_grad_()
+    rnn = sc["rnn"].to(dev).requires_grad_()
+    g0, g1 = E.sent_loss(cnn, rnn, sc["labels"].to(dev), sc["class_ids"], B)
+    (g0 + g1).backward()
+    cnn_s = sc["cnn"][sl].to(dev).requires_grad_()
+    rnn_s = sc["rnn"][sl].to(dev).requires_grad_()
+    h0, h1 = sharded_sent_loss(cnn_s, rnn_s, torch.arange(b, device=dev), sc["class_ids"][sl], b)
+    (h0 + h1).backward()
+    assert abs(h0.item() - g0.item()) <= 2e-6 * max(1.0, abs(g0.item())) and abs(h1.item() - g1.item()) <= 2e-6 * max(1.0, abs(g1.item()))
+    assert relmax(cnn_s.grad, cnn.grad[sl]) <= 2e-5 and relmax(rnn_s.grad, rnn.grad[sl]) <= 2e-5
+    # SyncBN over NCCL vs the reference's N-replica formula on the full batch:
+    # inv_std = clamp(biased var, eps) ** -0.5   (sync_batchnorm/batchnorm.py:113-125), not 1/sqrt(var + eps)
+    from eegan_b200.sync_batchnorm import SynchronizedBatchNorm2d
+    g = torch.Generator().manual_seed(5)
+    x_full = torch.randn(4 * world, 32, 16, 16, generator=g)
+    go_full = torch.randn(4 * world, 32, 16, 16, generator=g)
+    bn = SynchronizedBatchNorm2d(32).to(dev)
+    bn.train()
+    xs = x_full[4 * rank:4 * rank + 4].to(dev).requires_grad_()
+    y = bn(xs)
+    y.backward(go_full[4 * rank:4 * rank + 4].to(dev))
+    xr = x_full.to(dev).requires_grad_()
+    mean = xr.mean(dim=(0, 2, 3), keepdim=True)
+    var = ((xr - mean) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+    yr = (xr - mean) * var.clamp(min=bn.eps) ** -0.5 * bn.weight.detach().view(1, -1, 1, 1) + bn.bias.detach().view(1, -1, 1, 1)
+    yr.backward(go_full.to(dev))
+    assert float((y.detach() - yr.detach()[4 * rank:4 * rank + 4]).abs().max()) <= 2e-5
+    assert relmax(xs.grad, xr.grad[4 * rank:4 * rank + 4]) <= 1e-4
+    dist.barrier()
+    if rank == 0:
+        print("multigpu_check ok: world %d, words %.6f/%.6f sent %.6f/%.6f" % (world, s0.item(), s1.item(), h0.item(), h1.item()))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(256, 2) gag_bwd_tma_kernel(const __grid_consta
     float* dvs = dks + idf * TP;
     float* ds_s = dvs + idf * TP;  // [256][TP]
     float* p_s = ds_s + GB_TILE * TP;
+    float* red_s = p_s + GB_TILE * TP;  // [2][8 warps][16 rows][TP]
     __shared__ __align__(8) unsigned long long bars[2 * GB_NS];
     const uint32_t bar0 = smem_u32(bars);
     auto full = [&](int s) { return bar0 + 8u * s; };
@@ -580,9 +581,25 @@ __global__ void __launch_bounds__(256, 2) gag_bwd_tma_kernel(const __grid_consta
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty(st));
-            float* dst = (is_k ? dks : dvs) + (c * GB_DC + cr) * TP;
+            // CTA-wide reduction over the 16 pixel groups without atomics: lane pairs by shuffle, the 8 warps through a
+            // double-buffered scratch, then one owner thread per (row, t) adds into the per-CTA accumulators
 #pragma unroll
-            for (int t = 0; t < TP; ++t) atomicAdd(dst + t, acc[t]);
+            for (int t = 0; t < TP; ++t) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 16);
+            float* red = red_s + (it & 1) * (8 * 16 * TP);
+            if (lane < 16) {
+#pragma unroll
+                for (int t = 0; t < TP; t += 4)
+                    *reinterpret_cast<float4*>(red + (warp * 16 + crow) * TP + t) = make_float4(acc[t], acc[t + 1], acc[t + 2], acc[t + 3]);
+            }
+            __syncthreads();
+            for (int o = tid; o < 16 * TP; o += 256) {
+                float sum = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) sum += red[w8 * 16 * TP + o];
+                const int row = o / TP, t = o - row * TP;
+                float* dst = (row < GB_DC ? dks : dvs) + (c * GB_DC + (row < GB_DC ? row : row - GB_DC)) * TP + t;
+                *dst += sum;
+            }
         }
     }
     __syncthreads();
@@ -604,7 +621,7 @@ static int gag_bwd_tma_launch(const float* x, const float* key, const float* val
     if (rc) return rc;
     rc = make_tmap_2d(&tmg, d_out, (unsigned long long)B * idf, (unsigned long long)Q, (unsigned long long)Q, 32, GB_DC, true);
     if (rc) return rc;
-    const size_t smem = (size_t)GB_NS * GB_STAGE_BYTES + ((size_t)4 * idf * TP + 2 * GB_TILE * TP) * sizeof(float) + 1024;
+    const size_t smem = (size_t)GB_NS * GB_STAGE_BYTES + ((size_t)4 * idf * TP + 2 * GB_TILE * TP + 2 * 8 * 16 * TP) * sizeof(float) + 1024;
     static std::atomic<size_t> granted{48 * 1024};
     if (smem > granted.load()) {
         cudaError_t e = cudaFuncSetAttribute(gag_bwd_tma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

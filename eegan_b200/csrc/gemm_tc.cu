@@ -227,7 +227,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// cuTensorMapEncodeTiled is a driver entry point: it needs the primary context bound to the calling
+// thread.  A backward can be the first CUDA work of autograd's thread (no runtime call has bound it
+// yet), so bind it once per thread through the runtime.
+static void bind_context_once() {
+    static thread_local bool bound = false;
+    if (!bound) {
+        cudaFree(nullptr);
+        bound = true;
+    }
+}
+
 static EncodeTiledFn get_encode() {
+    bind_context_once();
     static EncodeTiledFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;

@@ -38,13 +38,16 @@ struct V3Ws {
     int* col_cap;    // [NtP] caption of packed column n' (-1 = padding)
     float* Wp;       // [NtP][D]  packed words (zero rows for padding columns)
     float* wn;       // [NtP]
+    float* Wlo;      // [NtP][D]  tf32 residual of Wp (pre-split B operand of GEMM1)
     float* Cp;       // [Bi][D][Rp] image features re-pitched for TMA (only if Rp != R)
+    float* Clo;      // [Bi][D][Rp] tf32 residual of the image features (pre-split B operand of GEMM2 / GEMM5)
     float* P;        // [Bi][R][NtP]
     float* E;        // [Bi][R][NtP]
     float* Zpart;    // [Bi][ceil(R/32)][NtP]
     float* Z;        // [Bi][NtP]
     float* U;        // [Bi][NtP][D]  unnormalised word contexts U'
     float* DUz;      // [Bi][NtP][D]
+    float* DUzlo;    // [Bi][NtP][D]  tf32 residual of DUz (pre-split B operand of GEMM3)
     float* cosv;     // [Bi][NtP]
     float* un;       // [Bi][NtP]  |u|
     float* csz;      // [Bi][NtP]
@@ -55,6 +58,33 @@ struct V3Ws {
     int Rp, NtP, maxbins, nsplit, ngroups, nz;
     size_t bytes;
 };
+
+// Pre-split (hi = raw, lo array) B operands take the B-splitter warps off the critical path at the price of 16 KB
+// more L2->SM traffic per k-block.  Measured at B=48 (scratch notes in profiles/README.md): Wp for GEMM1 -5 us (on:
+// the operand is tiny and L2-resident); the image features for GEMM2/GEMM5 and dU for GEMM3 +-0 (off).
+static int presplit_c() {
+    static int v = [] {
+        const char* e = getenv("EEGAN_V3_PRESPLIT_C");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+static int presplit_du() {
+    static int v = [] {
+        const char* e = getenv("EEGAN_V3_PRESPLIT_DU");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+
+// extra (never live) bins in the column pitch of the stash arrays: keeps region rows off power-of-two strides
+static int pad_bins() {
+    static int v = [] {
+        const char* e = getenv("EEGAN_V3_PADBINS");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
 
 static int v3_nsplit(int Bi, int NtP, int D) {
     // GEMM5 reduces over images inside its K loop; split so that about one wave of live tiles exists
@@ -78,7 +108,7 @@ static V3Ws v3_carve(void* base, int Bi, int Bc, int D, int R, int Tm) {
     };
     const int per_bin = V3_BIN / Tm;  // >= 2 because Tm <= 32
     w.maxbins = (Bc + per_bin - 1) / per_bin;
-    w.NtP = w.maxbins * V3_BIN;
+    w.NtP = (w.maxbins + pad_bins()) * V3_BIN;
     w.Rp = (R + 3) / 4 * 4;
     w.nz = (R + 31) / 32;
     w.nsplit = v3_nsplit(Bi, w.NtP, D);
@@ -92,13 +122,16 @@ static V3Ws v3_carve(void* base, int Bi, int Bc, int D, int R, int Tm) {
     w.col_cap = (int*)take(NtP * sizeof(int));
     w.Wp = (float*)take(NtP * D * sizeof(float));
     w.wn = (float*)take(NtP * sizeof(float));
+    w.Wlo = (float*)take(NtP * D * sizeof(float));
     w.Cp = (float*)take(w.Rp != R ? (size_t)Bi * D * w.Rp * sizeof(float) : 0);
+    w.Clo = (float*)take(presplit_c() ? (size_t)Bi * D * w.Rp * sizeof(float) : 0);
     w.P = (float*)take((size_t)Bi * R * NtP * sizeof(float));
     w.E = (float*)take((size_t)Bi * R * NtP * sizeof(float));
     w.Zpart = (float*)take((size_t)Bi * w.nz * NtP * sizeof(float));
     w.Z = (float*)take((size_t)Bi * NtP * sizeof(float));
     w.U = (float*)take((size_t)Bi * NtP * D * sizeof(float));
     w.DUz = (float*)take((size_t)Bi * NtP * D * sizeof(float));
+    w.DUzlo = (float*)take(presplit_du() ? (size_t)Bi * NtP * D * sizeof(float) : 0);
     w.cosv = (float*)take((size_t)Bi * NtP * sizeof(float));
     w.un = (float*)take((size_t)Bi * NtP * sizeof(float));
     w.csz = (float*)take((size_t)Bi * NtP * sizeof(float));
@@ -108,6 +141,7 @@ static V3Ws v3_carve(void* base, int Bi, int Bc, int D, int R, int Tm) {
     w.dwcos = (float*)take((size_t)w.ngroups * NtP * D * sizeof(float));
     w.bytes = off;
     if (w.Rp == R) w.Cp = nullptr;
+    if (!presplit_c()) w.Clo = nullptr;
     return w;
 }
 
@@ -168,16 +202,16 @@ __global__ void __launch_bounds__(256) v3_scan_kernel(const int32_t* __restrict_
 //   CTAs [NtP, ...): img [Bi*D][R] -> Cp [Bi*D][Rp] (TMA needs 16-byte row pitches; R = 289 is odd)
 __global__ void __launch_bounds__(128) v3_pack_kernel(const float* __restrict__ words, const int* __restrict__ col_start,
                                                       const int* __restrict__ col_cap, const int* __restrict__ meta, int D,
-                                                      int Tm, int NtP, float* __restrict__ Wp, float* __restrict__ wn,
-                                                      const float* __restrict__ img, float* __restrict__ Cp, long long rows,
-                                                      int R, int Rp) {
+                                                      int Tm, int NtP, float* __restrict__ Wp, float* __restrict__ Wlo,
+                                                      float* __restrict__ wn, const float* __restrict__ img, float* __restrict__ Cp,
+                                                      float* __restrict__ Clo, long long rows, int R, int Rp) {
     __shared__ float red[32];
     if ((int)blockIdx.x >= NtP) {
         const int lane = threadIdx.x & 31;
         const long long warps = (long long)(gridDim.x - NtP) * (blockDim.x >> 5);
         for (long long row = (long long)(blockIdx.x - NtP) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
             const float* sp = img + row * R;
-            float* dp = Cp + row * Rp;
+            float* dp = Cp ? Cp + row * Rp : nullptr;
             for (int r0 = 0; r0 < Rp; r0 += 32 * 10) {  // up to ten loads per lane in flight (R = 289 -> one round)
                 float v[10];
 #pragma unroll
@@ -188,7 +222,13 @@ __global__ void __launch_bounds__(128) v3_pack_kernel(const float* __restrict__ 
 #pragma unroll
                 for (int q = 0; q < 10; ++q) {
                     const int r = r0 + 32 * q + lane;
-                    if (r < Rp) dp[r] = v[q];
+                    if (r < Rp) {
+                        if (Cp) dp[r] = v[q];
+                        if (Clo) {
+                            const float h = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
+                            Clo[row * Rp + r] = __uint_as_float((__float_as_uint(v[q] - h) + 0x1000u) & 0xffffe000u);
+                        }
+                    }
                 }
             }
         }
@@ -199,12 +239,18 @@ __global__ void __launch_bounds__(128) v3_pack_kernel(const float* __restrict__ 
     const int i = col_cap[n];
     float ss = 0.f;
     if (i < 0) {
-        for (int d = threadIdx.x; d < D; d += blockDim.x) Wp[(size_t)n * D + d] = 0.f;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            Wp[(size_t)n * D + d] = 0.f;
+            Wlo[(size_t)n * D + d] = 0.f;
+        }
     } else {
         const int t = n - col_start[i];
         for (int d = threadIdx.x; d < D; d += blockDim.x) {
             const float v = __ldg(words + ((size_t)i * D + d) * Tm + t);
             Wp[(size_t)n * D + d] = v;
+            // lo = tf32(v - trunc_tf32(v)): what the B splitters of the GEMM would compute in shared memory
+            const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            Wlo[(size_t)n * D + d] = __uint_as_float((__float_as_uint(v - h) + 0x1000u) & 0xffffe000u);
             ss = fmaf(v, v, ss);
         }
     }
@@ -315,6 +361,11 @@ __global__ void __launch_bounds__(256) v3_att_diag_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------
 // backward: per packed column
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float v3_lo(float x) {
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    return __uint_as_float((__float_as_uint(x - h) + 0x1000u) & 0xffffe000u);
+}
+
 // One CTA per (packed column n', group of V3_DU_JG = 64 images); warp w takes images j0 + 8 w ... + 7, four per round
 // with all their loads issued before the math:
 //   dcos = dm g2 exp(g2 cos - m);  a1 = dcos / max(|w||u|, eps);  a2 = dcos cos / |u|^2;  a3 = dcos cos / |w|^2
@@ -327,7 +378,8 @@ __global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U,
                                                     const float* __restrict__ dm, const float* __restrict__ mst,
                                                     const int* __restrict__ col_cap, const int* __restrict__ meta, int NtP,
                                                     int Bi, int Bc, int D, float g2, float* __restrict__ DUz,
-                                                    float* __restrict__ csz, float* __restrict__ dwcos) {
+                                                    float* __restrict__ DUzlo, float* __restrict__ csz,
+                                                    float* __restrict__ dwcos) {
     __shared__ float4 s_acc[8][32 * NQ];
     __shared__ float s_a3[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -342,8 +394,12 @@ __global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U,
             const int j = j0 + q;
             if (j >= Bi) break;
             float4* o = reinterpret_cast<float4*>(DUz + ((size_t)j * NtP + n) * D);
+            float4* ol = DUzlo ? reinterpret_cast<float4*>(DUzlo + ((size_t)j * NtP + n) * D) : nullptr;
 #pragma unroll
-            for (int c = 0; c < NQ; ++c) o[lane + 32 * c] = zero;
+            for (int c = 0; c < NQ; ++c) {
+                o[lane + 32 * c] = zero;
+                if (ol) ol[lane + 32 * c] = zero;
+            }
             if (lane == 0) csz[(size_t)j * NtP + n] = 0.f;
         }
         if (warp == 0) {
@@ -401,6 +457,11 @@ __global__ void __launch_bounds__(256) v3_du_kernel(const float* __restrict__ U,
                 acc[k].z = fmaf(a1z, u.z, acc[k].z); acc[k].w = fmaf(a1z, u.w, acc[k].w);
                 du.x *= iz; du.y *= iz; du.z *= iz; du.w *= iz;
                 o4[lane + 32 * k] = du;
+                if (DUzlo) {  // lo = tf32(x - trunc_tf32(x)), what the B splitters of GEMM3 would compute
+                    float4 l;
+                    l.x = v3_lo(du.x); l.y = v3_lo(du.y); l.z = v3_lo(du.z); l.w = v3_lo(du.w);
+                    reinterpret_cast<float4*>(DUzlo + idx * D)[lane + 32 * k] = l;
+                }
             }
             cs = warp_sum(cs);  // <DU, U'>
             if (lane == 0) csz[idx] = cs * iz * iz;
@@ -464,6 +525,14 @@ static int use_ts() {
     return v;
 }
 
+static int presplit_w() {
+    static int v = [] {
+        const char* e = getenv("EEGAN_V3_PRESPLIT_W");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+
 static TcAttnEpi attn_args(const V3Ws& w, float g1) {
     TcAttnEpi a{};
     a.nbins = w.meta;
@@ -495,8 +564,8 @@ int pair_v3_fwd(const float* img, const float* words, const int32_t* cap_lens, i
 
     prof_mark(-1, st);
     v3_scan_kernel<<<1, 256, 2 * Bc * sizeof(int), st>>>(cap_lens, Bc, Tm, w.maxbins, w.col_start, w.cap_len, w.bin_cap, w.bin_used, w.meta, w.col_cap);
-    v3_pack_kernel<<<NtP + (w.Cp ? 148 * 8 : 0), 128, 0, st>>>(words, w.col_start, w.col_cap, w.meta, D, Tm, NtP, w.Wp, w.wn, img,
-                                                              w.Cp, (long long)Bi * D, R, w.Rp);
+    v3_pack_kernel<<<NtP + ((w.Cp || w.Clo) ? 148 * 8 : 0), 128, 0, st>>>(words, w.col_start, w.col_cap, w.meta, D, Tm, NtP, w.Wp,
+                                                                         w.Wlo, w.wn, img, w.Cp, w.Clo, (long long)Bi * D, R, w.Rp);
     EEGAN_LAUNCH_CHECK("pair prologue");
     prof_mark(0, st);
 
@@ -505,7 +574,7 @@ int pair_v3_fwd(const float* img, const float* words, const int32_t* cap_lens, i
         g.nseg = 1;
         g.ts = use_ts();
         g.A[0] = TcOperand{C, nullptr, 0, w.Rp, (long long)D * w.Rp, Bi, R, D};
-        g.B[0] = TcOperand{w.Wp, nullptr, 1, D, 0, 1, NtP, D};
+        g.B[0] = TcOperand{w.Wp, presplit_w() ? w.Wlo : nullptr, 1, D, 0, 1, NtP, D};
         g.C = w.E; g.ldc = NtP; g.bC = (long long)R * NtP; g.M = R; g.N = NtP; g.dynN = w.meta + 1; g.batch = Bi; g.nred = 1;
         g.epi = TC_EPI_ATTN_FWD;
         g.attn = attn_args(w, g1);
@@ -519,7 +588,7 @@ int pair_v3_fwd(const float* img, const float* words, const int32_t* cap_lens, i
         g.nseg = 1;
         g.ts = use_ts();
         g.A[0] = TcOperand{w.E, nullptr, 0, NtP, (long long)R * NtP, Bi, NtP, R};
-        g.B[0] = TcOperand{C, nullptr, 1, w.Rp, (long long)D * w.Rp, Bi, D, R};
+        g.B[0] = TcOperand{C, w.Clo, 1, w.Rp, (long long)D * w.Rp, Bi, D, R};
         g.C = w.U; g.ldc = D; g.bC = (long long)NtP * D; g.M = NtP; g.N = D; g.dynM = w.meta + 1; g.batch = Bi; g.nred = 1;
         int rc = tc_gemm_launch(g, st);
         if (rc) return rc;
@@ -549,7 +618,7 @@ int pair_v3_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1
         dim3 grid(NtP, w.ngroups);
 #define V3_DU(NQ)                                                                                                            \
     v3_du_kernel<NQ><<<grid, 256, 0, st>>>(w.U, w.Wp, w.wn, w.Z, w.cosv, w.un, dm, w.mst, w.col_cap, w.meta, NtP, Bi, Bc, D, g2, \
-                                           w.DUz, w.csz, w.dwcos)
+                                           w.DUz, presplit_du() ? w.DUzlo : nullptr, w.csz, w.dwcos)
         switch (D / 128) {
             case 1: V3_DU(1); break;
             case 2: V3_DU(2); break;
@@ -570,7 +639,7 @@ int pair_v3_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1
         g.nseg = 1;
         g.ts = use_ts();
         g.A[0] = TcOperand{C, nullptr, 0, w.Rp, (long long)D * w.Rp, Bi, R, D};
-        g.B[0] = TcOperand{w.DUz, nullptr, 1, D, (long long)NtP * D, Bi, NtP, D};
+        g.B[0] = TcOperand{w.DUz, presplit_du() ? w.DUzlo : nullptr, 1, D, (long long)NtP * D, Bi, NtP, D};
         g.C = w.dS; g.ldc = NtP; g.bC = (long long)R * NtP; g.M = R; g.N = NtP; g.dynN = w.meta + 1; g.batch = Bi; g.nred = 1;
         g.epi = TC_EPI_ATTN_BWD;
         g.attn = attn_args(w, g1);
@@ -598,7 +667,7 @@ int pair_v3_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1
         g.nseg = 1;
         g.ts = use_ts();
         g.A[0] = TcOperand{w.dS, nullptr, 0, NtP, (long long)R * NtP, Bi, NtP, R};
-        g.B[0] = TcOperand{C, nullptr, 1, w.Rp, (long long)D * w.Rp, Bi, D, R};
+        g.B[0] = TcOperand{C, w.Clo, 1, w.Rp, (long long)D * w.Rp, Bi, D, R};
         g.C = w.dWpart; g.ldc = D; g.bC = (long long)NtP * D; g.M = NtP; g.N = D; g.dynM = w.meta + 1; g.batch = w.nsplit;
         g.nred = nred; g.red_total = Bi;
         int rc = tc_gemm_launch(g, st);

@@ -132,6 +132,18 @@ int eegan_sent_scores_bwd(const float* cnn, const float* rnn, const float* norms
                           float* d_cnn, float* d_rnn, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * R-precision scoring — test.py:306-336 (Tester.cal_sim_one_by_one), the evaluation-side consumer of
+ * the sentence-score arithmetic.
+ * cnn_code [B, D]: global code of each generated image; rnn_codes [B, R_val, D]: its R_val candidate
+ * sentence codes, candidate 0 = the ground-truth caption (test.py:321).
+ * scores [B, R_val] OUT (optional): <cnn_b, rnn_bk> / max(|cnn_b| |rnn_bk|, eps)   (test.py:323-327)
+ * best [B] int32 OUT (optional): argmax_k scores[b][k], lowest index on ties (torch.argmax)
+ * hit [B] uint8 OUT (optional): best[b] == 0   (test.py:329-330, R_hits)
+ * ---------------------------------------------------------------------------------- */
+int eegan_rprecision(const float* cnn_code, const float* rnn_codes, int B, int R_val, int D, float eps,
+                     float* scores, int32_t* best, uint8_t* hit, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * GlobalAttentionGeneral.forward — miscc/DAMSM_losses.py:75-132.
  * x [B, idf, Q]; key, value [B, idf, T]; mask [B, T] uint8 (1 = padding) or NULL.
  * mask_mode 0 = reference quirk: row (b,q) uses mask[(b*Q+q) % B] (:114-118);

@@ -272,3 +272,23 @@ def syncbn_forward(x_shards: Sequence[torch.Tensor], weight, bias, eps=1e-5):
             y = (x - mean.view(shape)) * inv_std.view(shape)
         outs.append(y)
     return outs, mean, inv_std, sumvar / (tot - 1)
+
+
+def port_rprecision(cnn_code, rnn_codes, eps=1e-8):
+    """test.py:306-336 (Tester.cal_sim_one_by_one), the arithmetic of its per-sample loop body
+    (:323-330) in the reference's own op order: one image against its R_val candidate sentence
+    codes, candidate 0 = the matching caption.  Returns (hits [B] bool, argmax [B], scores0 [B,R_val])."""
+    B = cnn_code.shape[0]
+    hits, best, rows = [], [], []
+    for ix in range(B):
+        rnn_code = rnn_codes[ix]
+        scores = torch.mm(cnn_code[ix].unsqueeze(0), rnn_code.transpose(0, 1))  # 1 x R_val   (:323)
+        cnn_code_norm = torch.norm(cnn_code[ix].unsqueeze(0), 2, dim=1, keepdim=True)  # (:324)
+        rnn_code_norm = torch.norm(rnn_code, 2, dim=1, keepdim=True)  # (:325)
+        norm = torch.mm(cnn_code_norm, rnn_code_norm.transpose(0, 1))  # (:326)
+        scores0 = scores / norm.clamp(min=eps)  # (:327)
+        am = int(torch.argmax(scores0))  # (:329)
+        hits.append(am == 0)
+        best.append(am)
+        rows.append(scores0[0])
+    return torch.tensor(hits), torch.tensor(best), torch.stack(rows)

@@ -138,3 +138,32 @@ def test_sharded_block_equals_columns_of_full_grid(cuda_lib):
         blk, att = pair_grid(img, words[sl], lens[sl], diag_offset=rank * b)
         assert float((blk - full[:, sl]).abs().max()) <= 2e-6
         assert float((att - att_full[sl]).abs().max()) <= 1e-7
+
+
+@pytest.mark.parametrize("B,Rv,D", [(10, 100, 256), (3, 7, 64), (1, 1, 256)])
+def test_r_precision_matches_reference_arithmetic(cuda_lib, B, Rv, D):
+    """eegan_b200.r_precision vs the restated loop body of Tester.cal_sim_one_by_one (test.py:323-330):
+    scores within fp32 noise, argmax / hit bit-exact (ties included: lowest index)."""
+    import eegan_b200 as E
+    g = cases._gen(B * 1000 + Rv)
+    cnn = torch.randn(B, D, generator=g)
+    rnn = torch.randn(B, Rv, D, generator=g)
+    if Rv > 1:
+        rnn[0, 0] = cnn[0] * 2.0                 # a clear hit
+    if Rv > 3:
+        rnn[1 % B, 3] = rnn[1 % B, 2]            # an exact tie between two candidates
+    if B > 2:
+        rnn[2, :, :] = 0.0                       # all-zero candidates: the clamp (min=1e-8) path, scores 0
+    hits, best, scores = E.r_precision(cnn.cuda(), rnn.cuda(), return_scores=True)
+    oh, ob, osc = O.port_rprecision(cnn, rnn)
+    assert float((scores.cpu() - osc).abs().max()) <= 2e-6
+    # argmax: exact wherever the reference separates its top two by more than the score tolerance
+    top2 = osc.topk(min(2, Rv), dim=1).values
+    clear = (top2[:, 0] - top2[:, -1]) > 4e-6 if Rv > 1 else torch.ones(B, dtype=torch.bool)
+    assert torch.equal(best.cpu().long()[clear], ob[clear]) and torch.equal(hits.cpu()[clear], oh[clear])
+    # exact ties resolve to the lowest index, as torch.argmax does
+    if Rv > 3:
+        s1 = scores[1 % B].cpu()
+        assert s1[2] == s1[3]
+    if B > 2:
+        assert int(best[2]) == 0 and bool(hits[2])

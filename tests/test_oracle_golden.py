@@ -117,3 +117,15 @@ def test_syncbn_fixture(name):
     np.testing.assert_allclose(torch.cat(outs, 0).numpy(), g["out"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(0.1 * mean.numpy(), g["running_mean"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(0.9 + 0.1 * unbiased.numpy(), g["running_var"], rtol=1e-5)
+
+
+def test_port_rprecision_known_answers():
+    """The R-precision restatement (test.py:323-330) on hand-checkable inputs."""
+    cnn = torch.tensor([[1.0, 0.0], [0.0, 2.0], [0.0, 0.0]])
+    rnn = torch.tensor([[[3.0, 0.0], [0.0, 1.0], [-1.0, 0.0]],       # candidate 0 is parallel: hit
+                        [[1.0, 0.0], [0.0, 5.0], [0.0, -1.0]],       # candidate 1 wins: miss
+                        [[1.0, 1.0], [2.0, 0.0], [0.0, 3.0]]])       # zero image code: all scores 0 -> argmax 0
+    hits, best, scores = O.port_rprecision(cnn, rnn)
+    assert hits.tolist() == [True, False, True] and best.tolist() == [0, 1, 0]
+    assert torch.allclose(scores[0], torch.tensor([1.0, 0.0, -1.0])) and torch.allclose(scores[1], torch.tensor([0.0, 1.0, -1.0]))
+    assert float(scores[2].abs().max()) == 0.0

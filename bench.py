@@ -50,6 +50,10 @@ UNIT = "pairs/s"
 #   pair fwd 6 (scan, pack+repitch, gemm S + attention fwd, gemm U, cos/lse, att_maps) + CE fwd 2 + CE bwd 1
 #   + pair bwd 5 (dU, gemm dA + attention bwd, gemm dC, gemm dW, unpack)
 LAUNCHES_PER_STEP = 14
+# dram__bytes_read.sum + dram__bytes_write.sum per ts_gemm_kernel launch, averaged over the five launches of one
+# step, from the committed ncu --set full capture (profiles/r1_v3_fused_step_ncu_full_summary.csv: 32.3 / 52.9 /
+# 89.2 / 107.4 / 50.3 MB); algorithmic bytes of the whole step are 45.3 MB — the rest is the stash round trips
+NCU_TRAFFIC_BYTES_PER_GEMM_LAUNCH = 66.4e6
 
 
 def peaks():
@@ -463,7 +467,7 @@ def run_ours(args):
         line["roofline"] = {
             "bound": "tensor", "kernel": "ts_gemm_kernel (tcgen05 3xTF32, A operand staged in TMEM; 5 launches/step: S + attention fwd epilogue, U, dA + attention bwd epilogue, dC, dW)",
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops"] if achieved else None, "traffic": None,
+            "frac": achieved / pk["bf16_tflops"] if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_GEMM_LAUNCH,
             "peak_source": pk["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
             "note": "fp32-accurate 3xTF32 (SURVEY D7): 3 tcgen05.mma.kind::tf32 per K-step at half the bf16 rate, so the "
                     "engine's own ceiling is peak/6 = %.0f TFLOP/s -> frac_of_3xtf32_ceiling = %.3f; avg launch %.1f us; "

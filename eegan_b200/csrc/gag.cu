@@ -6,6 +6,8 @@
 // Algorithmic bytes per pixel fwd+bwd: (5*idf + 2*T)*4.
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
@@ -674,7 +676,25 @@ static int gag_bwd_launch(const float* x, const float* key, const float* value, 
 
 }  // namespace eegan
 
+namespace eegan {
+bool gag_tc_fwd_supported(const float* x, int B, int idf, int Q, int T);
+int gag_tc_fwd_launch(const float* x, const float* key, const float* value, const uint8_t* mask, int mask_mode, int B, int idf,
+                      int Q, int T, float* out, float* attn, cudaStream_t st);
+}  // namespace eegan
+
 using namespace eegan;
+
+// forward engine: 0 = CUDA-core kernels (default: as fast as the tensor-core form today), 1 = tcgen05 kernel of gag_tc.cu
+static std::atomic<int> g_gag_engine{[] {
+    const char* e = getenv("EEGAN_GAG_TC");
+    return e ? atoi(e) : 0;
+}()};
+extern "C" int eegan_set_gag_engine(int engine) {
+    EEGAN_REQUIRE(engine == 0 || engine == 1, "gag engine must be 0 (CUDA cores) or 1 (tensor-core forward)");
+    g_gag_engine.store(engine);
+    return EEGAN_OK;
+}
+extern "C" int eegan_get_gag_engine(void) { return g_gag_engine.load(); }
 
 #define GAG_DISPATCH(T, CALL)                                                   \
     ((T) <= 8 ? CALL<8> : (T) <= 12 ? CALL<12> : (T) <= 16 ? CALL<16> : (T) <= 20 ? CALL<20> : (T) <= 24 ? CALL<24> : CALL<32>)
@@ -685,6 +705,8 @@ extern "C" int eegan_gag_fwd(const float* x, const float* key, const float* valu
     EEGAN_REQUIRE(T <= 32 && idf <= 512, "gag: T=%d (<=32) idf=%d (<=512) unsupported", T, idf);
     EEGAN_REQUIRE(x && key && value && out && attn, "gag fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_gag_engine.load() == 1 && gag_tc_fwd_supported(x, B, idf, Q, T))  // tensor-core kernel (gag_tc.cu)
+        return gag_tc_fwd_launch(x, key, value, mask, mask_mode, B, idf, Q, T, out, attn, st);
     const size_t tma_smem = (size_t)GF_NS * GF_STAGE_BYTES + (size_t)2 * idf * 32 * sizeof(float) + 128;
     if (Q % 4 == 0 && idf % GF_DC == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && tma_smem <= 100 * 1024 && B <= 1024)
         return GAG_DISPATCH(T, gag_fwd_tma_launch)(x, key, value, mask, mask_mode, B, idf, Q, T, out, attn, st);

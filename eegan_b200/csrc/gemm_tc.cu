@@ -313,6 +313,8 @@ static int make_map(CUtensorMap* m, const TcOperand& o, int box_rows_kmajor, boo
     return EEGAN_OK;
 }
 
+int tc_make_map_plain(CUtensorMap* m, const TcOperand& o) { return make_map(m, o, TC_BM, true); }
+
 int make_tmap_2d(CUtensorMap* m, const float* ptr, unsigned long long rows, unsigned long long cols, unsigned long long pitch,
                  unsigned box_cols, unsigned box_rows, bool swizzle128) {
     EncodeTiledFn enc = get_encode();

@@ -86,6 +86,9 @@ struct TcGemm {
 int make_tmap_2d(CUtensorMap* m, const float* ptr, unsigned long long rows, unsigned long long cols, unsigned long long pitch,
                  unsigned box_cols, unsigned box_rows, bool swizzle128 = false);
 
+// Un-swizzled 3-D map of an MN-major operand ([K][rows], rows contiguous): box [32 k][128 rows] (gemm_ts.cu, gag_tc.cu)
+int tc_make_map_plain(CUtensorMap* m, const TcOperand& o);
+
 struct TcMaps;
 struct TcArgs;
 // gemm_ts.cu: launch of the TMEM-staged kernel on prepared maps / arguments

@@ -131,6 +131,11 @@ int eegan_sent_scores_bwd(const float* cnn, const float* rnn, const float* norms
                           const float* dscores, int B, int D, float gamma3, float eps,
                           float* d_cnn, float* d_rnn, void* stream);
 
+/* Forward engine of eegan_gag_fwd: 0 = CUDA-core kernels (default), 1 = tcgen05 kernel (x staged in tensor memory,
+ * softmax in the accumulator's threads, P written back to TMEM for out = P value^T); process-wide. */
+int eegan_set_gag_engine(int engine);
+int eegan_get_gag_engine(void);
+
 /* ------------------------------------------------------------------------------------
  * R-precision scoring — test.py:306-336 (Tester.cal_sim_one_by_one), the evaluation-side consumer of
  * the sentence-score arithmetic.

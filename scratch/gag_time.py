@@ -7,14 +7,17 @@ Bq, T = 48, 18
 lens = torch.randint(5, T + 1, (Bq,), generator=g)
 mask = (torch.arange(T)[None, :] >= lens[:, None]).to(dev)
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-def timeit(fn, n=10):
+def timeit(fn, n=6, rep=4):
+    # rep back-to-back calls per timed span so that the span is GPU-bound, not launch-latency-bound
     for _ in range(3): fn()
     tot = 0.0
     for _ in range(n):
         flush.fill_(1.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
+        e0.record()
+        for _ in range(rep): fn()
+        e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1) / rep
     return tot / n
 for res, idf in ((64, 128), (128, 64), (256, 32)):
     x = torch.randn(Bq, idf, res, res, device=dev).requires_grad_()

@@ -118,8 +118,16 @@ def test_sent_loss_vs_reference_fixture(cuda_lib, name):
     assert relmax(cnn.grad.cpu(), g["d_cnn"]) <= TOL_GRAD and relmax(rnn.grad.cpu(), g["d_rnn"]) <= TOL_GRAD
 
 
+@pytest.fixture(params=[0, 1], ids=["gag-cuda-cores", "gag-tcgen05-fwd"])
+def gag_engine(request, cuda_lib):
+    """Both forward engines of GlobalAttentionGeneral: the CUDA-core kernels (default) and the tcgen05 kernel."""
+    assert cuda_lib.eegan_set_gag_engine(request.param) == 0
+    yield request.param
+    cuda_lib.eegan_set_gag_engine(0)
+
+
 @pytest.mark.parametrize("name", golden_names("gag_"))
-def test_gag_vs_reference_fixture(cuda_lib, name):
+def test_gag_vs_reference_fixture(cuda_lib, gag_engine, name):
     import eegan_b200 as E
     g = load_golden(name)
     kw, c = gag_inputs(g)
@@ -142,7 +150,7 @@ def test_gag_vs_reference_fixture(cuda_lib, name):
     assert relmax(v.grad.cpu(), g["d_value"]) <= TOL_GRAD
 
 
-def test_gag_intended_mask_mode_and_big_shape(cuda_lib):
+def test_gag_intended_mask_mode_and_big_shape(cuda_lib, gag_engine):
     import eegan_b200 as E
     c = cases.gag_case(4, 64, 64, 18, seed=9)  # Q = 4096 pixels
     mod = E.GlobalAttentionGeneral(64, 256, mask_mode="intended")
@@ -150,6 +158,33 @@ def test_gag_intended_mask_mode_and_big_shape(cuda_lib):
     out, attn = mod(c["x"].cuda(), c["key"].cuda(), c["value"].cuda())
     oo, oa = O.port_global_attention(c["x"], c["key"], c["value"], c["mask"], "intended")
     assert relmax(out.cpu(), oo) <= 1e-5 and float((attn.cpu() - oa).abs().max()) <= TOL_ATT
+
+
+@pytest.mark.parametrize("B,idf,H,T", [(3, 256, 16, 20), (2, 48, 12, 7), (5, 32, 23, 18)])
+def test_gag_tensor_core_forward_shapes(cuda_lib, B, idf, H, T):
+    """The tcgen05 forward at its shape edges: idf = 256 (two TMEM x stages, 256 accumulator columns), idf = 48
+    (K tail zero-filled by TMA, 16-column tail of the accumulator), Q = 529 (not a multiple of the 128-pixel
+    tile; Q % 4 != 0 falls back to the CUDA-core kernel, which must agree too), quirk mask mode."""
+    import eegan_b200 as E
+    c = cases.gag_case(B, idf, H, T, seed=B + idf)
+    res = {}
+    try:
+        for eng in (0, 1):
+            cuda_lib.eegan_set_gag_engine(eng)
+            mod = E.GlobalAttentionGeneral(idf, 256)
+            mod.applyMask(c["mask"].cuda())
+            res[eng] = mod(c["x"].cuda(), c["key"].cuda(), c["value"].cuda())
+    finally:
+        cuda_lib.eegan_set_gag_engine(0)
+    # float64 oracle: with K = idf up to 256 an fp32 reference carries ~1e-6 of its own rounding in a probability near 1
+    oo, oa = O.port_global_attention(c["x"].double(), c["key"].double(), c["value"].double(), c["mask"], "reference")
+    for eng in (0, 1):
+        out, attn = res[eng]
+        ok = torch.isfinite(oa)  # fully masked rows are NaN in the reference (softmax of all -inf) and here
+        assert torch.equal(torch.isnan(attn.cpu()), torch.isnan(oa))
+        assert float((attn.cpu().double()[ok] - oa[ok]).abs().max()) <= 2.5e-6, eng
+        okr = torch.isfinite(oo)
+        assert float((out.cpu().double()[okr] - oo[okr]).abs().max()) <= 1e-5 * float(oo[okr].abs().max()), eng
 
 
 @pytest.mark.parametrize("name", golden_names("words_")[:3])

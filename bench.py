@@ -256,6 +256,45 @@ def syncbn_extra(dev, flush, hbm_gbs):
     return out
 
 
+def ssa_extra(dev, flush, hbm_gbs):
+    """Fused affine_ssa (models.py:43-86: SyncBN(affine=False) + mask-gated modulation) fwd+bwd, single replica,
+    at generator shapes (B=32), next to the reference's own op sequence run eagerly by torch on the same GPU.
+    Bytes counted: the 8 full-tensor passes the fused kernels make (fwd: stats read, apply read + write;
+    bwd: reduce reads x, dy; apply reads x, dy, writes dx); the reference sequence makes ~19."""
+    import eegan_b200 as E
+    from eegan_b200.sync_batchnorm import SynchronizedBatchNorm2d
+    out = []
+    for C, hw in ((256, 16), (64, 128), (32, 256)):
+        x = torch.randn(32, C, hw, hw, device=dev).requires_grad_()
+        w = (torch.randn(32, C, device=dev) * 0.3).requires_grad_()
+        b = (torch.randn(32, C, device=dev) * 0.3).requires_grad_()
+        m = torch.sigmoid(torch.randn(32, 1, hw, hw, device=dev)).requires_grad_()
+        gy = torch.randn_like(x)
+        norm = SynchronizedBatchNorm2d(C, affine=False).to(dev)
+
+        def fwd_bwd():
+            x.grad = w.grad = b.grad = m.grad = None
+            E.ssa_modulate(x, w, b, m, norm).backward(gy)
+
+        def torch_seq():  # models.py:69-86 as written, with torch's own batch norm
+            x.grad = w.grad = b.grad = m.grad = None
+            f = torch.nn.functional.batch_norm(x, None, None, None, None, True, 0.1, 1e-5)
+            ww = w.unsqueeze(-1).unsqueeze(-1).expand(f.size()) * m + 1
+            bb = b.unsqueeze(-1).unsqueeze(-1).expand(f.size()) * m
+            (ww * f + bb).backward(gy)
+
+        for _ in range(3):
+            fwd_bwd()
+            torch_seq()
+        ms = _time_cuda(fwd_bwd, 10, flush)
+        ms_t = _time_cuda(torch_seq, 10, flush)
+        by = 8 * x.numel() * 4
+        out.append({"shape": [32, C, hw, hw], "ms_fwd_bwd": ms, "hbm_gbs": by / (ms / 1e3) / 1e9,
+                    "hbm_frac": by / (ms / 1e3) / 1e9 / hbm_gbs, "ms_torch_eager_same_gpu": ms_t})
+        del x, gy, w, b, m
+    return out
+
+
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
@@ -482,7 +521,8 @@ def run_ours(args):
     if world == 1:
         if not args.no_extra:
             line["extra"] = {"global_attention_general": gag_extra(dev, flush, pk["hbm_gbs"]),
-                             "sync_batchnorm_1replica": syncbn_extra(dev, flush, pk["hbm_gbs"])}
+                             "sync_batchnorm_1replica": syncbn_extra(dev, flush, pk["hbm_gbs"]),
+                             "affine_ssa_1replica": ssa_extra(dev, flush, pk["hbm_gbs"])}
         base, _, _ = cpu_arm(args.steps, 1)
         line["cpu_baseline"] = base
     print(json.dumps(line))

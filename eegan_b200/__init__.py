@@ -16,6 +16,7 @@ from . import damsm_losses  # noqa: F401
 from .damsm_losses import (GlobalAttentionGeneral, cosine_similarity, func_attention, sent_loss,  # noqa: F401
                            sent_similarity, words_loss, words_similarity)
 from .evaluation import r_precision  # noqa: F401
+from .ssa import affine_ssa, ssa_modulate  # noqa: F401
 
 __version__ = "0.1.0"
 

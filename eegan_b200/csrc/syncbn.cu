@@ -3,6 +3,8 @@
 // x**2) and a third to normalise; here the statistics are one fused pass, the cross-replica
 // reduction is an NCCL all-reduce of the 2*C floats issued by the host between these calls,
 // and normalise / backward are single streaming passes.  x is [N, C, HW] contiguous.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace eegan {
@@ -221,5 +223,187 @@ extern "C" int eegan_syncbn_bwd_apply(const float* x, const float* dy, const flo
     bn_apply_kernel<1><<<apply_grid(N, C, HW), BN_THREADS, 0, (cudaStream_t)stream>>>(
         x, dy, mean, inv_std, weight, nullptr, red, (float)count, count_dev, clamp_mode, 1.0f / sqrtf(eps), C, HW, dx);
     EEGAN_LAUNCH_CHECK("syncbn bwd_apply");
+    return EEGAN_OK;
+}
+
+// =======================================================================================
+// affine_ssa (models.py:43-86): SyncBN(affine=False) followed by the mask-gated modulation
+//   out = (gamma[n,c] * mask[n,hw] + 1) * xhat + beta[n,c] * mask[n,hw]
+// The reference normalises (three passes), expands gamma / beta to the full tensor and runs four
+// more elementwise passes; here the modulation rides on the normalise pass, and the backward is
+// the two passes batch norm needs anyway (one reduction, one apply) with d_gamma, d_beta and
+// d_mask produced by the reduction pass.  SURVEY.md §8f rank 3.
+// =======================================================================================
+namespace eegan {
+
+// MODE 0: y = (g m + 1) xhat + b m ;  MODE 1: dx = inv_std * (dxh - r0 - xhat r1), dxh = dy (g m + 1)
+template <int MODE>
+__global__ void __launch_bounds__(BN_THREADS) ssa_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ inv_std,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta,
+                                                               const float* __restrict__ mask,
+                                                               const float* __restrict__ red, float host_count,
+                                                               const float* __restrict__ count_dev, int kill_var_term,
+                                                               float clamp_inv_std, int C, int HW,
+                                                               float* __restrict__ out) {
+    const int nc = blockIdx.y;  // n*C + c
+    const int n = nc / C, c = nc - n * C;
+    const float mu = mean[c], is = inv_std[c];
+    const float g = gamma[nc], b = MODE == 0 ? beta[nc] : 0.f;
+    float r0 = 0.f, r1 = 0.f;
+    if (MODE == 1 && red) {
+        const float inv_count = 1.0f / dev_count(count_dev, host_count);
+        r0 = red[c] * inv_count;
+        r1 = (kill_var_term && is >= clamp_inv_std) ? 0.f : red[C + c] * inv_count;
+    }
+    const size_t base = (size_t)nc * HW;
+    const float* mrow = mask + (size_t)n * HW;
+    const bool vec = (HW % 4 == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                                         reinterpret_cast<uintptr_t>(mask) |
+                                         (MODE == 1 ? reinterpret_cast<uintptr_t>(dy) : 0)) & 15) == 0);
+    if (vec) {
+        const int hw4 = HW / 4;
+        for (int k = blockIdx.x * BN_THREADS + threadIdx.x; k < hw4; k += gridDim.x * BN_THREADS) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + base + (size_t)k * 4);
+            const float4 mv = *reinterpret_cast<const float4*>(mrow + (size_t)k * 4);
+            float4 o;
+            if (MODE == 0) {
+                o.x = fmaf(fmaf(g, mv.x, 1.f), (xv.x - mu) * is, b * mv.x); o.y = fmaf(fmaf(g, mv.y, 1.f), (xv.y - mu) * is, b * mv.y);
+                o.z = fmaf(fmaf(g, mv.z, 1.f), (xv.z - mu) * is, b * mv.z); o.w = fmaf(fmaf(g, mv.w, 1.f), (xv.w - mu) * is, b * mv.w);
+            } else {
+                const float4 gv = *reinterpret_cast<const float4*>(dy + base + (size_t)k * 4);
+                o.x = is * (gv.x * fmaf(g, mv.x, 1.f) - r0 - (xv.x - mu) * is * r1);
+                o.y = is * (gv.y * fmaf(g, mv.y, 1.f) - r0 - (xv.y - mu) * is * r1);
+                o.z = is * (gv.z * fmaf(g, mv.z, 1.f) - r0 - (xv.z - mu) * is * r1);
+                o.w = is * (gv.w * fmaf(g, mv.w, 1.f) - r0 - (xv.w - mu) * is * r1);
+            }
+            *reinterpret_cast<float4*>(out + base + (size_t)k * 4) = o;
+        }
+    } else {
+        for (int k = blockIdx.x * BN_THREADS + threadIdx.x; k < HW; k += gridDim.x * BN_THREADS) {
+            const float xh = (x[base + k] - mu) * is, m = mrow[k];
+            out[base + k] = (MODE == 0) ? fmaf(fmaf(g, m, 1.f), xh, b * m) : is * (dy[base + k] * fmaf(g, m, 1.f) - r0 - xh * r1);
+        }
+    }
+}
+
+// Backward reduction.  CTA = (sample n, tile of 1024 pixels), thread = 4 pixels, loop over channels:
+//   dxh = dy (g m + 1);  per (n, c): S0 = sum dxh, S1 = sum dxh xhat, S2 = sum dy xhat m (d_gamma), S3 = sum dy m (d_beta);
+//   per pixel: d_mask = sum_c dy (g xhat + b)      (each pixel has one owner thread: no atomics)
+// The per-warp parts of S0..S3 for every channel wait in shared memory; after the channel loop the CTA adds
+// them up and issues 4 C atomics (red[c], red[C+c] across samples and tiles; d_gamma / d_beta across tiles).
+__global__ void __launch_bounds__(BN_THREADS) ssa_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ inv_std,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta,
+                                                                    const float* __restrict__ mask, int C, int HW,
+                                                                    float* __restrict__ red, float* __restrict__ dgamma,
+                                                                    float* __restrict__ dbeta, float* __restrict__ dmask) {
+    extern __shared__ float s_part[];  // [C][8 warps][4]
+    const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p0 = blockIdx.x * (BN_THREADS * 4) + threadIdx.x * 4;
+    const bool vec = (HW % 4 == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
+                                         reinterpret_cast<uintptr_t>(mask)) & 15) == 0);
+    float m[4], dm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = (p0 + k < HW) ? mask[(size_t)n * HW + p0 + k] : 0.f;
+    auto load4 = [&](const float* src, float (&v)[4]) {
+        if (vec && p0 + 3 < HW) {
+            const float4 t = *reinterpret_cast<const float4*>(src + p0);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (p0 + k < HW) ? src[p0 + k] : 0.f;
+        }
+    };
+#pragma unroll 2
+    for (int c = 0; c < C; ++c) {
+        const size_t base = ((size_t)n * C + c) * HW;
+        float xv[4], gv[4];
+        load4(x + base, xv);
+        load4(dy + base, gv);
+        const float mu = __ldg(mean + c), is = __ldg(inv_std + c), g = __ldg(gamma + (size_t)n * C + c), b = __ldg(beta + (size_t)n * C + c);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float xh = (p0 + k < HW) ? (xv[k] - mu) * is : 0.f;
+            const float dxh = gv[k] * fmaf(g, m[k], 1.f);
+            s0 += dxh;
+            s1 = fmaf(dxh, xh, s1);
+            s2 = fmaf(gv[k] * xh, m[k], s2);
+            s3 = fmaf(gv[k], m[k], s3);
+            dm[k] = fmaf(gv[k], fmaf(g, xh, b), dm[k]);
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        if (lane == 0) *reinterpret_cast<float4*>(s_part + ((size_t)c * 8 + warp) * 4) = make_float4(s0, s1, s2, s3);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (p0 + k < HW) dmask[(size_t)n * HW + p0 + k] = dm[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float4 o = *reinterpret_cast<const float4*>(s_part + ((size_t)c * 8 + w) * 4);
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        }
+        atomicAdd(red + c, t.x);
+        atomicAdd(red + C + c, t.y);
+        atomicAdd(dgamma + (size_t)n * C + c, t.z);
+        atomicAdd(dbeta + (size_t)n * C + c, t.w);
+    }
+}
+
+}  // namespace eegan
+
+extern "C" int eegan_ssa_apply(const float* x, const float* mean, const float* inv_std, const float* gamma, const float* beta,
+                               const float* mask, int N, int C, int HW, float* y, void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && mean && inv_std && gamma && beta && mask && y, "ssa apply: null pointer");
+    ssa_apply_kernel<0><<<apply_grid(N, C, HW), BN_THREADS, 0, (cudaStream_t)stream>>>(x, nullptr, mean, inv_std, gamma, beta, mask, nullptr,
+                                                                                       1.f, nullptr, 0, 0.f, C, HW, y);
+    EEGAN_LAUNCH_CHECK("ssa apply");
+    return EEGAN_OK;
+}
+
+extern "C" int eegan_ssa_bwd_reduce(const float* x, const float* dy, const float* mean, const float* inv_std, const float* gamma,
+                                    const float* beta, const float* mask, int N, int C, int HW, float* red, float* dgamma,
+                                    float* dbeta, float* dmask, void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && dy && mean && inv_std && gamma && beta && mask && red && dgamma && dbeta && dmask, "ssa bwd_reduce: null pointer");
+    EEGAN_REQUIRE(C <= 1536 && N <= 65535, "ssa bwd_reduce: C=%d (<=1536) N=%d (<=65535) unsupported", C, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(red, 0, 2 * (size_t)C * sizeof(float), st);
+    cudaMemsetAsync(dgamma, 0, (size_t)N * C * sizeof(float), st);
+    cudaMemsetAsync(dbeta, 0, (size_t)N * C * sizeof(float), st);
+    const size_t smem = (size_t)C * 8 * 4 * sizeof(float);
+    static std::atomic<size_t> granted{48 * 1024};
+    if (smem > granted.load()) {
+        cudaError_t e = cudaFuncSetAttribute(ssa_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("ssa bwd_reduce smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+        granted.store(smem);
+    }
+    ssa_bwd_reduce_kernel<<<dim3((HW + BN_THREADS * 4 - 1) / (BN_THREADS * 4), N), BN_THREADS, smem, st>>>(
+        x, dy, mean, inv_std, gamma, beta, mask, C, HW, red, dgamma, dbeta, dmask);
+    EEGAN_LAUNCH_CHECK("ssa bwd_reduce");
+    return EEGAN_OK;
+}
+
+extern "C" int eegan_ssa_bwd_apply(const float* x, const float* dy, const float* mean, const float* inv_std, const float* gamma,
+                                   const float* mask, const float* red, double count, const float* count_dev, float eps,
+                                   int clamp_mode, int N, int C, int HW, float* dx, void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && dy && mean && inv_std && gamma && mask && dx, "ssa bwd_apply: null pointer");
+    EEGAN_REQUIRE(!red || count_dev || count > 0, "ssa bwd_apply: element count missing");
+    ssa_apply_kernel<1><<<apply_grid(N, C, HW), BN_THREADS, 0, (cudaStream_t)stream>>>(
+        x, dy, mean, inv_std, gamma, nullptr, mask, red, (float)count, count_dev, clamp_mode, 1.0f / sqrtf(eps), C, HW, dx);
+    EEGAN_LAUNCH_CHECK("ssa bwd_apply");
     return EEGAN_OK;
 }

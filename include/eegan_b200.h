@@ -206,6 +206,26 @@ int eegan_set_contraction_engine(int engine);
 int eegan_get_contraction_engine(void);
 
 /* ------------------------------------------------------------------------------------
+ * affine_ssa — models.py:43-86: SyncBN(affine=False) + mask-gated modulation
+ *   out[n,c,hw] = (gamma[n,c] * mask[n,hw] + 1) * xhat[n,c,hw] + beta[n,c] * mask[n,hw]     (:84-86)
+ * with xhat = (x - mean[c]) * inv_std[c] from eegan_syncbn_stats / _finalize (models.py:69).
+ * x, y, dy, dx [N,C,HW]; gamma, beta, dgamma, dbeta [N,C]; mask, dmask [N,HW]; mean, inv_std [C].
+ * bwd_reduce writes red [2C] = {sum dxh, sum dxh*xhat} (dxh = dy*(gamma*mask+1); all-reduce it across
+ * replicas before bwd_apply, as for eegan_syncbn_bwd_reduce) and the complete d_gamma, d_beta, d_mask.
+ * bwd_apply: dx = inv_std * (dxh - red[c]/count - xhat * red[C+c]/count); red == NULL = statistics were
+ * constants (eval mode): dx = inv_std * dxh.
+ * ---------------------------------------------------------------------------------- */
+int eegan_ssa_apply(const float* x, const float* mean, const float* inv_std, const float* gamma,
+                    const float* beta, const float* mask, int N, int C, int HW, float* y, void* stream);
+int eegan_ssa_bwd_reduce(const float* x, const float* dy, const float* mean, const float* inv_std,
+                         const float* gamma, const float* beta, const float* mask, int N, int C, int HW,
+                         float* red, float* dgamma, float* dbeta, float* dmask, void* stream);
+int eegan_ssa_bwd_apply(const float* x, const float* dy, const float* mean, const float* inv_std,
+                        const float* gamma, const float* mask, const float* red, double count,
+                        const float* count_dev, float eps, int clamp_mode, int N, int C, int HW,
+                        float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * The tensor-core contraction engine on its own (tests / microbenchmarks):
  *   C[z][m][n] = sum_k A[z](m,k) * B[z](n,k), fp32 in / fp32 out, computed as fp32-accurate
  *   3xTF32 on tcgen05 (hi/lo operand split, three MMAs per K-step, fp32 accumulators in TMEM).

@@ -292,3 +292,20 @@ def port_rprecision(cnn_code, rnn_codes, eps=1e-8):
         best.append(am)
         rows.append(scores0[0])
     return torch.tensor(hits), torch.tensor(best), torch.stack(rows)
+
+
+def port_affine_ssa(feat, weight, bias, semi_mask, eps=1e-5, n_replica_formula=False):
+    """models.py:68-86 (affine_ssa.forward) after its two MLPs: ``weight`` / ``bias`` are the outputs
+    of fc_gamma / fc_beta [N,C].  norm2d is SyncBN(affine=False) in training mode: batch statistics
+    over (N,H,W); a single replica goes through F.batch_norm (sync_batchnorm/batchnorm.py:50-53,
+    1/sqrt(var+eps)), several replicas through the clamp formula (:113-125)."""
+    mean = feat.mean(dim=(0, 2, 3), keepdim=True)
+    var = ((feat - mean) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+    inv_std = var.clamp(min=eps) ** -0.5 if n_replica_formula else (var + eps) ** -0.5
+    xhat = (feat - mean) * inv_std  # :69
+    size = xhat.size()
+    w = weight.unsqueeze(-1).unsqueeze(-1).expand(size)  # :79-81
+    b = bias.unsqueeze(-1).unsqueeze(-1).expand(size)
+    w = w * semi_mask + 1  # :84
+    b = b * semi_mask  # :85
+    return w * xhat + b  # :86

@@ -80,6 +80,23 @@ def main():
     yr.backward(go_full.to(dev))
     assert float((y.detach() - yr.detach()[4 * rank:4 * rank + 4]).abs().max()) <= 2e-5
     assert relmax(xs.grad, xr.grad[4 * rank:4 * rank + 4]) <= 1e-4
+    # fused affine_ssa over NCCL vs the N-replica restatement on the full batch
+    from oracle import damsm_oracle as O
+    norm = SynchronizedBatchNorm2d(32, affine=False).to(dev)
+    norm.train()
+    wf = torch.randn(4 * world, 32, generator=g) * 0.5
+    bf = torch.randn(4 * world, 32, generator=g) * 0.5
+    mf = torch.sigmoid(torch.randn(4 * world, 1, 16, 16, generator=g))
+    sl4 = slice(4 * rank, 4 * rank + 4)
+    ts = [v[sl4].to(dev).requires_grad_() for v in (x_full, wf, bf, mf)]
+    ys = E.ssa_modulate(ts[0], ts[1], ts[2], ts[3], norm)
+    ys.backward(go_full[sl4].to(dev))
+    tf = [v.to(dev).double().requires_grad_() for v in (x_full, wf, bf, mf)]
+    yf = O.port_affine_ssa(tf[0], tf[1], tf[2], tf[3], eps=norm.eps, n_replica_formula=True)
+    yf.backward(go_full.to(dev).double())
+    assert float((ys.detach().double() - yf.detach()[sl4]).abs().max()) <= 5e-5
+    for a, b_ in zip(ts, tf):
+        assert relmax(a.grad.double(), b_.grad[sl4]) <= 1e-4
     dist.barrier()
     if rank == 0:
         print("multigpu_check ok: world %d, words %.6f/%.6f sent %.6f/%.6f" % (world, s0.item(), s1.item(), h0.item(), h1.item()))

@@ -1,0 +1,71 @@
+"""GPU: the fused affine_ssa modulation (models.py:43-86; eegan_ssa_*) against the float64 restatement
+(oracle.port_affine_ssa, pinned to the live reference in tests/test_oracle_vs_reference.py): output and
+all four gradients (feat, gamma, beta, mask), training and eval mode, vectorised and odd spatial sizes."""
+import pytest
+import torch
+
+from helpers import relmax
+from oracle import cases
+from oracle import damsm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(N, C, H, seed):
+    g = cases._gen(seed)
+    feat = torch.randn(N, C, H, H, generator=g) * 1.7 + 0.4
+    weight = torch.randn(N, C, generator=g) * 0.5
+    bias = torch.randn(N, C, generator=g) * 0.5
+    mask = torch.sigmoid(torch.randn(N, 1, H, H, generator=g))
+    go = torch.randn(N, C, H, H, generator=g)
+    return feat, weight, bias, mask, go
+
+
+@pytest.mark.parametrize("N,C,H", [(4, 32, 16), (3, 100, 7), (2, 256, 4), (2, 64, 33)])
+def test_ssa_modulate_training_matches_oracle(cuda_lib, N, C, H):
+    import eegan_b200 as E
+    from eegan_b200.sync_batchnorm import SynchronizedBatchNorm2d
+    feat, weight, bias, mask, go = _inputs(N, C, H, 100 * N + C + H)
+    norm = SynchronizedBatchNorm2d(C, affine=False).cuda().train()
+    t = [v.cuda().requires_grad_() for v in (feat, weight, bias, mask)]
+    y = E.ssa_modulate(t[0], t[1], t[2], t[3], norm)
+    y.backward(go.cuda())
+    o = [v.double().requires_grad_() for v in (feat, weight, bias, mask)]
+    yo = O.port_affine_ssa(o[0], o[1], o[2], o[3], eps=norm.eps)
+    yo.backward(go.double())
+    assert float((y.detach().cpu().double() - yo.detach()).abs().max()) <= 2e-5
+    for a, b, name in zip(t, o, ("feat", "gamma", "beta", "mask")):
+        assert relmax(a.grad.cpu().double(), b.grad) <= 2e-5, name
+    # running statistics follow F.batch_norm (momentum 0.1, unbiased variance)
+    mean = feat.double().mean(dim=(0, 2, 3))
+    var_unb = feat.double().transpose(0, 1).reshape(C, -1).var(dim=1, unbiased=True)
+    assert float((norm.running_mean.cpu().double() - 0.1 * mean).abs().max()) <= 1e-5
+    assert float((norm.running_var.cpu().double() - (0.9 + 0.1 * var_unb)).abs().max()) <= 1e-4
+
+
+def test_affine_ssa_module_eval_and_grad(cuda_lib):
+    """Eval mode uses the running statistics as constants (batchnorm.py:50-53); gradients still flow."""
+    import eegan_b200 as E
+    N, C, H = 3, 48, 8
+    feat, _, _, mask, go = _inputs(N, C, H, 7)
+    mod = E.affine_ssa(C, ntf=32).cuda()
+    for p in mod.parameters():
+        torch.nn.init.normal_(p, std=0.2)
+    mod.norm2d.running_mean.normal_(0.2, 0.5)
+    mod.norm2d.running_var.uniform_(0.5, 2.0)
+    mod.eval()
+    cond = torch.randn(N, 32, generator=cases._gen(8)).cuda()
+    x = feat.cuda().requires_grad_()
+    m = mask.cuda().requires_grad_()
+    y = mod(x, cond, m)
+    y.backward(go.cuda())
+    rm, rv = mod.norm2d.running_mean.double().cpu(), mod.norm2d.running_var.double().cpu()
+    xo, mo = feat.double().requires_grad_(), mask.double().requires_grad_()
+    w = mod.fc_gamma(cond).detach().cpu().double()
+    b = mod.fc_beta(cond).detach().cpu().double()
+    xhat = (xo - rm.view(1, -1, 1, 1)) * (rv.view(1, -1, 1, 1) + mod.norm2d.eps) ** -0.5
+    yo = (w[:, :, None, None] * mo + 1) * xhat + b[:, :, None, None] * mo
+    yo.backward(go.double())
+    assert float((y.detach().cpu().double() - yo.detach()).abs().max()) <= 2e-5
+    assert relmax(x.grad.cpu().double(), xo.grad) <= 2e-5 and relmax(m.grad.cpu().double(), mo.grad) <= 2e-5
+    assert mod.fc_gamma.linear2.weight.grad is not None and mod.fc_beta.linear1.weight.grad is not None

@@ -38,3 +38,28 @@ def test_sent_and_gag_bit_exact():
     ro, ra = mod(g["x"], g["key"], g["value"])
     po, pa = O.port_global_attention(g["x"], g["key"], g["value"], g["mask"])
     assert torch.equal(ro, po) and torch.equal(ra, pa)
+
+
+def test_affine_ssa_port_and_state_dict_match_reference():
+    """models.py:43-86 run live (single replica, training mode) against the restatement, and the drop-in
+    module's parameter / buffer names against the reference's state_dict."""
+    import importlib
+    load_reference()
+    with __import__("warnings").catch_warnings():
+        __import__("warnings").simplefilter("ignore")
+        models = importlib.import_module("models")
+    torch.manual_seed(3)
+    ref = models.affine_ssa(8, ntf=16)
+    for p in ref.parameters():
+        torch.nn.init.normal_(p, std=0.3)
+    ref.train()
+    feat = torch.randn(4, 8, 5, 5) * 1.5 + 0.3
+    cond = torch.randn(4, 16)
+    mask = torch.sigmoid(torch.randn(4, 1, 5, 5))
+    out = ref(feat, cond, mask)
+    port = O.port_affine_ssa(feat, ref.fc_gamma(cond), ref.fc_beta(cond), mask, eps=ref.norm2d.eps)
+    assert float((out - port).abs().max()) <= 2e-6
+    import eegan_b200.ssa as ssa
+    ours = ssa.affine_ssa(8, ntf=16)
+    assert set(ours.state_dict().keys()) == set(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())

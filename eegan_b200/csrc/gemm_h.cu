@@ -1,0 +1,699 @@
+// tcgen05 3xFP16 GEMM on pre-split half operands — see gemm_h.cuh for the design.
+#include <stdlib.h>
+
+#include "gemm_h.cuh"
+#include "ptx.cuh"
+#include "tc_device.cuh"
+
+namespace eegan {
+
+struct HMaps {
+    CUtensorMap m[2][2][2];  // [segment][0 = A, 1 = B][0 = hi, 1 = lo]
+};
+
+struct HArgs {
+    float* C;
+    long long ldc, bC;
+    int M, N;
+    const int* dynM;
+    const int* dynN;
+    const int* dynK;
+    int K[2];
+    int nseg, nred, red_total, batch;
+    int a_batched[2], b_batched[2];
+    const float* inv_a[2];
+    const float* inv_b[2];
+    HAttnEpi attn;
+};
+
+template <int EPI, bool DUAL>
+struct HCfg {
+    static constexpr bool kAttn = EPI != TC_EPI_PLAIN;
+    static constexpr int kEWarps = kAttn ? 8 : 4;  // epilogue warps (two per TMEM lane quarter in the attention forms)
+    static constexpr int kStages = kAttn ? 4 : 6;
+    static constexpr int kThreads = 32 * (2 + kEWarps);
+    static constexpr int kEpiPitch = kAttn ? TC_EPI_PITCH : 33;
+    static constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4;
+    static constexpr int kSmem = kStages * H_STAGE_BYTES + kEWarps * (kEpiWarpBytes + 256) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kAccStride = DUAL ? 2 * H_BN : H_BN;  // TMEM columns between the two accumulator buffers
+};
+static_assert(HCfg<TC_EPI_PLAIN, false>::kSmem <= 232448 && HCfg<TC_EPI_ATTN_FWD, false>::kSmem <= 232448, "shared memory budget");
+
+__device__ __forceinline__ void h_mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Shared-memory descriptors (version 1 = Blackwell) of the two canonical layouts the TMA boxes land in:
+//   A, MN-major, SWIZZLE_128B: box = [32 k][64 rows] halves = 32 rows of 128 B; 8-k groups 1024 B apart (SBO),
+//      the second 64-row chunk of the 128-row tile is the next box, 4096 B on (LBO); a K-step of 16 = 2048 B.
+//   B, K-major, SWIZZLE_64B: box = [128 rows][32 k] halves = rows of 64 B; 8-row groups 512 B apart (SBO);
+//      a K-step of 16 halves advances the start address by 32 B inside the swizzle row.
+__device__ __forceinline__ uint64_t h_desc_a(uint32_t tile, int kstep) {
+    const uint32_t start = tile + (uint32_t)kstep * 2048u;
+    uint64_t d = (uint64_t)((start & 0x3FFFF) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint64_t h_desc_b(uint32_t tile, int kstep) {
+    const uint32_t start = tile + (uint32_t)kstep * 32u;
+    uint64_t d = (uint64_t)((start & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------
+// epilogues (one call = one output tile for one epilogue warp); same structure as tc_device.cuh,
+// plus the power-of-two descale of the accumulator and half-pair outputs
+// ---------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void h_attn_fwd_caption(const uint32_t (&vr)[32], int T, uint32_t cap_row, float inv) {
+    float x[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) x[q] = (q < NV - 3 || q < T) ? __uint_as_float(vr[q]) * inv : -INFINITY;
+    float m4[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+    for (int q = 4; q < NV; ++q) m4[q & 3] = fmaxf(m4[q & 3], x[q]);
+    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        x[q] = fast_exp(x[q] - mx);
+        s4[q & 3] += x[q];
+    }
+    const float invs = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+        if (q < NV - 3 || q < T) sts_f32(cap_row + (uint32_t)q * 4u, x[q] * invs);
+}
+
+// dS = v - P sum_t v,  v = g1 P E (acc - csz),  E = exp(g1 (P - 1))
+template <int NV>
+__device__ __forceinline__ void h_attn_bwd_caption(const uint32_t (&vr)[32], int T, uint32_t cap_row, uint32_t cz_row, float g1,
+                                                   float inv) {
+    float pv[NV], vv[NV];
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const bool ok = (q < NV - 3 || q < T);
+        pv[q] = ok ? lds_f32(cap_row + (uint32_t)q * 4u) : 0.f;
+        const float cz = lds_f32(cz_row + (uint32_t)q * 4u);
+        const float ev = fast_exp(g1 * (pv[q] - 1.0f));
+        const float t = g1 * pv[q] * ev * (__uint_as_float(vr[q]) * inv - cz);
+        vv[q] = ok ? t : 0.f;
+        s4[q & 3] += vv[q];
+    }
+    const float qs = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+        if (q < NV - 3 || q < T) sts_f32(cap_row + (uint32_t)q * 4u, vv[q] - pv[q] * qs);
+}
+
+template <int EPI>
+__device__ __forceinline__ void h_attn_caption(uint32_t taddr, int T, uint32_t cap_row, uint32_t cz_row, float g1, float inv) {
+    uint32_t vr[32];
+    const int bucket = (T + 3) >> 2;  // 1..8, warp-uniform
+    if (bucket <= 2) tmem_ld8(taddr, vr);
+    else if (bucket <= 4) tmem_ld16(taddr, vr);
+    else tmem_ld32(taddr, vr);
+    tmem_ld_wait();
+#define H_CAP(NV)                                                                   \
+    case (NV) / 4:                                                                  \
+        if (EPI == TC_EPI_ATTN_FWD) h_attn_fwd_caption<NV>(vr, T, cap_row, inv);    \
+        else h_attn_bwd_caption<NV>(vr, T, cap_row, cz_row, g1, inv);               \
+        break;
+    switch (bucket) {
+        H_CAP(4) H_CAP(8) H_CAP(12) H_CAP(16) H_CAP(20) H_CAP(24) H_CAP(28) H_CAP(32)
+        default: break;
+    }
+#undef H_CAP
+}
+
+template <int EPI, bool DUAL>
+__device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t, int lane, float inv0, float inv1) {
+    using Cfg = HCfg<EPI, DUAL>;
+    float* Cz = p.C + (long long)t.z * p.bC;
+    const int row0 = t.m0 + t.quarter * 32;
+    const int rows_live = max(0, min(32, t.Mlive - row0));
+    if (EPI == TC_EPI_PLAIN) {
+        mbar_wait(t.full_bar, t.full_parity);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < H_BN / 32; ++c) {
+            float v[32];
+            if (t.total > 0) {
+                uint32_t r0[32];
+                tmem_ld32(t.tacc + (uint32_t)(c * 32), r0);
+                if (DUAL) {
+                    uint32_t r1[32];
+                    tmem_ld32(t.tacc + (uint32_t)(H_BN + c * 32), r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = fmaf(__uint_as_float(r1[q]), inv1, __uint_as_float(r0[q]) * inv0);
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r0[q]) * inv0;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = 0.f;
+            }
+            if (c == H_BN / 32 - 1) {  // accumulator read: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t.empty_bar);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) sts_f32(t.stage + (uint32_t)(lane * 33 + q) * 4u, v[q]);
+            __syncwarp();
+            const int gn = t.n0 + c * 32 + lane;
+            if (gn < t.Nlive) {
+                float* dst = Cz + (long long)row0 * p.ldc + gn;
+#pragma unroll 1
+                for (int r8 = 0; r8 < rows_live; r8 += 8) {
+                    float a[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) a[q] = lds_f32(t.stage + (uint32_t)((r8 + q) * 33 + lane) * 4u);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (r8 + q < rows_live) dst[(long long)(r8 + q) * p.ldc] = a[q];
+                }
+            }
+        }
+        return;
+    }
+    // ---- word-region attention on the accumulator: thread = region (TMEM lane), columns = packed words ----
+    const TcAttnEpi& e = p.attn.base;
+    const int nbins = *e.nbins;
+    const uint32_t my_row = t.stage + (uint32_t)(lane * TC_EPI_PITCH) * 4u;
+    float* Pz = e.P + (long long)t.z * p.bC;
+    __half* Hz = p.attn.out_hi + (long long)t.z * p.bC;
+    __half* Lz = p.attn.out_lo + (long long)t.z * p.bC;
+    const float oscale = EPI == TC_EPI_ATTN_FWD ? H_E_SCALE : *p.attn.out_scale;
+    const int b0 = t.n0 >> 6;
+    const int bc_l = e.bin_cap[min(b0 + lane, nbins)];
+    const int bu_l = (lane < 2 && b0 + lane < nbins) ? e.bin_used[b0 + lane] : 0;
+    auto load_p_bin = [&](int col0) {
+#pragma unroll 1
+        for (int r8 = 0; r8 < rows_live; r8 += 8) {
+            float a0[8], a1[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int rr = min(r8 + q, rows_live - 1);
+                const float* src = Pz + (long long)(row0 + rr) * p.ldc + col0 + lane;
+                a0[q] = __ldg(src);
+                a1[q] = __ldg(src + 32);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                sts_f32(t.stage + (uint32_t)((r8 + q) * TC_EPI_PITCH + lane) * 4u, a0[q]);
+                sts_f32(t.stage + (uint32_t)((r8 + q) * TC_EPI_PITCH + lane + 32) * 4u, a1[q]);
+            }
+        }
+    };
+    __syncwarp();
+    const int h = t.half;  // the 64-column bin of the tile this warp handles
+    const int b = b0 + h;
+    if (b >= nbins) {  // no live bin for this warp in the tile: only keep the accumulator hand-shake going
+        mbar_wait(t.full_bar, t.full_parity);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t.empty_bar);
+        return;
+    }
+    const int i0 = __shfl_sync(0xffffffffu, bc_l, h), i1 = __shfl_sync(0xffffffffu, bc_l, h + 1);
+    const int used = __shfl_sync(0xffffffffu, bu_l, h);
+    const int col0 = t.n0 + 64 * h;
+    const bool c0ok = lane < used, c1ok = lane + 32 < used;
+    if (EPI == TC_EPI_ATTN_BWD) {
+        load_p_bin(col0);
+        sts_f32(t.czs + (uint32_t)lane * 4u, __ldg(e.csz + (long long)t.z * p.ldc + col0 + lane));
+        sts_f32(t.czs + (uint32_t)(lane + 32) * 4u, __ldg(e.csz + (long long)t.z * p.ldc + col0 + lane + 32));
+    }
+    __syncwarp();
+    bool waited = false;
+#pragma unroll 1
+    for (int ic = i0; ic < i1; ic += 32) {
+        const int nc = min(32, i1 - ic);
+        const int myT = lane < nc ? e.cap_len[ic + lane] : 0;
+        const int myC = lane < nc ? e.col_start[ic + lane] - col0 : 0;
+        if (!waited) {
+            mbar_wait(t.full_bar, t.full_parity);
+            tc_fence_after();
+            waited = true;
+        }
+#pragma unroll 1
+        for (int ci = 0; ci < nc; ++ci) {
+            const int T = __shfl_sync(0xffffffffu, myT, ci);
+            if (T <= 0) continue;
+            const int cl = __shfl_sync(0xffffffffu, myC, ci);
+            h_attn_caption<EPI>(t.tacc + (uint32_t)(64 * h + cl), T, my_row + (uint32_t)cl * 4u, t.czs + (uint32_t)cl * 4u, e.g1, inv0);
+        }
+    }
+    if (!waited) {
+        mbar_wait(t.full_bar, t.full_parity);
+        tc_fence_after();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(t.empty_bar);
+    for (int c = used; c < 64; ++c) sts_f32(my_row + (uint32_t)c * 4u, 0.f);  // padding columns of the bin
+    __syncwarp();
+    // read-out: region rows, coalesced, 4 rows per round
+    if (EPI == TC_EPI_ATTN_FWD) {
+        float z0 = 0.f, z1 = 0.f, em = 0.f;
+#pragma unroll 1
+        for (int r4 = 0; r4 < rows_live; r4 += 4) {
+            float p0[4], p1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                p0[q] = lds_f32(t.stage + (uint32_t)((r4 + q) * TC_EPI_PITCH + lane) * 4u);
+                p1[q] = lds_f32(t.stage + (uint32_t)((r4 + q) * TC_EPI_PITCH + lane + 32) * 4u);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (r4 + q < rows_live) {
+                    const float e0 = c0ok ? fast_exp(e.g1 * (p0[q] - 1.0f)) : 0.f;
+                    const float e1 = c1ok ? fast_exp(e.g1 * (p1[q] - 1.0f)) : 0.f;
+                    const long long o = (long long)(row0 + r4 + q) * p.ldc + col0 + lane;
+                    Pz[o] = p0[q];
+                    Pz[o + 32] = p1[q];
+                    __half h0, l0, h1, l1;
+                    h_split(e0 * oscale, h0, l0);
+                    h_split(e1 * oscale, h1, l1);
+                    Hz[o] = h0;
+                    Hz[o + 32] = h1;
+                    Lz[o] = l0;
+                    Lz[o + 32] = l1;
+                    z0 += e0;
+                    z1 += e1;
+                    em = fmaxf(em, fmaxf(e0, e1));
+                }
+            }
+        }
+        float* zp = e.Zpart + ((long long)t.z * ((p.M + 31) / 32) + (row0 >> 5)) * p.ldc + col0 + lane;
+        if (rows_live > 0) {
+            zp[0] = z0;
+            zp[32] = z1;
+        }
+        em = warp_max(em);
+        if (lane == 0 && em > 0.f) atomicMax(reinterpret_cast<int*>(p.attn.emax), __float_as_int(em));
+    } else {
+#pragma unroll 1
+        for (int r4 = 0; r4 < rows_live; r4 += 4) {
+            float d0[4], d1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                d0[q] = lds_f32(t.stage + (uint32_t)((r4 + q) * TC_EPI_PITCH + lane) * 4u);
+                d1[q] = lds_f32(t.stage + (uint32_t)((r4 + q) * TC_EPI_PITCH + lane + 32) * 4u);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (r4 + q < rows_live) {
+                    const long long o = (long long)(row0 + r4 + q) * p.ldc + col0 + lane;
+                    __half h0, l0, h1, l1;
+                    h_split(d0[q] * oscale, h0, l0);
+                    h_split(d1[q] * oscale, h1, l1);
+                    Hz[o] = h0;
+                    Hz[o + 32] = h1;
+                    Lz[o] = l0;
+                    Lz[o + 32] = l1;
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel: persistent CTAs (one per SM) walk 128 x 128 output tiles (n fastest, then m, then batch)
+// ---------------------------------------------------------------------------------------
+template <int EPI, bool DUAL>
+__global__ void __launch_bounds__(HCfg<EPI, DUAL>::kThreads, 1)
+h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
+    using Cfg = HCfg<EPI, DUAL>;
+    constexpr int NS = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Mlive = p.dynM ? min(*p.dynM, p.M) : p.M;
+    const int Nlive = p.dynN ? min(*p.dynN, p.N) : p.N;
+    const int mt = (Mlive + H_BM - 1) / H_BM, nt = (Nlive + H_BN - 1) / H_BN;
+    const int ntiles = mt * nt * p.batch;
+    if ((int)blockIdx.x >= ntiles) return;  // uniform: before any barrier / TMEM state exists
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t epi_stage = base + NS * H_STAGE_BYTES;
+    const uint32_t epi_czs = epi_stage + Cfg::kEWarps * Cfg::kEpiWarpBytes;
+    const uint32_t bars = epi_czs + Cfg::kEWarps * 256u;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (NS + s); };
+    auto tmem_full = [&](int a) { return bars + 8u * (2 * NS + a); };
+    auto tmem_empty = [&](int a) { return bars + 8u * (2 * NS + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * NS + 4);
+
+    int kb0 = 0, kb1 = 0;
+    {
+        const int K0 = p.dynK ? min(*p.dynK, p.K[0]) : p.K[0];
+        kb0 = (K0 + H_BK - 1) / H_BK;
+        if (p.nseg > 1) {
+            const int K1 = p.dynK ? min(*p.dynK, p.K[1]) : p.K[1];
+            kb1 = (K1 + H_BK - 1) / H_BK;
+        }
+    }
+    const int kbt = kb0 + kb1;
+    auto tile_total = [&](int z) {
+        int nred = p.nred;
+        if (p.red_total > 0) nred = max(0, min(p.nred, p.red_total - z * p.nred));
+        return nred * kbt;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), Cfg::kEWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // all 512 columns: the attention epilogues read 32-column windows that may overhang an accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int z = t / (mt * nt), rem_t = t - z * (mt * nt);
+                const int m0 = (rem_t / nt) * H_BM, n0 = (rem_t % nt) * H_BN;
+                const int total = tile_total(z);
+                for (int k = 0; k < total; ++k, ++it) {
+                    const int s = it % NS, ph = (it / NS) & 1;
+                    const int red = k / kbt, rem = k - red * kbt;
+                    const int seg = rem >= kb0 ? 1 : 0;
+                    const int k0 = (seg ? rem - kb0 : rem) * H_BK;
+                    const int zr = z * p.nred + red;
+                    const int zA = p.a_batched[seg] ? zr : 0, zB = p.b_batched[seg] ? zr : 0;
+                    mbar_wait(empty(s), ph ^ 1);
+                    mbar_arrive_expect_tx(full(s), (uint32_t)H_STAGE_BYTES);
+                    const uint32_t sA = base + s * H_STAGE_BYTES, sB = sA + 2 * H_A_TILE;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const CUtensorMap* ta = &tm.m[seg][0][h];
+                        tma_load_3d(sA + h * H_A_TILE, ta, full(s), m0, k0, zA);
+                        tma_load_3d(sA + h * H_A_TILE + 4096, ta, full(s), m0 + 64, k0, zA);
+                        tma_load_3d(sB + h * H_B_TILE, &tm.m[seg][1][h], full(s), k0, n0, zB);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | (1u << 15) /*A MN-major*/ |
+                                       (0u << 16) /*B K-major*/ | ((uint32_t)(H_BN >> 3) << 17) | ((uint32_t)(H_BM >> 4) << 24);
+            int it = 0, ti = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+                const int z = t / (mt * nt);
+                const int total = tile_total(z);
+                const int acc = ti & 1;
+                const uint32_t tmem_d0 = tmem_base + (uint32_t)(acc * Cfg::kAccStride);
+                mbar_wait(tmem_empty(acc), ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int k = 0; k < total; ++k, ++it) {
+                    const int s = it % NS, ph = (it / NS) & 1;
+                    const int rem = k % kbt;
+                    const int seg = rem >= kb0 ? 1 : 0;
+                    const bool first = DUAL ? (k < kbt && (seg ? rem == kb0 : rem == 0)) : (k == 0);
+                    const uint32_t tmem_d = tmem_d0 + (DUAL ? (uint32_t)(seg * H_BN) : 0u);
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + s * H_STAGE_BYTES, a_lo = a_hi + H_A_TILE;
+                    const uint32_t b_hi = a_hi + 2 * H_A_TILE, b_lo = b_hi + H_B_TILE;
+#pragma unroll
+                    for (int ks = 0; ks < H_BK / 16; ++ks) {
+                        const uint64_t dah = h_desc_a(a_hi, ks), dal = h_desc_a(a_lo, ks);
+                        const uint64_t dbh = h_desc_b(b_hi, ks), dbl = h_desc_b(b_lo, ks);
+                        h_mma_f16(tmem_d, dal, dbh, idesc, (!first || ks > 0) ? 1u : 0u);
+                        h_mma_f16(tmem_d, dah, dbl, idesc, 1u);
+                        h_mma_f16(tmem_d, dah, dbh, idesc, 1u);
+                    }
+                    tc_commit(empty(s));
+                }
+                tc_commit(tmem_full(acc));
+            }
+        }
+    } else {
+        // ===== epilogue =====
+        const int ew = warp - 2;
+        float inv0 = __ldg(p.inv_a[0]) * __ldg(p.inv_b[0]);
+        float inv1 = (DUAL && p.nseg > 1) ? __ldg(p.inv_a[1]) * __ldg(p.inv_b[1]) : 0.f;
+        EpiTile et;
+        et.quarter = warp & 3;
+        et.half = Cfg::kAttn ? (ew >> 2) : -1;
+        et.stage = epi_stage + (uint32_t)ew * Cfg::kEpiWarpBytes;
+        et.czs = epi_czs + (uint32_t)ew * 256u;
+        et.Mlive = Mlive;
+        et.Nlive = Nlive;
+        int ti = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+            const int rem_t = t % (mt * nt);
+            const int acc = ti & 1;
+            et.z = t / (mt * nt);
+            et.m0 = (rem_t / nt) * H_BM;
+            et.n0 = (rem_t % nt) * H_BN;
+            et.total = tile_total(et.z);
+            et.tacc = tmem_base + ((uint32_t)(et.quarter * 32) << 16) + (uint32_t)(acc * Cfg::kAccStride);
+            et.full_bar = tmem_full(acc);
+            et.full_parity = (uint32_t)((ti >> 1) & 1);
+            et.empty_bar = tmem_empty(acc);
+            h_epilogue_tile<EPI, DUAL>(p, et, lane, inv0, inv1);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn h_get_encode() {
+    static thread_local bool bound = false;  // the driver entry point needs the primary context bound to this thread
+    if (!bound) {
+        cudaFree(nullptr);
+        bound = true;
+    }
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+struct HMapKey {
+    const __half* ptr;
+    long long ld, bstride;
+    int is_b, nbatch, rows, K;
+    bool operator==(const HMapKey& o) const {
+        return ptr == o.ptr && ld == o.ld && bstride == o.bstride && is_b == o.is_b && nbatch == o.nbatch && rows == o.rows && K == o.K;
+    }
+};
+struct HMapSlot {
+    HMapKey key;
+    CUtensorMap map;
+    bool used;
+};
+static thread_local HMapSlot g_hmap_cache[48];
+static thread_local int g_hmap_next = 0;
+
+static int h_make_map(CUtensorMap* m, const __half* ptr, const HOperand& o, bool is_b) {
+    const HMapKey key{ptr, o.ld, o.bstride, is_b ? 1 : 0, o.nbatch, o.rows, o.K};
+    for (int i = 0; i < 48; ++i)
+        if (g_hmap_cache[i].used && g_hmap_cache[i].key == key) {
+            *m = g_hmap_cache[i].map;
+            return EEGAN_OK;
+        }
+    EncodeTiledFn enc = h_get_encode();
+    if (!enc) { set_error("h gemm: cuTensorMapEncodeTiled unavailable"); return EEGAN_ERR_CUDA; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (o.ld % 8) || (o.bstride % 8)) {
+        set_error("h gemm: operand base/pitch must be 16-byte aligned (ptr=%p ld=%lld bstride=%lld)", (const void*)ptr, o.ld, o.bstride);
+        return EEGAN_ERR_INVALID;
+    }
+    cuuint64_t dims[3], strides[2];
+    cuuint32_t box[3], estr[3] = {1, 1, 1};
+    if (is_b) {  // K-major [rows][K]
+        dims[0] = (cuuint64_t)o.K; dims[1] = (cuuint64_t)o.rows;
+        box[0] = H_BK; box[1] = H_BN;
+    } else {     // MN-major [K][rows]
+        dims[0] = (cuuint64_t)o.rows; dims[1] = (cuuint64_t)o.K;
+        box[0] = 64; box[1] = H_BK;
+    }
+    dims[2] = (cuuint64_t)(o.nbatch > 0 ? o.nbatch : 1);
+    box[2] = 1;
+    strides[0] = (cuuint64_t)o.ld * 2;
+    strides[1] = (cuuint64_t)(o.bstride > 0 ? o.bstride : (long long)dims[1] * o.ld) * 2;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, is_b ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("h gemm: cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu ld=%lld", (int)r, (unsigned long long)dims[0],
+                  (unsigned long long)dims[1], (unsigned long long)dims[2], o.ld);
+        return EEGAN_ERR_CUDA;
+    }
+    HMapSlot& slot = g_hmap_cache[g_hmap_next];
+    g_hmap_next = (g_hmap_next + 1) % 48;
+    slot.key = key;
+    slot.map = *m;
+    slot.used = true;
+    return EEGAN_OK;
+}
+
+static int h_num_sms() {
+    static int n = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    return n;
+}
+
+template <int EPI, bool DUAL>
+static int h_launch_t(const HMaps& maps, const HArgs& a, unsigned grid, cudaStream_t st) {
+    using Cfg = HCfg<EPI, DUAL>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(h_gemm_kernel<EPI, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        if (e != cudaSuccess) { set_error("h gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+        attr_set = true;
+    }
+    h_gemm_kernel<EPI, DUAL><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
+    return check_launch("h gemm");
+}
+
+int h_gemm_launch(const HGemm& g, cudaStream_t st) {
+    EEGAN_REQUIRE(g.nseg == 1 || g.nseg == 2, "h gemm: nseg=%d", g.nseg);
+    EEGAN_REQUIRE(g.M > 0 && g.N > 0 && g.batch > 0, "h gemm: empty problem");
+    HMaps maps;
+    HArgs a{};
+    for (int s = 0; s < 2; ++s) {
+        const int src = s < g.nseg ? s : 0;
+        const HOperand* ops[2] = {&g.A[src], &g.B[src]};
+        for (int o = 0; o < 2; ++o) {
+            EEGAN_REQUIRE(ops[o]->hi && ops[o]->lo && ops[o]->inv_scale, "h gemm: operand arrays missing");
+            int rc = h_make_map(&maps.m[s][o][0], ops[o]->hi, *ops[o], o == 1);
+            if (rc) return rc;
+            rc = h_make_map(&maps.m[s][o][1], ops[o]->lo, *ops[o], o == 1);
+            if (rc) return rc;
+        }
+        a.K[s] = s < g.nseg ? g.A[src].K : 0;
+        a.a_batched[s] = g.A[src].bstride > 0;
+        a.b_batched[s] = g.B[src].bstride > 0;
+        a.inv_a[s] = g.A[src].inv_scale;
+        a.inv_b[s] = g.B[src].inv_scale;
+    }
+    a.C = g.C; a.ldc = g.ldc; a.bC = g.bC; a.M = g.M; a.N = g.N; a.dynM = g.dynM; a.dynN = g.dynN; a.dynK = g.dynK;
+    a.attn = g.attn;
+    a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total; a.batch = g.batch;
+    const long long tiles = (long long)((g.N + H_BN - 1) / H_BN) * ((g.M + H_BM - 1) / H_BM) * g.batch;
+    const unsigned grid = (unsigned)(tiles < h_num_sms() ? tiles : h_num_sms());
+    if (g.epi != TC_EPI_PLAIN) {
+        const TcAttnEpi& e = g.attn.base;
+        EEGAN_REQUIRE(g.nseg == 1, "h gemm: the attention epilogues take one segment");
+        EEGAN_REQUIRE(e.nbins && e.bin_cap && e.bin_used && e.col_start && e.cap_len && e.P && g.attn.out_hi && g.attn.out_lo,
+                      "h gemm: attention epilogue arguments missing");
+        EEGAN_REQUIRE(g.ldc % 64 == 0, "h gemm: attention epilogue needs a column pitch that is a multiple of 64");
+        if (g.epi == TC_EPI_ATTN_FWD) {
+            EEGAN_REQUIRE(e.Zpart && g.attn.emax, "h gemm: attention forward epilogue needs Zpart and emax");
+            return h_launch_t<TC_EPI_ATTN_FWD, false>(maps, a, grid, st);
+        }
+        EEGAN_REQUIRE(g.epi == TC_EPI_ATTN_BWD && e.csz && g.attn.out_scale, "h gemm: attention backward epilogue needs csz and the dS scale");
+        return h_launch_t<TC_EPI_ATTN_BWD, false>(maps, a, grid, st);
+    }
+    EEGAN_REQUIRE(g.C, "h gemm: no output");
+    if (g.nseg == 2) return h_launch_t<TC_EPI_PLAIN, true>(maps, a, grid, st);
+    return h_launch_t<TC_EPI_PLAIN, false>(maps, a, grid, st);
+}
+
+// elementwise split of an fp32 array into the half pair of x * s (test entry point below)
+__global__ void h_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, long long n, float s) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        __half h, l;
+        h_split(x[i] * s, h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+__global__ void h_set2_kernel(float* p, float a, float b, float c, float d) {
+    p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+}
+
+}  // namespace eegan
+
+using namespace eegan;
+
+// Stand-alone entry point (tests / microbench): C[z] = A[z] * B[z]^T through the half-pair engine.
+//   A is MN-major: [K][lda] with the M index contiguous;  B is K-major: [N][ldb].  lda, ldb multiples of 8.
+//   sa, sb: power-of-two scales the operands are stored with.  dual != 0 runs the two-accumulator form with the
+//   same operands in both segments (the second stored with scales 4 sa, sb / 8): the result is 2 A B^T.
+//   workspace: 2 * (elements of A + elements of B) halves (x2 when dual) + 16 bytes.
+extern "C" int eegan_gemm_f16x3(const float* A, const float* B, float* C, int M, int N, int K, long long lda, long long ldb,
+                                long long ldc, long long bsA, long long bsB, long long bsC, int batch, float sa, float sb, int dual,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    EEGAN_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0 && workspace, "gemm_f16x3: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nA = bsA > 0 ? bsA * batch : (long long)K * lda, nB = bsB > 0 ? bsB * batch : (long long)N * ldb;
+    const int nset = dual ? 2 : 1;
+    const size_t need = (size_t)nset * 2 * (align_up(nA * 2, 256) + align_up(nB * 2, 256)) + 256;
+    EEGAN_REQUIRE(workspace_bytes >= need, "gemm_f16x3: workspace %zu < %zu", workspace_bytes, need);
+    char* p = (char*)workspace;
+    float* scales = (float*)p;
+    p += 256;
+    HGemm g{};
+    g.nseg = nset;
+    h_set2_kernel<<<1, 1, 0, st>>>(scales, 1.0f / sa, 1.0f / sb, 1.0f / (4.0f * sa), 8.0f / sb);
+    for (int s = 0; s < nset; ++s) {
+        __half* ah = (__half*)p; p += align_up(nA * 2, 256);
+        __half* al = (__half*)p; p += align_up(nA * 2, 256);
+        __half* bh = (__half*)p; p += align_up(nB * 2, 256);
+        __half* bl = (__half*)p; p += align_up(nB * 2, 256);
+        h_split_kernel<<<296, 256, 0, st>>>(A, ah, al, nA, s ? 4.0f * sa : sa);
+        h_split_kernel<<<296, 256, 0, st>>>(B, bh, bl, nB, s ? sb / 8.0f : sb);
+        g.A[s] = HOperand{ah, al, lda, bsA, batch, M, K, scales + 2 * s};
+        g.B[s] = HOperand{bh, bl, ldb, bsB, batch, N, K, scales + 2 * s + 1};
+    }
+    EEGAN_LAUNCH_CHECK("gemm_f16x3 split");
+    g.C = C; g.ldc = ldc; g.bC = bsC; g.M = M; g.N = N; g.batch = batch; g.nred = 1; g.red_total = 0;
+    g.epi = TC_EPI_PLAIN;
+    return h_gemm_launch(g, st);
+}

@@ -199,9 +199,12 @@ int eegan_syncbn_bwd_apply(const float* x, const float* dy, const float* mean,
                            int N, int C, int HW,
                            float* dx, void* stream);
 
-/* Contraction engine of the pair grid's six GEMM-shaped stages: 1 (default) = tcgen05
- * 3xTF32 tensor-core engine, 0 = exact-fp32 CUDA-core FFMA engine (validation / A-B runs).
- * Both are sm_100a kernels of this library; process-wide setting. */
+/* Contraction engine of the pair grid's GEMM-shaped stages (process-wide setting; all are sm_100a
+ * kernels of this library):
+ *   3 = tcgen05 "3xFP16": operands stored pre-split as fp16 hi/lo pairs with per-tensor power-of-two
+ *       scales, attention fused into the GEMM epilogues (pair_grid_h.cu, gemm_h.cu)
+ *   2 = tcgen05 3xTF32, operands split in the kernel, attention fused into the GEMM epilogues
+ *   1 = tcgen05 3xTF32 with separate softmax kernels;  0 = exact-fp32 CUDA-core FFMA (validation). */
 int eegan_set_contraction_engine(int engine);
 int eegan_get_contraction_engine(void);
 
@@ -238,6 +241,16 @@ int eegan_ssa_bwd_apply(const float* x, const float* dy, const float* mean, cons
 int eegan_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, int K,
                       int a_kmajor, int b_kmajor, long long lda, long long ldb, long long ldc,
                       long long bsA, long long bsB, long long bsC, int batch, int staging, void* stream);
+
+/* The half-pair engine on its own (tests / microbenchmarks): C[z] = A[z] B[z]^T, fp32 in / out.
+ * A is MN-major ([K][lda], M contiguous), B is K-major ([N][ldb]); lda, ldb and the batch strides are
+ * multiples of 8 elements.  sa, sb: power-of-two scales the operands are stored with (x*s must stay
+ * below 65504).  dual != 0 runs the two-accumulator form on the same operands twice (second copy stored
+ * with other scales): the result is 2 A B^T.  workspace: (dual ? 2 : 1) * 2 * (bytes of A/2 + bytes of
+ * B/2, each rounded up to 256) + 256 bytes. */
+int eegan_gemm_f16x3(const float* A, const float* B, float* C, int M, int N, int K, long long lda,
+                     long long ldb, long long ldc, long long bsA, long long bsB, long long bsC, int batch,
+                     float sa, float sb, int dual, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Bench-only stage timing of the multi-kernel entry points (eegan_damsm_pair_fwd/_bwd).

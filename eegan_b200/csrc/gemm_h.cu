@@ -7,6 +7,10 @@
 
 namespace eegan {
 
+// staging row pitch of the attention epilogues (floats): even, so that the read-out takes a lane's two adjacent
+// columns with one 8-byte load; the thread-per-row writes of the caption phase pay a 2-way bank conflict for it
+constexpr int H_EPI_PITCH = 66;
+
 struct HMaps {
     CUtensorMap m[2][2][2];  // [segment][0 = A, 1 = B][0 = hi, 1 = lo]
 };
@@ -32,12 +36,18 @@ struct HCfg {
     static constexpr int kEWarps = kAttn ? 8 : 4;  // epilogue warps (two per TMEM lane quarter in the attention forms)
     static constexpr int kStages = kAttn ? 4 : 6;
     static constexpr int kThreads = 32 * (2 + kEWarps);
-    static constexpr int kEpiPitch = kAttn ? TC_EPI_PITCH : 33;
+    static constexpr int kEpiPitch = kAttn ? H_EPI_PITCH : 33;
     static constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4;
     static constexpr int kSmem = kStages * H_STAGE_BYTES + kEWarps * (kEpiWarpBytes + 256) + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int kAccStride = DUAL ? 2 * H_BN : H_BN;  // TMEM columns between the two accumulator buffers
 };
 static_assert(HCfg<TC_EPI_PLAIN, false>::kSmem <= 232448 && HCfg<TC_EPI_ATTN_FWD, false>::kSmem <= 232448, "shared memory budget");
+
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ void h_mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -199,7 +209,7 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
     // ---- word-region attention on the accumulator: thread = region (TMEM lane), columns = packed words ----
     const TcAttnEpi& e = p.attn.base;
     const int nbins = *e.nbins;
-    const uint32_t my_row = t.stage + (uint32_t)(lane * TC_EPI_PITCH) * 4u;
+    const uint32_t my_row = t.stage + (uint32_t)(lane * H_EPI_PITCH) * 4u;
     float* Pz = e.P + (long long)t.z * p.bC;
     __half* Hz = p.attn.out_hi + (long long)t.z * p.bC;
     __half* Lz = p.attn.out_lo + (long long)t.z * p.bC;
@@ -220,8 +230,8 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                sts_f32(t.stage + (uint32_t)((r8 + q) * TC_EPI_PITCH + lane) * 4u, a0[q]);
-                sts_f32(t.stage + (uint32_t)((r8 + q) * TC_EPI_PITCH + lane + 32) * 4u, a1[q]);
+                sts_f32(t.stage + (uint32_t)((r8 + q) * H_EPI_PITCH + lane) * 4u, a0[q]);
+                sts_f32(t.stage + (uint32_t)((r8 + q) * H_EPI_PITCH + lane + 32) * 4u, a1[q]);
             }
         }
     };
@@ -238,7 +248,6 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
     const int i0 = __shfl_sync(0xffffffffu, bc_l, h), i1 = __shfl_sync(0xffffffffu, bc_l, h + 1);
     const int used = __shfl_sync(0xffffffffu, bu_l, h);
     const int col0 = t.n0 + 64 * h;
-    const bool c0ok = lane < used, c1ok = lane + 32 < used;
     if (EPI == TC_EPI_ATTN_BWD) {
         load_p_bin(col0);
         sts_f32(t.czs + (uint32_t)lane * 4u, __ldg(e.csz + (long long)t.z * p.ldc + col0 + lane));
@@ -273,67 +282,72 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
     if (lane == 0) mbar_arrive(t.empty_bar);
     for (int c = used; c < 64; ++c) sts_f32(my_row + (uint32_t)c * 4u, 0.f);  // padding columns of the bin
     __syncwarp();
-    // read-out: region rows, coalesced, 4 rows per round
+    // read-out: region rows, coalesced; a lane owns the adjacent columns 2 lane, 2 lane + 1 of the bin: one 8-byte P store and
+    // one 4-byte store per half array and row.  Padding columns of the bin hold P = 0, hence finite E' / dS' = 0 — every
+    // consumer multiplies them by zero rows (GEMM4) or never reads the outputs they feed (GEMM2 / GEMM5 rows, Zpart).
+    const uint32_t rd0 = t.stage + (uint32_t)(2 * lane) * 4u;
+    const long long o0 = (long long)row0 * p.ldc + col0 + 2 * lane;
+    uint32_t* hp = reinterpret_cast<uint32_t*>(Hz + o0);
+    uint32_t* lp = reinterpret_cast<uint32_t*>(Lz + o0);
+    const long long hstep = p.ldc >> 1;  // row pitch in 4-byte units of the half arrays
+    const int full = rows_live & ~3;
     if (EPI == TC_EPI_ATTN_FWD) {
+        // E' = 2^12 exp(g1 (P - 1)) = ex2(P a + b)
+        const float a = e.g1 * 1.4426950408889634f, bb = 12.0f - a;
+        float2* pp = reinterpret_cast<float2*>(Pz + o0);
+        const long long pstep = p.ldc >> 1;
         float z0 = 0.f, z1 = 0.f, em = 0.f;
+        auto row_out = [&](float2 pv) {
+            float e0, e1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(pv.x, a, bb)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(pv.y, a, bb)));
+            const __half2 h = __floats2half2_rn(e0, e1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(e0 - hf.x, e1 - hf.y);
+            *pp = pv;
+            *hp = *reinterpret_cast<const uint32_t*>(&h);
+            *lp = *reinterpret_cast<const uint32_t*>(&l);
+            pp += pstep; hp += hstep; lp += hstep;
+            z0 += e0;
+            z1 += e1;
+            em = fmaxf(em, fmaxf(e0, e1));
+        };
 #pragma unroll 1
-        for (int r4 = 0; r4 < rows_live; r4 += 4) {
-            float p0[4], p1[4];
+        for (int r4 = 0; r4 < full; r4 += 4) {
+            float2 pv[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                p0[q] = lds_f32(t.stage + (uint32_t)((r4 + q) * TC_EPI_PITCH + lane) * 4u);
-                p1[q] = lds_f32(t.stage + (uint32_t)((r4 + q) * TC_EPI_PITCH + lane + 32) * 4u);
-            }
+            for (int q = 0; q < 4; ++q) pv[q] = lds_f32x2(rd0 + (uint32_t)((r4 + q) * H_EPI_PITCH) * 4u);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (r4 + q < rows_live) {
-                    const float e0 = c0ok ? fast_exp(e.g1 * (p0[q] - 1.0f)) : 0.f;
-                    const float e1 = c1ok ? fast_exp(e.g1 * (p1[q] - 1.0f)) : 0.f;
-                    const long long o = (long long)(row0 + r4 + q) * p.ldc + col0 + lane;
-                    Pz[o] = p0[q];
-                    Pz[o + 32] = p1[q];
-                    __half h0, l0, h1, l1;
-                    h_split(e0 * oscale, h0, l0);
-                    h_split(e1 * oscale, h1, l1);
-                    Hz[o] = h0;
-                    Hz[o + 32] = h1;
-                    Lz[o] = l0;
-                    Lz[o + 32] = l1;
-                    z0 += e0;
-                    z1 += e1;
-                    em = fmaxf(em, fmaxf(e0, e1));
-                }
-            }
+            for (int q = 0; q < 4; ++q) row_out(pv[q]);
         }
-        float* zp = e.Zpart + ((long long)t.z * ((p.M + 31) / 32) + (row0 >> 5)) * p.ldc + col0 + lane;
+#pragma unroll 1
+        for (int r = full; r < rows_live; ++r) row_out(lds_f32x2(rd0 + (uint32_t)(r * H_EPI_PITCH) * 4u));
         if (rows_live > 0) {
-            zp[0] = z0;
-            zp[32] = z1;
+            float* zp = e.Zpart + ((long long)t.z * ((p.M + 31) / 32) + (row0 >> 5)) * p.ldc + col0 + 2 * lane;
+            *reinterpret_cast<float2*>(zp) = make_float2(z0 * (1.0f / H_E_SCALE), z1 * (1.0f / H_E_SCALE));
         }
-        em = warp_max(em);
+        em = warp_max(em) * (1.0f / H_E_SCALE);
         if (lane == 0 && em > 0.f) atomicMax(reinterpret_cast<int*>(p.attn.emax), __float_as_int(em));
     } else {
+        auto row_out = [&](float2 dv) {
+            const float x0 = dv.x * oscale, x1 = dv.y * oscale;  // |dS'| < 2^14 by construction of the scale (pair_grid_h.cu)
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            *hp = *reinterpret_cast<const uint32_t*>(&h);
+            *lp = *reinterpret_cast<const uint32_t*>(&l);
+            hp += hstep; lp += hstep;
+        };
 #pragma unroll 1
-        for (int r4 = 0; r4 < rows_live; r4 += 4) {
-            float d0[4], d1[4];
+        for (int r4 = 0; r4 < full; r4 += 4) {
+            float2 dv[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                d0[q] = lds_f32(t.stage + (uint32_t)((r4 + q) * TC_EPI_PITCH + lane) * 4u);
-                d1[q] = lds_f32(t.stage + (uint32_t)((r4 + q) * TC_EPI_PITCH + lane + 32) * 4u);
-            }
+            for (int q = 0; q < 4; ++q) dv[q] = lds_f32x2(rd0 + (uint32_t)((r4 + q) * H_EPI_PITCH) * 4u);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (r4 + q < rows_live) {
-                    const long long o = (long long)(row0 + r4 + q) * p.ldc + col0 + lane;
-                    __half h0, l0, h1, l1;
-                    h_split(d0[q] * oscale, h0, l0);
-                    h_split(d1[q] * oscale, h1, l1);
-                    Hz[o] = h0;
-                    Hz[o + 32] = h1;
-                    Lz[o] = l0;
-                    Lz[o + 32] = l1;
-                }
+            for (int q = 0; q < 4; ++q) row_out(dv[q]);
         }
+#pragma unroll 1
+        for (int r = full; r < rows_live; ++r) row_out(lds_f32x2(rd0 + (uint32_t)(r * H_EPI_PITCH) * 4u));
     }
 }
 

@@ -17,18 +17,27 @@
 #include "common.cuh"
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "gemm_ffma.cuh"
 #include "gemm_tc.cuh"
+#include "pair_h.cuh"
 #include "pair_v3.cuh"
 #include "ptx.cuh"
 
 namespace eegan {
 
-// contraction engine: 2 = tcgen05 3xTF32 with the attention fused into the GEMM epilogues
+// contraction engine: 3 = tcgen05 half-pair ("3xFP16") engine, operands pre-split as fp16 hi/lo, attention fused
+// into the GEMM epilogues (pair_grid_h.cu), 2 = tcgen05 3xTF32 with the attention fused into the GEMM epilogues
 // (pair_grid_v3.cu, default), 1 = tcgen05 3xTF32 GEMMs + separate row/column kernels,
 // 0 = CUDA-core fp32 FFMA (exact-fp32 A/B reference).  Process-wide (the backward runs on
 // autograd's thread); set via eegan_set_contraction_engine().
-static std::atomic<int> g_engine{2};
+static int default_engine() {
+    const char* e = getenv("EEGAN_ENGINE");  // A/B runs of the whole test suite / bench on another engine
+    const int v = e ? atoi(e) : 2;
+    return (v >= 0 && v <= 3) ? v : 2;
+}
+static std::atomic<int> g_engine{default_engine()};
 static bool fused_ok(int D) { return D % 128 == 0; }  // the fused engine's dU kernel works in 128-float chunks
 
 constexpr int PAIR_DU_JG = 8;  // images per CTA of the dU kernel
@@ -582,7 +591,8 @@ extern "C" size_t eegan_damsm_pair_workspace_bytes(int B_img, int B_cap, int D, 
     if (B_img <= 0 || B_cap <= 0 || D <= 0 || R <= 0 || T_max <= 0 || T_max > 32) return 0;
     const size_t a = carve(nullptr, B_img, B_cap, D, R, T_max).bytes;
     const size_t b = pair_v3_workspace_bytes(B_img, B_cap, D, R, T_max);
-    return a > b ? a : b;
+    const size_t c = pair_h_workspace_bytes(B_img, B_cap, D, R, T_max);
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 // ---- the six contractions, on either engine -------------------------------------------
@@ -660,7 +670,8 @@ static int gemm_dc(const PairWs& w, float* d_img, int Bi, int NtM, int D, int R,
 }
 
 extern "C" int eegan_set_contraction_engine(int engine) {
-    EEGAN_REQUIRE(engine >= 0 && engine <= 2, "contraction engine must be 0 (fp32 FFMA), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xTF32, fused attention)");
+    EEGAN_REQUIRE(engine >= 0 && engine <= 3,
+                  "contraction engine must be 0 (fp32 FFMA), 1 (tcgen05 3xTF32), 2 (tcgen05 3xTF32, fused attention) or 3 (tcgen05 half pairs, fused attention)");
     g_engine.store(engine);
     return EEGAN_OK;
 }
@@ -672,7 +683,10 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
     int rc = validate(Bi, Bc, D, R, Tm);
     if (rc) return rc;
     EEGAN_REQUIRE(img && words && cap_lens && m && workspace, "pair fwd: null pointer");
-    if (g_engine.load() == 2 && fused_ok(D))
+    if (g_engine.load() == 3 && fused_ok(D))
+        return pair_h_fwd(img, words, cap_lens, Bi, Bc, D, R, Tm, g1, g2, m, att, diag_offset, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+    if (g_engine.load() >= 2 && fused_ok(D))
         return pair_v3_fwd(img, words, cap_lens, Bi, Bc, D, R, Tm, g1, g2, m, att, diag_offset, workspace, workspace_bytes,
                            (cudaStream_t)stream);
     PairWs w = carve(workspace, Bi, Bc, D, R, Tm);
@@ -717,7 +731,9 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
     int rc = validate(Bi, Bc, D, R, Tm);
     if (rc) return rc;
     EEGAN_REQUIRE(img && dm && workspace, "pair bwd: null pointer");
-    if (g_engine.load() == 2 && fused_ok(D))
+    if (g_engine.load() == 3 && fused_ok(D))
+        return pair_h_bwd(img, Bi, Bc, D, R, Tm, g1, g2, dm, d_img, d_words, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (g_engine.load() >= 2 && fused_ok(D))
         return pair_v3_bwd(img, Bi, Bc, D, R, Tm, g1, g2, dm, d_img, d_words, workspace, workspace_bytes, (cudaStream_t)stream);
     PairWs w = carve(workspace, Bi, Bc, D, R, Tm);
     if (workspace_bytes < w.bytes) {

@@ -1,0 +1,569 @@
+// DAMSM pair grid on the half-pair ("3xFP16") contraction engine (contraction engine 3).
+//
+// Same region-major fused pipeline as pair_grid_v3.cu (miscc/DAMSM_losses.py:272-342):
+// five tcgen05 contractions with the word-region attention inside the GEMM1 / GEMM3 epilogues.  What changes
+// is how the GEMM operands live in HBM: every tensor a contraction reads — image features C, packed words W,
+// E = exp(g1 (P - 1)), DUz, dS — is written ONCE, by the kernel that produces it, as two fp16 arrays
+// (hi, lo) of x * 2^e with one power-of-two scale per tensor (gemm_h.cuh).  That is the same 4 bytes per element as
+// fp32 and the same 22 mantissa bits the 3xTF32 engine used, but the GEMM main loop becomes pure TMA -> MMA at the
+// fp16 rate with no operand split in the kernel.
+//
+// Scales (all on the device, no host sync; `scal` block of the workspace):
+//   C, W   exact max |x| (h_stats_kernel)               -> max scaled into [2^7, 2^8)
+//   E      in (0, 1]: constant 2^12
+//   DUz    exact row 2-norms |dcos| sqrt(1 - cos^2) / (|u| Z) from the per-column scalars (h_duscale_kernel)
+//          -> largest row norm scaled into [2^11, 2^12): elements <= 2^12
+//   dS     rigorous bound |dS| <= 4 g1 max(E) max_r|C[:,r]| max|DUz row|  -> bound scaled into [2^13, 2^14)
+// so nothing can overflow fp16; a loose bound only costs low-order bits of the smallest elements.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "gemm_h.cuh"
+#include "pair_h.cuh"
+#include "pair_v3_kernels.cuh"
+
+namespace eegan {
+
+enum HScal {
+    HS_MAXC = 0, HS_MAXW = 1, HS_MAXCN2 = 2, HS_EMAX = 3, HS_MAXDUN = 4,
+    HS_SC = 8, HS_IC = 9, HS_SW = 10, HS_IW = 11, HS_SE = 12, HS_IE = 13, HS_SDU = 14, HS_IDU = 15, HS_SDS = 16, HS_IDS = 17,
+    HS_COUNT = 32
+};
+
+struct HWs {
+    int* col_start;
+    int* cap_len;
+    int* bin_cap;
+    int* bin_used;
+    int* meta;
+    int* col_cap;
+    float* scal;     // [HS_COUNT] maxima and scales
+    float* Wp;       // [NtP][D] packed words, fp32 (cos/lse, dU)
+    float* wn;       // [NtP]
+    __half* Wh;      // [NtP][D]
+    __half* Wl;
+    __half* Ch;      // [Bi][D][Rp]
+    __half* Cl;
+    float* P;        // [Bi][R][NtP]
+    __half* Eh;      // [Bi][R][NtP]
+    __half* El;
+    float* Zpart;    // [Bi][ceil(R/32)][NtP]
+    float* Z;        // [Bi][NtP]
+    float* U;        // [Bi][NtP][D]
+    __half* DUh;     // [Bi][NtP][D]
+    __half* DUl;
+    float* cosv;
+    float* un;
+    float* csz;
+    float* mst;      // [Bi][Bc]
+    __half* dSh;     // [Bi][R][NtP]
+    __half* dSl;
+    float* dWpart;   // [nsplit][NtP][D]
+    float* dwcos;    // [ngroups][NtP][D]
+    int Rp, NtP, maxbins, nsplit, ngroups, nz;
+    size_t bytes;
+};
+
+static HWs h_carve(void* base, int Bi, int Bc, int D, int R, int Tm) {
+    HWs w;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* q = p ? p + off : nullptr;
+        off += align_up(bytes, 256);
+        return q;
+    };
+    const int per_bin = V3_BIN / Tm;
+    w.maxbins = (Bc + per_bin - 1) / per_bin;
+    w.NtP = w.maxbins * V3_BIN;
+    w.Rp = (R + 7) / 8 * 8;  // 16-byte row pitch for the half arrays
+    w.nz = (R + 31) / 32;
+    w.nsplit = v3_nsplit(Bi, w.NtP, D);
+    w.ngroups = (Bi + V3_DU_JG - 1) / V3_DU_JG;
+    const size_t NtP = (size_t)w.NtP;
+    w.col_start = (int*)take((Bc + 1) * sizeof(int));
+    w.cap_len = (int*)take(Bc * sizeof(int));
+    w.bin_cap = (int*)take((w.maxbins + 1) * sizeof(int));
+    w.bin_used = (int*)take(w.maxbins * sizeof(int));
+    w.meta = (int*)take(4 * sizeof(int));
+    w.col_cap = (int*)take(NtP * sizeof(int));
+    w.scal = (float*)take(HS_COUNT * sizeof(float));
+    w.Wp = (float*)take(NtP * D * sizeof(float));
+    w.wn = (float*)take(NtP * sizeof(float));
+    w.Wh = (__half*)take(NtP * D * sizeof(__half));
+    w.Wl = (__half*)take(NtP * D * sizeof(__half));
+    w.Ch = (__half*)take((size_t)Bi * D * w.Rp * sizeof(__half));
+    w.Cl = (__half*)take((size_t)Bi * D * w.Rp * sizeof(__half));
+    w.P = (float*)take((size_t)Bi * R * NtP * sizeof(float));
+    w.Eh = (__half*)take((size_t)Bi * R * NtP * sizeof(__half));
+    w.El = (__half*)take((size_t)Bi * R * NtP * sizeof(__half));
+    w.Zpart = (float*)take((size_t)Bi * w.nz * NtP * sizeof(float));
+    w.Z = (float*)take((size_t)Bi * NtP * sizeof(float));
+    w.U = (float*)take((size_t)Bi * NtP * D * sizeof(float));
+    w.DUh = (__half*)take((size_t)Bi * NtP * D * sizeof(__half));
+    w.DUl = (__half*)take((size_t)Bi * NtP * D * sizeof(__half));
+    w.cosv = (float*)take((size_t)Bi * NtP * sizeof(float));
+    w.un = (float*)take((size_t)Bi * NtP * sizeof(float));
+    w.csz = (float*)take((size_t)Bi * NtP * sizeof(float));
+    w.mst = (float*)take((size_t)Bi * Bc * sizeof(float));
+    w.dSh = (__half*)take((size_t)Bi * R * NtP * sizeof(__half));
+    w.dSl = (__half*)take((size_t)Bi * R * NtP * sizeof(__half));
+    w.dWpart = (float*)take((size_t)w.nsplit * NtP * D * sizeof(float));
+    w.dwcos = (float*)take((size_t)w.ngroups * NtP * D * sizeof(float));
+    w.bytes = off;
+    return w;
+}
+
+// largest power of two s with maxv * s < 2^target_exp (1 for a zero or non-finite maximum)
+__device__ __forceinline__ float h_pow2_scale(float maxv, int target_exp) {
+    if (!(maxv > 0.f) || !(maxv < INFINITY)) return 1.0f;
+    int e;
+    frexpf(maxv, &e);  // maxv = f 2^e, f in [0.5, 1)
+    const int k = max(-120, min(120, target_exp - e));
+    return ldexpf(1.0f, k);
+}
+__device__ __forceinline__ void h_atomic_max_pos(float* addr, float v) {  // v >= 0: the bit patterns order like the values
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+__device__ __forceinline__ uint32_t h_pack2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void h_split4(const float4 v, float s, uint2& hi, uint2& lo) {
+    __half h0, h1, h2, h3, l0, l1, l2, l3;
+    h_split(v.x * s, h0, l0);
+    h_split(v.y * s, h1, l1);
+    h_split(v.z * s, h2, l2);
+    h_split(v.w * s, h3, l3);
+    hi = make_uint2(h_pack2(h0, h1), h_pack2(h2, h3));
+    lo = make_uint2(h_pack2(l0, l1), h_pack2(l2, l3));
+}
+
+// ---------------------------------------------------------------------------------------
+// prologue
+// ---------------------------------------------------------------------------------------
+// One launch, two roles:
+//   CTAs [0, NtP):   one packed column each: gather the word vector (words is [i][d][t]) -> Wp, |w|, max |w_d|
+//   CTAs [NtP, ...): one (image, 32-region slab) each: max |c| and the largest column norm |C[j][:, r]|^2
+__global__ void __launch_bounds__(256) h_stats_kernel(const float* __restrict__ words, const int* __restrict__ col_start,
+                                                      const int* __restrict__ col_cap, const int* __restrict__ meta, int D, int Tm,
+                                                      int NtP, float* __restrict__ Wp, float* __restrict__ wn,
+                                                      const float* __restrict__ img, int R, int nslab, float* __restrict__ scal) {
+    __shared__ float red[32];
+    __shared__ float s_part[8][32];
+    if ((int)blockIdx.x >= NtP) {
+        const int idx = blockIdx.x - NtP, j = idx / nslab, r = (idx % nslab) * 32 + (threadIdx.x & 31);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const float* src = img + (size_t)j * D * R + r;
+        float ss = 0.f, am = 0.f;
+        if (r < R) {
+            for (int d0 = warp; d0 < D; d0 += 32) {  // four loads in flight per thread
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = d0 + 8 * q < D ? __ldg(src + (size_t)(d0 + 8 * q) * R) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    ss = fmaf(v[q], v[q], ss);
+                    am = fmaxf(am, fabsf(v[q]));
+                }
+            }
+        }
+        s_part[warp][lane] = ss;
+        am = block_max(am, red);  // has the __syncthreads that also publishes s_part
+        if (warp == 0) {
+            float n2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) n2 += s_part[q][lane];
+            n2 = warp_max(n2);
+            if (lane == 0) {
+                h_atomic_max_pos(scal + HS_MAXCN2, n2);
+                h_atomic_max_pos(scal + HS_MAXC, am);
+            }
+        }
+        return;
+    }
+    const int n = blockIdx.x;
+    if (n >= meta[1]) return;
+    const int i = col_cap[n];
+    float ss = 0.f, am = 0.f;
+    if (i < 0) {
+        for (int d = threadIdx.x; d < D; d += blockDim.x) Wp[(size_t)n * D + d] = 0.f;
+    } else {
+        const int t = n - col_start[i];
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const float v = __ldg(words + ((size_t)i * D + d) * Tm + t);
+            Wp[(size_t)n * D + d] = v;
+            ss = fmaf(v, v, ss);
+            am = fmaxf(am, fabsf(v));
+        }
+    }
+    ss = block_sum(ss, red);
+    am = block_max(am, red);
+    if (threadIdx.x == 0) {
+        wn[n] = sqrtf(ss);
+        if (i >= 0) h_atomic_max_pos(scal + HS_MAXW, am);
+    }
+}
+
+// Scales of C and W from the maxima, then the half pairs:
+//   CTAs [0, NtP): Wp row n' -> Wh, Wl;   CTAs [NtP, ...): img rows [Bi*D][R] -> Ch, Cl [Bi*D][Rp] (pad columns zero)
+__global__ void __launch_bounds__(256) h_convert_kernel(const float* __restrict__ Wp, const int* __restrict__ meta, int D, int NtP,
+                                                        __half* __restrict__ Wh, __half* __restrict__ Wl,
+                                                        const float* __restrict__ img, long long rows, int R, int Rp,
+                                                        __half* __restrict__ Ch, __half* __restrict__ Cl, float* __restrict__ scal) {
+    const float sC = h_pow2_scale(scal[HS_MAXC], 8), sW = h_pow2_scale(scal[HS_MAXW], 8);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[HS_SC] = sC; scal[HS_IC] = 1.0f / sC;
+        scal[HS_SW] = sW; scal[HS_IW] = 1.0f / sW;
+        scal[HS_SE] = H_E_SCALE; scal[HS_IE] = 1.0f / H_E_SCALE;
+    }
+    if ((int)blockIdx.x >= NtP) {
+        const int lane = threadIdx.x & 31;
+        const long long warps = (long long)(gridDim.x - NtP) * (blockDim.x >> 5);
+        for (long long row = (long long)(blockIdx.x - NtP) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+            const float* sp = img + row * R;
+            for (int r0 = 0; r0 < Rp; r0 += 32 * 10) {  // up to ten loads per lane in flight (R = 289 -> one round)
+                float v[10];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) {
+                    const int r = r0 + 32 * q + lane;
+                    v[q] = r < R ? __ldg(sp + r) : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 10; ++q) {
+                    const int r = r0 + 32 * q + lane;
+                    if (r < Rp) {
+                        __half h, l;
+                        h_split(v[q] * sC, h, l);
+                        Ch[row * Rp + r] = h;
+                        Cl[row * Rp + r] = l;
+                    }
+                }
+            }
+        }
+        return;
+    }
+    const int n = blockIdx.x;
+    if (n >= meta[1]) return;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        __half h, l;
+        h_split(Wp[(size_t)n * D + d] * sW, h, l);
+        Wh[(size_t)n * D + d] = h;
+        Wl[(size_t)n * D + d] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward: per packed column
+// ---------------------------------------------------------------------------------------
+// Largest row 2-norm of DUz over all (image j, packed column n'), from the per-column scalars alone:
+//   du = dcos (w / (|w||u|) - cos u / |u|^2)  =>  |du| = |dcos| sqrt(1 - cos^2) / |u|,  DUz = du / Z
+// (clamped columns, |w||u| <= 1e-8: du = dcos w / 1e-8).  The 1e-6 floor under 1 - cos^2 keeps rounding noise of
+// near-parallel columns inside the bound.  grid (bins, images), 64 threads = the bin's columns.
+__global__ void __launch_bounds__(64) h_duscale_kernel(const float* __restrict__ wn, const float* __restrict__ Z,
+                                                       const float* __restrict__ cosv, const float* __restrict__ un,
+                                                       const float* __restrict__ dm, const float* __restrict__ mst,
+                                                       const int* __restrict__ col_cap, const int* __restrict__ meta, int NtP, int Bc,
+                                                       float g2, float* __restrict__ scal) {
+    __shared__ float red[32];
+    const int b = blockIdx.x, j = blockIdx.y;
+    if (b >= meta[0]) return;
+    const int n = b * V3_BIN + threadIdx.x;
+    const int i = col_cap[n];
+    float nz = 0.f;
+    if (i >= 0) {
+        const size_t idx = (size_t)j * NtP + n;
+        const float c = cosv[idx], unv = un[idx];
+        const float dcos = fabsf(dm[(size_t)j * Bc + i] * g2 * expf(g2 * c - mst[(size_t)j * Bc + i]));
+        const float nn = wn[n] * unv;
+        const float nrm = nn > 1e-8f ? dcos * sqrtf(fmaxf(1.0f - c * c, 1e-6f)) / unv : dcos * 1e8f * wn[n];
+        nz = nrm / Z[idx];
+        if (!(nz >= 0.f)) nz = INFINITY;  // NaN upstream: poison the maximum so that the scale falls back to 1
+    }
+    nz = block_max(nz, red);
+    if (threadIdx.x == 0 && nz > 0.f) h_atomic_max_pos(scal + HS_MAXDUN, nz);
+}
+
+// One CTA per (packed column n', group of 64 images): as v3_du_kernel (pair_grid_v3.cu), with DUz written as half pairs.
+//   dcos = dm g2 exp(g2 cos - m);  a1 = dcos / max(|w||u|, eps);  a2 = dcos cos / |u|^2;  a3 = dcos cos / |w|^2
+//   DU = a1 w - a2 u  (u = U'/Z);  DUz = DU / Z;  csz = <DU, u> / Z;  dwcos[g][n'] = sum_j a1 u - (sum_j a3) w
+template <int NQ>  // float4 per lane: D = 128 * NQ
+__global__ void __launch_bounds__(256) h_du_kernel(const float* __restrict__ U, const float* __restrict__ Wp,
+                                                   const float* __restrict__ wn, const float* __restrict__ Z,
+                                                   const float* __restrict__ cosv, const float* __restrict__ un,
+                                                   const float* __restrict__ dm, const float* __restrict__ mst,
+                                                   const int* __restrict__ col_cap, const int* __restrict__ meta, int NtP, int Bi,
+                                                   int Bc, int D, float g1, float g2, __half* __restrict__ DUh,
+                                                   __half* __restrict__ DUl, float* __restrict__ csz, float* __restrict__ dwcos,
+                                                   float* __restrict__ scal) {
+    __shared__ float4 s_acc[8][32 * NQ];
+    __shared__ float s_a3[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x;
+    if (n >= meta[1]) return;
+    const float maxdun = scal[HS_MAXDUN];
+    const float sDU = h_pow2_scale(maxdun, 12);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        scal[HS_SDU] = sDU; scal[HS_IDU] = 1.0f / sDU;
+        const float bound = 4.0f * g1 * fmaxf(scal[HS_EMAX], 1e-30f) * sqrtf(scal[HS_MAXCN2]) * maxdun;
+        const float sDS = h_pow2_scale(bound, 14);
+        scal[HS_SDS] = sDS; scal[HS_IDS] = 1.0f / sDS;
+    }
+    const int g = blockIdx.y, j0 = g * V3_DU_JG + warp * 8;
+    const int i = col_cap[n];
+    float4* dwc = reinterpret_cast<float4*>(dwcos + ((size_t)g * NtP + n) * D);
+    if (i < 0) {  // padding column: zero operand rows so that GEMM4's K loop adds nothing
+        const uint2 zero2 = make_uint2(0u, 0u);
+        for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q;
+            if (j >= Bi) break;
+            uint2* oh = reinterpret_cast<uint2*>(DUh + ((size_t)j * NtP + n) * D);
+            uint2* ol = reinterpret_cast<uint2*>(DUl + ((size_t)j * NtP + n) * D);
+#pragma unroll
+            for (int c = 0; c < NQ; ++c) {
+                oh[lane + 32 * c] = zero2;
+                ol[lane + 32 * c] = zero2;
+            }
+            if (lane == 0) csz[(size_t)j * NtP + n] = 0.f;
+        }
+        if (warp == 0) {
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < NQ; ++c) dwc[lane + 32 * c] = zero;
+        }
+        return;
+    }
+    float4 wv[NQ], acc[NQ];
+#pragma unroll
+    for (int c = 0; c < NQ; ++c) {
+        wv[c] = __ldg(reinterpret_cast<const float4*>(Wp + (size_t)n * D) + lane + 32 * c);
+        acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float wnv = wn[n];
+    float a3s = 0.f;
+#pragma unroll 1
+    for (int q0 = 0; q0 < 8 && j0 + q0 < Bi; q0 += 4) {
+        float zs[4], cs4[4], us[4], dms[4], ms[4];
+        float4 uv[4][NQ];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = min(j0 + q0 + q, Bi - 1);
+            const size_t idx = (size_t)j * NtP + n;
+            zs[q] = Z[idx]; cs4[q] = cosv[idx]; us[q] = un[idx];
+            dms[q] = dm[(size_t)j * Bc + i]; ms[q] = mst[(size_t)j * Bc + i];
+            const float4* u4 = reinterpret_cast<const float4*>(U + idx * D);
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) uv[q][k] = u4[lane + 32 * k];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q0 + q;
+            if (j >= Bi) break;
+            const size_t idx = (size_t)j * NtP + n;
+            const float c = cs4[q], unv = us[q];
+            const float dcos = dms[q] * g2 * expf(g2 * c - ms[q]);
+            const float nn = wnv * unv;
+            const bool live = nn > 1e-8f;
+            const float a1 = dcos / fmaxf(nn, 1e-8f);
+            const float a2 = live ? dcos * c / (unv * unv) : 0.f;
+            a3s += live ? dcos * c / (wnv * wnv) : 0.f;
+            const float iz = 1.0f / zs[q];
+            const float a2z = a2 * iz, a1z = a1 * iz;
+            const float izs = iz * sDU;
+            uint2* oh = reinterpret_cast<uint2*>(DUh + idx * D);
+            uint2* ol = reinterpret_cast<uint2*>(DUl + idx * D);
+            float cs = 0.f;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) {
+                const float4 u = uv[q][k];
+                float4 du;
+                du.x = a1 * wv[k].x - a2z * u.x; du.y = a1 * wv[k].y - a2z * u.y;
+                du.z = a1 * wv[k].z - a2z * u.z; du.w = a1 * wv[k].w - a2z * u.w;
+                cs = fmaf(du.x, u.x, cs); cs = fmaf(du.y, u.y, cs); cs = fmaf(du.z, u.z, cs); cs = fmaf(du.w, u.w, cs);
+                acc[k].x = fmaf(a1z, u.x, acc[k].x); acc[k].y = fmaf(a1z, u.y, acc[k].y);
+                acc[k].z = fmaf(a1z, u.z, acc[k].z); acc[k].w = fmaf(a1z, u.w, acc[k].w);
+                uint2 hi, lo;
+                h_split4(du, izs, hi, lo);
+                oh[lane + 32 * k] = hi;
+                ol[lane + 32 * k] = lo;
+            }
+            cs = warp_sum(cs);  // <DU, U'>
+            if (lane == 0) csz[idx] = cs * iz * iz;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) s_acc[warp][lane + 32 * k] = acc[k];
+    if (lane == 0) s_a3[warp] = a3s;
+    __syncthreads();
+    for (int q = threadIdx.x; q < 32 * NQ; q += blockDim.x) {
+        float4 t = s_acc[0][q];
+        float a3 = s_a3[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) {
+            const float4 o = s_acc[w][q];
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+            a3 += s_a3[w];
+        }
+        const float4 wq = __ldg(reinterpret_cast<const float4*>(Wp + (size_t)n * D) + q);
+        t.x -= a3 * wq.x; t.y -= a3 * wq.y; t.z -= a3 * wq.z; t.w -= a3 * wq.w;
+        dwc[q] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------
+static HAttnEpi h_attn_args(const HWs& w, float g1) {
+    HAttnEpi a{};
+    a.base.nbins = w.meta;
+    a.base.bin_cap = w.bin_cap;
+    a.base.bin_used = w.bin_used;
+    a.base.col_start = w.col_start;
+    a.base.cap_len = w.cap_len;
+    a.base.P = w.P;
+    a.base.Zpart = w.Zpart;
+    a.base.csz = w.csz;
+    a.base.g1 = g1;
+    return a;
+}
+
+size_t pair_h_workspace_bytes(int Bi, int Bc, int D, int R, int Tm) { return h_carve(nullptr, Bi, Bc, D, R, Tm).bytes; }
+
+int pair_h_fwd(const float* img, const float* words, const int32_t* cap_lens, int Bi, int Bc, int D, int R, int Tm, float g1,
+               float g2, float* m, float* att, int diag_offset, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    EEGAN_REQUIRE(D % 128 == 0 && D <= 1024, "pair grid (half-pair engine): D=%d must be a multiple of 128 and <= 1024", D);
+    EEGAN_REQUIRE(R <= 1024, "pair grid (half-pair engine): R=%d must be <= 1024", R);
+    EEGAN_REQUIRE(Bc <= 4096, "pair grid (half-pair engine): at most 4096 captions per call (got %d)", Bc);
+    HWs w = h_carve(workspace, Bi, Bc, D, R, Tm);
+    if (workspace_bytes < w.bytes) {
+        set_error("pair fwd: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return EEGAN_ERR_WORKSPACE;
+    }
+    const int NtP = w.NtP;
+    const int nslab = (R + 31) / 32;
+
+    prof_mark(-1, st);
+    cudaMemsetAsync(w.scal, 0, HS_COUNT * sizeof(float), st);
+    v3_scan_kernel<<<1, 256, 2 * Bc * sizeof(int), st>>>(cap_lens, Bc, Tm, w.maxbins, w.col_start, w.cap_len, w.bin_cap, w.bin_used, w.meta, w.col_cap);
+    h_stats_kernel<<<NtP + Bi * nslab, 256, 0, st>>>(words, w.col_start, w.col_cap, w.meta, D, Tm, NtP, w.Wp, w.wn, img, R, nslab, w.scal);
+    h_convert_kernel<<<NtP + 148 * 4, 256, 0, st>>>(w.Wp, w.meta, D, NtP, w.Wh, w.Wl, img, (long long)Bi * D, R, w.Rp, w.Ch, w.Cl, w.scal);
+    EEGAN_LAUNCH_CHECK("pair prologue");
+    prof_mark(0, st);
+
+    const HOperand opC_mn{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, R, D, w.scal + HS_IC};  // A: rows = regions, K = channels
+    const HOperand opC_k{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, D, R, w.scal + HS_IC};   // B: rows = channels, K = regions
+    {  // GEMM1 + attention forward: S^T[j][r][n'] -> P^T, E^T (half pairs), Zpart
+        HGemm g{};
+        g.nseg = 1;
+        g.A[0] = opC_mn;
+        g.B[0] = HOperand{w.Wh, w.Wl, D, 0, 1, NtP, D, w.scal + HS_IW};
+        g.ldc = NtP; g.bC = (long long)R * NtP; g.M = R; g.N = NtP; g.dynN = w.meta + 1; g.batch = Bi; g.nred = 1;
+        g.epi = TC_EPI_ATTN_FWD;
+        g.attn = h_attn_args(w, g1);
+        g.attn.out_hi = w.Eh; g.attn.out_lo = w.El; g.attn.emax = w.scal + HS_EMAX;
+        int rc = h_gemm_launch(g, st);
+        if (rc) return rc;
+    }
+    prof_mark(1, st);
+
+    {  // GEMM2: U'[j][n'][d] = sum_r E^T[j][r][n'] C[j][d][r]
+        HGemm g{};
+        g.nseg = 1;
+        g.A[0] = HOperand{w.Eh, w.El, NtP, (long long)R * NtP, Bi, NtP, R, w.scal + HS_IE};
+        g.B[0] = opC_k;
+        g.C = w.U; g.ldc = D; g.bC = (long long)NtP * D; g.M = NtP; g.N = D; g.dynM = w.meta + 1; g.batch = Bi; g.nred = 1;
+        g.epi = TC_EPI_PLAIN;
+        int rc = h_gemm_launch(g, st);
+        if (rc) return rc;
+    }
+    prof_mark(3, st);
+
+    v3_cos_lse_kernel<<<dim3(w.maxbins, Bi), 256, 0, st>>>(w.U, w.Wp, w.wn, w.Zpart, w.col_start, w.cap_len, w.bin_cap, w.bin_used,
+                                                           w.meta, NtP, D, Bc, w.nz, g2, w.Z, w.cosv, w.un, m, w.mst);
+    if (att) v3_att_diag_kernel<<<dim3(Bc, (R + 31) / 32), 256, 0, st>>>(w.P, w.Z, w.col_start, w.cap_len, NtP, R, Tm, Bi, diag_offset, att, 1, g1);
+    EEGAN_LAUNCH_CHECK("pair cos/lse");
+    prof_mark(4, st);
+    return EEGAN_OK;
+}
+
+int pair_h_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1, float g2, const float* dm, float* d_img,
+               float* d_words, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    (void)img;
+    HWs w = h_carve(workspace, Bi, Bc, D, R, Tm);
+    if (workspace_bytes < w.bytes) {
+        set_error("pair bwd: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return EEGAN_ERR_WORKSPACE;
+    }
+    const int NtP = w.NtP;
+
+    prof_mark(-1, st);
+    cudaMemsetAsync(w.scal + HS_MAXDUN, 0, sizeof(float), st);
+    h_duscale_kernel<<<dim3(w.maxbins, Bi), 64, 0, st>>>(w.wn, w.Z, w.cosv, w.un, dm, w.mst, w.col_cap, w.meta, NtP, Bc, g2, w.scal);
+    {
+        dim3 grid(NtP, w.ngroups);
+#define H_DU(NQ)                                                                                                              \
+    h_du_kernel<NQ><<<grid, 256, 0, st>>>(w.U, w.Wp, w.wn, w.Z, w.cosv, w.un, dm, w.mst, w.col_cap, w.meta, NtP, Bi, Bc, D, g1, g2, \
+                                          w.DUh, w.DUl, w.csz, w.dwcos, w.scal)
+        switch (D / 128) {
+            case 1: H_DU(1); break;
+            case 2: H_DU(2); break;
+            case 3: H_DU(3); break;
+            case 4: H_DU(4); break;
+            case 5: H_DU(5); break;
+            case 6: H_DU(6); break;
+            case 7: H_DU(7); break;
+            default: H_DU(8); break;
+        }
+#undef H_DU
+    }
+    EEGAN_LAUNCH_CHECK("pair dU");
+    prof_mark(5, st);
+
+    const HOperand opC_mn{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, R, D, w.scal + HS_IC};
+    const HOperand opC_k{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, D, R, w.scal + HS_IC};
+    {  // GEMM3 + attention backward: acc = C^T DUz^T = dA / Z -> dS^T (half pairs)
+        HGemm g{};
+        g.nseg = 1;
+        g.A[0] = opC_mn;
+        g.B[0] = HOperand{w.DUh, w.DUl, D, (long long)NtP * D, Bi, NtP, D, w.scal + HS_IDU};
+        g.ldc = NtP; g.bC = (long long)R * NtP; g.M = R; g.N = NtP; g.dynN = w.meta + 1; g.batch = Bi; g.nred = 1;
+        g.epi = TC_EPI_ATTN_BWD;
+        g.attn = h_attn_args(w, g1);
+        g.attn.out_hi = w.dSh; g.attn.out_lo = w.dSl; g.attn.out_scale = w.scal + HS_SDS;
+        int rc = h_gemm_launch(g, st);
+        if (rc) return rc;
+    }
+    prof_mark(6, st);
+
+    if (d_img) {  // GEMM4: dC[j][d][r] = sum_n' DUz[j][n'][d] E^T[j][r][n'] + Wp[n'][d] dS^T[j][r][n']  (one accumulator per term)
+        HGemm g{};
+        g.nseg = 2;
+        g.A[0] = HOperand{w.DUh, w.DUl, D, (long long)NtP * D, Bi, D, NtP, w.scal + HS_IDU};
+        g.B[0] = HOperand{w.Eh, w.El, NtP, (long long)R * NtP, Bi, R, NtP, w.scal + HS_IE};
+        g.A[1] = HOperand{w.Wh, w.Wl, D, 0, 1, D, NtP, w.scal + HS_IW};
+        g.B[1] = HOperand{w.dSh, w.dSl, NtP, (long long)R * NtP, Bi, R, NtP, w.scal + HS_IDS};
+        g.C = d_img; g.ldc = R; g.bC = (long long)D * R; g.M = D; g.N = R; g.dynK = w.meta + 1; g.batch = Bi; g.nred = 1;
+        g.epi = TC_EPI_PLAIN;
+        int rc = h_gemm_launch(g, st);
+        if (rc) return rc;
+        prof_mark(8, st);
+    }
+    if (d_words) {  // GEMM5: dWp[n'][d] = sum_j sum_r dS^T[j][r][n'] C[j][d][r], images split in nsplit groups
+        const int nred = (Bi + w.nsplit - 1) / w.nsplit;
+        HGemm g{};
+        g.nseg = 1;
+        g.A[0] = HOperand{w.dSh, w.dSl, NtP, (long long)R * NtP, Bi, NtP, R, w.scal + HS_IDS};
+        g.B[0] = opC_k;
+        g.C = w.dWpart; g.ldc = D; g.bC = (long long)NtP * D; g.M = NtP; g.N = D; g.dynM = w.meta + 1; g.batch = w.nsplit;
+        g.nred = nred; g.red_total = Bi;
+        g.epi = TC_EPI_PLAIN;
+        int rc = h_gemm_launch(g, st);
+        if (rc) return rc;
+        v3_unpack_dw_kernel<<<dim3(Bc, (D + 31) / 32), 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.cap_len, w.nsplit, w.ngroups,
+                                                                     NtP, D, Tm, d_words);
+        EEGAN_LAUNCH_CHECK("pair GEMM5");
+        prof_mark(9, st);
+    }
+    return EEGAN_OK;
+}
+
+}  // namespace eegan

@@ -70,15 +70,15 @@ class _PairGridFn(torch.autograd.Function):
         dm = _lib.f32c(dm)
         if ctx.ws is None:
             raise RuntimeError("words_loss backward: the forward stash was consumed by an earlier backward "
-                               "(only the fused contraction engine, 2, keeps it for retain_graph)")
+                               "(only the fused contraction engines, 2 and 3, keep it for retain_graph)")
         if L.eegan_get_contraction_engine() != ctx.engine:
             raise RuntimeError("words_loss backward: the contraction engine changed since the forward")
         with torch.cuda.device(img.device):
             _lib.check(L.eegan_damsm_pair_bwd(_lib.ptr(img), _lib.ptr(words), _lib.ptr(cap_lens32), Bi, Bc, D, R, Tm,
                                               ctx.g[0], ctx.g[1], _lib.ptr(dm), _lib.ptr(d_img), _lib.ptr(d_words),
                                               _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr()), "damsm_pair_bwd")
-        if ctx.engine != 2 or D % 128:
-            ctx.ws = None  # engines 0/1 consume the stash (U and dA are overwritten in place); the fused engine keeps it
+        if ctx.engine < 2 or D % 128:
+            ctx.ws = None  # engines 0/1 consume the stash (U and dA are overwritten in place); the fused engines keep it
         return d_img, d_words, None, None, None, None, None
 
 

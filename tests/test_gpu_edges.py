@@ -58,7 +58,7 @@ def test_small_and_odd_shapes(cuda_lib, B, T, D, H, lens):
 def test_fused_engine_shapes(cuda_lib, B, T, D, H, lens):
     """Shapes that exercise the fused engine's packing (64-column bins, 128-column tiles), its
     per-caption word buckets and the region-tile edges, against the float64 dense oracle."""
-    assert cuda_lib.eegan_get_contraction_engine() == 2 and D % 128 == 0
+    assert cuda_lib.eegan_get_contraction_engine() >= 2 and D % 128 == 0
     c = cases.words_case(B, T, D=D, H=H, seed=B * 100 + T + D, class_mode="none", min_len=1)
     c["cap_lens"] = torch.tensor(lens)
     got, ref = _run_both(c, B, 1.0, 0.5)

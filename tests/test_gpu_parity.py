@@ -251,13 +251,14 @@ def test_full_size_properties(cuda_lib):
 
 
 def test_ffma_engine_still_matches(cuda_lib):
-    """The exact-fp32 CUDA-core engine (0) and the unfused tensor-core pipeline (1) stay selectable
-    for A/B validation of the default fused engine (2): all agree to fp32 noise."""
+    """The exact-fp32 CUDA-core engine (0), the unfused tensor-core pipeline (1), the fused 3xTF32 engine (2) and the
+    fused half-pair engine (3) stay selectable for A/B validation: all agree to fp32 noise."""
     import eegan_b200 as E
     c = cases.words_case(12, 18, seed=5)
     res = {}
+    default = cuda_lib.eegan_get_contraction_engine()
     try:
-        for eng in (0, 1, 2):
+        for eng in (0, 1, 2, 3):
             assert cuda_lib.eegan_set_contraction_engine(eng) == 0
             img = c["img"].cuda().requires_grad_()
             words = c["words"].cuda().requires_grad_()
@@ -265,8 +266,8 @@ def test_ffma_engine_still_matches(cuda_lib):
             (l0 + l1).backward()
             res[eng] = (l0.item(), l1.item(), img.grad.clone(), words.grad.clone())
     finally:
-        cuda_lib.eegan_set_contraction_engine(2)
-    for eng in (1, 2):
+        cuda_lib.eegan_set_contraction_engine(default)
+    for eng in (1, 2, 3):
         assert abs(res[0][0] - res[eng][0]) <= 2e-5 and abs(res[0][1] - res[eng][1]) <= 2e-5, eng
         assert relmax(res[eng][2], res[0][2]) <= TOL_GRAD and relmax(res[eng][3], res[0][3]) <= TOL_GRAD, eng
 

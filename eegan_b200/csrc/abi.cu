@@ -1,4 +1,6 @@
 // Error channel + version of the C ABI (include/eegan_b200.h).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace eegan {
@@ -8,6 +10,13 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("EEGAN_PDL");
+        return e ? atoi(e) != 0 : true;
+    }();
+    return on;
 }
 }  // namespace eegan
 

@@ -40,6 +40,32 @@ void prof_mark(int stage, cudaStream_t st);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// A kernel launched through launch_pdl() may become resident while the previous kernel of the stream is still
+// draining: its CTAs run their set-up (barriers, TMEM allocation, tensor-map prefetch) and then block in
+// pdl_wait() until the previous grid has completed and its writes are visible.  Every kernel of a PDL chain
+// therefore calls pdl_trigger() first (lets the NEXT kernel's CTAs be scheduled once all CTAs of this grid run)
+// and pdl_wait() before its first global-memory access.  Both are no-ops in a kernel launched the plain way.
+// EEGAN_PDL=0 turns the launch attribute off (A/B timing).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -28,13 +28,14 @@ struct HArgs {
     const float* inv_a[2];
     const float* inv_b[2];
     HAttnEpi attn;
+    int dbg;  // timing experiments only (EEGAN_H_DBG): 1 read-out without global stores, 2 no read-out, 4 no caption phase
 };
 
 template <int EPI, bool DUAL>
 struct HCfg {
     static constexpr bool kAttn = EPI != TC_EPI_PLAIN;
-    static constexpr int kEWarps = kAttn ? 8 : 4;  // epilogue warps (two per TMEM lane quarter in the attention forms)
-    static constexpr int kStages = kAttn ? 4 : 6;
+    static constexpr int kEWarps = 8;  // epilogue warps: two per TMEM lane quarter, one 64-column half of the tile each
+    static constexpr int kStages = kAttn ? 4 : 5;
     static constexpr int kThreads = 32 * (2 + kEWarps);
     static constexpr int kEpiPitch = kAttn ? H_EPI_PITCH : 33;
     static constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4;
@@ -160,8 +161,9 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
     if (EPI == TC_EPI_PLAIN) {
         mbar_wait(t.full_bar, t.full_parity);
         tc_fence_after();
+        const int c_lo = t.half * (H_BN / 64), c_hi = c_lo + H_BN / 64;
 #pragma unroll 1
-        for (int c = 0; c < H_BN / 32; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
             float v[32];
             if (t.total > 0) {
                 uint32_t r0[32];
@@ -181,7 +183,7 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
 #pragma unroll
                 for (int q = 0; q < 32; ++q) v[q] = 0.f;
             }
-            if (c == H_BN / 32 - 1) {  // accumulator read: hand it back to the MMA warp
+            if (c == c_hi - 1) {  // this warp's share of the accumulator is read: hand it back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t.empty_bar);
@@ -270,7 +272,7 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
             const int T = __shfl_sync(0xffffffffu, myT, ci);
             if (T <= 0) continue;
             const int cl = __shfl_sync(0xffffffffu, myC, ci);
-            h_attn_caption<EPI>(t.tacc + (uint32_t)(64 * h + cl), T, my_row + (uint32_t)cl * 4u, t.czs + (uint32_t)cl * 4u, e.g1, inv0);
+            if (!(p.dbg & 4)) h_attn_caption<EPI>(t.tacc + (uint32_t)(64 * h + cl), T, my_row + (uint32_t)cl * 4u, t.czs + (uint32_t)cl * 4u, e.g1, inv0);
         }
     }
     if (!waited) {
@@ -285,6 +287,8 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
     // read-out: region rows, coalesced; a lane owns the adjacent columns 2 lane, 2 lane + 1 of the bin: one 8-byte P store and
     // one 4-byte store per half array and row.  Padding columns of the bin hold P = 0, hence finite E' / dS' = 0 — every
     // consumer multiplies them by zero rows (GEMM4) or never reads the outputs they feed (GEMM2 / GEMM5 rows, Zpart).
+    if (p.dbg & 2) return;
+    const bool nostore = p.dbg & 1;
     const uint32_t rd0 = t.stage + (uint32_t)(2 * lane) * 4u;
     const long long o0 = (long long)row0 * p.ldc + col0 + 2 * lane;
     uint32_t* hp = reinterpret_cast<uint32_t*>(Hz + o0);
@@ -304,9 +308,13 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
             const __half2 h = __floats2half2_rn(e0, e1);
             const float2 hf = __half22float2(h);
             const __half2 l = __floats2half2_rn(e0 - hf.x, e1 - hf.y);
-            *pp = pv;
-            *hp = *reinterpret_cast<const uint32_t*>(&h);
-            *lp = *reinterpret_cast<const uint32_t*>(&l);
+            if (!nostore) {
+                *pp = pv;
+                *hp = *reinterpret_cast<const uint32_t*>(&h);
+                *lp = *reinterpret_cast<const uint32_t*>(&l);
+            } else {
+                z0 += hf.x + __half22float2(l).x;
+            }
             pp += pstep; hp += hstep; lp += hstep;
             z0 += e0;
             z1 += e1;
@@ -334,8 +342,12 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
             const __half2 h = __floats2half2_rn(x0, x1);
             const float2 hf = __half22float2(h);
             const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-            *hp = *reinterpret_cast<const uint32_t*>(&h);
-            *lp = *reinterpret_cast<const uint32_t*>(&l);
+            if (!nostore) {
+                *hp = *reinterpret_cast<const uint32_t*>(&h);
+                *lp = *reinterpret_cast<const uint32_t*>(&l);
+            } else if (hf.x + __half22float2(l).y == 123.456f) {
+                *hp = 0u;
+            }
             hp += hstep; lp += hstep;
         };
 #pragma unroll 1
@@ -361,12 +373,6 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
     constexpr int NS = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int Mlive = p.dynM ? min(*p.dynM, p.M) : p.M;
-    const int Nlive = p.dynN ? min(*p.dynN, p.N) : p.N;
-    const int mt = (Mlive + H_BM - 1) / H_BM, nt = (Nlive + H_BN - 1) / H_BN;
-    const int ntiles = mt * nt * p.batch;
-    if ((int)blockIdx.x >= ntiles) return;  // uniform: before any barrier / TMEM state exists
-
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t epi_stage = base + NS * H_STAGE_BYTES;
     const uint32_t epi_czs = epi_stage + Cfg::kEWarps * Cfg::kEpiWarpBytes;
@@ -376,6 +382,37 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
     auto tmem_full = [&](int a) { return bars + 8u * (2 * NS + a); };
     auto tmem_empty = [&](int a) { return bars + 8u * (2 * NS + 2 + a); };
     const uint32_t tmem_slot = bars + 8u * (2 * NS + 4);
+
+    // ---- set-up that depends on nothing the previous kernel wrote: overlaps its tail under PDL ----
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), Cfg::kEWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 8; ++q) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.m[q >> 2][(q >> 1) & 1][q & 1]) : "memory");
+    }
+    if (warp == 1) {  // all 512 columns: the attention epilogues read 32-column windows that may overhang an accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+    pdl_wait();  // from here on: global memory written by the previous kernels
+
+    const int Mlive = p.dynM ? min(*p.dynM, p.M) : p.M;
+    const int Nlive = p.dynN ? min(*p.dynN, p.N) : p.N;
+    const int mt = (Mlive + H_BM - 1) / H_BM, nt = (Nlive + H_BN - 1) / H_BN;
+    const int ntiles = mt * nt * p.batch;  // CTAs beyond the live tiles fall through the role loops
 
     int kb0 = 0, kb1 = 0;
     {
@@ -392,27 +429,6 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
         if (p.red_total > 0) nred = max(0, min(p.nred, p.red_total - z * p.nred));
         return nred * kbt;
     };
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(full(s), 1);
-            mbar_init(empty(s), 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tmem_full(a), 1);
-            mbar_init(tmem_empty(a), Cfg::kEWarps);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {  // all 512 columns: the attention epilogues read 32-column windows that may overhang an accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -485,7 +501,7 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
         float inv1 = (DUAL && p.nseg > 1) ? __ldg(p.inv_a[1]) * __ldg(p.inv_b[1]) : 0.f;
         EpiTile et;
         et.quarter = warp & 3;
-        et.half = Cfg::kAttn ? (ew >> 2) : -1;
+        et.half = ew >> 2;
         et.stage = epi_stage + (uint32_t)ew * Cfg::kEpiWarpBytes;
         et.czs = epi_czs + (uint32_t)ew * 256u;
         et.Mlive = Mlive;
@@ -611,7 +627,8 @@ static int h_launch_t(const HMaps& maps, const HArgs& a, unsigned grid, cudaStre
         if (e != cudaSuccess) { set_error("h gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
         attr_set = true;
     }
-    h_gemm_kernel<EPI, DUAL><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
+    cudaError_t e = launch_pdl(h_gemm_kernel<EPI, DUAL>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmem, st, maps, a);
+    if (e != cudaSuccess) { set_error("h gemm launch: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
     return check_launch("h gemm");
 }
 
@@ -639,6 +656,7 @@ int h_gemm_launch(const HGemm& g, cudaStream_t st) {
     a.C = g.C; a.ldc = g.ldc; a.bC = g.bC; a.M = g.M; a.N = g.N; a.dynM = g.dynM; a.dynN = g.dynN; a.dynK = g.dynK;
     a.attn = g.attn;
     a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total; a.batch = g.batch;
+    if (const char* e = getenv("EEGAN_H_DBG")) a.dbg = atoi(e);
     const long long tiles = (long long)((g.N + H_BN - 1) / H_BN) * ((g.M + H_BM - 1) / H_BM) * g.batch;
     const unsigned grid = (unsigned)(tiles < h_num_sms() ? tiles : h_num_sms());
     if (g.epi != TC_EPI_PLAIN) {
@@ -687,7 +705,7 @@ extern "C" int eegan_gemm_f16x3(const float* A, const float* B, float* C, int M,
     EEGAN_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0 && workspace, "gemm_f16x3: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const long long nA = bsA > 0 ? bsA * batch : (long long)K * lda, nB = bsB > 0 ? bsB * batch : (long long)N * ldb;
-    const int nset = dual ? 2 : 1;
+    const int nset = (dual & 1) ? 2 : 1;
     const size_t need = (size_t)nset * 2 * (align_up(nA * 2, 256) + align_up(nB * 2, 256)) + 256;
     EEGAN_REQUIRE(workspace_bytes >= need, "gemm_f16x3: workspace %zu < %zu", workspace_bytes, need);
     char* p = (char*)workspace;
@@ -701,8 +719,10 @@ extern "C" int eegan_gemm_f16x3(const float* A, const float* B, float* C, int M,
         __half* al = (__half*)p; p += align_up(nA * 2, 256);
         __half* bh = (__half*)p; p += align_up(nB * 2, 256);
         __half* bl = (__half*)p; p += align_up(nB * 2, 256);
-        h_split_kernel<<<296, 256, 0, st>>>(A, ah, al, nA, s ? 4.0f * sa : sa);
-        h_split_kernel<<<296, 256, 0, st>>>(B, bh, bl, nB, s ? sb / 8.0f : sb);
+        if (!(dual & 4)) {  // dual & 4 (microbenchmarks): the workspace already holds the split operands of an earlier call
+            h_split_kernel<<<296, 256, 0, st>>>(A, ah, al, nA, s ? 4.0f * sa : sa);
+            h_split_kernel<<<296, 256, 0, st>>>(B, bh, bl, nB, s ? sb / 8.0f : sb);
+        }
         g.A[s] = HOperand{ah, al, lda, bsA, batch, M, K, scales + 2 * s};
         g.B[s] = HOperand{bh, bl, ldb, bsB, batch, N, K, scales + 2 * s + 1};
     }

@@ -24,7 +24,7 @@
 //
 //   warp 0      TMA producer (6 boxes per 32 KB stage: A hi/lo x 2, B hi/lo)
 //   warp 1      TMEM allocator + single-thread MMA issuer; tcgen05.commit frees the stage
-//   warps 2-..  epilogue (4, or 8 in the attention instantiations)
+//   warps 2-9   epilogue: two warps per TMEM lane quarter, one 64-column half of the tile each
 // Two TMEM accumulator buffers overlap a tile's epilogue with the next main loop.  A two-segment
 // GEMM (GEMM4: dC = DUz^T E + Wp^T dS) gives each segment its own accumulator (DUAL), because the
 // two products carry different scales; the epilogue adds them after descaling.

@@ -10,6 +10,8 @@ __global__ void __launch_bounds__(256) pair_ce_lse_kernel(const float* __restric
                                                           const int64_t* __restrict__ class_ids, int B,
                                                           float* __restrict__ out, float* __restrict__ lse) {
     __shared__ float red[32];
+    pdl_trigger();
+    pdl_wait();
     const bool is_row = blockIdx.x < B;
     const int fixed = is_row ? blockIdx.x : blockIdx.x - B;
     const int64_t cf = class_ids ? class_ids[fixed] : 0;
@@ -38,6 +40,8 @@ __global__ void __launch_bounds__(256) pair_ce_loss_kernel(const float* __restri
                                                            const int64_t* __restrict__ labels, int B,
                                                            float* __restrict__ loss01) {
     __shared__ float red[32];
+    pdl_trigger();
+    pdl_wait();
     float l0 = 0.f, l1 = 0.f;
     for (int k = threadIdx.x; k < B; k += blockDim.x) {
         const int lab = (int)labels[k];
@@ -57,6 +61,8 @@ __global__ void __launch_bounds__(256) pair_ce_bwd_kernel(const float* __restric
                                                           const float* __restrict__ g, float scale, int B,
                                                           float* __restrict__ ds) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (idx >= (size_t)B * B) return;
     const int a = (int)(idx / B), b = (int)(idx - (size_t)a * B);
     const float v = s[idx];
@@ -159,8 +165,8 @@ extern "C" int eegan_pair_ce_fwd(const float* scores_in, float scale, const int6
     EEGAN_REQUIRE(B > 0, "pair_ce: B=%d", B);
     EEGAN_REQUIRE(scores_in && scores_out && lse, "pair_ce fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    pair_ce_lse_kernel<<<2 * B, 256, 0, st>>>(scores_in, scale, class_ids, B, scores_out, lse);
-    if (labels && loss01) pair_ce_loss_kernel<<<1, 256, 0, st>>>(scores_out, lse, labels, B, loss01);
+    launch_pdl(pair_ce_lse_kernel, dim3(2 * B), dim3(256), 0, st, scores_in, scale, class_ids, B, scores_out, lse);
+    if (labels && loss01) launch_pdl(pair_ce_loss_kernel, dim3(1), dim3(256), 0, st, (const float*)scores_out, (const float*)lse, labels, B, loss01);
     EEGAN_LAUNCH_CHECK("pair_ce fwd");
     return EEGAN_OK;
 }
@@ -170,8 +176,8 @@ extern "C" int eegan_pair_ce_bwd(const float* scores_out, const float* lse, cons
     EEGAN_REQUIRE(B > 0, "pair_ce: B=%d", B);
     EEGAN_REQUIRE(scores_out && lse && labels && g_loss01 && dscores_in, "pair_ce bwd: null pointer");
     const size_t n = (size_t)B * B;
-    pair_ce_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(scores_out, lse, labels, g_loss01,
-                                                                                      scale, B, dscores_in);
+    launch_pdl(pair_ce_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, scores_out, lse, labels,
+               g_loss01, scale, B, dscores_in);
     EEGAN_LAUNCH_CHECK("pair_ce bwd");
     return EEGAN_OK;
 }

@@ -9,7 +9,7 @@
 // fp16 rate with no operand split in the kernel.
 //
 // Scales (all on the device, no host sync; `scal` block of the workspace):
-//   C, W   exact max |x| (h_stats_kernel)               -> max scaled into [2^7, 2^8)
+//   C, W   exact max |x| (h_pre_kernel partials)        -> max scaled into [2^7, 2^8)
 //   E      in (0, 1]: constant 2^12
 //   DUz    exact row 2-norms |dcos| sqrt(1 - cos^2) / (|u| Z) from the per-column scalars (h_duscale_kernel)
 //          -> largest row norm scaled into [2^11, 2^12): elements <= 2^12
@@ -38,6 +38,8 @@ struct HWs {
     int* meta;
     int* col_cap;
     float* scal;     // [HS_COUNT] maxima and scales
+    float* pmax;     // [3][npart] per-CTA partial maxima of the prologue: |c|, column norm^2 of C, |w|
+    float* pdun;     // [Bi][maxbins] per-CTA partial maxima of the DUz row norms
     float* Wp;       // [NtP][D] packed words, fp32 (cos/lse, dU)
     float* wn;       // [NtP]
     __half* Wh;      // [NtP][D]
@@ -60,7 +62,7 @@ struct HWs {
     __half* dSl;
     float* dWpart;   // [nsplit][NtP][D]
     float* dwcos;    // [ngroups][NtP][D]
-    int Rp, NtP, maxbins, nsplit, ngroups, nz;
+    int Rp, NtP, maxbins, nsplit, ngroups, nz, npart;
     size_t bytes;
 };
 
@@ -88,6 +90,9 @@ static HWs h_carve(void* base, int Bi, int Bc, int D, int R, int Tm) {
     w.meta = (int*)take(4 * sizeof(int));
     w.col_cap = (int*)take(NtP * sizeof(int));
     w.scal = (float*)take(HS_COUNT * sizeof(float));
+    w.npart = Bi * w.nz > Bc ? Bi * w.nz : Bc;
+    w.pmax = (float*)take((size_t)3 * w.npart * sizeof(float));
+    w.pdun = (float*)take((size_t)Bi * w.maxbins * sizeof(float));
     w.Wp = (float*)take(NtP * D * sizeof(float));
     w.wn = (float*)take(NtP * sizeof(float));
     w.Wh = (__half*)take(NtP * D * sizeof(__half));
@@ -139,20 +144,31 @@ __device__ __forceinline__ void h_split4(const float4 v, float s, uint2& hi, uin
 }
 
 // ---------------------------------------------------------------------------------------
-// prologue
+// prologue: two launches
 // ---------------------------------------------------------------------------------------
-// One launch, two roles:
-//   CTAs [0, NtP):   one packed column each: gather the word vector (words is [i][d][t]) -> Wp, |w|, max |w_d|
-//   CTAs [NtP, ...): one (image, 32-region slab) each: max |c| and the largest column norm |C[j][:, r]|^2
-__global__ void __launch_bounds__(256) h_stats_kernel(const float* __restrict__ words, const int* __restrict__ col_start,
-                                                      const int* __restrict__ col_cap, const int* __restrict__ meta, int D, int Tm,
-                                                      int NtP, float* __restrict__ Wp, float* __restrict__ wn,
-                                                      const float* __restrict__ img, int R, int nslab, float* __restrict__ scal) {
+// Launch 1, three independent roles (none needs another's result):
+//   CTA 0                      caption packing (v3_scan_body)
+//   CTAs 1 .. Bi*nslab         one (image, 32-region slab) each: max |c| and the largest column norm |C[j][:, r]|^2
+//   the last Bc CTAs           one caption each: max |w| over its live words
+// The maxima leave as per-CTA partials (no atomics, nothing to zero); launch 2 reduces them.
+__global__ void __launch_bounds__(256) h_pre_kernel(const int32_t* __restrict__ cap_lens, int Bc, int Tm, int maxbins,
+                                                    int* __restrict__ col_start, int* __restrict__ cap_len, int* __restrict__ bin_cap,
+                                                    int* __restrict__ bin_used, int* __restrict__ meta, int* __restrict__ col_cap,
+                                                    const float* __restrict__ img, int Bi, int D, int R, int nslab,
+                                                    const float* __restrict__ words, float* __restrict__ pmax, int npart) {
+    extern __shared__ int s_pre_buf[];
     __shared__ float red[32];
     __shared__ float s_part[8][32];
-    if ((int)blockIdx.x >= NtP) {
-        const int idx = blockIdx.x - NtP, j = idx / nslab, r = (idx % nslab) * 32 + (threadIdx.x & 31);
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
+    if (blockIdx.x == 0) {
+        v3_scan_body(s_pre_buf, cap_lens, Bc, Tm, maxbins, col_start, cap_len, bin_cap, bin_used, meta, col_cap);
+        return;
+    }
+    const int idx = blockIdx.x - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (idx < Bi * nslab) {
+        const int j = idx / nslab, r = (idx % nslab) * 32 + lane;
         const float* src = img + (size_t)j * D * R + r;
         float ss = 0.f, am = 0.f;
         if (r < R) {
@@ -168,53 +184,62 @@ __global__ void __launch_bounds__(256) h_stats_kernel(const float* __restrict__ 
             }
         }
         s_part[warp][lane] = ss;
-        am = block_max(am, red);  // has the __syncthreads that also publishes s_part
+        am = block_max(am, red);  // its __syncthreads also publishes s_part
         if (warp == 0) {
             float n2 = 0.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) n2 += s_part[q][lane];
             n2 = warp_max(n2);
             if (lane == 0) {
-                h_atomic_max_pos(scal + HS_MAXCN2, n2);
-                h_atomic_max_pos(scal + HS_MAXC, am);
+                pmax[idx] = am;
+                pmax[npart + idx] = n2;
             }
         }
         return;
     }
-    const int n = blockIdx.x;
-    if (n >= meta[1]) return;
-    const int i = col_cap[n];
-    float ss = 0.f, am = 0.f;
-    if (i < 0) {
-        for (int d = threadIdx.x; d < D; d += blockDim.x) Wp[(size_t)n * D + d] = 0.f;
-    } else {
-        const int t = n - col_start[i];
-        for (int d = threadIdx.x; d < D; d += blockDim.x) {
-            const float v = __ldg(words + ((size_t)i * D + d) * Tm + t);
-            Wp[(size_t)n * D + d] = v;
-            ss = fmaf(v, v, ss);
-            am = fmaxf(am, fabsf(v));
-        }
+    const int i = idx - Bi * nslab;
+    const int T = min(max(cap_lens[i], 0), Tm);
+    const float* wsrc = words + (size_t)i * D * Tm;
+    float am = 0.f;
+    for (int k = threadIdx.x; k < D * Tm; k += blockDim.x) {
+        const float v = __ldg(wsrc + k);
+        if (k % Tm < T) am = fmaxf(am, fabsf(v));
     }
-    ss = block_sum(ss, red);
     am = block_max(am, red);
-    if (threadIdx.x == 0) {
-        wn[n] = sqrtf(ss);
-        if (i >= 0) h_atomic_max_pos(scal + HS_MAXW, am);
-    }
+    if (threadIdx.x == 0) pmax[2 * npart + i] = am;
 }
 
-// Scales of C and W from the maxima, then the half pairs:
-//   CTAs [0, NtP): Wp row n' -> Wh, Wl;   CTAs [NtP, ...): img rows [Bi*D][R] -> Ch, Cl [Bi*D][Rp] (pad columns zero)
-__global__ void __launch_bounds__(256) h_convert_kernel(const float* __restrict__ Wp, const int* __restrict__ meta, int D, int NtP,
-                                                        __half* __restrict__ Wh, __half* __restrict__ Wl,
-                                                        const float* __restrict__ img, long long rows, int R, int Rp,
-                                                        __half* __restrict__ Ch, __half* __restrict__ Cl, float* __restrict__ scal) {
-    const float sC = h_pow2_scale(scal[HS_MAXC], 8), sW = h_pow2_scale(scal[HS_MAXW], 8);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        scal[HS_SC] = sC; scal[HS_IC] = 1.0f / sC;
-        scal[HS_SW] = sW; scal[HS_IW] = 1.0f / sW;
-        scal[HS_SE] = H_E_SCALE; scal[HS_IE] = 1.0f / H_E_SCALE;
+// Launch 2: every CTA reduces the partial maxima to the scales of C and W (CTA 0 publishes them), then
+//   CTAs [0, NtP):   one packed column each: gather the word vector (words is [i][d][t]) -> Wp (fp32), |w|, Wh / Wl
+//   CTAs [NtP, ...): img rows [Bi*D][R] -> Ch, Cl [Bi*D][Rp] (pad columns zero)
+__global__ void __launch_bounds__(256) h_pack_kernel(const float* __restrict__ words, const int* __restrict__ col_start,
+                                                     const int* __restrict__ col_cap, const int* __restrict__ meta, int D, int Tm,
+                                                     int NtP, float* __restrict__ Wp, float* __restrict__ wn, __half* __restrict__ Wh,
+                                                     __half* __restrict__ Wl, const float* __restrict__ img, long long rows, int R,
+                                                     int Rp, __half* __restrict__ Ch, __half* __restrict__ Cl,
+                                                     const float* __restrict__ pmax, int nC, int nW, int npart,
+                                                     float* __restrict__ scal) {
+    __shared__ float red[32];
+    pdl_trigger();
+    pdl_wait();
+    float mc = 0.f, mn = 0.f, mw = 0.f;
+    for (int k = threadIdx.x; k < nC; k += blockDim.x) {
+        mc = fmaxf(mc, pmax[k]);
+        mn = fmaxf(mn, pmax[npart + k]);
+    }
+    for (int k = threadIdx.x; k < nW; k += blockDim.x) mw = fmaxf(mw, pmax[2 * npart + k]);
+    mc = block_max(mc, red);
+    mw = block_max(mw, red);
+    const float sC = h_pow2_scale(mc, 8), sW = h_pow2_scale(mw, 8);
+    if (blockIdx.x == 0) {
+        mn = block_max(mn, red);
+        if (threadIdx.x == 0) {
+            scal[HS_MAXC] = mc; scal[HS_MAXW] = mw; scal[HS_MAXCN2] = mn;
+            scal[HS_EMAX] = 0.f;  // GEMM1's epilogue collects max E with atomicMax
+            scal[HS_SC] = sC; scal[HS_IC] = 1.0f / sC;
+            scal[HS_SW] = sW; scal[HS_IW] = 1.0f / sW;
+            scal[HS_SE] = H_E_SCALE; scal[HS_IE] = 1.0f / H_E_SCALE;
+        }
     }
     if ((int)blockIdx.x >= NtP) {
         const int lane = threadIdx.x & 31;
@@ -244,12 +269,29 @@ __global__ void __launch_bounds__(256) h_convert_kernel(const float* __restrict_
     }
     const int n = blockIdx.x;
     if (n >= meta[1]) return;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        __half h, l;
-        h_split(Wp[(size_t)n * D + d] * sW, h, l);
-        Wh[(size_t)n * D + d] = h;
-        Wl[(size_t)n * D + d] = l;
+    const int i = col_cap[n];
+    float ss = 0.f;
+    if (i < 0) {
+        const __half zero = __float2half_rn(0.f);
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            Wp[(size_t)n * D + d] = 0.f;
+            Wh[(size_t)n * D + d] = zero;
+            Wl[(size_t)n * D + d] = zero;
+        }
+    } else {
+        const int t = n - col_start[i];
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const float v = __ldg(words + ((size_t)i * D + d) * Tm + t);
+            Wp[(size_t)n * D + d] = v;
+            __half h, l;
+            h_split(v * sW, h, l);
+            Wh[(size_t)n * D + d] = h;
+            Wl[(size_t)n * D + d] = l;
+            ss = fmaf(v, v, ss);
+        }
     }
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) wn[n] = sqrtf(ss);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -263,24 +305,27 @@ __global__ void __launch_bounds__(64) h_duscale_kernel(const float* __restrict__
                                                        const float* __restrict__ cosv, const float* __restrict__ un,
                                                        const float* __restrict__ dm, const float* __restrict__ mst,
                                                        const int* __restrict__ col_cap, const int* __restrict__ meta, int NtP, int Bc,
-                                                       float g2, float* __restrict__ scal) {
+                                                       float g2, float* __restrict__ pdun) {
     __shared__ float red[32];
     const int b = blockIdx.x, j = blockIdx.y;
-    if (b >= meta[0]) return;
-    const int n = b * V3_BIN + threadIdx.x;
-    const int i = col_cap[n];
+    pdl_trigger();
+    pdl_wait();
     float nz = 0.f;
-    if (i >= 0) {
-        const size_t idx = (size_t)j * NtP + n;
-        const float c = cosv[idx], unv = un[idx];
-        const float dcos = fabsf(dm[(size_t)j * Bc + i] * g2 * expf(g2 * c - mst[(size_t)j * Bc + i]));
-        const float nn = wn[n] * unv;
-        const float nrm = nn > 1e-8f ? dcos * sqrtf(fmaxf(1.0f - c * c, 1e-6f)) / unv : dcos * 1e8f * wn[n];
-        nz = nrm / Z[idx];
-        if (!(nz >= 0.f)) nz = INFINITY;  // NaN upstream: poison the maximum so that the scale falls back to 1
+    if (b < meta[0]) {
+        const int n = b * V3_BIN + threadIdx.x;
+        const int i = col_cap[n];
+        if (i >= 0) {
+            const size_t idx = (size_t)j * NtP + n;
+            const float c = cosv[idx], unv = un[idx];
+            const float dcos = fabsf(dm[(size_t)j * Bc + i] * g2 * expf(g2 * c - mst[(size_t)j * Bc + i]));
+            const float nn = wn[n] * unv;
+            const float nrm = nn > 1e-8f ? dcos * sqrtf(fmaxf(1.0f - c * c, 1e-6f)) / unv : dcos * 1e8f * wn[n];
+            nz = nrm / Z[idx];
+            if (!(nz >= 0.f)) nz = INFINITY;  // NaN upstream: poison the maximum so that the scale falls back to 1
+        }
     }
     nz = block_max(nz, red);
-    if (threadIdx.x == 0 && nz > 0.f) h_atomic_max_pos(scal + HS_MAXDUN, nz);
+    if (threadIdx.x == 0) pdun[(size_t)j * gridDim.x + b] = nz;  // every CTA writes (0 for dead bins): nothing to zero beforehand
 }
 
 // One CTA per (packed column n', group of 64 images): as v3_du_kernel (pair_grid_v3.cu), with DUz written as half pairs.
@@ -294,15 +339,21 @@ __global__ void __launch_bounds__(256) h_du_kernel(const float* __restrict__ U, 
                                                    const int* __restrict__ col_cap, const int* __restrict__ meta, int NtP, int Bi,
                                                    int Bc, int D, float g1, float g2, __half* __restrict__ DUh,
                                                    __half* __restrict__ DUl, float* __restrict__ csz, float* __restrict__ dwcos,
-                                                   float* __restrict__ scal) {
+                                                   const float* __restrict__ pdun, int npdun, float* __restrict__ scal) {
     __shared__ float4 s_acc[8][32 * NQ];
     __shared__ float s_a3[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (n >= meta[1]) return;
-    const float maxdun = scal[HS_MAXDUN];
+    __shared__ float red[32];
+    float maxdun = 0.f;
+    for (int k = threadIdx.x; k < npdun; k += blockDim.x) maxdun = fmaxf(maxdun, pdun[k]);
+    maxdun = block_max(maxdun, red);
     const float sDU = h_pow2_scale(maxdun, 12);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        scal[HS_MAXDUN] = maxdun;
         scal[HS_SDU] = sDU; scal[HS_IDU] = 1.0f / sDU;
         const float bound = 4.0f * g1 * fmaxf(scal[HS_EMAX], 1e-30f) * sqrtf(scal[HS_MAXCN2]) * maxdun;
         const float sDS = h_pow2_scale(bound, 14);
@@ -442,10 +493,11 @@ int pair_h_fwd(const float* img, const float* words, const int32_t* cap_lens, in
     const int nslab = (R + 31) / 32;
 
     prof_mark(-1, st);
-    cudaMemsetAsync(w.scal, 0, HS_COUNT * sizeof(float), st);
-    v3_scan_kernel<<<1, 256, 2 * Bc * sizeof(int), st>>>(cap_lens, Bc, Tm, w.maxbins, w.col_start, w.cap_len, w.bin_cap, w.bin_used, w.meta, w.col_cap);
-    h_stats_kernel<<<NtP + Bi * nslab, 256, 0, st>>>(words, w.col_start, w.col_cap, w.meta, D, Tm, NtP, w.Wp, w.wn, img, R, nslab, w.scal);
-    h_convert_kernel<<<NtP + 148 * 4, 256, 0, st>>>(w.Wp, w.meta, D, NtP, w.Wh, w.Wl, img, (long long)Bi * D, R, w.Rp, w.Ch, w.Cl, w.scal);
+    launch_pdl(h_pre_kernel, dim3(1 + Bi * nslab + Bc), dim3(256), 2 * Bc * sizeof(int), st, cap_lens, Bc, Tm, w.maxbins, w.col_start,
+               w.cap_len, w.bin_cap, w.bin_used, w.meta, w.col_cap, img, Bi, D, R, nslab, words, w.pmax, w.npart);
+    launch_pdl(h_pack_kernel, dim3(NtP + 148 * 4), dim3(256), 0, st, words, (const int*)w.col_start, (const int*)w.col_cap,
+               (const int*)w.meta, D, Tm, NtP, w.Wp, w.wn, w.Wh, w.Wl, img, (long long)Bi * D, R, w.Rp, w.Ch, w.Cl,
+               (const float*)w.pmax, Bi * nslab, Bc, w.npart, w.scal);
     EEGAN_LAUNCH_CHECK("pair prologue");
     prof_mark(0, st);
 
@@ -477,9 +529,12 @@ int pair_h_fwd(const float* img, const float* words, const int32_t* cap_lens, in
     }
     prof_mark(3, st);
 
-    v3_cos_lse_kernel<<<dim3(w.maxbins, Bi), 256, 0, st>>>(w.U, w.Wp, w.wn, w.Zpart, w.col_start, w.cap_len, w.bin_cap, w.bin_used,
-                                                           w.meta, NtP, D, Bc, w.nz, g2, w.Z, w.cosv, w.un, m, w.mst);
-    if (att) v3_att_diag_kernel<<<dim3(Bc, (R + 31) / 32), 256, 0, st>>>(w.P, w.Z, w.col_start, w.cap_len, NtP, R, Tm, Bi, diag_offset, att, 1, g1);
+    launch_pdl(v3_cos_lse_kernel, dim3(w.maxbins, Bi), dim3(256), 0, st, (const float*)w.U, (const float*)w.Wp, (const float*)w.wn,
+               (const float*)w.Zpart, (const int*)w.col_start, (const int*)w.cap_len, (const int*)w.bin_cap, (const int*)w.bin_used,
+               (const int*)w.meta, NtP, D, Bc, w.nz, g2, w.Z, w.cosv, w.un, m, w.mst);
+    if (att)
+        launch_pdl(v3_att_diag_kernel, dim3(Bc, (R + 31) / 32), dim3(256), 0, st, (const float*)w.P, (const float*)w.Z,
+                   (const int*)w.col_start, (const int*)w.cap_len, NtP, R, Tm, Bi, diag_offset, att, 1, g1);
     EEGAN_LAUNCH_CHECK("pair cos/lse");
     prof_mark(4, st);
     return EEGAN_OK;
@@ -496,13 +551,14 @@ int pair_h_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1,
     const int NtP = w.NtP;
 
     prof_mark(-1, st);
-    cudaMemsetAsync(w.scal + HS_MAXDUN, 0, sizeof(float), st);
-    h_duscale_kernel<<<dim3(w.maxbins, Bi), 64, 0, st>>>(w.wn, w.Z, w.cosv, w.un, dm, w.mst, w.col_cap, w.meta, NtP, Bc, g2, w.scal);
+    launch_pdl(h_duscale_kernel, dim3(w.maxbins, Bi), dim3(64), 0, st, (const float*)w.wn, (const float*)w.Z, (const float*)w.cosv,
+               (const float*)w.un, dm, (const float*)w.mst, (const int*)w.col_cap, (const int*)w.meta, NtP, Bc, g2, w.pdun);
     {
         dim3 grid(NtP, w.ngroups);
-#define H_DU(NQ)                                                                                                              \
-    h_du_kernel<NQ><<<grid, 256, 0, st>>>(w.U, w.Wp, w.wn, w.Z, w.cosv, w.un, dm, w.mst, w.col_cap, w.meta, NtP, Bi, Bc, D, g1, g2, \
-                                          w.DUh, w.DUl, w.csz, w.dwcos, w.scal)
+#define H_DU(NQ)                                                                                                                  \
+    launch_pdl(h_du_kernel<NQ>, grid, dim3(256), 0, st, (const float*)w.U, (const float*)w.Wp, (const float*)w.wn, (const float*)w.Z, \
+               (const float*)w.cosv, (const float*)w.un, dm, (const float*)w.mst, (const int*)w.col_cap, (const int*)w.meta, NtP, Bi, \
+               Bc, D, g1, g2, w.DUh, w.DUl, w.csz, w.dwcos, (const float*)w.pdun, Bi * w.maxbins, w.scal)
         switch (D / 128) {
             case 1: H_DU(1); break;
             case 2: H_DU(2); break;
@@ -558,8 +614,8 @@ int pair_h_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1,
         g.epi = TC_EPI_PLAIN;
         int rc = h_gemm_launch(g, st);
         if (rc) return rc;
-        v3_unpack_dw_kernel<<<dim3(Bc, (D + 31) / 32), 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.cap_len, w.nsplit, w.ngroups,
-                                                                     NtP, D, Tm, d_words);
+        launch_pdl(v3_unpack_dw_kernel, dim3(Bc, (D + 31) / 32), dim3(256), 0, st, (const float*)w.dWpart, (const float*)w.dwcos,
+                   (const int*)w.col_start, (const int*)w.cap_len, w.nsplit, w.ngroups, NtP, D, Tm, d_words);
         EEGAN_LAUNCH_CHECK("pair GEMM5");
         prof_mark(9, st);
     }

@@ -26,12 +26,11 @@ static int v3_nsplit(int Bi, int NtP, int D) {
 // Greedy, order-preserving packing of whole captions into 64-column bins, then the column ->
 // caption map.  The lengths are staged in shared memory so that the one sequential pass (thread
 // 0; B is at most a few thousand) never waits on global memory.
-static __global__ void __launch_bounds__(256) v3_scan_kernel(const int32_t* __restrict__ cap_lens, int Bc, int Tm, int maxbins,
-                                                      int* __restrict__ col_start, int* __restrict__ cap_len,
-                                                      int* __restrict__ bin_cap, int* __restrict__ bin_used,
-                                                      int* __restrict__ meta, int* __restrict__ col_cap) {
-    extern __shared__ int s_buf[];  // [Bc] lengths, [Bc] first columns
-    int* s_len = s_buf;
+__device__ __forceinline__ void v3_scan_body(int* s_buf /* shared: [2 Bc] */, const int32_t* __restrict__ cap_lens, int Bc, int Tm,
+                                             int maxbins, int* __restrict__ col_start, int* __restrict__ cap_len,
+                                             int* __restrict__ bin_cap, int* __restrict__ bin_used, int* __restrict__ meta,
+                                             int* __restrict__ col_cap) {
+    int* s_len = s_buf;  // [Bc] lengths, then [Bc] first columns
     int* s_cs = s_buf + Bc;
     __shared__ int s_nbins;
     for (int i = threadIdx.x; i < Bc; i += blockDim.x) s_len[i] = min(max(cap_lens[i], 0), Tm);
@@ -72,6 +71,16 @@ static __global__ void __launch_bounds__(256) v3_scan_kernel(const int32_t* __re
     }
 }
 
+static __global__ void __launch_bounds__(256) v3_scan_kernel(const int32_t* __restrict__ cap_lens, int Bc, int Tm, int maxbins,
+                                                             int* __restrict__ col_start, int* __restrict__ cap_len,
+                                                             int* __restrict__ bin_cap, int* __restrict__ bin_used,
+                                                             int* __restrict__ meta, int* __restrict__ col_cap) {
+    extern __shared__ int s_scan_buf[];
+    pdl_trigger();
+    pdl_wait();
+    v3_scan_body(s_scan_buf, cap_lens, Bc, Tm, maxbins, col_start, cap_len, bin_cap, bin_used, meta, col_cap);
+}
+
 // ---------------------------------------------------------------------------------------
 // forward: cosine + log-sum-exp   (DAMSM_losses.py:17-23, :315-317)
 // ---------------------------------------------------------------------------------------
@@ -87,6 +96,8 @@ static __global__ void __launch_bounds__(256) v3_cos_lse_kernel(const float* __r
                                                          float* __restrict__ m, float* __restrict__ mst) {
     __shared__ float s_cos[V3_BIN];
     const int b = blockIdx.x, j = blockIdx.y;
+    pdl_trigger();
+    pdl_wait();
     if (b >= meta[0]) return;
     const int used = bin_used[b];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -158,6 +169,8 @@ static __global__ void __launch_bounds__(256) v3_att_diag_kernel(const float* __
                                                           int from_p, float g1) {
     __shared__ float tile[32][33];
     const int i = blockIdx.x, j = i + diag_offset, r0 = blockIdx.y * 32;
+    pdl_trigger();
+    pdl_wait();
     float* out = att + (size_t)i * Tm * R;
     const bool have = j >= 0 && j < Bi;
     const int cs = col_start[i], T = have ? cap_len[i] : 0;
@@ -189,6 +202,8 @@ static __global__ void __launch_bounds__(256) v3_unpack_dw_kernel(const float* _
                                                            float* __restrict__ d_words) {
     __shared__ float tile[32][33];
     const int i = blockIdx.x, d0 = blockIdx.y * 32;
+    pdl_trigger();
+    pdl_wait();
     const int cs = col_start[i], T = cap_len[i];
     for (int idx = threadIdx.x; idx < 32 * Tm; idx += blockDim.x) {
         const int t = idx / 32, dd = idx % 32;

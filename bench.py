@@ -46,14 +46,25 @@ B_PER_GPU, T_MAX, D, HW = 48, 18, 256, 17
 R = HW * HW
 METRIC = "attn+DAMSM fwd/bwd pairs/s at CUB shape"
 UNIT = "pairs/s"
-# kernels launched per step by OUR library with the fused tcgen05 engine:
-#   pair fwd 6 (scan, pack+repitch, gemm S + attention fwd, gemm U, cos/lse, att_maps) + CE fwd 2 + CE bwd 1
-#   + pair bwd 5 (dU, gemm dA + attention bwd, gemm dC, gemm dW, unpack)
-LAUNCHES_PER_STEP = 14
-# dram__bytes_read.sum + dram__bytes_write.sum per ts_gemm_kernel launch, averaged over the five launches of one
-# step, from the committed ncu --set full capture (profiles/r1_v3_fused_step_ncu_full_summary.csv: 32.3 / 52.9 /
-# 89.2 / 107.4 / 50.3 MB); algorithmic bytes of the whole step are 45.3 MB — the rest is the stash round trips
-NCU_TRAFFIC_BYTES_PER_GEMM_LAUNCH = 66.4e6
+# kernels launched per step by OUR library, default engine (3, half-pair operands):
+#   pair fwd 6 (pre: scan + maxima, pack: words + image features -> fp16 hi/lo, gemm S + attention fwd, gemm U, cos/lse,
+#   att_maps) + CE fwd 2 + CE bwd 1 + pair bwd 6 (dU scale, dU, gemm dA + attention bwd, gemm dC, gemm dW, unpack)
+LAUNCHES_PER_STEP = {3: 15, 2: 14}
+# dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, averaged over the five launches of one step, from the
+# committed ncu --set full captures: engine 3 profiles/r1_h_gemm_ncu_full_summary.csv (33.9 / 53.0 / 90.8 / 108.3 /
+# 50.3 MB), engine 2 profiles/r1_v3_fused_step_ncu_full_summary.csv (32.3 / 52.9 / 89.2 / 107.4 / 50.3 MB);
+# algorithmic bytes of the whole step are 45.3 MB — the rest is the stash round trips
+NCU_TRAFFIC_BYTES_PER_GEMM_LAUNCH = {3: 67.3e6, 2: 66.4e6}
+ENGINE_NOTE = {
+    3: ("h_gemm_kernel (tcgen05.mma.kind::f16 on operands stored as fp16 hi/lo pairs with power-of-two scales; TMA -> MMA, no "
+        "in-kernel split; 5 launches/step: S + attention fwd epilogue, U, dA + attention bwd epilogue, dC (two accumulators), dW)",
+        3.0, "fp32-accurate 3xFP16 (SURVEY D7: single-pass TF32/BF16 flips argmax words): 3 tcgen05.mma.kind::f16 per K-step at "
+             "the bf16 rate, so the engine's own ceiling is peak/3"),
+    2: ("ts_gemm_kernel (tcgen05 3xTF32, A operand staged in TMEM; 5 launches/step: S + attention fwd epilogue, U, dA + attention "
+        "bwd epilogue, dC, dW)",
+        6.0, "fp32-accurate 3xTF32 (SURVEY D7): 3 tcgen05.mma.kind::tf32 per K-step at half the bf16 rate, so the engine's own "
+             "ceiling is peak/6"),
+}
 
 
 def peaks():
@@ -349,6 +360,7 @@ def run_ours(args):
 
     # N>1 stays eager: capturing the NCCL collectives of the sharded path into the graph hung on
     # this stack (torch 2.11 / NCCL 2.28.9); at N>=4 the per-rank GPU work exceeds the host time anyway
+    engine = int(L.eegan_get_contraction_engine())
     use_graph = (world == 1) and not args.eager
     graphed = None
     if use_graph:
@@ -497,23 +509,26 @@ def run_ours(args):
                        "pairs_per_step": pairs_per_step,
                        "launch": "one CUDA graph per step (eegan_b200.graphed.GraphedWordsLoss)" if use_graph else "eager launches",
                        "eager_ms_per_step": eager_ms},
-            "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": clocks}
+            "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP.get(engine, 15) * args.steps, "clocks": clocks}
+    line["config"]["contraction_engine"] = engine
     if stage is not None:
         gemm = [s for s in stage if s[0].startswith("gemm")]
         gemm_ms = sum(s[1] for s in gemm)
         gemm_launch_count = args.steps * 5  # S, U, dA, dC, dW
         achieved = flops_rank * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        kname, div, why = ENGINE_NOTE.get(engine, ENGINE_NOTE[3])
+        ceiling = pk["bf16_tflops"] / div
         line["roofline"] = {
-            "bound": "tensor", "kernel": "ts_gemm_kernel (tcgen05 3xTF32, A operand staged in TMEM; 5 launches/step: S + attention fwd epilogue, U, dA + attention bwd epilogue, dC, dW)",
+            "bound": "tensor", "kernel": kname,
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops"] if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_GEMM_LAUNCH,
+            "frac": achieved / pk["bf16_tflops"] if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_GEMM_LAUNCH.get(engine),
             "peak_source": pk["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
-            "note": "fp32-accurate 3xTF32 (SURVEY D7): 3 tcgen05.mma.kind::tf32 per K-step at half the bf16 rate, so the "
-                    "engine's own ceiling is peak/6 = %.0f TFLOP/s -> frac_of_3xtf32_ceiling = %.3f; avg launch %.1f us; "
-                    "achieved = algorithmic 12*R*D*sum(T)*B FLOP per step / summed duration of the 5 GEMM launches "
-                    "(their epilogues carry the softmax work of the path)"
-                    % (pk["bf16_tflops"] / 6.0, (achieved / (pk["bf16_tflops"] / 6.0)) if achieved else 0.0,
-                       1e3 * gemm_ms / max(1, gemm_launch_count)),
+            "engine_ceiling_tflops": ceiling, "frac_of_engine_ceiling": (achieved / ceiling) if achieved else None,
+            "note": "%s = %.0f TFLOP/s; avg launch %.1f us; achieved = algorithmic 12*R*D*sum(T)*B FLOP per step / summed "
+                    "duration of the 5 GEMM launches (their epilogues carry the softmax work of the path), measured with stage "
+                    "events on eager launches of the same kernels (the headline value replays them as one CUDA graph with "
+                    "programmatic dependent launch between them)"
+                    % (why, ceiling, 1e3 * gemm_ms / max(1, gemm_launch_count)),
             "stage_ms_per_step": {s[0]: s[1] / args.steps for s in stage},
             "hbm_equiv": {"algorithmic_bytes_per_step": 3 * B * D * (R + T_MAX) * 4 + 3 * B * B * 4,
                           "achieved_gbs": (3 * B * D * (R + T_MAX) * 4 + 3 * B * B * 4) / (ms_step / 1e3) / 1e9,

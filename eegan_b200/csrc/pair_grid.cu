@@ -28,14 +28,14 @@
 namespace eegan {
 
 // contraction engine: 3 = tcgen05 half-pair ("3xFP16") engine, operands pre-split as fp16 hi/lo, attention fused
-// into the GEMM epilogues (pair_grid_h.cu), 2 = tcgen05 3xTF32 with the attention fused into the GEMM epilogues
-// (pair_grid_v3.cu, default), 1 = tcgen05 3xTF32 GEMMs + separate row/column kernels,
+// into the GEMM epilogues (pair_grid_h.cu, default), 2 = tcgen05 3xTF32 with the attention fused into the GEMM
+// epilogues (pair_grid_v3.cu), 1 = tcgen05 3xTF32 GEMMs + separate row/column kernels,
 // 0 = CUDA-core fp32 FFMA (exact-fp32 A/B reference).  Process-wide (the backward runs on
 // autograd's thread); set via eegan_set_contraction_engine().
 static int default_engine() {
     const char* e = getenv("EEGAN_ENGINE");  // A/B runs of the whole test suite / bench on another engine
-    const int v = e ? atoi(e) : 2;
-    return (v >= 0 && v <= 3) ? v : 2;
+    const int v = e ? atoi(e) : 3;
+    return (v >= 0 && v <= 3) ? v : 3;
 }
 static std::atomic<int> g_engine{default_engine()};
 static bool fused_ok(int D) { return D % 128 == 0; }  // the fused engine's dU kernel works in 128-float chunks

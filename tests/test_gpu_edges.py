@@ -55,10 +55,21 @@ def test_small_and_odd_shapes(cuda_lib, B, T, D, H, lens):
     (6, 18, 256, 20, [18, 7, 12, 5, 18, 9]),             # R = 400: four region tiles, last one 16 rows
     (7, 18, 384, 17, [18, 18, 18, 10, 18, 18, 18]),      # odd number of bins: the last tile has one live bin
 ])
-def test_fused_engine_shapes(cuda_lib, B, T, D, H, lens):
-    """Shapes that exercise the fused engine's packing (64-column bins, 128-column tiles), its
-    per-caption word buckets and the region-tile edges, against the float64 dense oracle."""
-    assert cuda_lib.eegan_get_contraction_engine() >= 2 and D % 128 == 0
+@pytest.mark.parametrize("engine", [3, 2])
+def test_fused_engine_shapes(cuda_lib, engine, B, T, D, H, lens):
+    """Shapes that exercise the fused engines' packing (64-column bins, 128-column tiles), their
+    per-caption word buckets and the region-tile edges, against the float64 dense oracle.
+    engine 3 = half-pair operands (default), 2 = 3xTF32 with the split in the kernel."""
+    assert D % 128 == 0
+    default = cuda_lib.eegan_get_contraction_engine()
+    assert cuda_lib.eegan_set_contraction_engine(engine) == 0
+    try:
+        _fused_engine_shapes(cuda_lib, B, T, D, H, lens)
+    finally:
+        cuda_lib.eegan_set_contraction_engine(default)
+
+
+def _fused_engine_shapes(cuda_lib, B, T, D, H, lens):
     c = cases.words_case(B, T, D=D, H=H, seed=B * 100 + T + D, class_mode="none", min_len=1)
     c["cap_lens"] = torch.tensor(lens)
     got, ref = _run_both(c, B, 1.0, 0.5)
@@ -77,6 +88,24 @@ def test_fused_engine_shapes(cuda_lib, B, T, D, H, lens):
     assert relmax(got[3].cpu(), ref[3]) <= 1e-4 and relmax(got[4].cpu(), ref[4]) <= 1e-4
     for i, n in enumerate(lens):  # padded words receive exactly zero gradient
         assert float(got[4][i, :, n:].abs().max()) == 0.0 if n < T else True
+
+
+@pytest.mark.parametrize("img_amp,word_amp,loss_amp", [(1e-3, 1e-3, 1.0), (20.0, 0.05, 1.0), (1.0, 1.0, 1e-6), (1.0, 1.0, 3e4),
+                                                         (1e-2, 40.0, 1e-3)])
+def test_half_pair_engine_operand_scales(cuda_lib, img_amp, word_amp, loss_amp):
+    """The half-pair engine stores every GEMM operand as fp16 hi/lo of x * 2^e: inputs and upstream gradients far from
+    unit magnitude must keep the fp32-class accuracy (the scales come from device-side maxima / bounds, pair_grid_h.cu)."""
+    assert cuda_lib.eegan_get_contraction_engine() == 3
+    B, T = 9, 18
+    c = cases.words_case(B, T, seed=91, class_mode="cub")
+    c["img"] = c["img"] * img_amp
+    c["words"] = c["words"] * word_amp
+    got, ref = _run_both(c, B, loss_amp, 0.5 * loss_amp)
+    assert abs(got[0].item() - ref[0].item()) <= 2e-5 * max(1.0, abs(ref[0].item()))
+    assert abs(got[1].item() - ref[1].item()) <= 2e-5 * max(1.0, abs(ref[1].item()))
+    assert relmax(got[3].cpu(), ref[3]) <= 1e-4 and relmax(got[4].cpu(), ref[4]) <= 1e-4
+    for a, b in zip(got[2], ref[2]):
+        assert float((a.cpu().double() - b.detach()).abs().max()) <= 2.5e-6
 
 
 def test_backward_twice_on_one_forward(cuda_lib):

@@ -15,6 +15,8 @@ import sys
 from . import damsm_losses  # noqa: F401
 from .damsm_losses import (GlobalAttentionGeneral, cosine_similarity, func_attention, sent_loss,  # noqa: F401
                            sent_similarity, words_loss, words_similarity)
+from .attr_enhance import ATTR_Enhance, attr_enhance  # noqa: F401
+from .encoder import EmbFeatures, conv1x1_features, fuse_emb_features  # noqa: F401
 from .evaluation import r_precision  # noqa: F401
 from .ssa import affine_ssa, ssa_modulate  # noqa: F401
 

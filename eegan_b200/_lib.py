@@ -46,6 +46,11 @@ SIGNATURES = {
     "eegan_cosine_rows_bwd": (_c_int, [_p, _p, _p, _p, _p, ctypes.c_longlong, _c_int, _c_float, _p, _p, _p]),
     "eegan_gemm_tf32x3": (_c_int, [_p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int] + [ctypes.c_longlong] * 6 + [_c_int, _c_int, _p]),
     "eegan_gemm_f16x3": (_c_int, [_p, _p, _p, _c_int, _c_int, _c_int] + [ctypes.c_longlong] * 6 + [_c_int, _c_float, _c_float, _c_int, _p, _c_size_t, _p]),
+    "eegan_conv1x1_workspace_bytes": (_c_size_t, [_c_int] * 5),
+    "eegan_conv1x1_fwd": (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _c_size_t, _p]),
+    "eegan_conv1x1_bwd": (_c_int, [_p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _c_size_t, _p]),
+    "eegan_attr_enhance_fwd": (_c_int, [_p] * 8 + [_c_int, _c_int, _c_int, _c_float, _p, _p, _p, _p]),
+    "eegan_attr_enhance_bwd": (_c_int, [_p] * 9 + [_c_int, _c_int, _c_int, _c_float] + [_p] * 10),
     "eegan_rprecision": (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_float, _p, _p, _p, _p]),
     "eegan_ssa_apply": (_c_int, [_p] * 6 + [_c_int] * 3 + [_p, _p]),
     "eegan_ssa_bwd_reduce": (_c_int, [_p] * 7 + [_c_int] * 3 + [_p] * 5),

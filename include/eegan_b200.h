@@ -242,6 +242,39 @@ int eegan_gemm_tf32x3(const float* A, const float* B, float* C, int M, int N, in
                       int a_kmajor, int b_kmajor, long long lda, long long ldb, long long ldc,
                       long long bsA, long long bsB, long long bsC, int batch, int staging, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * CNN_ENCODER.emb_features — DAMSM.py:162, 229: conv1x1(768, nef), bias=False, on the
+ * 17x17 Inception map; its output is the img_features argument of words_loss.
+ *   y[b][co][r] = sum_ci w[co][ci] x[b][ci][r]        x [B,Cin,R], w [Cout,Cin], y [B,Cout,R], fp32
+ * computed as batched fp32-accurate 3xTF32 GEMMs on tcgen05.  Cin, Cout multiples of 4.
+ * fwd also writes xp = x re-pitched to rows of 4*ceil(R/4) floats (eegan_conv1x1_workspace_bytes(.., 0) bytes,
+ * caller-owned): the backward takes xp instead of x.  bwd: dx and/or dw may be NULL; workspace
+ * eegan_conv1x1_workspace_bytes(.., 1) bytes.  dw is reduced over the batch deterministically.
+ * ---------------------------------------------------------------------------------- */
+size_t eegan_conv1x1_workspace_bytes(int B, int Cin, int Cout, int R, int backward);
+int eegan_conv1x1_fwd(const float* x, const float* w, int B, int Cin, int Cout, int R, float* y, float* xp,
+                      size_t xp_bytes, void* stream);
+int eegan_conv1x1_bwd(const float* xp, const float* w, const float* dy, int B, int Cin, int Cout, int R, float* dx,
+                      float* dw, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * ATTR_Enhance.forward — models.py:146-168: self-attention over [sent ; attrs]
+ *   combine [B,1+attr_num,D];  q,k,v = Linear(combine);  a = softmax(q k^T, -1) * norm_fact (scale after the
+ *   softmax, :166);  out = a v  (= attn_attrs [B,1+attr_num,D]; attn_sent = out[:,0,:]).
+ * sent [B,D], attrs [B,attr_num,D], W* [D,D] (nn.Linear weight: [out][in]), b* [D]; attr_num <= 7.
+ * fwd: one launch; qkv [B,3,1+attr_num,D] and p [B,1+attr_num,1+attr_num] are the backward's stash (may be NULL
+ * for inference).  bwd: d_attn_sent [B,D] and/or d_attn_attrs [B,1+attr_num,D] (NULL = zero); g [B,3,1+attr_num,D]
+ * is scratch; every output pointer may be NULL.  Weight gradients are reduced in a fixed order (no atomics).
+ * ---------------------------------------------------------------------------------- */
+int eegan_attr_enhance_fwd(const float* sent, const float* attrs, const float* Wq, const float* bq,
+                           const float* Wk, const float* bk, const float* Wv, const float* bv, int B, int D,
+                           int attr_num, float norm_fact, float* out, float* qkv, float* p, void* stream);
+int eegan_attr_enhance_bwd(const float* d_attn_sent, const float* d_attn_attrs, const float* sent,
+                           const float* attrs, const float* qkv, const float* p, const float* Wq, const float* Wk,
+                           const float* Wv, int B, int D, int attr_num, float norm_fact, float* g, float* d_sent,
+                           float* d_attrs, float* dWq, float* dbq, float* dWk, float* dbk, float* dWv, float* dbv,
+                           void* stream);
+
 /* The half-pair engine on its own (tests / microbenchmarks): C[z] = A[z] B[z]^T, fp32 in / out.
  * A is MN-major ([K][lda], M contiguous), B is K-major ([N][ldb]); lda, ldb and the batch strides are
  * multiples of 8 elements.  sa, sb: power-of-two scales the operands are stored with (x*s must stay

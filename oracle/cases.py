@@ -78,6 +78,16 @@ def bn_case(N, C, H, seed=SEED):
     return dict(x=x, weight=w, bias=b)
 
 
+def emb_case(B, Cin=768, Cout=256, H=17, seed=SEED):
+    """CNN_ENCODER.emb_features inputs: weight ~ uniform(-0.1, 0.1) (DAMSM.py:166-167), x = relu(randn) like the
+    Inception Mixed_6e map, an upstream gradient go."""
+    g = _gen(seed)
+    weight = (torch.rand(Cout, Cin, 1, 1, generator=g) - 0.5) * 0.2
+    x = torch.relu(torch.randn(B, Cin, H, H, generator=g))
+    go = torch.randn(B, Cout, H, H, generator=g)
+    return dict(weight=weight, x=x, go=go)
+
+
 def checksum(t: torch.Tensor):
     t = t.double()
     return [float(t.sum()), float(t.abs().sum())]

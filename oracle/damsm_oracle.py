@@ -309,3 +309,22 @@ def port_affine_ssa(feat, weight, bias, semi_mask, eps=1e-5, n_replica_formula=F
     w = w * semi_mask + 1  # :84
     b = b * semi_mask  # :85
     return w * xhat + b  # :86
+
+
+def port_attr_enhance(sent, attrs, Wq, bq, Wk, bk, Wv, bv, norm_fact):
+    """models.py:154-169 (ATTR_Enhance.forward), op for op: cat, three Linear, softmax(q k^T, -1) * norm_fact
+    (the scale comes AFTER the softmax, :166), bmm with v.  Returns (attn_sent, attn_attrs).  dtype-generic."""
+    import torch.nn.functional as F
+    combine = torch.cat([sent.unsqueeze(1), attrs], dim=1)
+    q = F.linear(combine, Wq, bq)
+    k = F.linear(combine, Wk, bk)
+    v = F.linear(combine, Wv, bv)
+    attn = torch.softmax(torch.bmm(q, k.permute(0, 2, 1)), dim=-1) * norm_fact
+    out = torch.bmm(attn, v)
+    return out[:, 0, :], out
+
+
+def port_emb_features(x, weight):
+    """DAMSM.py:23-26, 229: conv1x1(768, nef) without bias = a per-pixel matrix product over the channels."""
+    import torch.nn.functional as F
+    return F.conv2d(x, weight.reshape(weight.shape[0], -1, 1, 1))

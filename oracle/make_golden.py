@@ -52,8 +52,74 @@ BN_CASES = {
 }
 
 
+ATTR_CASES = {
+    "attr_b6_d128": dict(B=6, D=128, A=3, seed=11),
+    "attr_b3_d64_a5": dict(B=3, D=64, A=5, seed=12),
+}
+EMB_SUB = (4, 3, 7)  # strides of the stored subsets: output channels, regions, input channels
+EMB_CASES = {
+    "emb_b2_768_256": dict(B=2, Cin=768, Cout=256, H=17, seed=21),
+    "emb_b3_64_32_h5": dict(B=3, Cin=64, Cout=32, H=5, seed=22),
+}
+
+
 def _np(t):
     return t.detach().cpu().numpy()
+
+
+def _ref_module(name):
+    import importlib
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return importlib.import_module(name)
+
+
+def gen_attr(ref, name, kw):
+    """models.py:146-169 (ATTR_Enhance) executed live with seeded parameters; gradients of
+    loss = sum(attn_sent * gs) + sum(attn_attrs * ga) w.r.t. both inputs and all six parameters."""
+    models = _ref_module("models")
+    g = cases._gen(kw["seed"])
+    B, D, A = kw["B"], kw["D"], kw["A"]
+    mod = models.ATTR_Enhance(ntf=D)
+    with torch.no_grad():
+        for p in mod.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (1.0 / D ** 0.5 if p.dim() == 2 else 0.1))
+    sent = (torch.randn(B, D, generator=g) * 0.7).requires_grad_()
+    attrs = (torch.randn(B, A, D, generator=g) * 0.7).requires_grad_()
+    gs, ga = torch.randn(B, D, generator=g), torch.randn(B, A + 1, D, generator=g)
+    a_sent, a_attrs = mod(sent, attrs)
+    ((a_sent * gs).sum() + (a_attrs * ga).sum()).backward()
+    d = dict(kind="attr", recipe=json.dumps(kw), sent=_np(sent), attrs=_np(attrs), gs=_np(gs), ga=_np(ga),
+             attn_sent=_np(a_sent), attn_attrs=_np(a_attrs), d_sent=_np(sent.grad), d_attrs=_np(attrs.grad),
+             merged=_np(models.ATTR_Enhance.attr_merge(a_attrs.detach())))
+    for k, v in mod.state_dict().items():
+        d["param." + k] = _np(v)
+    for k, v in mod.named_parameters():
+        d["grad." + k] = _np(v.grad)
+    return d
+
+
+def gen_emb(ref, name, kw):
+    """DAMSM.py:23-26 conv1x1(Cin, Cout) executed live (the layer CNN_ENCODER.emb_features, :162, 229)."""
+    damsm = _ref_module("DAMSM")
+    c = cases.emb_case(kw["B"], kw["Cin"], kw["Cout"], kw["H"], kw["seed"])
+    conv = damsm.conv1x1(kw["Cin"], kw["Cout"])
+    with torch.no_grad():
+        conv.weight.copy_(c["weight"])
+    x = c["x"].clone().requires_grad_()
+    go = c["go"]
+    y = conv(x)
+    (y * go).sum().backward()
+    dx = x.grad
+    dw = conv.weight.grad.reshape(kw["Cout"], kw["Cin"])
+    y3 = y.reshape(y.shape[0], y.shape[1], -1)
+    return dict(kind="emb", recipe=json.dumps(kw),
+                in_checksum=np.array(cases.checksum(c["x"]) + cases.checksum(c["weight"]) + cases.checksum(go)),
+                y_sub=_np(y3[:, ::EMB_SUB[0], ::EMB_SUB[1]]), y_checksum=np.array(cases.checksum(y)), y_absmax=np.array(float(y.abs().max())),
+                d_weight_sub=_np(dw[::EMB_SUB[0], ::EMB_SUB[2]]), d_weight_checksum=np.array(cases.checksum(dw)),
+                d_weight_absmax=np.array(float(dw.abs().max())),
+                d_x_sub=_np(dx.reshape(dx.shape[0], dx.shape[1], -1)[:, ::EMB_SUB[2], ::EMB_SUB[1]]),
+                d_x_checksum=np.array(cases.checksum(dx)), d_x_absmax=np.array(float(dx.abs().max())))
 
 
 def gen_words(ref, name, kw):
@@ -155,8 +221,13 @@ def main():
     ref = load_reference()
     os.makedirs(OUT, exist_ok=True)
     tot = 0
-    for table, fn in ((WORDS_CASES, gen_words), (SENT_CASES, gen_sent), (GAG_CASES, gen_gag), (BN_CASES, gen_bn)):
+    tables = ((WORDS_CASES, gen_words), (SENT_CASES, gen_sent), (GAG_CASES, gen_gag), (BN_CASES, gen_bn), (ATTR_CASES, gen_attr),
+              (EMB_CASES, gen_emb))
+    only = os.environ.get("EEGAN_GOLDEN_ONLY")  # e.g. "attr_,emb_": regenerate only these fixture families
+    for table, fn in tables:
         for name, kw in table.items():
+            if only and not any(name.startswith(p) for p in only.split(",")):
+                continue
             d = fn(ref, name, kw)
             path = os.path.join(OUT, name + ".npz")
             np.savez_compressed(path, **d)

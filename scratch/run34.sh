@@ -1,0 +1,2 @@
+cd /root/repo
+timeout 600 python -m pytest tests/test_aux_rows.py -m gpu -x -q 2>&1 | tail -12

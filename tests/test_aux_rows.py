@@ -1,0 +1,203 @@
+"""SURVEY.md §8f ranks 1-2 — CNN_ENCODER.emb_features (DAMSM.py:162, 229) and ATTR_Enhance (models.py:146-180).
+CPU: the oracle restatements against the fixtures generated from the live reference (and against the live reference when
+it is mounted), state_dict compatibility of the drop-in modules, no CPU fallback.  GPU (marked): the CUDA kernels, through
+the C ABI, against the fixtures and the float64 oracle.  Tolerances: outputs 2e-5 relative-to-max, gradients 1e-4
+relative-to-max (the same fp32-class bar as the pair grid)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from helpers import relmax
+from oracle import cases
+from oracle import damsm_oracle as O
+from oracle.make_golden import EMB_SUB
+from oracle.ref_loader import load_reference, reference_available
+
+PARAMS = ("attr_query.weight", "attr_query.bias", "attr_key.weight", "attr_key.bias", "attr_value.weight", "attr_value.bias")
+
+
+def _rel(a, b, floor):
+    """max |a - b| relative to max(|b|, floor): the gradient of attr_key.bias is identically zero in exact arithmetic
+    (a constant added to every key shifts all scores of a row alike and the softmax ignores it), so the reference
+    holds only rounding noise there; it is compared on the scale of the query-bias gradient instead."""
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor, 1e-30))
+
+
+def _attr_inputs(g, dtype=torch.float32, device="cpu"):
+    t = lambda k: torch.from_numpy(g[k]).to(device=device, dtype=dtype)
+    return t("sent"), t("attrs"), [t("param." + k) for k in PARAMS], t("gs"), t("ga")
+
+
+# ------------------------------------------------------------------------------------------ CPU
+@pytest.mark.parametrize("name", golden_names("attr_"))
+def test_attr_enhance_port_matches_reference_fixture(name):
+    g = load_golden(name)
+    kw = json.loads(str(g["recipe"]))
+    sent, attrs, P, gs, ga = _attr_inputs(g)
+    sent.requires_grad_(); attrs.requires_grad_()
+    P = [p.requires_grad_() for p in P]
+    a_sent, a_attrs = O.port_attr_enhance(sent, attrs, *P, 1.0 / kw["D"] ** 0.5)
+    ((a_sent * gs).sum() + (a_attrs * ga).sum()).backward()
+    np.testing.assert_allclose(a_attrs.detach().numpy(), g["attn_attrs"], atol=1e-6)
+    np.testing.assert_allclose(a_sent.detach().numpy(), g["attn_sent"], atol=1e-6)
+    assert relmax(sent.grad, g["d_sent"]) < 1e-5 and relmax(attrs.grad, g["d_attrs"]) < 1e-5
+    floor = float(np.abs(g["grad.attr_query.bias"]).max())
+    for p, k in zip(P, PARAMS):
+        assert _rel(p.grad, g["grad." + k], floor) < 1e-5, k
+    np.testing.assert_allclose(a_attrs.detach().sum(dim=1).numpy(), g["merged"], atol=1e-5)
+
+
+@pytest.mark.parametrize("name", golden_names("emb_"))
+def test_emb_features_port_matches_reference_fixture(name):
+    g = load_golden(name)
+    kw = json.loads(str(g["recipe"]))
+    c = cases.emb_case(kw["B"], kw["Cin"], kw["Cout"], kw["H"], kw["seed"])
+    np.testing.assert_allclose(cases.checksum(c["x"]) + cases.checksum(c["weight"]) + cases.checksum(c["go"]), g["in_checksum"], rtol=1e-12)
+    x, w = c["x"].clone().requires_grad_(), c["weight"].clone().requires_grad_()
+    y = O.port_emb_features(x, w)
+    (y * c["go"]).sum().backward()
+    y3 = y.detach().reshape(kw["B"], kw["Cout"], -1)
+    assert relmax(y3[:, ::EMB_SUB[0], ::EMB_SUB[1]], g["y_sub"]) < 1e-5
+    np.testing.assert_allclose(cases.checksum(y.detach()), g["y_checksum"], rtol=1e-4)
+    assert relmax(w.grad.reshape(kw["Cout"], kw["Cin"])[::EMB_SUB[0], ::EMB_SUB[2]], g["d_weight_sub"]) < 1e-5
+    assert relmax(x.grad.reshape(kw["B"], kw["Cin"], -1)[:, ::EMB_SUB[2], ::EMB_SUB[1]], g["d_x_sub"]) < 1e-5
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not mounted")
+def test_ports_and_modules_against_live_reference():
+    import importlib
+    import warnings
+    load_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        models = importlib.import_module("models")
+        damsm = importlib.import_module("DAMSM")
+    torch.manual_seed(5)
+    ref = models.ATTR_Enhance(ntf=32)
+    sent, attrs = torch.randn(4, 32), torch.randn(4, 3, 32)
+    rs, ra = ref(sent, attrs)
+    ps, pa = O.port_attr_enhance(sent, attrs, ref.attr_query.weight, ref.attr_query.bias, ref.attr_key.weight, ref.attr_key.bias,
+                                 ref.attr_value.weight, ref.attr_value.bias, ref._norm_fact)
+    assert torch.equal(rs, ps) and torch.equal(ra, pa)
+    import eegan_b200 as E
+    ours = E.ATTR_Enhance(ntf=32)
+    assert set(ours.state_dict().keys()) == set(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())
+    assert ours._norm_fact == ref._norm_fact
+    assert torch.equal(E.ATTR_Enhance.attr_merge(ra), models.ATTR_Enhance.attr_merge(ra))
+    conv = damsm.conv1x1(24, 8)
+    x = torch.randn(2, 24, 5, 5)
+    assert torch.equal(conv(x), O.port_emb_features(x, conv.weight))
+    mine = E.EmbFeatures(24, 8)
+    assert set(mine.state_dict().keys()) == set(conv.state_dict().keys())
+    mine.load_state_dict(conv.state_dict())
+
+    class Enc(torch.nn.Module):  # the attribute fuse_emb_features rewires, as in CNN_ENCODER (DAMSM.py:162)
+        def __init__(self):
+            super().__init__()
+            self.emb_features = damsm.conv1x1(24, 8)
+    enc = E.fuse_emb_features(Enc())
+    assert isinstance(enc.emb_features, E.EmbFeatures) and set(enc.state_dict().keys()) == {"emb_features.weight"}
+
+
+def test_aux_rows_have_no_cpu_path():
+    import eegan_b200 as E
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        E.ATTR_Enhance(ntf=16)(torch.randn(2, 16), torch.randn(2, 3, 16))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        E.EmbFeatures(8, 4)(torch.randn(1, 8, 3, 3))
+
+
+# ------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_names("attr_"))
+def test_attr_enhance_cuda_vs_reference_fixture(cuda_lib, name):
+    import eegan_b200 as E
+    g = load_golden(name)
+    kw = json.loads(str(g["recipe"]))
+    sent, attrs, P, gs, ga = _attr_inputs(g, device="cuda")
+    mod = E.ATTR_Enhance(ntf=kw["D"]).cuda()
+    mod.load_state_dict({k: torch.from_numpy(g["param." + k]) for k in PARAMS})
+    sent.requires_grad_(); attrs.requires_grad_()
+    a_sent, a_attrs = mod(sent, attrs)
+    ((a_sent * gs).sum() + (a_attrs * ga).sum()).backward()
+    assert relmax(a_attrs.detach().cpu(), g["attn_attrs"]) <= 2e-5 and relmax(a_sent.detach().cpu(), g["attn_sent"]) <= 2e-5
+    assert relmax(sent.grad.cpu(), g["d_sent"]) <= 1e-4 and relmax(attrs.grad.cpu(), g["d_attrs"]) <= 1e-4
+    floor = float(np.abs(g["grad.attr_query.bias"]).max())
+    for k, p in mod.named_parameters():
+        assert _rel(p.grad.cpu(), g["grad." + k], floor) <= 1e-4, k
+    assert relmax(E.ATTR_Enhance.attr_merge(a_attrs.detach()).cpu(), g["merged"]) <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,D,A", [(48, 256, 3), (5, 96, 7), (2, 512, 1), (3, 64, 0)])
+def test_attr_enhance_cuda_vs_float64_oracle(cuda_lib, B, D, A):
+    import eegan_b200 as E
+    g = cases._gen(B * 1000 + D + A)
+    mod = E.ATTR_Enhance(ntf=D)
+    sent, attrs = torch.randn(B, D, generator=g), torch.randn(B, A, D, generator=g)
+    gs, ga = torch.randn(B, D, generator=g), torch.randn(B, A + 1, D, generator=g)
+    Pd = [p.detach().double().requires_grad_() for p in mod.parameters()]
+    so, ao = sent.double().requires_grad_(), attrs.double().requires_grad_()
+    os_, oa = O.port_attr_enhance(so, ao, *Pd, mod._norm_fact)
+    ((os_ * gs.double()).sum() + (oa * ga.double()).sum()).backward()
+    mod = mod.cuda()
+    s, a = sent.cuda().requires_grad_(), attrs.cuda().requires_grad_()
+    ys, ya = mod(s, a)
+    ((ys * gs.cuda()).sum() + (ya * ga.cuda()).sum()).backward()
+    assert tuple(ys.shape) == (B, D) and tuple(ya.shape) == (B, A + 1, D)
+    assert relmax(ya.detach().cpu(), oa.detach()) <= 2e-5
+    assert relmax(s.grad.cpu(), so.grad) <= 1e-4
+    if A:
+        assert relmax(a.grad.cpu(), ao.grad) <= 1e-4
+    floor = float(Pd[1].grad.abs().max())  # attr_query.bias
+    for p, pd in zip(mod.parameters(), Pd):
+        assert _rel(p.grad.cpu(), pd.grad, floor) <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_names("emb_"))
+def test_emb_features_cuda_vs_reference_fixture(cuda_lib, name):
+    import eegan_b200 as E
+    g = load_golden(name)
+    kw = json.loads(str(g["recipe"]))
+    c = cases.emb_case(kw["B"], kw["Cin"], kw["Cout"], kw["H"], kw["seed"])
+    mod = E.EmbFeatures(kw["Cin"], kw["Cout"]).cuda()
+    mod.load_state_dict({"weight": c["weight"]})
+    x = c["x"].cuda().requires_grad_()
+    y = mod(x)
+    (y * c["go"].cuda()).sum().backward()
+    y3 = y.detach().cpu().reshape(kw["B"], kw["Cout"], -1)
+    assert float((y3[:, ::EMB_SUB[0], ::EMB_SUB[1]] - torch.from_numpy(g["y_sub"])).abs().max()) <= 2e-5 * float(g["y_absmax"])
+    np.testing.assert_allclose(cases.checksum(y.detach().cpu()), g["y_checksum"], rtol=1e-4)
+    dw = mod.weight.grad.cpu().reshape(kw["Cout"], kw["Cin"])
+    assert float((dw[::EMB_SUB[0], ::EMB_SUB[2]] - torch.from_numpy(g["d_weight_sub"])).abs().max()) <= 1e-4 * float(g["d_weight_absmax"])
+    np.testing.assert_allclose(cases.checksum(dw), g["d_weight_checksum"], rtol=2e-3)
+    dx = x.grad.cpu().reshape(kw["B"], kw["Cin"], -1)
+    assert float((dx[:, ::EMB_SUB[2], ::EMB_SUB[1]] - torch.from_numpy(g["d_x_sub"])).abs().max()) <= 1e-4 * float(g["d_x_absmax"])
+    np.testing.assert_allclose(cases.checksum(dx), g["d_x_checksum"], rtol=2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Cin,Cout,H", [(48, 768, 256, 17), (3, 100, 36, 8), (1, 768, 256, 17), (5, 32, 260, 3)])
+def test_emb_features_cuda_vs_float64_oracle(cuda_lib, B, Cin, Cout, H):
+    import eegan_b200 as E
+    c = cases.emb_case(B, Cin, Cout, H, seed=B + Cin + Cout + H)
+    xo, wo = c["x"].double().requires_grad_(), c["weight"].double().requires_grad_()
+    yo = O.port_emb_features(xo, wo)
+    (yo * c["go"].double()).sum().backward()
+    x, w = c["x"].cuda().requires_grad_(), c["weight"].cuda().requires_grad_()
+    y = E.conv1x1_features(x, w)
+    (y * c["go"].cuda()).sum().backward()
+    assert tuple(y.shape) == (B, Cout, H, H)
+    assert relmax(y.detach().cpu(), yo.detach()) <= 2e-5
+    assert relmax(x.grad.cpu(), xo.grad) <= 1e-4 and relmax(w.grad.cpu(), wo.grad) <= 1e-4
+    # emb_features feeds words_loss (DAMSM.py:229 -> train.py:428): the projected map goes straight into the pair grid
+    if (Cout, H) == (256, 17) and B > 1:
+        wc = cases.words_case(B, 18, seed=9)
+        l0, l1, _ = E.words_loss(y, wc["words"].cuda(), wc["labels"].cuda(), wc["cap_lens"].cuda(), wc["class_ids"], B)
+        assert torch.isfinite(l0) and torch.isfinite(l1)

@@ -306,6 +306,81 @@ def ssa_extra(dev, flush, hbm_gbs):
     return out
 
 
+def aux_rows_extra(dev, flush, bf16_tflops):
+    """SURVEY.md 8f ranks 1-2 at CUB sizes (B=48), fwd+bwd with all gradients, next to torch's own eager ops on the
+    same GPU (fp32 matmul precision 'highest', i.e. the reference's arithmetic).
+    emb_features: conv1x1 768 -> 256 on the 17x17 map (DAMSM.py:162, 229); algorithmic FLOP = 3 GEMMs of 2*B*R*Cin*Cout.
+    ATTR_Enhance: 4 tokens x 256 channels (models.py:146-169): launch-latency-bound, reported in microseconds."""
+    import eegan_b200 as E
+    out = {}
+    B, Cin, Cout, H = 48, 768, 256, 17
+    x = torch.relu(torch.randn(B, Cin, H, H, device=dev)).requires_grad_()
+    mod = E.EmbFeatures(Cin, Cout).to(dev)
+    conv = torch.nn.Conv2d(Cin, Cout, 1, bias=False).to(dev)
+    gy = torch.randn(B, Cout, H, H, device=dev)
+
+    def ours():
+        x.grad = None
+        mod.weight.grad = None
+        mod(x).backward(gy)
+
+    def ref():
+        x.grad = None
+        conv.weight.grad = None
+        conv(x).backward(gy)
+
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    for _ in range(3):
+        ours()
+        ref()
+    ms, ms_t = _time_cuda(ours, 10, flush), _time_cuda(ref, 10, flush)
+    flop = 3 * 2.0 * B * H * H * Cin * Cout
+    out["emb_features_conv1x1"] = {"shape": [B, Cin, H, H], "cout": Cout, "ms_fwd_bwd": ms, "tflops": flop / (ms / 1e3) / 1e12,
+                                   "frac_of_3xtf32_ceiling": flop / (ms / 1e3) / 1e12 / (bf16_tflops / 6.0),
+                                   "ms_torch_eager_fp32_same_gpu": ms_t}
+    D, A = 256, 3
+    ae = E.ATTR_Enhance(ntf=D).to(dev)
+    sent = torch.randn(B, D, device=dev).requires_grad_()
+    attrs = torch.randn(B, A, D, device=dev).requires_grad_()
+    gs, ga = torch.randn(B, D, device=dev), torch.randn(B, A + 1, D, device=dev)
+    from oracle import damsm_oracle as O  # the reference's op sequence (validated port) run by torch on the GPU
+
+    def ours2():
+        sent.grad = attrs.grad = None
+        ae.zero_grad(set_to_none=True)
+        a, b = ae(sent, attrs)
+        ((a * gs).sum() + (b * ga).sum()).backward()
+
+    def ref2():
+        sent.grad = attrs.grad = None
+        ae.zero_grad(set_to_none=True)
+        a, b = O.port_attr_enhance(sent, attrs, ae.attr_query.weight, ae.attr_query.bias, ae.attr_key.weight, ae.attr_key.bias,
+                                   ae.attr_value.weight, ae.attr_value.bias, ae._norm_fact)
+        ((a * gs).sum() + (b * ga).sum()).backward()
+
+    # a few microseconds of device work behind ~30 Python-level ops: time CUDA-graph replays of both, so that the number
+    # is the device time of the launches and not the interpreter
+    def graphed(fn):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g.replay
+
+    r_ours, r_ref = graphed(ours2), graphed(ref2)
+    out["attr_enhance"] = {"shape": [B, A + 1, D], "us_fwd_bwd": 1e3 * _time_cuda(r_ours, 20, flush),
+                           "us_torch_ops_same_gpu": 1e3 * _time_cuda(r_ref, 20, flush),
+                           "timing": "CUDA-graph replay of forward + backward (device time of the launches)"}
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
@@ -358,11 +433,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # N>1 stays eager: capturing the NCCL collectives of the sharded path into the graph hung on
-    # this stack (torch 2.11 / NCCL 2.28.9); at N>=4 the per-rank GPU work exceeds the host time anyway
+    # N>1: capturing the autograd route with its NCCL collectives into a graph hung on this stack (torch 2.11 / NCCL 2.28.9;
+    # the backward runs on autograd's thread), so N>1 uses the autograd-free ShardedWordsLossStep below
     engine = int(L.eegan_get_contraction_engine())
     use_graph = (world == 1) and not args.eager
     graphed = None
+    sstep = None
     if use_graph:
         from eegan_b200.graphed import GraphedWordsLoss
         graphed = GraphedWordsLoss(B, D, HW, HW, T_MAX, dev, use_class_ids=True, words_grad=True, sharded=world > 1)
@@ -371,6 +447,16 @@ def run_ours(args):
 
         def run_step():
             graphed.graph.replay()
+    elif world > 1 and not args.autograd:
+        # N > 1: the autograd-free sharded step (same collectives and kernels, enqueued directly on static buffers);
+        # --sharded-graph additionally captures it, collectives included, into one CUDA graph
+        from eegan_b200.sharded import ShardedWordsLossStep
+        sstep = ShardedWordsLossStep(B, D, HW, HW, T_MAX, dev, use_class_ids=True, words_grad=True, graph=args.sharded_graph)
+        cls_d = cls.to(dev)
+        sstep.load(img_d.detach(), words_d.detach(), lens_d, cls_d)
+
+        def run_step():
+            sstep.run()
     else:
         def run_step():
             step(img_d, words_d, lens_d)
@@ -473,17 +559,21 @@ def run_ours(args):
             flush.fill_(1.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            img = img_h.to(dev, non_blocking=True).requires_grad_()
-            words = words_h.to(dev, non_blocking=True).requires_grad_()
-            lens = lens_h.to(dev, non_blocking=True)
-            l0, l1 = step(img, words, lens)
+            if sstep is not None:  # H2D straight into the step's static input buffers
+                l0, l1, _, _ = sstep(img_h, words_h, lens_h, cls_d)
+            else:
+                img = img_h.to(dev, non_blocking=True).requires_grad_()
+                words = words_h.to(dev, non_blocking=True).requires_grad_()
+                lens = lens_h.to(dev, non_blocking=True)
+                l0, l1 = step(img, words, lens)
             loss_h.copy_(torch.stack([l0.detach(), l1.detach()]), non_blocking=True)
             e1.record()
             e1.synchronize()  # the caller sees the loss on the host
             if k >= args.warmup:
                 e2e_evs.append(e0.elapsed_time(e1))
         e2e_total = sum(e2e_evs)
-        e2e_mode = "eager API; H2D, compute and D2H serial in every step"
+        e2e_mode = ("sharded step API (ShardedWordsLossStep); H2D, compute and D2H serial in every step" if sstep is not None
+                    else "eager API; H2D, compute and D2H serial in every step")
     barrier()
     clocks = sampler.summary(t_wall0, time.time()) if sampler else None
     t = torch.tensor([e2e_total], device=dev, dtype=torch.float64)
@@ -507,7 +597,9 @@ def run_ours(args):
                                    % (B, Btot, T_MAX, int(lens_sum.item()), D, HW, HW),
                        "l2": "256 MB fill between timed steps (outside the timed spans)",
                        "pairs_per_step": pairs_per_step,
-                       "launch": "one CUDA graph per step (eegan_b200.graphed.GraphedWordsLoss)" if use_graph else "eager launches",
+                       "launch": ("one CUDA graph per step (eegan_b200.graphed.GraphedWordsLoss)" if use_graph else
+                                  ("sharded step, %s (eegan_b200.sharded.ShardedWordsLossStep)" % ("one CUDA graph" if args.sharded_graph else "direct launches")
+                                   if sstep is not None else "eager autograd launches")),
                        "eager_ms_per_step": eager_ms},
             "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP.get(engine, 15) * args.steps, "clocks": clocks}
     line["config"]["contraction_engine"] = engine
@@ -537,7 +629,8 @@ def run_ours(args):
         if not args.no_extra:
             line["extra"] = {"global_attention_general": gag_extra(dev, flush, pk["hbm_gbs"]),
                              "sync_batchnorm_1replica": syncbn_extra(dev, flush, pk["hbm_gbs"]),
-                             "affine_ssa_1replica": ssa_extra(dev, flush, pk["hbm_gbs"])}
+                             "affine_ssa_1replica": ssa_extra(dev, flush, pk["hbm_gbs"]),
+                             "aux_rows_8f": aux_rows_extra(dev, flush, pk["bf16_tflops"])}
         base, _, _ = cpu_arm(args.steps, 1)
         line["cpu_baseline"] = base
     print(json.dumps(line))
@@ -553,6 +646,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the GlobalAttentionGeneral / SyncBN side measurements")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of the CUDA-graph replay")
+    ap.add_argument("--autograd", action="store_true", help="N>1: time the autograd route (sharded_words_loss + backward)")
+    ap.add_argument("--sharded-graph", action="store_true", help="N>1: capture the sharded step, collectives included, into a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

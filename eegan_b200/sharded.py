@@ -127,3 +127,117 @@ def sharded_sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-
     cls_all = _gather_ids(class_ids, cnn_all.device, group)
     lab_all = torch.arange(world * b, device=cnn_all.device, dtype=torch.int64)
     return (loss_fn or dl.sent_loss)(cnn_all, rnn_all, lab_all, cls_all, world * b, eps)
+
+
+class ShardedWordsLossStep:
+    """words_loss forward + backward over the GLOBAL batch from per-rank shards, without autograd: the same
+    collectives and kernels as ``sharded_words_loss(...)`` followed by ``(w0 * loss0 + w1 * loss1).backward()``,
+    enqueued directly (C ABI + torch.distributed) on static buffers.  At CUB sizes the autograd route spends ~1 ms
+    of host time per step on bookkeeping, several times what the GPU needs; this route costs the host four library
+    calls, four collectives and two small copies.
+
+        step = ShardedWordsLossStep(b, 256, 17, 17, T_max, device)        # b = local batch
+        loss0, loss1, d_img, d_words = step(img, words, cap_lens, class_ids)   # static tensors, valid until the next call
+
+    ``graph=True`` captures the step (collectives included) into one CUDA graph."""
+
+    def __init__(self, local_batch, D, H, W, T_max, device, group=None, use_class_ids=True, words_grad=True, w0=1.0, w1=1.0,
+                 graph=False):
+        from . import _lib
+        self._lib = _lib
+        L = _lib.lib()
+        self.group = group
+        self.world, self.rank = _world(group)
+        b, R = int(local_batch), H * W
+        Bt = b * self.world
+        dev = torch.device(device)
+        self.dims = (b, Bt, D, R, T_max)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.img = torch.zeros(b, D, H, W, **f32)
+        self.words = torch.zeros(b, D, T_max, **f32)
+        self.cap_lens32 = torch.full((b,), T_max, dtype=torch.int32, device=dev)
+        self.class_ids = torch.arange(self.rank * b, (self.rank + 1) * b, dtype=torch.int64, device=dev) if use_class_ids else None
+        self._cls_all = torch.zeros(Bt, dtype=torch.int64, device=dev) if use_class_ids else None
+        self._labels = torch.arange(Bt, dtype=torch.int64, device=dev)
+        self._img_all = torch.empty(Bt, D, R, **f32)
+        self._ws = torch.empty(L.eegan_damsm_pair_workspace_bytes(Bt, b, D, R, T_max), dtype=torch.uint8, device=dev)
+        self._m_block = torch.empty(Bt, b, **f32)
+        self._m_parts = torch.empty(self.world, Bt, b, **f32)
+        self._m_all = torch.empty(Bt, Bt, **f32)
+        self._sim = torch.empty(Bt, Bt, **f32)
+        self._lse = torch.empty(2, Bt, **f32)
+        self._loss01 = torch.zeros(2, **f32)
+        self._gvec = torch.tensor([float(w0), float(w1)], **f32)
+        self._dsim = torch.empty(Bt, Bt, **f32)
+        self._dm_block = torch.empty(Bt, b, **f32)
+        self._d_img_all = torch.empty(Bt, D, R, **f32)
+        self.att = torch.empty(b, T_max, R, **f32)
+        self.d_img = torch.zeros(b, D, H, W, **f32)
+        self.d_words = torch.zeros(b, D, T_max, **f32) if words_grad else None
+        self._use_graph, self._graph = bool(graph), None
+
+    def _enqueue(self):
+        _lib = self._lib
+        L, p, st = _lib.lib(), _lib.ptr, _lib.stream_ptr()
+        b, Bt, D, R, Tm = self.dims
+        g1, g2, g3 = gammas()
+        rank, grp = self.rank, self.group
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._img_all, self.img.view(b, D, R), group=grp)
+            if self._cls_all is not None:
+                dist.all_gather_into_tensor(self._cls_all, self.class_ids, group=grp)
+        else:
+            self._img_all.copy_(self.img.view(b, D, R))
+            if self._cls_all is not None:
+                self._cls_all.copy_(self.class_ids)
+        with torch.cuda.device(self.img.device):
+            _lib.check(L.eegan_damsm_pair_fwd(p(self._img_all), p(self.words), p(self.cap_lens32), Bt, b, D, R, Tm, g1, g2,
+                                              p(self._m_block), p(self.att), rank * b, p(self._ws), self._ws.numel(), st), "damsm_pair_fwd")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._m_parts.view(self.world * Bt, b), self._m_block, group=grp)
+            self._m_all.view(Bt, self.world, b).copy_(self._m_parts.permute(1, 0, 2))
+        else:
+            self._m_all.copy_(self._m_block)
+        with torch.cuda.device(self.img.device):
+            _lib.check(L.eegan_pair_ce_fwd(p(self._m_all), g3, p(self._cls_all), p(self._labels), Bt, p(self._sim), p(self._loss01),
+                                           p(self._lse), st), "pair_ce_fwd")
+            _lib.check(L.eegan_pair_ce_bwd(p(self._sim), p(self._lse), p(self._labels), p(self._gvec), g3, Bt, p(self._dsim), st),
+                       "pair_ce_bwd")
+        self._dm_block.copy_(self._dsim[:, rank * b:(rank + 1) * b])
+        with torch.cuda.device(self.img.device):
+            _lib.check(L.eegan_damsm_pair_bwd(p(self._img_all), p(self.words), p(self.cap_lens32), Bt, b, D, R, Tm, g1, g2,
+                                              p(self._dm_block), p(self._d_img_all), p(self.d_words), p(self._ws), self._ws.numel(), st),
+                       "damsm_pair_bwd")
+        if self.world > 1:
+            dist.reduce_scatter_tensor(self.d_img.view(b, D, R), self._d_img_all, op=dist.ReduceOp.SUM, group=grp)
+        else:
+            self.d_img.view(b, D, R).copy_(self._d_img_all)
+
+    def load(self, img, words, cap_lens, class_ids=None):
+        self.img.copy_(img.reshape(self.img.shape), non_blocking=True)
+        self.words.copy_(words, non_blocking=True)
+        self.cap_lens32.copy_(torch.as_tensor(cap_lens).reshape(-1), non_blocking=True)
+        if self.class_ids is not None and class_ids is not None:
+            self.class_ids.copy_(torch.as_tensor(class_ids).reshape(-1), non_blocking=True)
+
+    def run(self):
+        """Enqueue (or replay) one step on the data already in the static input buffers."""
+        if not self._use_graph:
+            self._enqueue()
+            return
+        if self._graph is None:
+            side = torch.cuda.Stream(device=self.img.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._enqueue()
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._enqueue()
+        self._graph.replay()
+
+    def __call__(self, img_features, words_emb, cap_lens, class_ids=None):
+        self.load(img_features, words_emb, cap_lens, class_ids)
+        self.run()
+        return self._loss01[0], self._loss01[1], self.d_img, self.d_words

@@ -50,6 +50,14 @@ def main():
     assert relmax(words_s.grad, words.grad[sl]) <= 2e-5, relmax(words_s.grad, words.grad[sl])
     for a, r in zip(satt, fatt[sl]):
         assert float((a - r).abs().max()) <= 1e-7
+    # the autograd-free step API (static buffers, direct launches; EEGAN_CHECK_SHARDED_GRAPH=1: also as one CUDA graph)
+    from eegan_b200.sharded import ShardedWordsLossStep
+    for use_graph in ([False, True] if os.environ.get("EEGAN_CHECK_SHARDED_GRAPH") == "1" else [False]):
+        sstep = ShardedWordsLossStep(b, 256, 17, 17, T, dev, w0=1.0, w1=2.0, graph=use_graph)
+        for _ in range(2):  # second call: replay on the same buffers
+            q0, q1, qdi, qdw = sstep(c["img"][sl].to(dev), c["words"][sl].to(dev), c["cap_lens"][sl].to(dev), c["class_ids"][sl].to(dev))
+        assert abs(q0.item() - f0.item()) <= 2e-6 * max(1.0, abs(f0.item())) and abs(q1.item() - f1.item()) <= 2e-6 * max(1.0, abs(f1.item()))
+        assert relmax(qdi, img.grad[sl]) <= 2e-5 and relmax(qdw, words.grad[sl]) <= 2e-5, (use_graph, relmax(qdi, img.grad[sl]))
     # sentence loss
     sc = cases.sent_case(B, seed=12)
     cnn = sc["cnn"].to(dev).requires_grad_()

@@ -201,6 +201,21 @@ def _time_cuda(fn, iters, flush):
     return ms / iters
 
 
+def _graph_replay(fn, dev):
+    """Capture fn (warmed up on a side stream) into a CUDA graph and return its replay: the side measurements time device
+    work, and at these sizes an eager autograd call costs the host more than the kernels cost the GPU."""
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g.replay
+
+
 def gag_extra(dev, flush, hbm_gbs):
     """GlobalAttentionGeneral fwd+bwd (grads on both outputs) at the synthetic generator shapes of
     SURVEY.md §8a-a7: B=48, T=18, (64^2,128ch) (128^2,64ch) (256^2,32ch).  HBM-bound: algorithmic
@@ -229,14 +244,12 @@ def gag_extra(dev, flush, hbm_gbs):
             with torch.no_grad():
                 mod(x, key, val)
 
-        for _ in range(3):
-            fwd_bwd()
-        ms = _time_cuda(fwd_bwd, 10, flush)
-        ms_f = _time_cuda(fwd_only, 10, flush)
+        ms = _time_cuda(_graph_replay(fwd_bwd, dev), 10, flush)
+        ms_f = _time_cuda(_graph_replay(fwd_only, dev), 10, flush)
         rows = Bq * res * res
         by = (5 * idf + 2 * T) * 4 * rows
         by_f = (2 * idf + T) * 4 * rows
-        out.append({"res": res, "idf": idf, "rows_per_s": rows / (ms / 1e3), "ms_fwd_bwd": ms, "ms_fwd": ms_f,
+        out.append({"res": res, "idf": idf, "timing": "CUDA-graph replay", "rows_per_s": rows / (ms / 1e3), "ms_fwd_bwd": ms, "ms_fwd": ms_f,
                     "hbm_gbs_fwd_bwd": by / (ms / 1e3) / 1e9, "hbm_frac_fwd_bwd": by / (ms / 1e3) / 1e9 / hbm_gbs,
                     "hbm_gbs_fwd": by_f / (ms_f / 1e3) / 1e9, "hbm_frac_fwd": by_f / (ms_f / 1e3) / 1e9 / hbm_gbs})
         del x, key, val, go, ga
@@ -361,19 +374,7 @@ def aux_rows_extra(dev, flush, bf16_tflops):
 
     # a few microseconds of device work behind ~30 Python-level ops: time CUDA-graph replays of both, so that the number
     # is the device time of the launches and not the interpreter
-    def graphed(fn):
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                fn()
-        torch.cuda.current_stream().wait_stream(side)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            fn()
-        return g.replay
-
-    r_ours, r_ref = graphed(ours2), graphed(ref2)
+    r_ours, r_ref = _graph_replay(ours2, dev), _graph_replay(ref2, dev)
     out["attr_enhance"] = {"shape": [B, A + 1, D], "us_fwd_bwd": 1e3 * _time_cuda(r_ours, 20, flush),
                            "us_torch_ops_same_gpu": 1e3 * _time_cuda(r_ref, 20, flush),
                            "timing": "CUDA-graph replay of forward + backward (device time of the launches)"}

@@ -32,6 +32,8 @@ SIGNATURES = {
     "eegan_sent_scores_bwd": (_c_int, [_p, _p, _p, _p, _c_int, _c_int, _c_float, _c_float, _p, _p, _p]),
     "eegan_gag_fwd": (_c_int, [_p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _p, _p]),
     "eegan_gag_bwd": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p]),
+    "eegan_gag_bwd_workspace_bytes": (_c_size_t, [_c_int] * 4),
+    "eegan_gag_bwd_ws": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p, _c_size_t, _p]),
     "eegan_syncbn_stats": (_c_int, [_p, _c_int, _c_int, _c_int, _p, _p]),
     "eegan_syncbn_finalize": (_c_int, [_p, _c_int, _c_double, _p, _c_float, _c_float, _c_int, _p, _p, _p, _p, _p]),
     "eegan_syncbn_apply": (_c_int, [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p]),

@@ -1,0 +1,305 @@
+// GlobalAttentionGeneral backward, second form (miscc/DAMSM_losses.py:96-132; math in SURVEY.md App. A).
+//
+// The first backward (gag.cu) does everything in one kernel and is bound by shared-memory operand fetches: every FMA of
+// its four contractions takes one operand from shared memory, and the d_key / d_value sums over pixels need a CTA-wide
+// reduction per 8-channel chunk.  Here the work is split so that every inner loop is FMA-bound out of registers:
+//
+//   kernel 1 (thread = PX pixels)   dp[t] = sum_d d_out[d,q] v[d,t] + d_attn[t,q];  ds = p (dp - sum_t p dp)
+//                                   d_x[d,q] = sum_t ds[t] key[d,t];  ds[t,q] -> workspace
+//                                   key / value rows are broadcast float4 reads shared by the thread's PX pixels.
+//   kernel 2, launched twice        d_key[d,:] = sum_q x[d,q] ds[:,q]   and   d_value[d,:] = sum_q d_out[d,q] p[:,q]
+//   (thread = 4 channels)           over one chunk of pixels: the thread keeps its 4 x TP sums in registers for the whole
+//                                   chunk, reads its four rows 8 pixels at a time (16-byte loads) and the ds / p rows of
+//                                   those pixels as broadcast float4 from shared memory: 16 FMA per 16-byte shared load
+//                                   (a broadcast LDS.128 still occupies the shared-memory pipe for four cycles, so one
+//                                   row per thread — 4 FMA per load — ran at 14 % of the FMA pipe).
+//   kernel 3                        fixed-order sum of the per-chunk partials (no atomics, nothing to zero).
+//
+// Extra HBM traffic against the one-kernel form: ds written and read once (2 T floats per pixel) and d_out read twice.
+#include "common.cuh"
+
+namespace eegan {
+
+constexpr int G2_THREADS = 128;
+
+template <int TP, int PX>
+__global__ void __launch_bounds__(G2_THREADS) gag_bwd_px_kernel(const float* __restrict__ key, const float* __restrict__ value,
+                                                                const float* __restrict__ attn, const float* __restrict__ d_out,
+                                                                const float* __restrict__ d_attn, int idf, int Q, int T,
+                                                                float* __restrict__ d_x, float* __restrict__ ds_out) {
+    extern __shared__ __align__(16) float g2sm[];
+    float* ks = g2sm;             // [idf][TP]
+    float* vs = ks + idf * TP;    // [idf][TP]
+    const int b = blockIdx.y, tid = threadIdx.x;
+    for (int idx = tid; idx < idf * TP; idx += G2_THREADS) {
+        const int d = idx / TP, t = idx - d * TP;
+        ks[idx] = t < T ? key[((size_t)b * idf + d) * T + t] : 0.f;
+        vs[idx] = t < T ? value[((size_t)b * idf + d) * T + t] : 0.f;
+    }
+    __syncthreads();
+    int q[PX];
+    bool ok[PX];
+    float dp[PX][TP];
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+        q[p] = (blockIdx.x * PX + p) * G2_THREADS + tid;
+        ok[p] = q[p] < Q;
+        if (!ok[p]) q[p] = Q - 1;  // clamped loads, guarded stores
+#pragma unroll
+        for (int t = 0; t < TP; ++t) dp[p][t] = (d_attn && t < T) ? d_attn[((size_t)b * T + t) * Q + q[p]] : 0.f;
+    }
+    if (d_out) {
+        const float* gbase = d_out + (size_t)b * idf * Q;
+#pragma unroll 4
+        for (int d = 0; d < idf; ++d) {
+            float g[PX];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) g[p] = __ldg(gbase + (size_t)d * Q + q[p]);
+            const float* vr = vs + d * TP;
+#pragma unroll
+            for (int t = 0; t < TP; t += 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(vr + t);
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    dp[p][t + 0] = fmaf(g[p], v4.x, dp[p][t + 0]);
+                    dp[p][t + 1] = fmaf(g[p], v4.y, dp[p][t + 1]);
+                    dp[p][t + 2] = fmaf(g[p], v4.z, dp[p][t + 2]);
+                    dp[p][t + 3] = fmaf(g[p], v4.w, dp[p][t + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {  // ds = p (dp - sum_t p dp), in place
+        float pr[TP];
+        float dot = 0.f;
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            pr[t] = t < T ? attn[((size_t)b * T + t) * Q + q[p]] : 0.f;
+            dot = fmaf(pr[t], dp[p][t], dot);
+        }
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            dp[p][t] = pr[t] * (dp[p][t] - dot);
+            if (t < T && ok[p]) ds_out[((size_t)b * T + t) * Q + q[p]] = dp[p][t];
+        }
+    }
+    float* xbase = d_x + (size_t)b * idf * Q;
+#pragma unroll 4
+    for (int d = 0; d < idf; ++d) {
+        const float* kr = ks + d * TP;
+        float acc[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) acc[p] = 0.f;
+#pragma unroll
+        for (int t = 0; t < TP; t += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(kr + t);
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                acc[p] = fmaf(dp[p][t + 0], k4.x, acc[p]);
+                acc[p] = fmaf(dp[p][t + 1], k4.y, acc[p]);
+                acc[p] = fmaf(dp[p][t + 2], k4.z, acc[p]);
+                acc[p] = fmaf(dp[p][t + 3], k4.w, acc[p]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+            if (ok[p]) xbase[(size_t)d * Q + q[p]] = acc[p];
+    }
+}
+
+// out[d,:] = sum over the chunk's pixels q of rows[d,q] * w[:,q]   (rows = x, w = ds -> d_key;  rows = d_out, w = p -> d_value)
+// grid (chunks, B); blockDim = (idf / 4) * sub: thread = (row group of 4 channels, pixel subgroup sg); a round covers
+// sub * 8 pixels; the subgroups meet in shared memory at the end (fixed order).
+constexpr int G2_RPT = 4;   // rows (channels) per thread
+constexpr int G2_PPR = 8;   // pixels per thread and round
+template <int TP>
+__global__ void __launch_bounds__(128) gag_bwd_rowsum_kernel(const float* __restrict__ rows, const float* __restrict__ w, int idf,
+                                                             int sub, int Q, int T, int Qc, float* __restrict__ part) {
+    extern __shared__ __align__(16) float g2sm[];
+    const int nrg = idf / G2_RPT, round_px = sub * G2_PPR;
+    float* w_s = g2sm;  // [round_px][TP]
+    const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
+    const int rg = tid % nrg, sg = tid / nrg;
+    const int q_beg = c * Qc, q_end = min(Q, q_beg + Qc);
+    float acc[G2_RPT][TP];
+#pragma unroll
+    for (int r = 0; r < G2_RPT; ++r)
+#pragma unroll
+        for (int t = 0; t < TP; ++t) acc[r][t] = 0.f;
+    const float* rbase = rows ? rows + ((size_t)b * idf + rg * G2_RPT) * Q : nullptr;
+    for (int q0 = q_beg; q0 < q_end; q0 += round_px) {
+        __syncthreads();  // the previous round's readers are done with w_s
+        for (int idx = tid; idx < TP * round_px; idx += blockDim.x) {
+            const int t = idx / round_px, qq = idx - t * round_px;  // consecutive threads -> consecutive pixels: coalesced
+            const int qg = q0 + qq;
+            w_s[qq * TP + t] = (t < T && qg < q_end) ? w[((size_t)b * T + t) * Q + qg] : 0.f;
+        }
+        const int qs = q0 + sg * G2_PPR;  // this thread's pixels of the round
+        float xr[G2_RPT][G2_PPR];
+        if (rbase && qs + G2_PPR <= q_end) {
+#pragma unroll
+            for (int r = 0; r < G2_RPT; ++r)
+#pragma unroll
+                for (int k = 0; k < G2_PPR / 4; ++k) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(rbase + (size_t)r * Q + qs) + k);
+                    xr[r][4 * k] = a.x; xr[r][4 * k + 1] = a.y; xr[r][4 * k + 2] = a.z; xr[r][4 * k + 3] = a.w;
+                }
+        } else {
+#pragma unroll
+            for (int r = 0; r < G2_RPT; ++r)
+#pragma unroll
+                for (int k = 0; k < G2_PPR; ++k) xr[r][k] = (rbase && qs + k < q_end) ? __ldg(rbase + (size_t)r * Q + qs + k) : 0.f;
+        }
+        __syncthreads();
+        const float* wr = w_s + sg * G2_PPR * TP;
+#pragma unroll
+        for (int k = 0; k < G2_PPR; ++k) {
+#pragma unroll
+            for (int t = 0; t < TP; t += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wr + k * TP + t);
+#pragma unroll
+                for (int r = 0; r < G2_RPT; ++r) {
+                    acc[r][t + 0] = fmaf(xr[r][k], w4.x, acc[r][t + 0]);
+                    acc[r][t + 1] = fmaf(xr[r][k], w4.y, acc[r][t + 1]);
+                    acc[r][t + 2] = fmaf(xr[r][k], w4.z, acc[r][t + 2]);
+                    acc[r][t + 3] = fmaf(xr[r][k], w4.w, acc[r][t + 3]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float* red = g2sm;  // [sub][idf][TP] (the host sizes the dynamic shared memory for the larger of the two uses)
+    if (sub > 1) {
+#pragma unroll
+        for (int r = 0; r < G2_RPT; ++r)
+#pragma unroll
+            for (int t = 0; t < TP; ++t) red[((size_t)sg * idf + rg * G2_RPT + r) * TP + t] = acc[r][t];
+        __syncthreads();
+        if (sg == 0)
+            for (int s2 = 1; s2 < sub; ++s2)
+#pragma unroll
+                for (int r = 0; r < G2_RPT; ++r)
+#pragma unroll
+                    for (int t = 0; t < TP; ++t) acc[r][t] += red[((size_t)s2 * idf + rg * G2_RPT + r) * TP + t];
+    }
+    if (sg == 0) {
+#pragma unroll
+        for (int r = 0; r < G2_RPT; ++r) {
+            float* pp = part + (((size_t)b * gridDim.x + c) * idf + rg * G2_RPT + r) * TP;
+#pragma unroll
+            for (int t = 0; t < TP; t += 4) *reinterpret_cast<float4*>(pp + t) = make_float4(acc[r][t], acc[r][t + 1], acc[r][t + 2], acc[r][t + 3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gag_bwd_kv_reduce_kernel(const float* __restrict__ part_k, const float* __restrict__ part_v,
+                                                                int B, int idf, int T, int TP, int S, float* __restrict__ d_key,
+                                                                float* __restrict__ d_value) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * idf * T) return;
+    const int t = (int)(i % T);
+    const long long bd = i / T;
+    const int d = (int)(bd % idf), b = (int)(bd / idf);
+    float sk = 0.f, sv = 0.f;
+    for (int c = 0; c < S; ++c) {
+        const size_t o = (((size_t)b * S + c) * idf + d) * TP + t;
+        sk += part_k[o];
+        sv += part_v[o];
+    }
+    d_key[i] = sk;
+    d_value[i] = sv;
+}
+
+struct G2Plan {
+    int TP, sub, threads, S, Qc;
+    size_t ds_bytes, part_bytes;
+};
+
+static bool g2_plan(int B, int idf, int Q, int T, G2Plan* pl) {
+    if (idf % 32 != 0 || idf > 512 || T > 32) return false;
+    pl->TP = T <= 8 ? 8 : T <= 12 ? 12 : T <= 16 ? 16 : T <= 20 ? 20 : T <= 24 ? 24 : 32;
+    const int nrg = idf / G2_RPT;              // 8 .. 128 row groups
+    pl->sub = 128 / nrg > 0 ? 128 / nrg : 1;   // pixel subgroups per CTA
+    pl->threads = nrg * pl->sub;               // <= 128
+    const int round_px = pl->sub * G2_PPR;
+    int S = (6 * 148 + B - 1) / B;  // about six CTAs per SM over the grid
+    const int max_s = (Q + round_px - 1) / round_px;
+    if (S > max_s) S = max_s;
+    if (S < 1) S = 1;
+    pl->Qc = ((Q + S - 1) / S + round_px - 1) / round_px * round_px;
+    pl->S = (Q + pl->Qc - 1) / pl->Qc;
+    pl->ds_bytes = align_up((size_t)B * T * Q * sizeof(float), 256);
+    pl->part_bytes = align_up((size_t)B * pl->S * idf * pl->TP * sizeof(float), 256);
+    return true;
+}
+
+template <int TP>
+static int g2_launch(const G2Plan& pl, const float* x, const float* key, const float* value, const float* attn, const float* d_out,
+                     const float* d_attn, int B, int idf, int Q, int T, float* d_x, float* d_key, float* d_value, float* dsw,
+                     float* pk, float* pv, cudaStream_t st) {
+    constexpr int PX = 4;
+    const size_t smem1 = (size_t)2 * idf * TP * sizeof(float);
+    if (smem1 > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(gag_bwd_px_kernel<TP, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) { set_error("gag bwd2 smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+    }
+    gag_bwd_px_kernel<TP, PX><<<dim3((Q + G2_THREADS * PX - 1) / (G2_THREADS * PX), B), G2_THREADS, smem1, st>>>(
+        key, value, attn, d_out, d_attn, idf, Q, T, d_x, dsw);
+    EEGAN_LAUNCH_CHECK("gag bwd2 (pixels)");
+    const size_t stage2 = (size_t)pl.sub * G2_PPR * TP * sizeof(float), red2 = pl.sub > 1 ? (size_t)pl.sub * idf * TP * sizeof(float) : 0;
+    const size_t smem2 = stage2 > red2 ? stage2 : red2;
+    if (smem2 > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(gag_bwd_rowsum_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) { set_error("gag bwd2 smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+    }
+    gag_bwd_rowsum_kernel<TP><<<dim3(pl.S, B), pl.threads, smem2, st>>>(x, dsw, idf, pl.sub, Q, T, pl.Qc, pk);
+    gag_bwd_rowsum_kernel<TP><<<dim3(pl.S, B), pl.threads, smem2, st>>>(d_out, attn, idf, pl.sub, Q, T, pl.Qc, pv);
+    EEGAN_LAUNCH_CHECK("gag bwd2 (key/value)");
+    const long long n = (long long)B * idf * T;
+    gag_bwd_kv_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pk, pv, B, idf, T, TP, pl.S, d_key, d_value);
+    return check_launch("gag bwd2 (reduce)");
+}
+
+}  // namespace eegan
+
+using namespace eegan;
+
+extern "C" size_t eegan_gag_bwd_workspace_bytes(int B, int idf, int Q, int T) {
+    G2Plan pl;
+    if (B <= 0 || idf <= 0 || Q <= 0 || T <= 0 || !g2_plan(B, idf, Q, T, &pl)) return 0;
+    return pl.ds_bytes + 2 * pl.part_bytes;
+}
+
+extern "C" int eegan_gag_bwd(const float* x, const float* key, const float* value, const float* attn, const float* d_out,
+                             const float* d_attn, int B, int idf, int Q, int T, float* d_x, float* d_key, float* d_value,
+                             void* stream);
+
+// Backward with a caller-owned workspace (eegan_gag_bwd_workspace_bytes): the two-kernel register-tiled form above.
+// Shapes it does not cover (idf not a multiple of 32, rows not 16-byte aligned) and workspace == NULL go to eegan_gag_bwd.
+extern "C" int eegan_gag_bwd_ws(const float* x, const float* key, const float* value, const float* attn, const float* d_out,
+                                const float* d_attn, int B, int idf, int Q, int T, float* d_x, float* d_key, float* d_value,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    EEGAN_REQUIRE(B > 0 && idf > 0 && Q > 0 && T > 0, "gag: empty shape B=%d idf=%d Q=%d T=%d", B, idf, Q, T);
+    EEGAN_REQUIRE(x && key && value && attn && d_x && d_key && d_value, "gag bwd: null pointer");
+    G2Plan pl;
+    const bool aligned = Q % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+    if (!workspace || !aligned || !g2_plan(B, idf, Q, T, &pl) || B > 65535)
+        return eegan_gag_bwd(x, key, value, attn, d_out, d_attn, B, idf, Q, T, d_x, d_key, d_value, stream);
+    EEGAN_REQUIRE(workspace_bytes >= pl.ds_bytes + 2 * pl.part_bytes, "gag bwd: workspace %zu < %zu bytes", workspace_bytes,
+                  pl.ds_bytes + 2 * pl.part_bytes);
+    float* dsw = (float*)workspace;
+    float* pk = (float*)((char*)workspace + pl.ds_bytes);
+    float* pv = (float*)((char*)workspace + pl.ds_bytes + pl.part_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+#define G2_CALL(TPV) g2_launch<TPV>(pl, x, key, value, attn, d_out, d_attn, B, idf, Q, T, d_x, d_key, d_value, dsw, pk, pv, st)
+    switch (pl.TP) {
+        case 8: return G2_CALL(8);
+        case 12: return G2_CALL(12);
+        case 16: return G2_CALL(16);
+        case 20: return G2_CALL(20);
+        case 24: return G2_CALL(24);
+        default: return G2_CALL(32);
+    }
+#undef G2_CALL
+}

@@ -193,10 +193,12 @@ class _GagFn(torch.autograd.Function):
         d_out = _lib.f32c(d_out) if d_out is not None else None
         d_attn = _lib.f32c(d_attn) if d_attn is not None else None
         d_x, d_key, d_val = torch.empty_like(x), torch.empty_like(key), torch.empty_like(value)
+        need = L.eegan_gag_bwd_workspace_bytes(B, idf, Q, T)  # 0: shape outside the two-kernel form -> one-kernel fallback
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device) if need else None
         with torch.cuda.device(x.device):
-            _lib.check(L.eegan_gag_bwd(_lib.ptr(x), _lib.ptr(key), _lib.ptr(value), _lib.ptr(attn), _lib.ptr(d_out),
-                                       _lib.ptr(d_attn), B, idf, Q, T, _lib.ptr(d_x), _lib.ptr(d_key), _lib.ptr(d_val),
-                                       _lib.stream_ptr()), "gag_bwd")
+            _lib.check(L.eegan_gag_bwd_ws(_lib.ptr(x), _lib.ptr(key), _lib.ptr(value), _lib.ptr(attn), _lib.ptr(d_out),
+                                          _lib.ptr(d_attn), B, idf, Q, T, _lib.ptr(d_x), _lib.ptr(d_key), _lib.ptr(d_val),
+                                          _lib.ptr(ws), need, _lib.stream_ptr()), "gag_bwd")
         return d_x, d_key, d_val, None, None
 
 

@@ -187,6 +187,39 @@ def test_gag_tensor_core_forward_shapes(cuda_lib, B, idf, H, T):
         assert float((out.cpu().double()[okr] - oo[okr]).abs().max()) <= 1e-5 * float(oo[okr].abs().max()), eng
 
 
+@pytest.mark.parametrize("B,idf,H,T,grads", [(3, 128, 16, 18, "both"), (2, 64, 20, 18, "both"), (4, 32, 24, 5, "both"),
+                                              (2, 96, 12, 20, "both"), (2, 256, 8, 32, "both"), (3, 64, 16, 18, "out"),
+                                              (3, 64, 16, 18, "attn"), (2, 48, 12, 7, "both"), (2, 32, 23, 18, "both")])
+def test_gag_backward_shapes(cuda_lib, B, idf, H, T, grads):
+    """The two-kernel backward (gag_bwd2.cu: per-pixel pass + per-channel key/value sums over pixel chunks) at its shape
+    edges — idf = 32 / 64 (4 / 2 pixel subgroups per CTA), 96 (one subgroup, 96 threads), 256, T = 5 … 32, Q not a
+    multiple of the chunk, a gradient on only one of the two outputs — and the one-kernel fallback it hands idf = 48 and
+    Q % 4 != 0 to, against the float64 oracle's autograd."""
+    import eegan_b200 as E
+    c = cases.gag_case(B, idf, H, T, seed=B * 7 + idf + T, masked=False)
+    gen = cases._gen(5)
+    go = torch.randn(B, idf, H, H, generator=gen)
+    ga = torch.randn(B, T, H, H, generator=gen)
+    xo, ko, vo = (c[n].double().requires_grad_() for n in ("x", "key", "value"))
+    oo, oa = O.port_global_attention(xo, ko, vo, None)
+    loss_o = (oo * go.double()).sum() * (grads != "attn") + (oa * ga.double()).sum() * (grads != "out")
+    loss_o.backward()
+    x, k, v = (c[n].cuda().requires_grad_() for n in ("x", "key", "value"))
+    out, attn = E.GlobalAttentionGeneral(idf, 256)(x, k, v)
+    loss = 0.0
+    if grads != "attn":
+        loss = loss + (out * go.cuda()).sum()
+    if grads != "out":
+        loss = loss + (attn * ga.cuda()).sum()
+    loss.backward()
+    assert relmax(x.grad.cpu(), xo.grad) <= TOL_GRAD
+    assert relmax(k.grad.cpu(), ko.grad) <= TOL_GRAD
+    if grads != "attn":
+        assert relmax(v.grad.cpu(), vo.grad) <= TOL_GRAD
+    else:  # value only feeds `out`
+        assert float(v.grad.abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("name", golden_names("words_")[:3])
 def test_func_attention_vs_reference_fixture(cuda_lib, name):
     import eegan_b200 as E

@@ -114,11 +114,10 @@ __global__ void __launch_bounds__(G2_THREADS) gag_bwd_px_kernel(const float* __r
 constexpr int G2_RPT = 4;   // rows (channels) per thread
 constexpr int G2_PPR = 8;   // pixels per thread and round
 template <int TP>
-__global__ void __launch_bounds__(128) gag_bwd_rowsum_kernel(const float* __restrict__ rows, const float* __restrict__ w, int idf,
+__global__ void __launch_bounds__(128, 3) gag_bwd_rowsum_kernel(const float* __restrict__ rows, const float* __restrict__ w, int idf,
                                                              int sub, int Q, int T, int Qc, float* __restrict__ part) {
     extern __shared__ __align__(16) float g2sm[];
     const int nrg = idf / G2_RPT, round_px = sub * G2_PPR;
-    float* w_s = g2sm;  // [round_px][TP]
     const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
     const int rg = tid % nrg, sg = tid / nrg;
     const int q_beg = c * Qc, q_end = min(Q, q_beg + Qc);
@@ -128,31 +127,50 @@ __global__ void __launch_bounds__(128) gag_bwd_rowsum_kernel(const float* __rest
 #pragma unroll
         for (int t = 0; t < TP; ++t) acc[r][t] = 0.f;
     const float* rbase = rows ? rows + ((size_t)b * idf + rg * G2_RPT) * Q : nullptr;
-    for (int q0 = q_beg; q0 < q_end; q0 += round_px) {
-        __syncthreads();  // the previous round's readers are done with w_s
-        for (int idx = tid; idx < TP * round_px; idx += blockDim.x) {
-            const int t = idx / round_px, qq = idx - t * round_px;  // consecutive threads -> consecutive pixels: coalesced
-            const int qg = q0 + qq;
-            w_s[qq * TP + t] = (t < T && qg < q_end) ? w[((size_t)b * T + t) * Q + qg] : 0.f;
-        }
-        const int qs = q0 + sg * G2_PPR;  // this thread's pixels of the round
-        float xr[G2_RPT][G2_PPR];
+    // Software pipeline over the rounds: the loads of round i+1 — this thread's 4 x 8 row values (registers, ping-pong)
+    // and its share of the w rows (4-byte cp.async straight into the other half of the double-buffered staging) — are
+    // issued right before the FMAs of round i, so their latency hides behind ~640 FMA per thread; one barrier per round.
+    float* w_s = g2sm;  // two buffers of [round_px][TP]
+    const int wbuf = round_px * TP;
+    auto load_x = [&](int q0, float (&xd)[G2_RPT][G2_PPR]) {
+        const int qs = q0 + sg * G2_PPR;
         if (rbase && qs + G2_PPR <= q_end) {
 #pragma unroll
             for (int r = 0; r < G2_RPT; ++r)
 #pragma unroll
                 for (int k = 0; k < G2_PPR / 4; ++k) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(rbase + (size_t)r * Q + qs) + k);
-                    xr[r][4 * k] = a.x; xr[r][4 * k + 1] = a.y; xr[r][4 * k + 2] = a.z; xr[r][4 * k + 3] = a.w;
+                    xd[r][4 * k] = a.x; xd[r][4 * k + 1] = a.y; xd[r][4 * k + 2] = a.z; xd[r][4 * k + 3] = a.w;
                 }
         } else {
 #pragma unroll
             for (int r = 0; r < G2_RPT; ++r)
 #pragma unroll
-                for (int k = 0; k < G2_PPR; ++k) xr[r][k] = (rbase && qs + k < q_end) ? __ldg(rbase + (size_t)r * Q + qs + k) : 0.f;
+                for (int k = 0; k < G2_PPR; ++k) xd[r][k] = (rbase && qs + k < q_end) ? __ldg(rbase + (size_t)r * Q + qs + k) : 0.f;
         }
-        __syncthreads();
-        const float* wr = w_s + sg * G2_PPR * TP;
+    };
+    auto issue_w = [&](int q0, float* dst) {
+        for (int idx = tid; idx < TP * round_px; idx += blockDim.x) {
+            const int t = idx / round_px, qq = idx - t * round_px;  // consecutive threads -> consecutive pixels: coalesced
+            const int qg = q0 + qq;
+            float* d = dst + qq * TP + t;
+            if (t < T && qg < q_end) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(d)),
+                             "l"(w + ((size_t)b * T + t) * Q + qg) : "memory");
+            } else {
+                *d = 0.f;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto do_round = [&](float (&xc)[G2_RPT][G2_PPR], float (&xnext)[G2_RPT][G2_PPR], int q0, int cur) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // w_s[cur] has landed for every thread; every thread is done reading w_s[cur ^ 1]
+        if (q0 + round_px < q_end) {
+            load_x(q0 + round_px, xnext);
+            issue_w(q0 + round_px, w_s + (cur ^ 1) * wbuf);
+        }
+        const float* wr = w_s + cur * wbuf + sg * G2_PPR * TP;
 #pragma unroll
         for (int k = 0; k < G2_PPR; ++k) {
 #pragma unroll
@@ -160,28 +178,37 @@ __global__ void __launch_bounds__(128) gag_bwd_rowsum_kernel(const float* __rest
                 const float4 w4 = *reinterpret_cast<const float4*>(wr + k * TP + t);
 #pragma unroll
                 for (int r = 0; r < G2_RPT; ++r) {
-                    acc[r][t + 0] = fmaf(xr[r][k], w4.x, acc[r][t + 0]);
-                    acc[r][t + 1] = fmaf(xr[r][k], w4.y, acc[r][t + 1]);
-                    acc[r][t + 2] = fmaf(xr[r][k], w4.z, acc[r][t + 2]);
-                    acc[r][t + 3] = fmaf(xr[r][k], w4.w, acc[r][t + 3]);
+                    acc[r][t + 0] = fmaf(xc[r][k], w4.x, acc[r][t + 0]);
+                    acc[r][t + 1] = fmaf(xc[r][k], w4.y, acc[r][t + 1]);
+                    acc[r][t + 2] = fmaf(xc[r][k], w4.z, acc[r][t + 2]);
+                    acc[r][t + 3] = fmaf(xc[r][k], w4.w, acc[r][t + 3]);
                 }
             }
         }
+    };
+    float xa[G2_RPT][G2_PPR], xb[G2_RPT][G2_PPR];
+    load_x(q_beg, xa);
+    issue_w(q_beg, w_s);
+    for (int q0 = q_beg; q0 < q_end; q0 += 2 * round_px) {
+        do_round(xa, xb, q0, 0);
+        if (q0 + round_px < q_end) do_round(xb, xa, q0 + round_px, 1);
     }
     __syncthreads();
-    float* red = g2sm;  // [sub][idf][TP] (the host sizes the dynamic shared memory for the larger of the two uses)
+    // subgroups meet in shared memory, laid out [row r][t][subgroup][row group] so that a warp's lanes (consecutive row
+    // groups) hit consecutive words
+    float* red = g2sm;
     if (sub > 1) {
 #pragma unroll
         for (int r = 0; r < G2_RPT; ++r)
 #pragma unroll
-            for (int t = 0; t < TP; ++t) red[((size_t)sg * idf + rg * G2_RPT + r) * TP + t] = acc[r][t];
+            for (int t = 0; t < TP; ++t) red[((size_t)(r * TP + t) * sub + sg) * nrg + rg] = acc[r][t];
         __syncthreads();
         if (sg == 0)
             for (int s2 = 1; s2 < sub; ++s2)
 #pragma unroll
                 for (int r = 0; r < G2_RPT; ++r)
 #pragma unroll
-                    for (int t = 0; t < TP; ++t) acc[r][t] += red[((size_t)s2 * idf + rg * G2_RPT + r) * TP + t];
+                    for (int t = 0; t < TP; ++t) acc[r][t] += red[((size_t)(r * TP + t) * sub + s2) * nrg + rg];
     }
     if (sg == 0) {
 #pragma unroll
@@ -247,7 +274,7 @@ static int g2_launch(const G2Plan& pl, const float* x, const float* key, const f
     gag_bwd_px_kernel<TP, PX><<<dim3((Q + G2_THREADS * PX - 1) / (G2_THREADS * PX), B), G2_THREADS, smem1, st>>>(
         key, value, attn, d_out, d_attn, idf, Q, T, d_x, dsw);
     EEGAN_LAUNCH_CHECK("gag bwd2 (pixels)");
-    const size_t stage2 = (size_t)pl.sub * G2_PPR * TP * sizeof(float), red2 = pl.sub > 1 ? (size_t)pl.sub * idf * TP * sizeof(float) : 0;
+    const size_t stage2 = (size_t)2 * pl.sub * G2_PPR * TP * sizeof(float), red2 = pl.sub > 1 ? (size_t)pl.sub * idf * TP * sizeof(float) : 0;
     const size_t smem2 = stage2 > red2 ? stage2 : red2;
     if (smem2 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(gag_bwd_rowsum_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);

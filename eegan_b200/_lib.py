@@ -51,8 +51,9 @@ SIGNATURES = {
     "eegan_conv1x1_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "eegan_conv1x1_fwd": (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _c_size_t, _p]),
     "eegan_conv1x1_bwd": (_c_int, [_p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _c_size_t, _p]),
-    "eegan_attr_enhance_fwd": (_c_int, [_p] * 8 + [_c_int, _c_int, _c_int, _c_float, _p, _p, _p, _p]),
-    "eegan_attr_enhance_bwd": (_c_int, [_p] * 9 + [_c_int, _c_int, _c_int, _c_float] + [_p] * 10),
+    "eegan_attr_enhance_fwd": (_c_int, [_p] * 8 + [_c_int, _c_int, _c_int, _c_float, _p, _p, _p, _p, _p]),
+    "eegan_attr_enhance_bwd": (_c_int, [_p] * 8 + [_c_int, _c_int, _c_int, _c_float] + [_p] * 11),
+    "eegan_attr_enhance_workspace_bytes": (_c_size_t, [_c_int] * 3),
     "eegan_rprecision": (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_float, _p, _p, _p, _p]),
     "eegan_ssa_apply": (_c_int, [_p] * 6 + [_c_int] * 3 + [_p, _p]),
     "eegan_ssa_bwd_reduce": (_c_int, [_p] * 7 + [_c_int] * 3 + [_p] * 5),

@@ -5,7 +5,8 @@ Self-attention of the sentence code over its attribute codes: ``combine = [sent 
 models.py:166 — reproduced), ``attn_attrs = a v``, ``attn_sent = attn_attrs[:, 0]``.  Its outputs feed ``sent_loss``
 (the attribute loss, train.py:432) and ``Gen``.  The module keeps the reference's sub-module names
 (``attr_query`` / ``attr_key`` / ``attr_value``: ``nn.Linear`` parameter holders), so a reference ``state_dict`` loads
-unchanged; the arithmetic runs in one fused forward launch and two backward launches (``eegan_attr_enhance_*``).
+unchanged; the arithmetic runs in three forward and four backward launches of the library (``eegan_attr_enhance_*``):
+cat, one batched small GEMM for the three projections, per-sample attention; and their transposes.
 """
 from __future__ import annotations
 
@@ -26,42 +27,45 @@ class _AttrEnhanceFn(torch.autograd.Function):
         B, D = sent.shape
         A = attrs.shape[1]
         Tk = A + 1
-        out = torch.empty(B, Tk, D, dtype=torch.float32, device=sent.device)
-        qkv = torch.empty(B, 3, Tk, D, dtype=torch.float32, device=sent.device)
-        p = torch.empty(B, Tk, Tk, dtype=torch.float32, device=sent.device)
+        f32 = dict(dtype=torch.float32, device=sent.device)
+        out = torch.empty(B, Tk, D, **f32)
+        qkv = torch.empty(3, B * Tk, D, **f32)
+        p = torch.empty(B, Tk, Tk, **f32)
+        combine = torch.empty(B * Tk, D, **f32)
         with torch.cuda.device(sent.device):
             _lib.check(L.eegan_attr_enhance_fwd(_lib.ptr(sent), _lib.ptr(attrs), _lib.ptr(Wq), _lib.ptr(bq), _lib.ptr(Wk),
                                                 _lib.ptr(bk), _lib.ptr(Wv), _lib.ptr(bv), B, D, A, norm_fact, _lib.ptr(out),
-                                                _lib.ptr(qkv), _lib.ptr(p), _lib.stream_ptr()), "attr_enhance_fwd")
-        ctx.save_for_backward(sent, attrs, qkv, p, Wq, Wk, Wv)
-        ctx.norm = norm_fact
+                                                _lib.ptr(qkv), _lib.ptr(p), _lib.ptr(combine), _lib.stream_ptr()), "attr_enhance_fwd")
+        ctx.save_for_backward(combine, qkv, p, Wq, Wk, Wv)
+        ctx.norm, ctx.dims = norm_fact, (B, D, A)
         return out
 
     @staticmethod
     def backward(ctx, d_attrs_out):
-        d_sent_out = None  # attn_sent is sliced out of attn_attrs by the caller: its gradient arrives inside d_attrs_out
-        sent, attrs, qkv, p, Wq, Wk, Wv = ctx.saved_tensors
+        # attn_sent is sliced out of attn_attrs by the caller: its gradient arrives inside d_attrs_out
+        combine, qkv, p, Wq, Wk, Wv = ctx.saved_tensors
         L = _lib.lib()
-        B, D = sent.shape
-        A = attrs.shape[1]
+        B, D, A = ctx.dims
+        Tk = A + 1
         need = ctx.needs_input_grad
-        dev = sent.device
-        d_sent_out = _lib.f32c(d_sent_out) if d_sent_out is not None else None
-        d_attrs_out = _lib.f32c(d_attrs_out) if d_attrs_out is not None else None
-        g = torch.empty(B, 3, A + 1, D, dtype=torch.float32, device=dev)
-        mk = lambda ok, ref: torch.empty_like(ref) if ok else None
-        d_sent, d_attrs = mk(need[0], sent), mk(need[1], attrs)
-        dWq, dWk, dWv = mk(need[2], Wq), mk(need[4], Wk), mk(need[6], Wv)
-        dbq = torch.empty(D, dtype=torch.float32, device=dev) if need[3] else None
-        dbk = torch.empty(D, dtype=torch.float32, device=dev) if need[5] else None
-        dbv = torch.empty(D, dtype=torch.float32, device=dev) if need[7] else None
-        with torch.cuda.device(dev):
-            _lib.check(L.eegan_attr_enhance_bwd(_lib.ptr(d_sent_out), _lib.ptr(d_attrs_out), _lib.ptr(sent), _lib.ptr(attrs),
-                                                _lib.ptr(qkv), _lib.ptr(p), _lib.ptr(Wq), _lib.ptr(Wk), _lib.ptr(Wv), B, D, A, ctx.norm,
-                                                _lib.ptr(g), _lib.ptr(d_sent), _lib.ptr(d_attrs), _lib.ptr(dWq), _lib.ptr(dbq),
+        f32 = dict(dtype=torch.float32, device=combine.device)
+        d_attrs_out = _lib.f32c(d_attrs_out)
+        g = torch.empty(3, B * Tk, D, **f32)
+        dtok = torch.empty(B * Tk, D, **f32)
+        d_sent = torch.empty(B, D, **f32) if need[0] else None
+        d_attrs = torch.empty(B, A, D, **f32) if need[1] else None
+        want_w = need[2] or need[4] or need[6]
+        dWq, dWk, dWv = (torch.empty_like(Wq), torch.empty_like(Wk), torch.empty_like(Wv)) if want_w else (None, None, None)
+        dbq = torch.empty(D, **f32) if need[3] else None
+        dbk = torch.empty(D, **f32) if need[5] else None
+        dbv = torch.empty(D, **f32) if need[7] else None
+        with torch.cuda.device(combine.device):
+            _lib.check(L.eegan_attr_enhance_bwd(None, _lib.ptr(d_attrs_out), _lib.ptr(combine), _lib.ptr(qkv), _lib.ptr(p),
+                                                _lib.ptr(Wq), _lib.ptr(Wk), _lib.ptr(Wv), B, D, A, ctx.norm, _lib.ptr(g),
+                                                _lib.ptr(dtok), _lib.ptr(d_sent), _lib.ptr(d_attrs), _lib.ptr(dWq), _lib.ptr(dbq),
                                                 _lib.ptr(dWk), _lib.ptr(dbk), _lib.ptr(dWv), _lib.ptr(dbv), _lib.stream_ptr()),
                        "attr_enhance_bwd")
-        return d_sent, d_attrs, dWq, dbq, dWk, dbk, dWv, dbv, None
+        return (d_sent, d_attrs, dWq if need[2] else None, dbq, dWk if need[4] else None, dbk, dWv if need[6] else None, dbv, None)
 
 
 def attr_enhance(sent, attrs, Wq, bq, Wk, bk, Wv, bv, norm_fact):

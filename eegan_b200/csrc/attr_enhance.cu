@@ -1,57 +1,101 @@
 // ATTR_Enhance (models.py:146-180): self-attention of the sentence code over its attribute
 // codes — Tk = 1 + attr_num tokens of ntf = D channels per sample:
-//     combine = [sent ; attrs]                                   [Tk][D]                        (:161-162)
+//     combine = [sent ; attrs]                                   [B*Tk][D]                      (:161-162)
 //     q, k, v = combine Wq^T + bq, combine Wk^T + bk, combine Wv^T + bv                         (:163-165)
 //     a       = softmax_j(q k^T) * (1 / sqrt(D))                 scale AFTER the softmax        (:166)
 //     out     = a v ;  attn_sent = out[0]                                                       (:167-168)
-// The reference runs 3 Linear + cat + permute + 2 bmm + softmax + mul (about ten launches of a few microseconds of
-// work each); here the forward is ONE launch (CTA = sample, everything in shared memory) and the backward two:
-// per-sample gradients (d_q/d_k/d_v, d_sent, d_attrs), then the weight / bias gradients as a deterministic
-// reduction over all B * Tk token rows (no atomics).
+// Everything is a few hundred kFLOP per sample, so the design goal is few, wide launches:
+//   fwd  pack (cat) -> one small-GEMM launch for the three projections (grid.z = q/k/v) -> per-sample attention
+//   bwd  per-sample attention backward (d_q, d_k, d_v) -> one small-GEMM launch for the token gradients
+//        (K runs over the three projections) -> one for dW_q/k/v (grid.z) -> bias gradients
+// The small GEMM is a plain 32x32x32 shared-memory tile kernel on the CUDA cores (M = B*Tk = 192 rows: far too small
+// for the tensor-core engine's ~10 us launch ramp).  Weight gradients are plain sums in a fixed order: no atomics.
 #include "common.cuh"
 
 namespace eegan {
 
 constexpr int AE_MAXTK = 8;
-constexpr int AE_THREADS = 256;
 
-// stash per sample: q, k, v [3][Tk][D] and the softmax p [Tk][Tk] (before the 1/sqrt(D) factor)
-__global__ void __launch_bounds__(AE_THREADS) attr_enhance_fwd_kernel(const float* __restrict__ sent, const float* __restrict__ attrs,
-                                                                      const float* __restrict__ Wq, const float* __restrict__ bq,
-                                                                      const float* __restrict__ Wk, const float* __restrict__ bk,
-                                                                      const float* __restrict__ Wv, const float* __restrict__ bv,
-                                                                      int D, int Tk, float norm, float* __restrict__ out,
-                                                                      float* __restrict__ qkv, float* __restrict__ pst) {
+// C_i[m][n] = sum over segments s, k of A_s(m,k) * B_s(n,k) (+ bias_i[n]);  element (m,k) of A at A[m*sAm + k*sAk].
+// grid.z = independent problems i (nseg == 1: pointers indexed by z), or nseg K-segments accumulated into one C.
+struct SgArgs {
+    const float* A[3];
+    const float* B[3];
+    float* C[3];
+    const float* bias[3];
+    int M, N, K, nseg;
+    long long sAm, sAk, sBn, sBk, ldc;
+};
+
+__global__ void __launch_bounds__(256) ae_sgemm_kernel(const SgArgs a) {
+    __shared__ float As[32][33], Bs[32][33];  // [k][m], [k][n]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32, z = blockIdx.z;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int s = 0; s < a.nseg; ++s) {
+        const int i = a.nseg > 1 ? s : z;
+        const float* A = a.A[i];
+        const float* B = a.B[i];
+        for (int k0 = 0; k0 < a.K; k0 += 32) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int idx = tid + 256 * e;
+                // lanes run along the operand's contiguous index
+                const int am = a.sAk == 1 ? idx >> 5 : idx & 31, ak = a.sAk == 1 ? idx & 31 : idx >> 5;
+                const int bn = a.sBk == 1 ? idx >> 5 : idx & 31, bk = a.sBk == 1 ? idx & 31 : idx >> 5;
+                As[ak][am] = (m0 + am < a.M && k0 + ak < a.K) ? __ldg(A + (long long)(m0 + am) * a.sAm + (long long)(k0 + ak) * a.sAk) : 0.f;
+                Bs[bk][bn] = (n0 + bn < a.N && k0 + bk < a.K) ? __ldg(B + (long long)(n0 + bn) * a.sBn + (long long)(k0 + bk) * a.sBk) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const float a0 = As[k][2 * ty], a1 = As[k][2 * ty + 1], b0 = Bs[k][2 * tx], b1 = Bs[k][2 * tx + 1];
+                acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+                acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+            }
+            __syncthreads();
+        }
+    }
+    const int i = a.nseg > 1 ? 0 : z;
+    float* C = a.C[i];
+    const float* bias = a.bias[i];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int m = m0 + 2 * ty + r, n = n0 + 2 * tx + c;
+            if (m < a.M && n < a.N) C[(long long)m * a.ldc + n] = acc[r][c] + (bias ? bias[n] : 0.f);
+        }
+}
+
+static int ae_sgemm(const SgArgs& a, int nz, cudaStream_t st) {
+    ae_sgemm_kernel<<<dim3((a.N + 31) / 32, (a.M + 31) / 32, nz), 256, 0, st>>>(a);
+    return check_launch("attr_enhance gemm");
+}
+
+// combine[b*Tk + t][:] = t == 0 ? sent[b] : attrs[b][t-1]
+__global__ void __launch_bounds__(256) ae_pack_kernel(const float* __restrict__ sent, const float* __restrict__ attrs, int B, int D,
+                                                      int Tk, float* __restrict__ combine) {
+    const long long n = (long long)B * Tk * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const long long row = i / D;
+        const int t = (int)(row % Tk), b = (int)(row / Tk);
+        combine[i] = t == 0 ? sent[(size_t)b * D + d] : attrs[((size_t)b * (Tk - 1) + (t - 1)) * D + d];
+    }
+}
+
+// per sample: scores, softmax, out = (norm p) v.   qkv is [3][B*Tk][D];  p stash [B][Tk][Tk] (before the norm factor)
+__global__ void __launch_bounds__(256) ae_attn_fwd_kernel(const float* __restrict__ qkv, int B, int D, int Tk, float norm,
+                                                          float* __restrict__ out, float* __restrict__ pst) {
     extern __shared__ float sm[];
-    float* tok = sm;                 // [Tk][D]
-    float* q = tok + Tk * D;         // [3][Tk][D]: q, k, v
+    float* q = sm;                   // [3][Tk][D]
     float* s = q + 3 * Tk * D;       // [Tk][Tk]
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < Tk * D; i += blockDim.x) {
-        const int t = i / D, d = i - t * D;
-        tok[i] = t == 0 ? sent[(size_t)b * D + d] : attrs[((size_t)b * (Tk - 1) + (t - 1)) * D + d];
-    }
-    __syncthreads();
-    // projections: one warp per (matrix, output channel); lanes split the reduction over the input channels
-    for (int mo = warp; mo < 3 * D; mo += nw) {
-        const int m = mo / D, o = mo - m * D;
-        const float* W = (m == 0 ? Wq : m == 1 ? Wk : Wv) + (size_t)o * D;
-        float acc[AE_MAXTK];
-#pragma unroll
-        for (int t = 0; t < AE_MAXTK; ++t) acc[t] = 0.f;
-        for (int c = lane; c < D; c += 32) {
-            const float w = __ldg(W + c);
-#pragma unroll
-            for (int t = 0; t < AE_MAXTK; ++t)
-                if (t < Tk) acc[t] = fmaf(w, tok[t * D + c], acc[t]);
-        }
-        const float bias = (m == 0 ? bq : m == 1 ? bk : bv)[o];
-#pragma unroll
-        for (int t = 0; t < AE_MAXTK; ++t)
-            if (t < Tk) {
-                const float v = warp_sum(acc[t]);
-                if (lane == 0) q[(m * Tk + t) * D + o] = v + bias;
-            }
+    const size_t plane = (size_t)B * Tk * D;
+    for (int i = threadIdx.x; i < 3 * Tk * D; i += blockDim.x) {
+        const int m = i / (Tk * D), r = i - m * Tk * D;
+        q[i] = qkv[m * plane + (size_t)b * Tk * D + r];
     }
     __syncthreads();
     const float* kk = q + Tk * D;
@@ -83,28 +127,24 @@ __global__ void __launch_bounds__(AE_THREADS) attr_enhance_fwd_kernel(const floa
         for (int j = 0; j < Tk; ++j) a = fmaf(s[t * Tk + j] * norm, vv[j * D + d], a);
         out[(size_t)b * Tk * D + i] = a;
     }
-    if (qkv)
-        for (int i = threadIdx.x; i < 3 * Tk * D; i += blockDim.x) qkv[(size_t)b * 3 * Tk * D + i] = q[i];
     if (pst && threadIdx.x < Tk * Tk) pst[(size_t)b * Tk * Tk + threadIdx.x] = s[threadIdx.x];
 }
 
-// per sample: d_out [Tk][D] (= d_attn_attrs, plus d_attn_sent on row 0) -> g = (d_q, d_k, d_v) [3][Tk][D] and the token
-// gradients d_sent / d_attrs = d_q Wq + d_k Wk + d_v Wv
-__global__ void __launch_bounds__(AE_THREADS) attr_enhance_bwd_kernel(const float* __restrict__ d_attn_sent,
-                                                                      const float* __restrict__ d_attn_attrs,
-                                                                      const float* __restrict__ qkv, const float* __restrict__ pst,
-                                                                      const float* __restrict__ Wq, const float* __restrict__ Wk,
-                                                                      const float* __restrict__ Wv, int D, int Tk, float norm,
-                                                                      float* __restrict__ g, float* __restrict__ d_sent,
-                                                                      float* __restrict__ d_attrs) {
+// per sample: d_out [Tk][D] -> g = (d_q, d_k, d_v), stored [3][B*Tk][D]
+__global__ void __launch_bounds__(256) ae_attn_bwd_kernel(const float* __restrict__ d_attn_sent, const float* __restrict__ d_attn_attrs,
+                                                          const float* __restrict__ qkv, const float* __restrict__ pst, int B, int D,
+                                                          int Tk, float norm, float* __restrict__ g) {
     extern __shared__ float sm[];
     float* q = sm;                   // [3][Tk][D]
     float* dout = q + 3 * Tk * D;    // [Tk][D]
-    float* dg = dout + Tk * D;       // [3][Tk][D]: d_q, d_k, d_v
-    float* p = dg + 3 * Tk * D;      // [Tk][Tk]
+    float* p = dout + Tk * D;        // [Tk][Tk]
     float* ds = p + Tk * Tk;         // [Tk][Tk]
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < 3 * Tk * D; i += blockDim.x) q[i] = qkv[(size_t)b * 3 * Tk * D + i];
+    const size_t plane = (size_t)B * Tk * D;
+    for (int i = threadIdx.x; i < 3 * Tk * D; i += blockDim.x) {
+        const int m = i / (Tk * D), r = i - m * Tk * D;
+        q[i] = qkv[m * plane + (size_t)b * Tk * D + r];
+    }
     for (int i = threadIdx.x; i < Tk * D; i += blockDim.x) {
         float v = d_attn_attrs ? d_attn_attrs[(size_t)b * Tk * D + i] : 0.f;
         if (i < D && d_attn_sent) v += d_attn_sent[(size_t)b * D + i];
@@ -137,108 +177,124 @@ __global__ void __launch_bounds__(AE_THREADS) attr_enhance_bwd_kernel(const floa
             ak = fmaf(ds[j * Tk + t], q[j * D + d], ak);             // d_k[t] = sum_i ds[i][t] q_i
             av = fmaf(p[j * Tk + t] * norm, dout[j * D + d], av);    // d_v[t] = sum_i a[i][t] d_out_i
         }
-        dg[i] = aq;
-        dg[Tk * D + i] = ak;
-        dg[2 * Tk * D + i] = av;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * Tk * D; i += blockDim.x) g[(size_t)b * 3 * Tk * D + i] = dg[i];
-    // token gradients: thread = input channel c (coalesced weight rows), loop over the output channels
-    for (int c = threadIdx.x; c < D; c += blockDim.x) {
-        float acc[AE_MAXTK];
-#pragma unroll
-        for (int t = 0; t < AE_MAXTK; ++t) acc[t] = 0.f;
-        for (int o = 0; o < D; ++o) {
-            const float wq = __ldg(Wq + (size_t)o * D + c), wk = __ldg(Wk + (size_t)o * D + c), wv = __ldg(Wv + (size_t)o * D + c);
-#pragma unroll
-            for (int t = 0; t < AE_MAXTK; ++t)
-                if (t < Tk) acc[t] = fmaf(dg[t * D + o], wq, fmaf(dg[(Tk + t) * D + o], wk, fmaf(dg[(2 * Tk + t) * D + o], wv, acc[t])));
-        }
-#pragma unroll
-        for (int t = 0; t < AE_MAXTK; ++t)
-            if (t < Tk) {
-                if (t == 0) {
-                    if (d_sent) d_sent[(size_t)b * D + c] = acc[0];
-                } else if (d_attrs) {
-                    d_attrs[((size_t)b * (Tk - 1) + (t - 1)) * D + c] = acc[t];
-                }
-            }
+        const size_t o = (size_t)b * Tk * D + i;
+        g[o] = aq;
+        g[plane + o] = ak;
+        g[2 * plane + o] = av;
     }
 }
 
-// dW_m[o][c] = sum over token rows (b, t) of g[b][m][t][o] * combine[b][t][c];  db_m[o] = sum of g[b][m][t][o]
-// grid (D/32, D/8, 3): warp = output channel o, lane = input channel c; fixed summation order.
-__global__ void __launch_bounds__(256) attr_enhance_dw_kernel(const float* __restrict__ g, const float* __restrict__ sent,
-                                                              const float* __restrict__ attrs, int B, int D, int Tk,
-                                                              float* __restrict__ dWq, float* __restrict__ dbq, float* __restrict__ dWk,
-                                                              float* __restrict__ dbk, float* __restrict__ dWv, float* __restrict__ dbv) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31), o = blockIdx.y * 8 + (threadIdx.x >> 5), m = blockIdx.z;
-    if (o >= D) return;
-    float acc = 0.f, accb = 0.f;
-    for (int b = 0; b < B; ++b) {
-        for (int t = 0; t < Tk; ++t) {
-            const float gv = g[(((size_t)b * 3 + m) * Tk + t) * D + o];
-            if (c < D) {
-                const float x = t == 0 ? __ldg(sent + (size_t)b * D + c) : __ldg(attrs + ((size_t)b * (Tk - 1) + (t - 1)) * D + c);
-                acc = fmaf(gv, x, acc);
-            }
-            accb += gv;
+// token gradients [B*Tk][D] -> d_sent [B][D], d_attrs [B][Tk-1][D]; bias gradients db_m[o] = sum over rows of g_m[row][o]
+__global__ void __launch_bounds__(256) ae_unpack_kernel(const float* __restrict__ dtok, const float* __restrict__ g, int B, int D, int Tk,
+                                                        float* __restrict__ d_sent, float* __restrict__ d_attrs, float* __restrict__ dbq,
+                                                        float* __restrict__ dbk, float* __restrict__ dbv) {
+    const long long n = (long long)B * Tk * D, i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int d = (int)(i % D);
+        const long long row = i / D;
+        const int t = (int)(row % Tk), b = (int)(row / Tk);
+        if (t == 0) {
+            if (d_sent) d_sent[(size_t)b * D + d] = dtok[i];
+        } else if (d_attrs) {
+            d_attrs[((size_t)b * (Tk - 1) + (t - 1)) * D + d] = dtok[i];
         }
     }
-    float* dW = m == 0 ? dWq : m == 1 ? dWk : dWv;
-    float* db = m == 0 ? dbq : m == 1 ? dbk : dbv;
-    if (c < D && dW) dW[(size_t)o * D + c] = acc;
-    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && db) db[o] = accb;
+    if (i < 3LL * D) {  // the first 3 D threads also own one bias-gradient entry each
+        const int m = (int)(i / D), o = (int)(i % D);
+        float* db = m == 0 ? dbq : m == 1 ? dbk : dbv;
+        if (db) {
+            float s = 0.f;
+            const float* gm = g + (size_t)m * B * Tk * D + o;
+            for (int r = 0; r < B * Tk; ++r) s += gm[(size_t)r * D];
+            db[o] = s;
+        }
+    }
 }
 
 static int ae_check(int B, int D, int Tk) {
     EEGAN_REQUIRE(B > 0 && D > 0 && Tk >= 1 && Tk <= AE_MAXTK, "attr_enhance: B=%d D=%d tokens=%d (1..%d tokens)", B, D, Tk, AE_MAXTK);
-    EEGAN_REQUIRE((size_t)(8 * Tk * D + 2 * Tk * Tk) * sizeof(float) <= 200 * 1024, "attr_enhance: D=%d too large for the shared-memory form", D);
+    EEGAN_REQUIRE((size_t)(4 * Tk * D + 2 * Tk * Tk) * sizeof(float) <= 200 * 1024, "attr_enhance: D=%d too large for the shared-memory form", D);
     return EEGAN_OK;
+}
+static int ae_smem_attr() {
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(ae_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(ae_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        done = true;
+    }
+    return 0;
 }
 
 }  // namespace eegan
 
 using namespace eegan;
 
+// scratch for both directions: combine [B*Tk][D] (fwd, kept for the backward) / dtok [B*Tk][D] (bwd)
+extern "C" size_t eegan_attr_enhance_workspace_bytes(int B, int D, int attr_num) {
+    if (B <= 0 || D <= 0 || attr_num < 0) return 0;
+    return align_up((size_t)B * (attr_num + 1) * D * sizeof(float), 256);
+}
+
 extern "C" int eegan_attr_enhance_fwd(const float* sent, const float* attrs, const float* Wq, const float* bq, const float* Wk,
                                       const float* bk, const float* Wv, const float* bv, int B, int D, int attr_num, float norm_fact,
-                                      float* out, float* qkv, float* p, void* stream) {
+                                      float* out, float* qkv, float* p, float* combine, void* stream) {
     const int Tk = attr_num + 1;
     int rc = ae_check(B, D, Tk);
     if (rc) return rc;
-    EEGAN_REQUIRE(sent && (attrs || attr_num == 0) && Wq && bq && Wk && bk && Wv && bv && out, "attr_enhance fwd: null pointer");
-    const size_t smem = (size_t)(4 * Tk * D + Tk * Tk) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(attr_enhance_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(attr_enhance_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
-    attr_enhance_fwd_kernel<<<B, AE_THREADS, smem, (cudaStream_t)stream>>>(sent, attrs, Wq, bq, Wk, bk, Wv, bv, D, Tk, norm_fact, out, qkv, p);
-    return check_launch("attr_enhance fwd");
+    EEGAN_REQUIRE(sent && (attrs || attr_num == 0) && Wq && bq && Wk && bk && Wv && bv && out && qkv && combine,
+                  "attr_enhance fwd: null pointer (qkv [3,B*Tk,D] and combine [B*Tk,D] are required scratch / stash)");
+    cudaStream_t st = (cudaStream_t)stream;
+    ae_smem_attr();
+    const int rows = B * Tk;
+    ae_pack_kernel<<<(unsigned)(((long long)rows * D + 255) / 256), 256, 0, st>>>(sent, attrs, B, D, Tk, combine);
+    EEGAN_LAUNCH_CHECK("attr_enhance pack");
+    SgArgs a{};
+    const size_t plane = (size_t)rows * D;
+    const float* W[3] = {Wq, Wk, Wv};
+    const float* bb[3] = {bq, bk, bv};
+    for (int m = 0; m < 3; ++m) { a.A[m] = combine; a.B[m] = W[m]; a.C[m] = qkv + m * plane; a.bias[m] = bb[m]; }
+    a.M = rows; a.N = D; a.K = D; a.nseg = 1; a.sAm = D; a.sAk = 1; a.sBn = D; a.sBk = 1; a.ldc = D;
+    rc = ae_sgemm(a, 3, st);
+    if (rc) return rc;
+    ae_attn_fwd_kernel<<<B, 256, (size_t)(3 * Tk * D + Tk * Tk) * sizeof(float), st>>>(qkv, B, D, Tk, norm_fact, out, p);
+    return check_launch("attr_enhance attention");
 }
 
-extern "C" int eegan_attr_enhance_bwd(const float* d_attn_sent, const float* d_attn_attrs, const float* sent, const float* attrs,
-                                      const float* qkv, const float* p, const float* Wq, const float* Wk, const float* Wv, int B, int D,
-                                      int attr_num, float norm_fact, float* g, float* d_sent, float* d_attrs, float* dWq, float* dbq,
+extern "C" int eegan_attr_enhance_bwd(const float* d_attn_sent, const float* d_attn_attrs, const float* combine, const float* qkv,
+                                      const float* p, const float* Wq, const float* Wk, const float* Wv, int B, int D, int attr_num,
+                                      float norm_fact, float* g, float* dtok, float* d_sent, float* d_attrs, float* dWq, float* dbq,
                                       float* dWk, float* dbk, float* dWv, float* dbv, void* stream) {
     const int Tk = attr_num + 1;
     int rc = ae_check(B, D, Tk);
     if (rc) return rc;
-    EEGAN_REQUIRE(sent && qkv && p && Wq && Wk && Wv && g, "attr_enhance bwd: null pointer");
+    EEGAN_REQUIRE(combine && qkv && p && Wq && Wk && Wv && g && dtok, "attr_enhance bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)(7 * Tk * D + 2 * Tk * Tk) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(attr_enhance_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
+    ae_smem_attr();
+    const int rows = B * Tk;
+    const size_t plane = (size_t)rows * D;
+    ae_attn_bwd_kernel<<<B, 256, (size_t)(4 * Tk * D + 2 * Tk * Tk) * sizeof(float), st>>>(d_attn_sent, d_attn_attrs, qkv, p, B, D, Tk,
+                                                                                          norm_fact, g);
+    EEGAN_LAUNCH_CHECK("attr_enhance attention bwd");
+    const float* W[3] = {Wq, Wk, Wv};
+    if (d_sent || d_attrs) {  // dtok[row][c] = sum_m sum_o g_m[row][o] W_m[o][c]
+        SgArgs a{};
+        for (int m = 0; m < 3; ++m) { a.A[m] = g + m * plane; a.B[m] = W[m]; }
+        a.C[0] = dtok;
+        a.M = rows; a.N = D; a.K = D; a.nseg = 3; a.sAm = D; a.sAk = 1; a.sBn = 1; a.sBk = D; a.ldc = D;
+        rc = ae_sgemm(a, 1, st);
+        if (rc) return rc;
     }
-    attr_enhance_bwd_kernel<<<B, AE_THREADS, smem, st>>>(d_attn_sent, d_attn_attrs, qkv, p, Wq, Wk, Wv, D, Tk, norm_fact, g, d_sent, d_attrs);
-    EEGAN_LAUNCH_CHECK("attr_enhance bwd");
-    if (dWq || dWk || dWv || dbq || dbk || dbv) {
-        attr_enhance_dw_kernel<<<dim3((D + 31) / 32, (D + 7) / 8, 3), 256, 0, st>>>(g, sent, attrs, B, D, Tk, dWq, dbq, dWk, dbk, dWv, dbv);
-        EEGAN_LAUNCH_CHECK("attr_enhance dW");
+    if (dWq || dWk || dWv) {  // dW_m[o][c] = sum_rows g_m[row][o] combine[row][c]
+        SgArgs a{};
+        float* dW[3] = {dWq, dWk, dWv};
+        EEGAN_REQUIRE(dWq && dWk && dWv, "attr_enhance bwd: the three weight gradients are computed together");
+        for (int m = 0; m < 3; ++m) { a.A[m] = g + m * plane; a.B[m] = combine; a.C[m] = dW[m]; }
+        a.M = D; a.N = D; a.K = rows; a.nseg = 1; a.sAm = 1; a.sAk = D; a.sBn = 1; a.sBk = D; a.ldc = D;
+        rc = ae_sgemm(a, 3, st);
+        if (rc) return rc;
     }
-    return EEGAN_OK;
+    const long long nun = (long long)rows * D > 3LL * D ? (long long)rows * D : 3LL * D;  // the bias gradients ride on the first 3 D threads
+    ae_unpack_kernel<<<(unsigned)((nun + 255) / 256), 256, 0, st>>>(dtok, g, B, D, Tk, d_sent, d_attrs, dbq, dbk, dbv);
+    return check_launch("attr_enhance unpack");
 }

@@ -271,18 +271,23 @@ int eegan_conv1x1_bwd(const float* xp, const float* w, const float* dy, int B, i
  *   combine [B,1+attr_num,D];  q,k,v = Linear(combine);  a = softmax(q k^T, -1) * norm_fact (scale after the
  *   softmax, :166);  out = a v  (= attn_attrs [B,1+attr_num,D]; attn_sent = out[:,0,:]).
  * sent [B,D], attrs [B,attr_num,D], W* [D,D] (nn.Linear weight: [out][in]), b* [D]; attr_num <= 7.
- * fwd: one launch; qkv [B,3,1+attr_num,D] and p [B,1+attr_num,1+attr_num] are the backward's stash (may be NULL
- * for inference).  bwd: d_attn_sent [B,D] and/or d_attn_attrs [B,1+attr_num,D] (NULL = zero); g [B,3,1+attr_num,D]
- * is scratch; every output pointer may be NULL.  Weight gradients are reduced in a fixed order (no atomics).
+ * fwd: three launches (cat; the three projections as one batched small GEMM; per-sample attention).  qkv
+ * [3, B*(1+attr_num), D], p [B,1+attr_num,1+attr_num] and combine [B*(1+attr_num), D] are the backward's stash
+ * (p may be NULL for inference; qkv and combine are required).
+ * bwd: d_attn_sent [B,D] and/or d_attn_attrs [B,1+attr_num,D] (NULL = zero); g [3, B*(1+attr_num), D] and dtok
+ * [B*(1+attr_num), D] are scratch; d_sent, d_attrs, db* may be NULL, the three dW* are computed together (all or
+ * none).  Weight gradients are plain fixed-order sums (no atomics).
  * ---------------------------------------------------------------------------------- */
 int eegan_attr_enhance_fwd(const float* sent, const float* attrs, const float* Wq, const float* bq,
                            const float* Wk, const float* bk, const float* Wv, const float* bv, int B, int D,
-                           int attr_num, float norm_fact, float* out, float* qkv, float* p, void* stream);
-int eegan_attr_enhance_bwd(const float* d_attn_sent, const float* d_attn_attrs, const float* sent,
-                           const float* attrs, const float* qkv, const float* p, const float* Wq, const float* Wk,
-                           const float* Wv, int B, int D, int attr_num, float norm_fact, float* g, float* d_sent,
+                           int attr_num, float norm_fact, float* out, float* qkv, float* p, float* combine,
+                           void* stream);
+int eegan_attr_enhance_bwd(const float* d_attn_sent, const float* d_attn_attrs, const float* combine,
+                           const float* qkv, const float* p, const float* Wq, const float* Wk, const float* Wv,
+                           int B, int D, int attr_num, float norm_fact, float* g, float* dtok, float* d_sent,
                            float* d_attrs, float* dWq, float* dbq, float* dWk, float* dbk, float* dWv, float* dbv,
                            void* stream);
+size_t eegan_attr_enhance_workspace_bytes(int B, int D, int attr_num);
 
 /* The half-pair engine on its own (tests / microbenchmarks): C[z] = A[z] B[z]^T, fp32 in / out.
  * A is MN-major ([K][lda], M contiguous), B is K-major ([N][ldb]); lda, ldb and the batch strides are

@@ -31,18 +31,21 @@ struct HArgs {
     int dbg;  // timing experiments only (EEGAN_H_DBG): 1 read-out without global stores, 2 no read-out, 4 no caption phase
 };
 
-template <int EPI, bool DUAL>
+template <int EPI, bool DUAL, int BN = H_BN>
 struct HCfg {
     static constexpr bool kAttn = EPI != TC_EPI_PLAIN;
+    static constexpr int kBTile = BN * H_BK * 2;                      // one of B hi / lo
+    static constexpr int kStageBytes = 2 * H_A_TILE + 2 * kBTile;     // A_hi A_lo B_hi B_lo
     static constexpr int kEWarps = 8;  // epilogue warps: two per TMEM lane quarter, one 64-column half of the tile each
-    static constexpr int kStages = kAttn ? 4 : 5;
+    static constexpr int kStages = kAttn ? 4 : (BN > 128 ? 3 : 5);
     static constexpr int kThreads = 32 * (2 + kEWarps);
     static constexpr int kEpiPitch = kAttn ? H_EPI_PITCH : 33;
     static constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4;
-    static constexpr int kSmem = kStages * H_STAGE_BYTES + kEWarps * (kEpiWarpBytes + 256) + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int kAccStride = DUAL ? 2 * H_BN : H_BN;  // TMEM columns between the two accumulator buffers
+    static constexpr int kSmem = kStages * kStageBytes + kEWarps * (kEpiWarpBytes + 256) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kAccStride = DUAL ? 2 * BN : BN;  // TMEM columns between the two accumulator buffers
 };
-static_assert(HCfg<TC_EPI_PLAIN, false>::kSmem <= 232448 && HCfg<TC_EPI_ATTN_FWD, false>::kSmem <= 232448, "shared memory budget");
+static_assert(HCfg<TC_EPI_PLAIN, false>::kSmem <= 232448 && HCfg<TC_EPI_ATTN_FWD, false>::kSmem <= 232448 &&
+                  HCfg<TC_EPI_PLAIN, false, 256>::kSmem <= 232448, "shared memory budget");
 
 __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
     float2 v;
@@ -152,16 +155,16 @@ __device__ __forceinline__ void h_attn_caption(uint32_t taddr, int T, uint32_t c
 #undef H_CAP
 }
 
-template <int EPI, bool DUAL>
+template <int EPI, bool DUAL, int BN>
 __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t, int lane, float inv0, float inv1) {
-    using Cfg = HCfg<EPI, DUAL>;
+    using Cfg = HCfg<EPI, DUAL, BN>;
     float* Cz = p.C + (long long)t.z * p.bC;
     const int row0 = t.m0 + t.quarter * 32;
     const int rows_live = max(0, min(32, t.Mlive - row0));
     if (EPI == TC_EPI_PLAIN) {
         mbar_wait(t.full_bar, t.full_parity);
         tc_fence_after();
-        const int c_lo = t.half * (H_BN / 64), c_hi = c_lo + H_BN / 64;
+        const int c_lo = t.half * (BN / 64), c_hi = c_lo + BN / 64;
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
             float v[32];
@@ -170,7 +173,7 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
                 tmem_ld32(t.tacc + (uint32_t)(c * 32), r0);
                 if (DUAL) {
                     uint32_t r1[32];
-                    tmem_ld32(t.tacc + (uint32_t)(H_BN + c * 32), r1);
+                    tmem_ld32(t.tacc + (uint32_t)(BN + c * 32), r1);
                     tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 32; ++q) v[q] = fmaf(__uint_as_float(r1[q]), inv1, __uint_as_float(r0[q]) * inv0);
@@ -366,15 +369,16 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
 // ---------------------------------------------------------------------------------------
 // kernel: persistent CTAs (one per SM) walk 128 x 128 output tiles (n fastest, then m, then batch)
 // ---------------------------------------------------------------------------------------
-template <int EPI, bool DUAL>
-__global__ void __launch_bounds__(HCfg<EPI, DUAL>::kThreads, 1)
+template <int EPI, bool DUAL, int BN>
+__global__ void __launch_bounds__(HCfg<EPI, DUAL, BN>::kThreads, 1)
 h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
-    using Cfg = HCfg<EPI, DUAL>;
+    using Cfg = HCfg<EPI, DUAL, BN>;
+    static_assert(BN == 128 || (BN == 256 && EPI == TC_EPI_PLAIN && !DUAL), "256-wide tiles: plain single-accumulator epilogue only");
     constexpr int NS = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t epi_stage = base + NS * H_STAGE_BYTES;
+    const uint32_t epi_stage = base + NS * Cfg::kStageBytes;
     const uint32_t epi_czs = epi_stage + Cfg::kEWarps * Cfg::kEpiWarpBytes;
     const uint32_t bars = epi_czs + Cfg::kEWarps * 256u;
     auto full = [&](int s) { return bars + 8u * s; };
@@ -411,7 +415,7 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
 
     const int Mlive = p.dynM ? min(*p.dynM, p.M) : p.M;
     const int Nlive = p.dynN ? min(*p.dynN, p.N) : p.N;
-    const int mt = (Mlive + H_BM - 1) / H_BM, nt = (Nlive + H_BN - 1) / H_BN;
+    const int mt = (Mlive + H_BM - 1) / H_BM, nt = (Nlive + BN - 1) / BN;
     const int ntiles = mt * nt * p.batch;  // CTAs beyond the live tiles fall through the role loops
 
     int kb0 = 0, kb1 = 0;
@@ -436,7 +440,7 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
             int it = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 const int z = t / (mt * nt), rem_t = t - z * (mt * nt);
-                const int m0 = (rem_t / nt) * H_BM, n0 = (rem_t % nt) * H_BN;
+                const int m0 = (rem_t / nt) * H_BM, n0 = (rem_t % nt) * BN;
                 const int total = tile_total(z);
                 for (int k = 0; k < total; ++k, ++it) {
                     const int s = it % NS, ph = (it / NS) & 1;
@@ -446,14 +450,14 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
                     const int zr = z * p.nred + red;
                     const int zA = p.a_batched[seg] ? zr : 0, zB = p.b_batched[seg] ? zr : 0;
                     mbar_wait(empty(s), ph ^ 1);
-                    mbar_arrive_expect_tx(full(s), (uint32_t)H_STAGE_BYTES);
-                    const uint32_t sA = base + s * H_STAGE_BYTES, sB = sA + 2 * H_A_TILE;
+                    mbar_arrive_expect_tx(full(s), (uint32_t)Cfg::kStageBytes);
+                    const uint32_t sA = base + s * Cfg::kStageBytes, sB = sA + 2 * H_A_TILE;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const CUtensorMap* ta = &tm.m[seg][0][h];
                         tma_load_3d(sA + h * H_A_TILE, ta, full(s), m0, k0, zA);
                         tma_load_3d(sA + h * H_A_TILE + 4096, ta, full(s), m0 + 64, k0, zA);
-                        tma_load_3d(sB + h * H_B_TILE, &tm.m[seg][1][h], full(s), k0, n0, zB);
+                        tma_load_3d(sB + h * Cfg::kBTile, &tm.m[seg][1][h], full(s), k0, n0, zB);
                     }
                 }
             }
@@ -462,7 +466,7 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | (1u << 15) /*A MN-major*/ |
-                                       (0u << 16) /*B K-major*/ | ((uint32_t)(H_BN >> 3) << 17) | ((uint32_t)(H_BM >> 4) << 24);
+                                       (0u << 16) /*B K-major*/ | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(H_BM >> 4) << 24);
             int it = 0, ti = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
                 const int z = t / (mt * nt);
@@ -476,11 +480,11 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
                     const int rem = k % kbt;
                     const int seg = rem >= kb0 ? 1 : 0;
                     const bool first = DUAL ? (k < kbt && (seg ? rem == kb0 : rem == 0)) : (k == 0);
-                    const uint32_t tmem_d = tmem_d0 + (DUAL ? (uint32_t)(seg * H_BN) : 0u);
+                    const uint32_t tmem_d = tmem_d0 + (DUAL ? (uint32_t)(seg * BN) : 0u);
                     mbar_wait(full(s), ph);
                     tc_fence_after();
-                    const uint32_t a_hi = base + s * H_STAGE_BYTES, a_lo = a_hi + H_A_TILE;
-                    const uint32_t b_hi = a_hi + 2 * H_A_TILE, b_lo = b_hi + H_B_TILE;
+                    const uint32_t a_hi = base + s * Cfg::kStageBytes, a_lo = a_hi + H_A_TILE;
+                    const uint32_t b_hi = a_hi + 2 * H_A_TILE, b_lo = b_hi + Cfg::kBTile;
 #pragma unroll
                     for (int ks = 0; ks < H_BK / 16; ++ks) {
                         const uint64_t dah = h_desc_a(a_hi, ks), dal = h_desc_a(a_lo, ks);
@@ -512,13 +516,13 @@ h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
             const int acc = ti & 1;
             et.z = t / (mt * nt);
             et.m0 = (rem_t / nt) * H_BM;
-            et.n0 = (rem_t % nt) * H_BN;
+            et.n0 = (rem_t % nt) * BN;
             et.total = tile_total(et.z);
             et.tacc = tmem_base + ((uint32_t)(et.quarter * 32) << 16) + (uint32_t)(acc * Cfg::kAccStride);
             et.full_bar = tmem_full(acc);
             et.full_parity = (uint32_t)((ti >> 1) & 1);
             et.empty_bar = tmem_empty(acc);
-            h_epilogue_tile<EPI, DUAL>(p, et, lane, inv0, inv1);
+            h_epilogue_tile<EPI, DUAL, BN>(p, et, lane, inv0, inv1);
         }
     }
     tc_fence_before();
@@ -567,8 +571,8 @@ struct HMapSlot {
 static thread_local HMapSlot g_hmap_cache[48];
 static thread_local int g_hmap_next = 0;
 
-static int h_make_map(CUtensorMap* m, const __half* ptr, const HOperand& o, bool is_b) {
-    const HMapKey key{ptr, o.ld, o.bstride, is_b ? 1 : 0, o.nbatch, o.rows, o.K};
+static int h_make_map(CUtensorMap* m, const __half* ptr, const HOperand& o, bool is_b, int bn) {
+    const HMapKey key{ptr, o.ld, o.bstride, is_b ? bn : 0, o.nbatch, o.rows, o.K};
     for (int i = 0; i < 48; ++i)
         if (g_hmap_cache[i].used && g_hmap_cache[i].key == key) {
             *m = g_hmap_cache[i].map;
@@ -584,7 +588,7 @@ static int h_make_map(CUtensorMap* m, const __half* ptr, const HOperand& o, bool
     cuuint32_t box[3], estr[3] = {1, 1, 1};
     if (is_b) {  // K-major [rows][K]
         dims[0] = (cuuint64_t)o.K; dims[1] = (cuuint64_t)o.rows;
-        box[0] = H_BK; box[1] = H_BN;
+        box[0] = H_BK; box[1] = (cuuint32_t)bn;
     } else {     // MN-major [K][rows]
         dims[0] = (cuuint64_t)o.rows; dims[1] = (cuuint64_t)o.K;
         box[0] = 64; box[1] = H_BK;
@@ -618,16 +622,16 @@ static int h_num_sms() {
     return n;
 }
 
-template <int EPI, bool DUAL>
+template <int EPI, bool DUAL, int BN = H_BN>
 static int h_launch_t(const HMaps& maps, const HArgs& a, unsigned grid, cudaStream_t st) {
-    using Cfg = HCfg<EPI, DUAL>;
+    using Cfg = HCfg<EPI, DUAL, BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(h_gemm_kernel<EPI, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(h_gemm_kernel<EPI, DUAL, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         if (e != cudaSuccess) { set_error("h gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
         attr_set = true;
     }
-    cudaError_t e = launch_pdl(h_gemm_kernel<EPI, DUAL>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmem, st, maps, a);
+    cudaError_t e = launch_pdl(h_gemm_kernel<EPI, DUAL, BN>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmem, st, maps, a);
     if (e != cudaSuccess) { set_error("h gemm launch: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
     return check_launch("h gemm");
 }
@@ -635,6 +639,12 @@ static int h_launch_t(const HMaps& maps, const HArgs& a, unsigned grid, cudaStre
 int h_gemm_launch(const HGemm& g, cudaStream_t st) {
     EEGAN_REQUIRE(g.nseg == 1 || g.nseg == 2, "h gemm: nseg=%d", g.nseg);
     EEGAN_REQUIRE(g.M > 0 && g.N > 0 && g.batch > 0, "h gemm: empty problem");
+    // 256-wide tiles (EEGAN_H_WIDE=1; off by default) for the plain single-segment GEMM whose N is a multiple of 256
+    // (U': N = D): one A tile feeds twice the output, 48 KB instead of 64 KB of operands per 128 x 256 x 32 of work.
+    // Measured neutral at B = 48 (GEMM2 30.8 vs 30.7 us): at 10 k-blocks per tile the launch is bound by its ramp and
+    // tile-boundary latencies, not by L2 -> SM bandwidth; kept for larger D / R.
+    static const bool wide_ok = [] { const char* e = getenv("EEGAN_H_WIDE"); return e ? atoi(e) != 0 : false; }();
+    const int bn = (wide_ok && g.epi == TC_EPI_PLAIN && g.nseg == 1 && g.N % 256 == 0 && !g.dynN && g.red_total == 0) ? 256 : H_BN;
     HMaps maps;
     HArgs a{};
     for (int s = 0; s < 2; ++s) {
@@ -642,9 +652,9 @@ int h_gemm_launch(const HGemm& g, cudaStream_t st) {
         const HOperand* ops[2] = {&g.A[src], &g.B[src]};
         for (int o = 0; o < 2; ++o) {
             EEGAN_REQUIRE(ops[o]->hi && ops[o]->lo && ops[o]->inv_scale, "h gemm: operand arrays missing");
-            int rc = h_make_map(&maps.m[s][o][0], ops[o]->hi, *ops[o], o == 1);
+            int rc = h_make_map(&maps.m[s][o][0], ops[o]->hi, *ops[o], o == 1, bn);
             if (rc) return rc;
-            rc = h_make_map(&maps.m[s][o][1], ops[o]->lo, *ops[o], o == 1);
+            rc = h_make_map(&maps.m[s][o][1], ops[o]->lo, *ops[o], o == 1, bn);
             if (rc) return rc;
         }
         a.K[s] = s < g.nseg ? g.A[src].K : 0;
@@ -657,7 +667,7 @@ int h_gemm_launch(const HGemm& g, cudaStream_t st) {
     a.attn = g.attn;
     a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total; a.batch = g.batch;
     if (const char* e = getenv("EEGAN_H_DBG")) a.dbg = atoi(e);
-    const long long tiles = (long long)((g.N + H_BN - 1) / H_BN) * ((g.M + H_BM - 1) / H_BM) * g.batch;
+    const long long tiles = (long long)((g.N + bn - 1) / bn) * ((g.M + H_BM - 1) / H_BM) * g.batch;
     const unsigned grid = (unsigned)(tiles < h_num_sms() ? tiles : h_num_sms());
     if (g.epi != TC_EPI_PLAIN) {
         const TcAttnEpi& e = g.attn.base;
@@ -674,6 +684,7 @@ int h_gemm_launch(const HGemm& g, cudaStream_t st) {
     }
     EEGAN_REQUIRE(g.C, "h gemm: no output");
     if (g.nseg == 2) return h_launch_t<TC_EPI_PLAIN, true>(maps, a, grid, st);
+    if (bn == 256) return h_launch_t<TC_EPI_PLAIN, false, 256>(maps, a, grid, st);
     return h_launch_t<TC_EPI_PLAIN, false>(maps, a, grid, st);
 }
 

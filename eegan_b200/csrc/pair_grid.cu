@@ -770,9 +770,10 @@ extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const 
     if (d_words) {
         rc = gemm_nr_dr(w, w.DA, img, w.dWpart, Bi, NtM, D, R, w.nsplit, st);  // GEMM5: dWp = sum_j DS . C^T
         if (rc) return rc;
+        prof_mark(9, st);
         pair_unpack_dw_kernel<<<dim3(Bc, (D + 31) / 32), 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.nsplit, (Bi + PAIR_DU_JG - 1) / PAIR_DU_JG, NtM, D, Tm, d_words);
         EEGAN_LAUNCH_CHECK("pair GEMM5");
-        prof_mark(9, st);
+        prof_mark(10, st);
     }
     return EEGAN_OK;
 }

@@ -614,10 +614,11 @@ int pair_h_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1,
         g.epi = TC_EPI_PLAIN;
         int rc = h_gemm_launch(g, st);
         if (rc) return rc;
+        prof_mark(9, st);
         launch_pdl(v3_unpack_dw_kernel, dim3(Bc, (D + 31) / 32), dim3(256), 0, st, (const float*)w.dWpart, (const float*)w.dwcos,
                    (const int*)w.col_start, (const int*)w.cap_len, w.nsplit, w.ngroups, NtP, D, Tm, d_words);
         EEGAN_LAUNCH_CHECK("pair GEMM5");
-        prof_mark(9, st);
+        prof_mark(10, st);
     }
     return EEGAN_OK;
 }

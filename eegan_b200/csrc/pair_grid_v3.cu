@@ -482,10 +482,11 @@ int pair_v3_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1
         g.nred = nred; g.red_total = Bi;
         int rc = tc_gemm_launch(g, st);
         if (rc) return rc;
+        prof_mark(9, st);
         v3_unpack_dw_kernel<<<dim3(Bc, (D + 31) / 32), 256, 0, st>>>(w.dWpart, w.dwcos, w.col_start, w.cap_len, w.nsplit, w.ngroups,
                                                                      NtP, D, Tm, d_words);
         EEGAN_LAUNCH_CHECK("pair GEMM5");
-        prof_mark(9, st);
+        prof_mark(10, st);
     }
     return EEGAN_OK;
 }

@@ -23,7 +23,7 @@ static std::vector<cudaEvent_t> g_pool;
 
 static const char* kStageNames[EEGAN_PROF_NSTAGES] = {
     "prologue(pack)", "gemm1(S=W.C)+attn_fwd", "attn_softmax(unfused engines)", "gemm2(U=A.C^T)", "cos_lse+att_maps",
-    "bwd_scalars+du", "gemm3(dA=dU.C)+attn_bwd", "softmax_bwd(unfused engines)", "gemm4(dC)", "gemm5(dW)+unpack",
+    "bwd_scalars+du", "gemm3(dA=dU.C)+attn_bwd", "softmax_bwd(unfused engines)", "gemm4(dC)", "gemm5(dW)", "unpack(d_words)",
 };
 
 void prof_mark(int stage, cudaStream_t st) {

@@ -306,7 +306,7 @@ int eegan_gemm_f16x3(const float* A, const float* B, float* C, int M, int N, int
  * synchronising entry point of the library) and returns, per stage, the summed device time
  * in ms and the number of times the stage ran since the previous collect.
  * ---------------------------------------------------------------------------------- */
-#define EEGAN_PROF_NSTAGES 10
+#define EEGAN_PROF_NSTAGES 11
 int eegan_profile_enable(int on);
 int eegan_profile_nstages(void);
 const char* eegan_profile_stage_name(int stage);

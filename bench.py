@@ -127,9 +127,19 @@ class ClockSampler:
 
 
 def make_inputs(B, seed):
-    from oracle import cases
-    c = cases.words_case(B, T_MAX, seed=seed, kind="realistic", class_mode="cub")
-    return c
+    """Synthetic CUB-shaped batch (SURVEY.md §8d "realistic set"): img = relu(randn) * 0.3 - 0.05, words = tanh(randn) * 0.5
+    (score std ~1), ragged caption lengths in [5, T_MAX] with at least one of each extreme, CUB-like class ids with
+    collisions (same-class cells become -inf).  Same recipe and RNG order as the tests' seeded cases."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    img = torch.relu(torch.randn(B, D, HW, HW, generator=g)) * 0.3 - 0.05
+    words = torch.tanh(torch.randn(B, D, T_MAX, generator=g)) * 0.5
+    cap = torch.randint(5, T_MAX + 1, (B,), generator=g)
+    cap[0] = T_MAX
+    if B > 1:
+        cap[1] = 5
+    cls = torch.randint(1, max(2, min(201, B // 2 + 2)), (B,), generator=g)
+    return dict(img=img, words=words, cap_lens=cap, labels=torch.arange(B), class_ids=cls)
 
 
 def algorithmic_flops(cap_lens_sum, B_img):
@@ -357,7 +367,7 @@ def aux_rows_extra(dev, flush, bf16_tflops):
     sent = torch.randn(B, D, device=dev).requires_grad_()
     attrs = torch.randn(B, A, D, device=dev).requires_grad_()
     gs, ga = torch.randn(B, D, device=dev), torch.randn(B, A + 1, D, device=dev)
-    from oracle import damsm_oracle as O  # the reference's op sequence (validated port) run by torch on the GPU
+    import torch.nn.functional as F
 
     def ours2():
         sent.grad = attrs.grad = None
@@ -368,8 +378,12 @@ def aux_rows_extra(dev, flush, bf16_tflops):
     def ref2():
         sent.grad = attrs.grad = None
         ae.zero_grad(set_to_none=True)
-        a, b = O.port_attr_enhance(sent, attrs, ae.attr_query.weight, ae.attr_query.bias, ae.attr_key.weight, ae.attr_key.bias,
-                                   ae.attr_value.weight, ae.attr_value.bias, ae._norm_fact)
+        # models.py:161-168 op for op (cat, three Linear, softmax(q k^T) * norm, bmm), run by torch on the same GPU
+        combine = torch.cat([sent.unsqueeze(1), attrs], dim=1)
+        q, k, v = F.linear(combine, ae.attr_query.weight, ae.attr_query.bias), F.linear(combine, ae.attr_key.weight, ae.attr_key.bias), \
+            F.linear(combine, ae.attr_value.weight, ae.attr_value.bias)
+        b = torch.bmm(torch.softmax(torch.bmm(q, k.permute(0, 2, 1)), dim=-1) * ae._norm_fact, v)
+        a = b[:, 0, :]
         ((a * gs).sum() + (b * ga).sum()).backward()
 
     # a few microseconds of device work behind ~30 Python-level ops: time CUDA-graph replays of both, so that the number

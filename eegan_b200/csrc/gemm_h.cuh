@@ -80,7 +80,7 @@ int h_gemm_launch(const HGemm& g, cudaStream_t st);
 
 // x -> (hi, lo) halves of x * s, clamped to the fp16 range
 __device__ __forceinline__ void h_split(float xs, __half& hi, __half& lo) {
-    xs = fminf(fmaxf(xs, -H_CLAMP), H_CLAMP);
+    xs = xs > H_CLAMP ? H_CLAMP : (xs < -H_CLAMP ? -H_CLAMP : xs);  // comparisons, not fminf/fmaxf: a NaN stays a NaN, as in the reference
     hi = __float2half_rn(xs);
     lo = __float2half_rn(xs - __half2float(hi));
 }

@@ -246,21 +246,25 @@ __global__ void __launch_bounds__(256) h_pack_kernel(const float* __restrict__ w
         const long long warps = (long long)(gridDim.x - NtP) * (blockDim.x >> 5);
         for (long long row = (long long)(blockIdx.x - NtP) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
             const float* sp = img + row * R;
-            for (int r0 = 0; r0 < Rp; r0 += 32 * 10) {  // up to ten loads per lane in flight (R = 289 -> one round)
+            uint32_t* dh = reinterpret_cast<uint32_t*>(Ch + row * Rp);  // Rp is even: a lane owns regions 2l, 2l + 1
+            uint32_t* dl = reinterpret_cast<uint32_t*>(Cl + row * Rp);
+            for (int r0 = 0; r0 < Rp; r0 += 64 * 5) {  // ten loads per lane in flight (R = 289 -> one round)
                 float v[10];
 #pragma unroll
-                for (int q = 0; q < 10; ++q) {
-                    const int r = r0 + 32 * q + lane;
-                    v[q] = r < R ? __ldg(sp + r) : 0.f;
+                for (int q = 0; q < 5; ++q) {
+                    const int r = r0 + 64 * q + 2 * lane;
+                    v[2 * q] = r < R ? __ldg(sp + r) : 0.f;
+                    v[2 * q + 1] = r + 1 < R ? __ldg(sp + r + 1) : 0.f;
                 }
 #pragma unroll
-                for (int q = 0; q < 10; ++q) {
-                    const int r = r0 + 32 * q + lane;
+                for (int q = 0; q < 5; ++q) {
+                    const int r = r0 + 64 * q + 2 * lane;
                     if (r < Rp) {
-                        __half h, l;
-                        h_split(v[q] * sC, h, l);
-                        Ch[row * Rp + r] = h;
-                        Cl[row * Rp + r] = l;
+                        __half h0, l0, h1, l1;
+                        h_split(v[2 * q] * sC, h0, l0);
+                        h_split(v[2 * q + 1] * sC, h1, l1);
+                        dh[r >> 1] = h_pack2(h0, h1);
+                        dl[r >> 1] = h_pack2(l0, l1);
                     }
                 }
             }
@@ -359,13 +363,14 @@ __global__ void __launch_bounds__(256) h_du_kernel(const float* __restrict__ U, 
         const float sDS = h_pow2_scale(bound, 14);
         scal[HS_SDS] = sDS; scal[HS_IDS] = 1.0f / sDS;
     }
-    const int g = blockIdx.y, j0 = g * V3_DU_JG + warp * 8;
+    // warp w takes images g*64 + w, w + 8, w + 16, ... (strided, so that all 8 warps share the work at any Bi), four per round
+    const int g = blockIdx.y, j0 = g * V3_DU_JG + warp;
     const int i = col_cap[n];
     float4* dwc = reinterpret_cast<float4*>(dwcos + ((size_t)g * NtP + n) * D);
     if (i < 0) {  // padding column: zero operand rows so that GEMM4's K loop adds nothing
         const uint2 zero2 = make_uint2(0u, 0u);
         for (int q = 0; q < 8; ++q) {
-            const int j = j0 + q;
+            const int j = j0 + 8 * q;
             if (j >= Bi) break;
             uint2* oh = reinterpret_cast<uint2*>(DUh + ((size_t)j * NtP + n) * D);
             uint2* ol = reinterpret_cast<uint2*>(DUl + ((size_t)j * NtP + n) * D);
@@ -392,12 +397,12 @@ __global__ void __launch_bounds__(256) h_du_kernel(const float* __restrict__ U, 
     const float wnv = wn[n];
     float a3s = 0.f;
 #pragma unroll 1
-    for (int q0 = 0; q0 < 8 && j0 + q0 < Bi; q0 += 4) {
+    for (int q0 = 0; q0 < 8 && j0 + 8 * q0 < Bi; q0 += 4) {
         float zs[4], cs4[4], us[4], dms[4], ms[4];
         float4 uv[4][NQ];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int j = min(j0 + q0 + q, Bi - 1);
+            const int j = min(j0 + 8 * (q0 + q), Bi - 1);
             const size_t idx = (size_t)j * NtP + n;
             zs[q] = Z[idx]; cs4[q] = cosv[idx]; us[q] = un[idx];
             dms[q] = dm[(size_t)j * Bc + i]; ms[q] = mst[(size_t)j * Bc + i];
@@ -407,7 +412,7 @@ __global__ void __launch_bounds__(256) h_du_kernel(const float* __restrict__ U, 
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int j = j0 + q0 + q;
+            const int j = j0 + 8 * (q0 + q);
             if (j >= Bi) break;
             const size_t idx = (size_t)j * NtP + n;
             const float c = cs4[q], unv = us[q];

@@ -108,6 +108,18 @@ def test_half_pair_engine_operand_scales(cuda_lib, img_amp, word_amp, loss_amp):
         assert float((a.cpu().double() - b.detach()).abs().max()) <= 2.5e-6
 
 
+def test_nan_input_propagates_like_the_reference(cuda_lib):
+    """A NaN in a live input element makes both losses NaN in the reference (it flows through bmm / softmax / CE); the
+    half-pair operand conversion must not launder it into a finite value."""
+    import eegan_b200 as E
+    c = cases.words_case(5, 18, seed=17, class_mode="none")
+    c["img"][2, 7, 3, 4] = float("nan")
+    l0, l1, _ = E.words_loss(c["img"].cuda(), c["words"].cuda(), c["labels"].cuda(), c["cap_lens"].cuda(), None, 5)
+    o0, o1, _ = O.port_words_loss(c["img"], c["words"], c["labels"], c["cap_lens"], None, 5)
+    assert torch.isnan(o0) and torch.isnan(o1)
+    assert torch.isnan(l0) and torch.isnan(l1)
+
+
 def test_backward_twice_on_one_forward(cuda_lib):
     """retain_graph: the backward leaves the forward stash intact (dU goes to its own buffer)."""
     import eegan_b200 as E

@@ -21,9 +21,11 @@
 namespace eegan {
 
 constexpr int G2_THREADS = 128;
+constexpr int G2_DC = 8;   // channels per streamed d_out chunk (pixel kernel)
+constexpr int G2_NS = 3;   // ring depth (3 x 16 KB + key/value: three CTAs per SM at idf = 128)
 
 template <int TP, int PX>
-__global__ void __launch_bounds__(G2_THREADS) gag_bwd_px_kernel(const float* __restrict__ key, const float* __restrict__ value,
+__global__ void __launch_bounds__(G2_THREADS, 3) gag_bwd_px_kernel(const float* __restrict__ key, const float* __restrict__ value,
                                                                 const float* __restrict__ attn, const float* __restrict__ d_out,
                                                                 const float* __restrict__ d_attn, int idf, int Q, int T,
                                                                 float* __restrict__ d_x, float* __restrict__ ds_out) {
@@ -49,22 +51,50 @@ __global__ void __launch_bounds__(G2_THREADS) gag_bwd_px_kernel(const float* __r
         for (int t = 0; t < TP; ++t) dp[p][t] = (d_attn && t < T) ? d_attn[((size_t)b * T + t) * Q + q[p]] : 0.f;
     }
     if (d_out) {
-        const float* gbase = d_out + (size_t)b * idf * Q;
-#pragma unroll 4
-        for (int d = 0; d < idf; ++d) {
-            float g[PX];
+        // d_out streams through a ring of [G2_DC channels][PX * 128 pixels] chunks filled by 16-byte cp.async, G2_NS - 1 chunks
+        // ahead of the FMAs, so that the HBM latency never stalls the (few, register-heavy) warps; a thread's pixels
+        // tid, tid + 128, ... are conflict-free 4-byte reads of a chunk row.
+        constexpr int CH = PX * G2_THREADS;  // pixels per chunk row
+        float* ring = vs + idf * TP;         // [G2_NS][G2_DC][CH]
+        const int q0 = blockIdx.x * CH;
+        const float* gbase = d_out + (size_t)b * idf * Q + q0;
+        const int nch = idf / G2_DC;
+        auto issue = [&](int c) {
+            if (c < nch) {
+                float* dst = ring + (size_t)(c % G2_NS) * G2_DC * CH;
 #pragma unroll
-            for (int p = 0; p < PX; ++p) g[p] = __ldg(gbase + (size_t)d * Q + q[p]);
-            const float* vr = vs + d * TP;
+                for (int i = 0; i < G2_DC * CH / 4 / G2_THREADS; ++i) {
+                    const int f = tid + i * G2_THREADS, dd = f / (CH / 4), c4 = f - dd * (CH / 4);
+                    const int src_bytes = q0 + 4 * c4 < Q ? 16 : 0;  // beyond the row: zero-fill (Q % 4 == 0)
+                    const float* src = gbase + (size_t)(c * G2_DC + dd) * Q + (src_bytes ? 4 * c4 : 0);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + dd * CH + 4 * c4)),
+                                 "l"(src), "r"(src_bytes) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");  // one group per chunk slot, empty past the end: uniform counting
+        };
+        for (int c = 0; c < G2_NS - 1; ++c) issue(c);
+        for (int c = 0; c < nch; ++c) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(G2_NS - 2) : "memory");  // chunk c has landed (this thread's copies)
+            __syncthreads();                                                     // ... and everyone's; stage (c-1) % NS is free
+            issue(c + G2_NS - 1);
+            const float* tile = ring + (size_t)(c % G2_NS) * G2_DC * CH;
 #pragma unroll
-            for (int t = 0; t < TP; t += 4) {
-                const float4 v4 = *reinterpret_cast<const float4*>(vr + t);
+            for (int dd = 0; dd < G2_DC; ++dd) {
+                float g[PX];
 #pragma unroll
-                for (int p = 0; p < PX; ++p) {
-                    dp[p][t + 0] = fmaf(g[p], v4.x, dp[p][t + 0]);
-                    dp[p][t + 1] = fmaf(g[p], v4.y, dp[p][t + 1]);
-                    dp[p][t + 2] = fmaf(g[p], v4.z, dp[p][t + 2]);
-                    dp[p][t + 3] = fmaf(g[p], v4.w, dp[p][t + 3]);
+                for (int p = 0; p < PX; ++p) g[p] = tile[dd * CH + p * G2_THREADS + tid];
+                const float* vr = vs + (c * G2_DC + dd) * TP;
+#pragma unroll
+                for (int t = 0; t < TP; t += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(vr + t);
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) {
+                        dp[p][t + 0] = fmaf(g[p], v4.x, dp[p][t + 0]);
+                        dp[p][t + 1] = fmaf(g[p], v4.y, dp[p][t + 1]);
+                        dp[p][t + 2] = fmaf(g[p], v4.z, dp[p][t + 2]);
+                        dp[p][t + 3] = fmaf(g[p], v4.w, dp[p][t + 3]);
+                    }
                 }
             }
         }
@@ -266,7 +296,7 @@ static int g2_launch(const G2Plan& pl, const float* x, const float* key, const f
                      const float* d_attn, int B, int idf, int Q, int T, float* d_x, float* d_key, float* d_value, float* dsw,
                      float* pk, float* pv, cudaStream_t st) {
     constexpr int PX = 4;
-    const size_t smem1 = (size_t)2 * idf * TP * sizeof(float);
+    const size_t smem1 = ((size_t)2 * idf * TP + (size_t)G2_NS * G2_DC * PX * G2_THREADS) * sizeof(float);
     if (smem1 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(gag_bwd_px_kernel<TP, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("gag bwd2 smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }

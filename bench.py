@@ -51,10 +51,10 @@ UNIT = "pairs/s"
 #   att_maps) + CE fwd 2 + CE bwd 1 + pair bwd 6 (dU scale, dU, gemm dA + attention bwd, gemm dC, gemm dW, unpack)
 LAUNCHES_PER_STEP = {3: 15, 2: 14}
 # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, averaged over the five launches of one step, from the
-# committed ncu --set full captures: engine 3 profiles/r1_h_gemm_ncu_full_summary.csv (33.9 / 53.0 / 90.8 / 108.3 /
+# committed ncu --set full captures: engine 3 profiles/r1_h_gemm_ncu_full_summary.csv (30.6 / 53.2 / 88.6 / 107.9 /
 # 50.3 MB), engine 2 profiles/r1_v3_fused_step_ncu_full_summary.csv (32.3 / 52.9 / 89.2 / 107.4 / 50.3 MB);
 # algorithmic bytes of the whole step are 45.3 MB — the rest is the stash round trips
-NCU_TRAFFIC_BYTES_PER_GEMM_LAUNCH = {3: 67.3e6, 2: 66.4e6}
+NCU_TRAFFIC_BYTES_PER_GEMM_LAUNCH = {3: 66.1e6, 2: 66.4e6}
 ENGINE_NOTE = {
     3: ("h_gemm_kernel (tcgen05.mma.kind::f16 on operands stored as fp16 hi/lo pairs with power-of-two scales; TMA -> MMA, no "
         "in-kernel split; 5 launches/step: S + attention fwd epilogue, U, dA + attention bwd epilogue, dC (two accumulators), dW)",

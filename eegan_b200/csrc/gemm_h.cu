@@ -31,13 +31,13 @@ struct HArgs {
     int dbg;  // timing experiments only (EEGAN_H_DBG): 1 read-out without global stores, 2 no read-out, 4 no caption phase
 };
 
-template <int EPI, bool DUAL, int BN = H_BN>
+template <int EPI, bool DUAL, int BN = H_BN, int NSO = 0>
 struct HCfg {
     static constexpr bool kAttn = EPI != TC_EPI_PLAIN;
     static constexpr int kBTile = BN * H_BK * 2;                      // one of B hi / lo
     static constexpr int kStageBytes = 2 * H_A_TILE + 2 * kBTile;     // A_hi A_lo B_hi B_lo
     static constexpr int kEWarps = 8;  // epilogue warps: two per TMEM lane quarter, one 64-column half of the tile each
-    static constexpr int kStages = kAttn ? 4 : (BN > 128 ? 3 : 5);
+    static constexpr int kStages = NSO ? NSO : (kAttn ? 4 : (BN > 128 ? 3 : 5));  // NSO: stage-count probe (EEGAN_H_STAGES)
     static constexpr int kThreads = 32 * (2 + kEWarps);
     static constexpr int kEpiPitch = kAttn ? H_EPI_PITCH : 33;
     static constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4;
@@ -157,7 +157,7 @@ __device__ __forceinline__ void h_attn_caption(uint32_t taddr, int T, uint32_t c
 
 template <int EPI, bool DUAL, int BN>
 __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t, int lane, float inv0, float inv1) {
-    using Cfg = HCfg<EPI, DUAL, BN>;
+    using Cfg = HCfg<EPI, DUAL, BN>;  // (the epilogue does not depend on the stage count)
     float* Cz = p.C + (long long)t.z * p.bC;
     const int row0 = t.m0 + t.quarter * 32;
     const int rows_live = max(0, min(32, t.Mlive - row0));
@@ -369,10 +369,10 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
 // ---------------------------------------------------------------------------------------
 // kernel: persistent CTAs (one per SM) walk 128 x 128 output tiles (n fastest, then m, then batch)
 // ---------------------------------------------------------------------------------------
-template <int EPI, bool DUAL, int BN>
-__global__ void __launch_bounds__(HCfg<EPI, DUAL, BN>::kThreads, 1)
+template <int EPI, bool DUAL, int BN, int NSO = 0>
+__global__ void __launch_bounds__(HCfg<EPI, DUAL, BN, NSO>::kThreads, 1)
 h_gemm_kernel(const __grid_constant__ HMaps tm, const HArgs p) {
-    using Cfg = HCfg<EPI, DUAL, BN>;
+    using Cfg = HCfg<EPI, DUAL, BN, NSO>;
     static_assert(BN == 128 || (BN == 256 && EPI == TC_EPI_PLAIN && !DUAL), "256-wide tiles: plain single-accumulator epilogue only");
     constexpr int NS = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -622,16 +622,16 @@ static int h_num_sms() {
     return n;
 }
 
-template <int EPI, bool DUAL, int BN = H_BN>
+template <int EPI, bool DUAL, int BN = H_BN, int NSO = 0>
 static int h_launch_t(const HMaps& maps, const HArgs& a, unsigned grid, cudaStream_t st) {
-    using Cfg = HCfg<EPI, DUAL, BN>;
+    using Cfg = HCfg<EPI, DUAL, BN, NSO>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(h_gemm_kernel<EPI, DUAL, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(h_gemm_kernel<EPI, DUAL, BN, NSO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         if (e != cudaSuccess) { set_error("h gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
         attr_set = true;
     }
-    cudaError_t e = launch_pdl(h_gemm_kernel<EPI, DUAL, BN>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmem, st, maps, a);
+    cudaError_t e = launch_pdl(h_gemm_kernel<EPI, DUAL, BN, NSO>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmem, st, maps, a);
     if (e != cudaSuccess) { set_error("h gemm launch: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
     return check_launch("h gemm");
 }
@@ -685,6 +685,10 @@ int h_gemm_launch(const HGemm& g, cudaStream_t st) {
     EEGAN_REQUIRE(g.C, "h gemm: no output");
     if (g.nseg == 2) return h_launch_t<TC_EPI_PLAIN, true>(maps, a, grid, st);
     if (bn == 256) return h_launch_t<TC_EPI_PLAIN, false, 256>(maps, a, grid, st);
+    static const int nso = [] { const char* e = getenv("EEGAN_H_STAGES"); return e ? atoi(e) : 0; }();  // microbenchmarks only
+    if (nso == 2) return h_launch_t<TC_EPI_PLAIN, false, H_BN, 2>(maps, a, grid, st);
+    if (nso == 3) return h_launch_t<TC_EPI_PLAIN, false, H_BN, 3>(maps, a, grid, st);
+    if (nso == 4) return h_launch_t<TC_EPI_PLAIN, false, H_BN, 4>(maps, a, grid, st);
     return h_launch_t<TC_EPI_PLAIN, false>(maps, a, grid, st);
 }
 

@@ -255,10 +255,12 @@ __global__ void __launch_bounds__(GAG_BT) gag_bwd_kernel(const float* __restrict
 // value stay in shared memory.  Needs Q % 4 == 0, idf % 16 == 0, 16-byte aligned x.
 // ---------------------------------------------------------------------------------------
 constexpr int GF_TILE = 512, GF_DC = 8, GF_NS = 3;
+constexpr int GF_NT = 128, GF_PX = GF_TILE / GF_NT;  // a thread owns 4 pixels: every key / value float4 (a broadcast LDS.128 holds the
+                                                     // shared-memory pipe for four cycles) feeds 16 FMA instead of 8
 constexpr int GF_STAGE_BYTES = GF_DC * GF_TILE * 4;  // 32 KB
 
 template <int TP>
-__global__ void __launch_bounds__(256, 2) gag_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ key,
+__global__ void __launch_bounds__(GF_NT, 3) gag_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ key,
                                                              const float* __restrict__ value, const uint8_t* __restrict__ mask,
                                                              int mask_mode, int B, int idf, int Q, int T, float* __restrict__ out,
                                                              float* __restrict__ attn) {
@@ -273,13 +275,13 @@ __global__ void __launch_bounds__(256, 2) gag_fwd_tma_kernel(const __grid_consta
     auto empty = [&](int s) { return bar0 + 8u * (GF_NS + s); };
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int q0 = blockIdx.x * GF_TILE;
-    for (int idx = tid; idx < idf * TP; idx += 256) {
+    for (int idx = tid; idx < idf * TP; idx += GF_NT) {
         const int d = idx / TP, t = idx - d * TP;
         ks[idx] = (t < T) ? key[((size_t)b * idf + d) * T + t] : 0.f;
         vs[idx] = (t < T) ? value[((size_t)b * idf + d) * T + t] : 0.f;
     }
     if (mask)
-        for (int row = tid; row < B; row += 256) {
+        for (int row = tid; row < B; row += GF_NT) {
             uint32_t bits = 0;
             for (int t = 0; t < T; ++t) bits |= (mask[(size_t)row * T + t] ? 1u : 0u) << t;
             mbits[row] = bits;
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256, 2) gag_fwd_tma_kernel(const __grid_consta
     if (tid == 0) {
         for (int s = 0; s < GF_NS; ++s) {
             mbar_init(full(s), 1);
-            mbar_init(empty(s), 8);
+            mbar_init(empty(s), GF_NT / 32);
         }
         fence_mbar_init();
     }
@@ -302,9 +304,9 @@ __global__ void __launch_bounds__(256, 2) gag_fwd_tma_kernel(const __grid_consta
     if (tid == 0)
         for (int c = 0; c < GF_NS - 1 && c < nchunks; ++c) issue(c);
 
-    float s[2][TP];
+    float s[GF_PX][TP];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < GF_PX; ++u)
 #pragma unroll
         for (int t = 0; t < TP; ++t) s[u][t] = 0.f;
 
@@ -321,26 +323,31 @@ __global__ void __launch_bounds__(256, 2) gag_fwd_tma_kernel(const __grid_consta
         const float* xs = reinterpret_cast<const float*>(gsm + (base - smem_u32(gsm)) + st * GF_STAGE_BYTES);
 #pragma unroll 4
         for (int dd = 0; dd < GF_DC; ++dd) {
-            const float x0 = xs[dd * 256 + tid], x1 = xs[GF_DC * 256 + dd * 256 + tid];
+            float xv[GF_PX];  // pixel u * 128 + tid of the tile: half u / 2 of the stage (two 256-pixel TMA boxes)
+#pragma unroll
+            for (int u = 0; u < GF_PX; ++u) xv[u] = xs[(u >> 1) * GF_DC * 256 + dd * 256 + (u & 1) * GF_NT + tid];
             const float* kr = ks + (c * GF_DC + dd) * TP;
 #pragma unroll
             for (int t = 0; t < TP; t += 4) {
                 const float4 k4 = *reinterpret_cast<const float4*>(kr + t);
-                s[0][t + 0] = fmaf(x0, k4.x, s[0][t + 0]); s[1][t + 0] = fmaf(x1, k4.x, s[1][t + 0]);
-                s[0][t + 1] = fmaf(x0, k4.y, s[0][t + 1]); s[1][t + 1] = fmaf(x1, k4.y, s[1][t + 1]);
-                s[0][t + 2] = fmaf(x0, k4.z, s[0][t + 2]); s[1][t + 2] = fmaf(x1, k4.z, s[1][t + 2]);
-                s[0][t + 3] = fmaf(x0, k4.w, s[0][t + 3]); s[1][t + 3] = fmaf(x1, k4.w, s[1][t + 3]);
+#pragma unroll
+                for (int u = 0; u < GF_PX; ++u) {
+                    s[u][t + 0] = fmaf(xv[u], k4.x, s[u][t + 0]);
+                    s[u][t + 1] = fmaf(xv[u], k4.y, s[u][t + 1]);
+                    s[u][t + 2] = fmaf(xv[u], k4.z, s[u][t + 2]);
+                    s[u][t + 3] = fmaf(xv[u], k4.w, s[u][t + 3]);
+                }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty(st));
     }
-    bool ok[2];
+    bool ok[GF_PX];
     const uint32_t tail = (T < 32) ? (0xffffffffu << T) : 0u;  // columns t >= T never exist
     const uint32_t rowbase = (uint32_t)(((long long)b * Q) % B);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int q = q0 + u * 256 + tid;
+    for (int u = 0; u < GF_PX; ++u) {
+        const int q = q0 + u * GF_NT + tid;
         ok[u] = q < Q;
         if (!ok[u]) continue;
         uint32_t dead = tail;
@@ -369,17 +376,23 @@ __global__ void __launch_bounds__(256, 2) gag_fwd_tma_kernel(const __grid_consta
     float* ob = out + (size_t)b * idf * Q;
 #pragma unroll 2
     for (int d = 0; d < idf; ++d) {
-        float a0 = 0.f, a1 = 0.f;
+        float acc[GF_PX];
+#pragma unroll
+        for (int u = 0; u < GF_PX; ++u) acc[u] = 0.f;
 #pragma unroll
         for (int t = 0; t < TP; t += 4) {
             const float4 v4 = *reinterpret_cast<const float4*>(vs + d * TP + t);
-            a0 = fmaf(v4.x, s[0][t + 0], a0); a1 = fmaf(v4.x, s[1][t + 0], a1);
-            a0 = fmaf(v4.y, s[0][t + 1], a0); a1 = fmaf(v4.y, s[1][t + 1], a1);
-            a0 = fmaf(v4.z, s[0][t + 2], a0); a1 = fmaf(v4.z, s[1][t + 2], a1);
-            a0 = fmaf(v4.w, s[0][t + 3], a0); a1 = fmaf(v4.w, s[1][t + 3], a1);
+#pragma unroll
+            for (int u = 0; u < GF_PX; ++u) {
+                acc[u] = fmaf(v4.x, s[u][t + 0], acc[u]);
+                acc[u] = fmaf(v4.y, s[u][t + 1], acc[u]);
+                acc[u] = fmaf(v4.z, s[u][t + 2], acc[u]);
+                acc[u] = fmaf(v4.w, s[u][t + 3], acc[u]);
+            }
         }
-        if (ok[0]) ob[(size_t)d * Q + q0 + tid] = a0;
-        if (ok[1]) ob[(size_t)d * Q + q0 + 256 + tid] = a1;
+#pragma unroll
+        for (int u = 0; u < GF_PX; ++u)
+            if (ok[u]) ob[(size_t)d * Q + q0 + u * GF_NT + tid] = acc[u];
     }
 }
 
@@ -396,7 +409,7 @@ static int gag_fwd_tma_launch(const float* x, const float* key, const float* val
         if (e != cudaSuccess) { set_error("gag fwd smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
         granted.store(smem);
     }
-    gag_fwd_tma_kernel<TP><<<dim3((Q + GF_TILE - 1) / GF_TILE, B), 256, smem, st>>>(tmx, key, value, mask, mask_mode, B, idf, Q,
+    gag_fwd_tma_kernel<TP><<<dim3((Q + GF_TILE - 1) / GF_TILE, B), GF_NT, smem, st>>>(tmx, key, value, mask, mask_mode, B, idf, Q,
                                                                                      T, out, attn);
     return check_launch("gag fwd (tma)");
 }

@@ -16,6 +16,8 @@
 //   kernel 3                        fixed-order sum of the per-chunk partials (no atomics, nothing to zero).
 //
 // Extra HBM traffic against the one-kernel form: ds written and read once (2 T floats per pixel) and d_out read twice.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace eegan {
@@ -250,6 +252,105 @@ __global__ void __launch_bounds__(128, 3) gag_bwd_rowsum_kernel(const float* __r
     }
 }
 
+// Row sums, second mapping (default): the same contraction as gag_bwd_rowsum_kernel, with the warp's lanes along the PIXELS.
+// The first mapping puts a warp's lanes on 32 different channel groups, so one 16-byte load per lane touches 32 different
+// rows Q floats apart — 32 DRAM pages for 1 KB, and 32 L1 tag look-ups per instruction.  Here a warp owns RPT channels and
+// a round of 256 pixels: lane l takes pixels 4l .. 4l+3 and 128 + 4l .. 128 + 4l + 3.  Both operands of a round arrive in
+// shared memory by 16-byte cp.async one round ahead (double-buffered): the warp's own RPT rows as contiguous 512-byte
+// segments, the w tile [TP][256] (shared by the CTA's 4 warps) likewise; every shared-memory read of the FMA loop is a
+// conflict-free LDS.128 (RPT x 8 FMA per w pair).  The RPT x TP sums stay in registers over the CTA's whole pixel chunk and
+// meet in one shuffle reduction at the end.  grid (chunks, idf / (4 RPT), B); 4 warps per CTA.
+constexpr int G3_RPX = 256;  // pixels per round
+template <int TP, int RPT>
+__global__ void __launch_bounds__(128, (RPT > 4 || TP > 20) ? 2 : 3)
+gag_bwd_rowsum_px_kernel(const float* __restrict__ rows, const float* __restrict__ w, int idf, int Q, int T, int Qc,
+                         float* __restrict__ part) {
+    extern __shared__ __align__(16) float g2sm[];
+    constexpr int WT = TP * G3_RPX;        // floats per w tile
+    constexpr int XT = 4 * RPT * G3_RPX;   // floats per x tile (4 warps x RPT rows)
+    float* w_s = g2sm;                     // [2][TP][256]
+    float* x_s = g2sm + 2 * WT;            // [2][4 warps][RPT][256]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x, b = blockIdx.z;
+    const int ch0 = (blockIdx.y * 4 + warp) * RPT;
+    const int q_beg = c * Qc, q_end = min(Q, q_beg + Qc);
+    float acc[RPT][TP];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int t = 0; t < TP; ++t) acc[r][t] = 0.f;
+    const float* rbase = rows ? rows + ((size_t)b * idf + ch0) * Q : nullptr;
+    const float* wbase = w + (size_t)b * T * Q;
+    auto issue = [&](int q0, int buf) {
+        float* xd = x_s + buf * XT + warp * RPT * G3_RPX;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = q0 + 128 * h + 4 * lane;  // q_end is a multiple of 4: a float4 group is all in or all out
+                float* d = xd + r * G3_RPX + 128 * h + 4 * lane;
+                if (rbase && q < q_end) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)),
+                                 "l"(rbase + (size_t)r * Q + q) : "memory");
+                } else {
+                    *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        float* wd = w_s + buf * WT;
+#pragma unroll
+        for (int k = 0; k < TP / 2; ++k) {  // TP * 64 float4 groups over 128 threads
+            const int idx = tid + 128 * k, t = idx >> 6, g = idx & 63;
+            float* d = wd + t * G3_RPX + 4 * g;
+            const int q = q0 + 4 * g;
+            if (t < T && q < q_end) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)),
+                             "l"(wbase + (size_t)t * Q + q) : "memory");
+            } else {
+                *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(q_beg, 0);
+    int cur = 0;
+    for (int q0 = q_beg; q0 < q_end; q0 += G3_RPX, cur ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // tiles `cur` have landed for every thread; every thread is done reading tiles `cur ^ 1`
+        if (q0 + G3_RPX < q_end) issue(q0 + G3_RPX, cur ^ 1);
+        const float* wt = w_s + cur * WT + 4 * lane;
+        const float* xt = x_s + cur * XT + warp * RPT * G3_RPX + 4 * lane;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 xv[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) xv[r] = *reinterpret_cast<const float4*>(xt + r * G3_RPX + 128 * h);
+#pragma unroll
+            for (int t = 0; t < TP; ++t) {
+                const float4 wv = *reinterpret_cast<const float4*>(wt + t * G3_RPX + 128 * h);
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    float a0 = acc[r][t];
+                    a0 = fmaf(xv[r].x, wv.x, a0); a0 = fmaf(xv[r].y, wv.y, a0);
+                    a0 = fmaf(xv[r].z, wv.z, a0); a0 = fmaf(xv[r].w, wv.w, a0);
+                    acc[r][t] = a0;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int t = 0; t < TP; ++t) acc[r][t] = warp_sum(acc[r][t]);
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            float* pp = part + (((size_t)b * gridDim.x + c) * idf + ch0 + r) * TP;
+#pragma unroll
+            for (int t = 0; t < TP; t += 4) *reinterpret_cast<float4*>(pp + t) = make_float4(acc[r][t], acc[r][t + 1], acc[r][t + 2], acc[r][t + 3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) gag_bwd_kv_reduce_kernel(const float* __restrict__ part_k, const float* __restrict__ part_v,
                                                                 int B, int idf, int T, int TP, int S, float* __restrict__ d_key,
                                                                 float* __restrict__ d_value) {
@@ -270,6 +371,7 @@ __global__ void __launch_bounds__(256) gag_bwd_kv_reduce_kernel(const float* __r
 
 struct G2Plan {
     int TP, sub, threads, S, Qc;
+    int px_map;  // 8 / 4: gag_bwd_rowsum_px_kernel with that many channels per warp (default 8; EEGAN_GAG_RPT=4); 0: gag_bwd_rowsum_kernel (EEGAN_GAG_ROWSUM=0)
     size_t ds_bytes, part_bytes;
 };
 
@@ -279,8 +381,33 @@ static bool g2_plan(int B, int idf, int Q, int T, G2Plan* pl) {
     const int nrg = idf / G2_RPT;              // 8 .. 128 row groups
     pl->sub = 128 / nrg > 0 ? 128 / nrg : 1;   // pixel subgroups per CTA
     pl->threads = nrg * pl->sub;               // <= 128
+    static const int px_map = [] { const char* e = getenv("EEGAN_GAG_ROWSUM"); return e ? atoi(e) != 0 : 1; }();
+    static const int px_rpt = [] { const char* e = getenv("EEGAN_GAG_RPT"); return (e && atoi(e) == 4) ? 4 : 8; }();
+    // 8 channels per warp need 8 x TP sums in registers: TP <= 20 (beyond that the kernel spills)
+    pl->px_map = px_map ? ((px_rpt == 8 && pl->TP <= 20 && idf % 32 == 0) ? 8 : (idf % 16 == 0 ? 4 : 0)) : 0;
+    if (pl->px_map) {
+        // pixel chunks of whole 256-pixel rounds; the chunk count that fills the CTA slots (2 or 3 per SM) best, at most 4 waves
+        const int rpt = pl->px_map;
+        const int slots = 148 * ((rpt > 4 || pl->TP > 20) ? 2 : 3);
+        const int per_chunk = B * (idf / (4 * rpt));
+        const int max_s = (Q + G3_RPX - 1) / G3_RPX;
+        int best = 1;
+        double best_eff = 0.0;
+        for (int S = 1; S <= max_s && (long long)S * per_chunk <= 4LL * slots; ++S) {
+            const long long n = (long long)S * per_chunk, waves = (n + slots - 1) / slots;
+            const double eff = (double)n / (double)(waves * slots);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = S; }
+        }
+        pl->Qc = ((Q + best - 1) / best + G3_RPX - 1) / G3_RPX * G3_RPX;
+        pl->S = (Q + pl->Qc - 1) / pl->Qc;
+        pl->ds_bytes = align_up((size_t)B * T * Q * sizeof(float), 256);
+        pl->part_bytes = align_up((size_t)B * pl->S * idf * pl->TP * sizeof(float), 256);
+        return true;
+    }
     const int round_px = pl->sub * G2_PPR;
-    int S = (6 * 148 + B - 1) / B;  // about six CTAs per SM over the grid
+    // about nine CTAs per SM over the grid (EEGAN_GAG_CPS probe: 3 / 4 / 6 / 9 / 12 -> backward 1.45 / 1.37 / 1.31 / 1.17 / 1.20 ms at 256^2 x 32, flat elsewhere)
+    static const int cps = [] { const char* e = getenv("EEGAN_GAG_CPS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 9; }();
+    int S = (cps * 148 + B - 1) / B;
     const int max_s = (Q + round_px - 1) / round_px;
     if (S > max_s) S = max_s;
     if (S < 1) S = 1;
@@ -310,8 +437,23 @@ static int g2_launch(const G2Plan& pl, const float* x, const float* key, const f
         cudaError_t e = cudaFuncSetAttribute(gag_bwd_rowsum_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e != cudaSuccess) { set_error("gag bwd2 smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
     }
-    gag_bwd_rowsum_kernel<TP><<<dim3(pl.S, B), pl.threads, smem2, st>>>(x, dsw, idf, pl.sub, Q, T, pl.Qc, pk);
-    gag_bwd_rowsum_kernel<TP><<<dim3(pl.S, B), pl.threads, smem2, st>>>(d_out, attn, idf, pl.sub, Q, T, pl.Qc, pv);
+    if (pl.px_map) {
+        const int rpt = pl.px_map;
+        const size_t smem3 = (size_t)2 * (TP + 4 * rpt) * G3_RPX * sizeof(float);
+        const dim3 grid3(pl.S, idf / (4 * rpt), B);
+        auto run = [&](auto kern) -> int {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+            if (e != cudaSuccess) { set_error("gag bwd2 smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
+            kern<<<grid3, 128, smem3, st>>>(x, dsw, idf, Q, T, pl.Qc, pk);
+            kern<<<grid3, 128, smem3, st>>>(d_out, attn, idf, Q, T, pl.Qc, pv);
+            return EEGAN_OK;
+        };
+        const int rc = rpt == 8 ? run(gag_bwd_rowsum_px_kernel<TP, 8>) : run(gag_bwd_rowsum_px_kernel<TP, 4>);
+        if (rc) return rc;
+    } else {
+        gag_bwd_rowsum_kernel<TP><<<dim3(pl.S, B), pl.threads, smem2, st>>>(x, dsw, idf, pl.sub, Q, T, pl.Qc, pk);
+        gag_bwd_rowsum_kernel<TP><<<dim3(pl.S, B), pl.threads, smem2, st>>>(d_out, attn, idf, pl.sub, Q, T, pl.Qc, pv);
+    }
     EEGAN_LAUNCH_CHECK("gag bwd2 (key/value)");
     const long long n = (long long)B * idf * T;
     gag_bwd_kv_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pk, pv, B, idf, T, TP, pl.S, d_key, d_value);
@@ -340,7 +482,8 @@ extern "C" int eegan_gag_bwd_ws(const float* x, const float* key, const float* v
     EEGAN_REQUIRE(B > 0 && idf > 0 && Q > 0 && T > 0, "gag: empty shape B=%d idf=%d Q=%d T=%d", B, idf, Q, T);
     EEGAN_REQUIRE(x && key && value && attn && d_x && d_key && d_value, "gag bwd: null pointer");
     G2Plan pl;
-    const bool aligned = Q % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+    const bool aligned = Q % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(attn) |
+                                         reinterpret_cast<uintptr_t>(workspace)) & 15) == 0;
     if (!workspace || !aligned || !g2_plan(B, idf, Q, T, &pl) || B > 65535)
         return eegan_gag_bwd(x, key, value, attn, d_out, d_attn, B, idf, Q, T, d_x, d_key, d_value, stream);
     EEGAN_REQUIRE(workspace_bytes >= pl.ds_bytes + 2 * pl.part_bytes, "gag bwd: workspace %zu < %zu bytes", workspace_bytes,

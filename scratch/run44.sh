@@ -1,11 +1,9 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_gemm_h.py tests/test_gpu_parity.py tests/test_gpu_edges.py -m gpu -x -q -k "not gag" 2>&1 | tail -3
-for w in 1 0; do
-EEGAN_H_WIDE=$w timeout 300 python bench.py --no-extra --steps 50 --warmup 10 > gpurun_out/bench_h_wide$w.json 2>/dev/null; echo "wide=$w rc=$?"
-python - <<PY
-import json
-d=json.load(open('gpurun_out/bench_h_wide$w.json'))
-s=d['roofline']['stage_ms_per_step']
-print(round(d['ms_per_step']*1e3,1), d['value'], {k[:5]:round(v*1e3,1) for k,v in s.items() if v>0})
-PY
-done
+mkdir -p gpurun_out
+T0=$(date +%s)
+timeout 420 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+echo "tests done $(( $(date +%s) - T0 )) s"
+timeout 300 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$? $(( $(date +%s) - T0 )) s"
+for c in 3 4 9 12; do echo "CPS=$c"; EEGAN_GAG_CPS=$c timeout 120 python scratch/gag_time.py 2>&1 | tail -3; done
+echo "CPS=6 (default)"; timeout 120 python scratch/gag_time.py 2>&1 | tail -3
+echo "total $(( $(date +%s) - T0 )) s"

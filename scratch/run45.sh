@@ -1,9 +1,8 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edges.py -m gpu -x -q -k "not gag" 2>&1 | tail -3
-timeout 300 python bench.py --no-extra --steps 50 --warmup 10 > gpurun_out/bench_h_v4.json 2>/dev/null; echo "rc=$?"
-python - <<PY
-import json
-d=json.load(open('gpurun_out/bench_h_v4.json'))
-s=d['roofline']['stage_ms_per_step']
-print(round(d['ms_per_step']*1e3,1), d['value'], d['e2e']['value'], d['roofline']['achieved'], {k[:5]:round(v*1e3,1) for k,v in s.items() if v>0})
-PY
+T0=$(date +%s)
+timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "gag" 2>&1 | tail -3
+EEGAN_GAG_RPT=4 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "gag" 2>&1 | tail -3
+echo "RPT=8 (default)"; timeout 120 python scratch/gag_time.py 2>&1 | tail -3
+echo "RPT=4"; EEGAN_GAG_RPT=4 timeout 120 python scratch/gag_time.py 2>&1 | tail -3
+echo "old rowsum"; EEGAN_GAG_ROWSUM=0 timeout 120 python scratch/gag_time.py 2>&1 | tail -3
+echo "total $(( $(date +%s) - T0 )) s"

@@ -255,21 +255,20 @@ __global__ void __launch_bounds__(128, 3) gag_bwd_rowsum_kernel(const float* __r
 // Row sums, second mapping (default): the same contraction as gag_bwd_rowsum_kernel, with the warp's lanes along the PIXELS.
 // The first mapping puts a warp's lanes on 32 different channel groups, so one 16-byte load per lane touches 32 different
 // rows Q floats apart — 32 DRAM pages for 1 KB, and 32 L1 tag look-ups per instruction.  Here a warp owns RPT channels and
-// a round of 256 pixels: lane l takes pixels 4l .. 4l+3 and 128 + 4l .. 128 + 4l + 3.  Both operands of a round arrive in
-// shared memory by 16-byte cp.async one round ahead (double-buffered): the warp's own RPT rows as contiguous 512-byte
-// segments, the w tile [TP][256] (shared by the CTA's 4 warps) likewise; every shared-memory read of the FMA loop is a
-// conflict-free LDS.128 (RPT x 8 FMA per w pair).  The RPT x TP sums stay in registers over the CTA's whole pixel chunk and
-// meet in one shuffle reduction at the end.  grid (chunks, idf / (4 RPT), B); 4 warps per CTA.
-constexpr int G3_RPX = 256;  // pixels per round
-template <int TP, int RPT>
+// a round of 128 pixels (lane l: pixels 4l .. 4l+3).  Both operands of a round arrive in shared memory by 16-byte cp.async
+// through an NS-deep ring filled NS - 1 rounds ahead of the FMAs: the warp's own RPT rows as contiguous 512-byte segments,
+// the w tile [TP][128] (shared by the CTA's 4 warps) likewise; every shared-memory read of the FMA loop is a conflict-free
+// LDS.128 (RPT x 4 FMA per w load).  The RPT x TP sums stay in registers over the CTA's whole pixel chunk and meet once,
+// through shared memory, at the end.  grid (chunks, idf / (4 RPT), B); 4 warps per CTA.
+constexpr int G3_RPX = 128;  // pixels per round
+template <int TP, int RPT, int NS>
 __global__ void __launch_bounds__(128, (RPT > 4 || TP > 20) ? 2 : 3)
 gag_bwd_rowsum_px_kernel(const float* __restrict__ rows, const float* __restrict__ w, int idf, int Q, int T, int Qc,
                          float* __restrict__ part) {
     extern __shared__ __align__(16) float g2sm[];
     constexpr int WT = TP * G3_RPX;        // floats per w tile
     constexpr int XT = 4 * RPT * G3_RPX;   // floats per x tile (4 warps x RPT rows)
-    float* w_s = g2sm;                     // [2][TP][256]
-    float* x_s = g2sm + 2 * WT;            // [2][4 warps][RPT][256]
+    constexpr int ST = WT + XT;            // floats per stage: [TP][128] then [4 warps][RPT][128]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x, b = blockIdx.z;
     const int ch0 = (blockIdx.y * 4 + warp) * RPT;
@@ -281,14 +280,14 @@ gag_bwd_rowsum_px_kernel(const float* __restrict__ rows, const float* __restrict
         for (int t = 0; t < TP; ++t) acc[r][t] = 0.f;
     const float* rbase = rows ? rows + ((size_t)b * idf + ch0) * Q : nullptr;
     const float* wbase = w + (size_t)b * T * Q;
-    auto issue = [&](int q0, int buf) {
-        float* xd = x_s + buf * XT + warp * RPT * G3_RPX;
+    auto issue = [&](int q0, int stage) {  // one commit group per call, empty past the chunk's end: uniform counting
+        if (q0 < q_end) {
+            float* wd = g2sm + stage * ST;
+            float* xd = wd + WT + warp * RPT * G3_RPX;
+            const int q = q0 + 4 * lane;  // q_end is a multiple of 4: a float4 group is all in or all out
 #pragma unroll
-        for (int r = 0; r < RPT; ++r)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int q = q0 + 128 * h + 4 * lane;  // q_end is a multiple of 4: a float4 group is all in or all out
-                float* d = xd + r * G3_RPX + 128 * h + 4 * lane;
+            for (int r = 0; r < RPT; ++r) {
+                float* d = xd + r * G3_RPX + 4 * lane;
                 if (rbase && q < q_end) {
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)),
                                  "l"(rbase + (size_t)r * Q + q) : "memory");
@@ -296,58 +295,61 @@ gag_bwd_rowsum_px_kernel(const float* __restrict__ rows, const float* __restrict
                     *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-        float* wd = w_s + buf * WT;
 #pragma unroll
-        for (int k = 0; k < TP / 2; ++k) {  // TP * 64 float4 groups over 128 threads
-            const int idx = tid + 128 * k, t = idx >> 6, g = idx & 63;
-            float* d = wd + t * G3_RPX + 4 * g;
-            const int q = q0 + 4 * g;
-            if (t < T && q < q_end) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)),
-                             "l"(wbase + (size_t)t * Q + q) : "memory");
-            } else {
-                *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < TP / 4; ++k) {  // TP * 32 float4 groups over 128 threads: warp `warp` takes rows warp, warp + 4, ...
+                const int t = warp + 4 * k;
+                float* d = wd + t * G3_RPX + 4 * lane;
+                if (t < T && q < q_end) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)),
+                                 "l"(wbase + (size_t)t * Q + q) : "memory");
+                } else {
+                    *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    issue(q_beg, 0);
-    int cur = 0;
-    for (int q0 = q_beg; q0 < q_end; q0 += G3_RPX, cur ^= 1) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();  // tiles `cur` have landed for every thread; every thread is done reading tiles `cur ^ 1`
-        if (q0 + G3_RPX < q_end) issue(q0 + G3_RPX, cur ^ 1);
-        const float* wt = w_s + cur * WT + 4 * lane;
-        const float* xt = x_s + cur * XT + warp * RPT * G3_RPX + 4 * lane;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float4 xv[RPT];
+    for (int s0 = 0; s0 < NS - 1; ++s0) issue(q_beg + s0 * G3_RPX, s0);
+    int i = 0;
+    for (int q0 = q_beg; q0 < q_end; q0 += G3_RPX, ++i) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(NS - 2) : "memory");  // round i has landed (this thread's copies)
+        __syncthreads();  // ... and everyone's; every thread is done reading round i - 1, whose stage is refilled next
+        issue(q0 + (NS - 1) * G3_RPX, (i + NS - 1) % NS);
+        const float* wt = g2sm + (i % NS) * ST + 4 * lane;
+        const float* xt = wt + WT + warp * RPT * G3_RPX;
+        float4 xv[RPT];
 #pragma unroll
-            for (int r = 0; r < RPT; ++r) xv[r] = *reinterpret_cast<const float4*>(xt + r * G3_RPX + 128 * h);
+        for (int r = 0; r < RPT; ++r) xv[r] = *reinterpret_cast<const float4*>(xt + r * G3_RPX);
 #pragma unroll
-            for (int t = 0; t < TP; ++t) {
-                const float4 wv = *reinterpret_cast<const float4*>(wt + t * G3_RPX + 128 * h);
+        for (int t = 0; t < TP; ++t) {
+            const float4 wv = *reinterpret_cast<const float4*>(wt + t * G3_RPX);
 #pragma unroll
-                for (int r = 0; r < RPT; ++r) {
-                    float a0 = acc[r][t];
-                    a0 = fmaf(xv[r].x, wv.x, a0); a0 = fmaf(xv[r].y, wv.y, a0);
-                    a0 = fmaf(xv[r].z, wv.z, a0); a0 = fmaf(xv[r].w, wv.w, a0);
-                    acc[r][t] = a0;
-                }
+            for (int r = 0; r < RPT; ++r) {
+                float a0 = acc[r][t];
+                a0 = fmaf(xv[r].x, wv.x, a0); a0 = fmaf(xv[r].y, wv.y, a0);
+                a0 = fmaf(xv[r].z, wv.z, a0); a0 = fmaf(xv[r].w, wv.w, a0);
+                acc[r][t] = a0;
             }
         }
     }
+    // the lanes' partial sums meet through shared memory (the ring is free now): each warp parks its RPT x TP values as
+    // [value][lane] with pitch 33 (conflict-free both ways), then lane l adds up values l, l + 32, ... and stores them —
+    // RPT * TP / 32 coalesced rows instead of RPT * TP five-step shuffle reductions
+    __syncthreads();
+    float* red = g2sm + warp * (RPT * TP * 33);
 #pragma unroll
     for (int r = 0; r < RPT; ++r)
 #pragma unroll
-        for (int t = 0; t < TP; ++t) acc[r][t] = warp_sum(acc[r][t]);
-    if (lane == 0) {
+        for (int t = 0; t < TP; ++t) red[(r * TP + t) * 33 + lane] = acc[r][t];
+    __syncwarp();
+    float* pp = part + (((size_t)b * gridDim.x + c) * idf + ch0) * TP;  // the warp's RPT rows are contiguous: [RPT][TP]
+    for (int v = lane; v < RPT * TP; v += 32) {
+        const float* rv = red + v * 33;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int r = 0; r < RPT; ++r) {
-            float* pp = part + (((size_t)b * gridDim.x + c) * idf + ch0 + r) * TP;
-#pragma unroll
-            for (int t = 0; t < TP; t += 4) *reinterpret_cast<float4*>(pp + t) = make_float4(acc[r][t], acc[r][t + 1], acc[r][t + 2], acc[r][t + 3]);
-        }
+        for (int k = 0; k < 32; ++k) s4[k & 3] += rv[k];
+        pp[v] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     }
 }
 
@@ -439,7 +441,10 @@ static int g2_launch(const G2Plan& pl, const float* x, const float* key, const f
     }
     if (pl.px_map) {
         const int rpt = pl.px_map;
-        const size_t smem3 = (size_t)2 * (TP + 4 * rpt) * G3_RPX * sizeof(float);
+        static const int ns_env = [] { const char* e = getenv("EEGAN_GAG_NS"); return e ? atoi(e) : 0; }();  // ring depth probe
+        const int ns = ns_env == 3 ? 3 : 4;
+        const size_t ring3 = (size_t)ns * (TP + 4 * rpt) * G3_RPX * sizeof(float), red3 = (size_t)4 * rpt * TP * 33 * sizeof(float);
+        const size_t smem3 = ring3 > red3 ? ring3 : red3;
         const dim3 grid3(pl.S, idf / (4 * rpt), B);
         auto run = [&](auto kern) -> int {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
@@ -448,7 +453,9 @@ static int g2_launch(const G2Plan& pl, const float* x, const float* key, const f
             kern<<<grid3, 128, smem3, st>>>(d_out, attn, idf, Q, T, pl.Qc, pv);
             return EEGAN_OK;
         };
-        const int rc = rpt == 8 ? run(gag_bwd_rowsum_px_kernel<TP, 8>) : run(gag_bwd_rowsum_px_kernel<TP, 4>);
+        int rc;
+        if (rpt == 8) rc = ns == 3 ? run(gag_bwd_rowsum_px_kernel<TP, 8, 3>) : run(gag_bwd_rowsum_px_kernel<TP, 8, 4>);
+        else rc = ns == 3 ? run(gag_bwd_rowsum_px_kernel<TP, 4, 3>) : run(gag_bwd_rowsum_px_kernel<TP, 4, 4>);
         if (rc) return rc;
     } else {
         gag_bwd_rowsum_kernel<TP><<<dim3(pl.S, B), pl.threads, smem2, st>>>(x, dsw, idf, pl.sub, Q, T, pl.Qc, pk);

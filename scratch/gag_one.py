@@ -3,7 +3,8 @@ sys.path.insert(0, '/root/repo')
 import eegan_b200 as E
 dev = torch.device('cuda')
 g = torch.Generator().manual_seed(7)
-Bq, T, res, idf = 48, 18, 64, 128
+Bq, T = 48, 18
+res, idf = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (64, 128)
 lens = torch.randint(5, T + 1, (Bq,), generator=g)
 mask = (torch.arange(T)[None, :] >= lens[:, None]).to(dev)
 x = torch.randn(Bq, idf, res, res, device=dev).requires_grad_()

@@ -1,11 +1,12 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edges.py -m gpu -x -q -k "not gag" 2>&1 | tail -3
-for f in 1 0; do
-EEGAN_H_COSFUSE=$f timeout 300 python bench.py --no-extra --steps 50 --warmup 10 > gpurun_out/bench_h_cos$f.json 2>/dev/null; echo "cosfuse=$f rc=$?"
-python - <<PY
-import json
-d=json.load(open('gpurun_out/bench_h_cos$f.json'))
-s=d['roofline']['stage_ms_per_step']
-print(round(d['ms_per_step']*1e3,1), d['value'], {k[:5]:round(v*1e3,1) for k,v in s.items() if v>0})
+for sh in "64 128" "128 64" "256 32"; do
+  set -- $sh
+  timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/gag_launch_$1.csv python scratch/gag_one.py $1 $2 > /dev/null 2>&1
+  echo "== $sh"; python - <<PY
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/gag_launch_$1.csv')) if len(r)>5 and r[0].isdigit()]
+# keep the last iteration's gag kernels
+out=[(r[4][:60], r[-1]) for r in rows if 'gag' in r[4]]
+for k,v in out[len(out)//2:]: print(k, v)
 PY
 done

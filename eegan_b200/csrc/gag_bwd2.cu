@@ -41,21 +41,23 @@ __global__ void __launch_bounds__(G2_THREADS, 3) gag_bwd_px_kernel(const float* 
         vs[idx] = t < T ? value[((size_t)b * idf + d) * T + t] : 0.f;
     }
     __syncthreads();
-    int q[PX];
-    bool ok[PX];
+    // a thread owns PX = 4 CONSECUTIVE pixels: every global access of the kernel is a 16-byte one (Q % 4 == 0, checked by
+    // the caller: a quad is entirely inside the row or entirely outside)
+    static_assert(PX == 4, "the pixel kernel is written for quads");
+    int qb = (blockIdx.x * G2_THREADS + tid) * PX;
+    const bool ok = qb < Q;
+    if (!ok) qb = Q - PX;  // clamped loads, guarded stores
     float dp[PX][TP];
 #pragma unroll
-    for (int p = 0; p < PX; ++p) {
-        q[p] = (blockIdx.x * PX + p) * G2_THREADS + tid;
-        ok[p] = q[p] < Q;
-        if (!ok[p]) q[p] = Q - 1;  // clamped loads, guarded stores
-#pragma unroll
-        for (int t = 0; t < TP; ++t) dp[p][t] = (d_attn && t < T) ? d_attn[((size_t)b * T + t) * Q + q[p]] : 0.f;
+    for (int t = 0; t < TP; ++t) {
+        const float4 v = (d_attn && t < T) ? __ldg(reinterpret_cast<const float4*>(d_attn + ((size_t)b * T + t) * Q + qb))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        dp[0][t] = v.x; dp[1][t] = v.y; dp[2][t] = v.z; dp[3][t] = v.w;
     }
     if (d_out) {
         // d_out streams through a ring of [G2_DC channels][PX * 128 pixels] chunks filled by 16-byte cp.async, G2_NS - 1 chunks
-        // ahead of the FMAs, so that the HBM latency never stalls the (few, register-heavy) warps; a thread's pixels
-        // tid, tid + 128, ... are conflict-free 4-byte reads of a chunk row.
+        // ahead of the FMAs, so that the HBM latency never stalls the (few, register-heavy) warps; a thread's quad is one
+        // conflict-free 16-byte read of a chunk row.
         constexpr int CH = PX * G2_THREADS;  // pixels per chunk row
         float* ring = vs + idf * TP;         // [G2_NS][G2_DC][CH]
         const int q0 = blockIdx.x * CH;
@@ -83,9 +85,8 @@ __global__ void __launch_bounds__(G2_THREADS, 3) gag_bwd_px_kernel(const float* 
             const float* tile = ring + (size_t)(c % G2_NS) * G2_DC * CH;
 #pragma unroll
             for (int dd = 0; dd < G2_DC; ++dd) {
-                float g[PX];
-#pragma unroll
-                for (int p = 0; p < PX; ++p) g[p] = tile[dd * CH + p * G2_THREADS + tid];
+                const float4 g4 = *reinterpret_cast<const float4*>(tile + dd * CH + PX * tid);
+                const float g[PX] = {g4.x, g4.y, g4.z, g4.w};
                 const float* vr = vs + (c * G2_DC + dd) * TP;
 #pragma unroll
                 for (int t = 0; t < TP; t += 4) {
@@ -101,19 +102,22 @@ __global__ void __launch_bounds__(G2_THREADS, 3) gag_bwd_px_kernel(const float* 
             }
         }
     }
-#pragma unroll
-    for (int p = 0; p < PX; ++p) {  // ds = p (dp - sum_t p dp), in place
-        float pr[TP];
-        float dot = 0.f;
+    {  // ds = p (dp - sum_t p dp), in place
+        float dot[PX] = {0.f, 0.f, 0.f, 0.f};
+        float pr[PX][TP];
 #pragma unroll
         for (int t = 0; t < TP; ++t) {
-            pr[t] = t < T ? attn[((size_t)b * T + t) * Q + q[p]] : 0.f;
-            dot = fmaf(pr[t], dp[p][t], dot);
+            const float4 v = t < T ? __ldg(reinterpret_cast<const float4*>(attn + ((size_t)b * T + t) * Q + qb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pr[0][t] = v.x; pr[1][t] = v.y; pr[2][t] = v.z; pr[3][t] = v.w;
+#pragma unroll
+            for (int p = 0; p < PX; ++p) dot[p] = fmaf(pr[p][t], dp[p][t], dot[p]);
         }
 #pragma unroll
         for (int t = 0; t < TP; ++t) {
-            dp[p][t] = pr[t] * (dp[p][t] - dot);
-            if (t < T && ok[p]) ds_out[((size_t)b * T + t) * Q + q[p]] = dp[p][t];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) dp[p][t] = pr[p][t] * (dp[p][t] - dot[p]);
+            if (t < T && ok)
+                *reinterpret_cast<float4*>(ds_out + ((size_t)b * T + t) * Q + qb) = make_float4(dp[0][t], dp[1][t], dp[2][t], dp[3][t]);
         }
     }
     float* xbase = d_x + (size_t)b * idf * Q;
@@ -134,9 +138,7 @@ __global__ void __launch_bounds__(G2_THREADS, 3) gag_bwd_px_kernel(const float* 
                 acc[p] = fmaf(dp[p][t + 3], k4.w, acc[p]);
             }
         }
-#pragma unroll
-        for (int p = 0; p < PX; ++p)
-            if (ok[p]) xbase[(size_t)d * Q + q[p]] = acc[p];
+        if (ok) *reinterpret_cast<float4*>(xbase + (size_t)d * Q + qb) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
 }
 
@@ -490,7 +492,7 @@ extern "C" int eegan_gag_bwd_ws(const float* x, const float* key, const float* v
     EEGAN_REQUIRE(x && key && value && attn && d_x && d_key && d_value, "gag bwd: null pointer");
     G2Plan pl;
     const bool aligned = Q % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(attn) |
-                                         reinterpret_cast<uintptr_t>(workspace)) & 15) == 0;
+                                         reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(d_attn) | reinterpret_cast<uintptr_t>(d_x)) & 15) == 0;
     if (!workspace || !aligned || !g2_plan(B, idf, Q, T, &pl) || B > 65535)
         return eegan_gag_bwd(x, key, value, attn, d_out, d_attn, B, idf, Q, T, d_x, d_key, d_value, stream);
     EEGAN_REQUIRE(workspace_bytes >= pl.ds_bytes + 2 * pl.part_bytes, "gag bwd: workspace %zu < %zu bytes", workspace_bytes,

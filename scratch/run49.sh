@@ -1,3 +1,3 @@
 cd /root/repo
-EEGAN_H_WIDE=0 timeout 120 python scratch/h_probe3.py 2>&1 | tail -3
-EEGAN_H_WIDE=1 timeout 120 python scratch/h_probe3.py 2>&1 | tail -3
+timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "gag" 2>&1 | tail -2
+echo "px quads"; timeout 120 python scratch/gag_time.py 2>&1 | tail -3

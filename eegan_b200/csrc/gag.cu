@@ -323,9 +323,9 @@ __global__ void __launch_bounds__(GF_NT, 3) gag_fwd_tma_kernel(const __grid_cons
         const float* xs = reinterpret_cast<const float*>(gsm + (base - smem_u32(gsm)) + st * GF_STAGE_BYTES);
 #pragma unroll 4
         for (int dd = 0; dd < GF_DC; ++dd) {
-            float xv[GF_PX];  // pixel u * 128 + tid of the tile: half u / 2 of the stage (two 256-pixel TMA boxes)
-#pragma unroll
-            for (int u = 0; u < GF_PX; ++u) xv[u] = xs[(u >> 1) * GF_DC * 256 + dd * 256 + (u & 1) * GF_NT + tid];
+            // the thread's quad = pixels 4 tid .. 4 tid + 3 of the tile: one 16-byte read (the stage holds two 256-pixel TMA boxes)
+            const float4 x4 = *reinterpret_cast<const float4*>(xs + (tid >> 6) * GF_DC * 256 + dd * 256 + 4 * (tid & 63));
+            const float xv[GF_PX] = {x4.x, x4.y, x4.z, x4.w};
             const float* kr = ks + (c * GF_DC + dd) * TP;
 #pragma unroll
             for (int t = 0; t < TP; t += 4) {
@@ -342,38 +342,40 @@ __global__ void __launch_bounds__(GF_NT, 3) gag_fwd_tma_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(empty(st));
     }
-    bool ok[GF_PX];
+    static_assert(GF_PX == 4, "the forward is written for pixel quads");
+    const int qb = q0 + GF_PX * tid;  // Q % 4 == 0: a quad is entirely inside the row or entirely outside
+    const bool ok = qb < Q;
     const uint32_t tail = (T < 32) ? (0xffffffffu << T) : 0u;  // columns t >= T never exist
     const uint32_t rowbase = (uint32_t)(((long long)b * Q) % B);
+    if (ok) {
 #pragma unroll
-    for (int u = 0; u < GF_PX; ++u) {
-        const int q = q0 + u * GF_NT + tid;
-        ok[u] = q < Q;
-        if (!ok[u]) continue;
-        uint32_t dead = tail;
-        if (mask) dead |= mbits[mask_mode == 0 ? (rowbase + (uint32_t)q) % (uint32_t)B : (uint32_t)b];
-        float mx = -INFINITY;
+        for (int u = 0; u < GF_PX; ++u) {
+            const int q = qb + u;
+            uint32_t dead = tail;
+            if (mask) dead |= mbits[mask_mode == 0 ? (rowbase + (uint32_t)q) % (uint32_t)B : (uint32_t)b];
+            float mx = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < TP; ++t) {
-            s[u][t] = ((dead >> t) & 1u) ? -INFINITY : s[u][t];
-            mx = fmaxf(mx, s[u][t]);
+            for (int t = 0; t < TP; ++t) {
+                s[u][t] = ((dead >> t) & 1u) ? -INFINITY : s[u][t];
+                mx = fmaxf(mx, s[u][t]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int t = 0; t < TP; ++t) {
+                // a fully masked row gives exp(-inf - -inf) = NaN exactly like the reference's softmax
+                const float e = (t < T) ? __expf(s[u][t] - mx) : 0.f;
+                s[u][t] = e;
+                sum += e;
+            }
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int t = 0; t < TP; ++t) s[u][t] *= inv;
         }
-        float sum = 0.f;
 #pragma unroll
-        for (int t = 0; t < TP; ++t) {
-            // a fully masked row gives exp(-inf - -inf) = NaN exactly like the reference's softmax
-            const float e = (t < T) ? __expf(s[u][t] - mx) : 0.f;
-            s[u][t] = e;
-            sum += e;
-        }
-        const float inv = 1.0f / sum;
-#pragma unroll
-        for (int t = 0; t < TP; ++t) {
-            s[u][t] *= inv;
-            if (t < T) attn[((size_t)b * T + t) * Q + q] = s[u][t];
-        }
+        for (int t = 0; t < TP; ++t)
+            if (t < T) *reinterpret_cast<float4*>(attn + ((size_t)b * T + t) * Q + qb) = make_float4(s[0][t], s[1][t], s[2][t], s[3][t]);
     }
-    float* ob = out + (size_t)b * idf * Q;
+    float* ob = out + (size_t)b * idf * Q + qb;
 #pragma unroll 2
     for (int d = 0; d < idf; ++d) {
         float acc[GF_PX];
@@ -390,9 +392,7 @@ __global__ void __launch_bounds__(GF_NT, 3) gag_fwd_tma_kernel(const __grid_cons
                 acc[u] = fmaf(v4.w, s[u][t + 3], acc[u]);
             }
         }
-#pragma unroll
-        for (int u = 0; u < GF_PX; ++u)
-            if (ok[u]) ob[(size_t)d * Q + q0 + u * GF_NT + tid] = acc[u];
+        if (ok) *reinterpret_cast<float4*>(ob + (size_t)d * Q) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
 }
 
@@ -721,7 +721,8 @@ extern "C" int eegan_gag_fwd(const float* x, const float* key, const float* valu
     if (g_gag_engine.load() == 1 && gag_tc_fwd_supported(x, B, idf, Q, T))  // tensor-core kernel (gag_tc.cu)
         return gag_tc_fwd_launch(x, key, value, mask, mask_mode, B, idf, Q, T, out, attn, st);
     const size_t tma_smem = (size_t)GF_NS * GF_STAGE_BYTES + (size_t)2 * idf * 32 * sizeof(float) + 128;
-    if (Q % 4 == 0 && idf % GF_DC == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && tma_smem <= 100 * 1024 && B <= 1024)
+    if (Q % 4 == 0 && idf % GF_DC == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(attn)) & 15) == 0 &&
+        tma_smem <= 100 * 1024 && B <= 1024)
         return GAG_DISPATCH(T, gag_fwd_tma_launch)(x, key, value, mask, mask_mode, B, idf, Q, T, out, attn, st);
     return GAG_DISPATCH(T, gag_fwd_launch)(x, key, value, mask, mask_mode, B, idf, Q, T, out, attn, st);
 }

@@ -191,10 +191,11 @@ def test_gag_tensor_core_forward_shapes(cuda_lib, B, idf, H, T):
                                               (2, 96, 12, 20, "both"), (2, 256, 8, 32, "both"), (3, 64, 16, 18, "out"),
                                               (3, 64, 16, 18, "attn"), (2, 48, 12, 7, "both"), (2, 32, 23, 18, "both")])
 def test_gag_backward_shapes(cuda_lib, B, idf, H, T, grads):
-    """The two-kernel backward (gag_bwd2.cu: per-pixel pass + per-channel key/value sums over pixel chunks) at its shape
-    edges — idf = 32 / 64 (4 / 2 pixel subgroups per CTA), 96 (one subgroup, 96 threads), 256, T = 5 … 32, Q not a
-    multiple of the chunk, a gradient on only one of the two outputs — and the one-kernel fallback it hands idf = 48 and
-    Q % 4 != 0 to, against the float64 oracle's autograd."""
+    """The two-kernel backward (gag_bwd2.cu: per-pixel-quad pass + key/value row sums with the lanes along the pixels) at its
+    shape edges — idf = 32 / 64 / 96 / 128 / 256 (1 … 8 channel sets of 8 channels per warp; 4 per warp once T > 20),
+    T = 5 … 32 (every TP instantiation), Q = 144 … 576 (partial 128-pixel rounds, several pixel chunks), a gradient on only
+    one of the two outputs — and the one-kernel fallback it hands idf = 48 and Q % 4 != 0 to, against the float64
+    oracle's autograd."""
     import eegan_b200 as E
     c = cases.gag_case(B, idf, H, T, seed=B * 7 + idf + T, masked=False)
     gen = cases._gen(5)

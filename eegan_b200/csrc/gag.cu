@@ -304,11 +304,15 @@ __global__ void __launch_bounds__(GF_NT, 3) gag_fwd_tma_kernel(const __grid_cons
     if (tid == 0)
         for (int c = 0; c < GF_NS - 1 && c < nchunks; ++c) issue(c);
 
-    float s[GF_PX][TP];
+    // scores as PAIRS of adjacent words: every multiply-add of the two contractions is a packed fma.rn.f32x2 (FFMA2) — a
+    // three-register FFMA issues every other cycle per scheduler on sm_100, the packed form does two per issue
+    // (each half is an exact fma, so the scores are bit-identical to the scalar form)
+    float2 s2[GF_PX][TP / 2];
+#define GF_S(u, t) (((t) & 1) ? s2[u][(t) >> 1].y : s2[u][(t) >> 1].x)
 #pragma unroll
     for (int u = 0; u < GF_PX; ++u)
 #pragma unroll
-        for (int t = 0; t < TP; ++t) s[u][t] = 0.f;
+        for (int t = 0; t < TP / 2; ++t) s2[u][t] = make_float2(0.f, 0.f);
 
     for (int c = 0; c < nchunks; ++c) {
         if (tid == 0) {
@@ -325,17 +329,16 @@ __global__ void __launch_bounds__(GF_NT, 3) gag_fwd_tma_kernel(const __grid_cons
         for (int dd = 0; dd < GF_DC; ++dd) {
             // the thread's quad = pixels 4 tid .. 4 tid + 3 of the tile: one 16-byte read (the stage holds two 256-pixel TMA boxes)
             const float4 x4 = *reinterpret_cast<const float4*>(xs + (tid >> 6) * GF_DC * 256 + dd * 256 + 4 * (tid & 63));
-            const float xv[GF_PX] = {x4.x, x4.y, x4.z, x4.w};
+            const float2 xd[GF_PX] = {make_float2(x4.x, x4.x), make_float2(x4.y, x4.y), make_float2(x4.z, x4.z), make_float2(x4.w, x4.w)};
             const float* kr = ks + (c * GF_DC + dd) * TP;
 #pragma unroll
             for (int t = 0; t < TP; t += 4) {
                 const float4 k4 = *reinterpret_cast<const float4*>(kr + t);
+                const float2 k01 = make_float2(k4.x, k4.y), k23 = make_float2(k4.z, k4.w);
 #pragma unroll
                 for (int u = 0; u < GF_PX; ++u) {
-                    s[u][t + 0] = fmaf(xv[u], k4.x, s[u][t + 0]);
-                    s[u][t + 1] = fmaf(xv[u], k4.y, s[u][t + 1]);
-                    s[u][t + 2] = fmaf(xv[u], k4.z, s[u][t + 2]);
-                    s[u][t + 3] = fmaf(xv[u], k4.w, s[u][t + 3]);
+                    s2[u][t / 2] = __ffma2_rn(xd[u], k01, s2[u][t / 2]);
+                    s2[u][t / 2 + 1] = __ffma2_rn(xd[u], k23, s2[u][t / 2 + 1]);
                 }
             }
         }
@@ -356,44 +359,44 @@ __global__ void __launch_bounds__(GF_NT, 3) gag_fwd_tma_kernel(const __grid_cons
             float mx = -INFINITY;
 #pragma unroll
             for (int t = 0; t < TP; ++t) {
-                s[u][t] = ((dead >> t) & 1u) ? -INFINITY : s[u][t];
-                mx = fmaxf(mx, s[u][t]);
+                GF_S(u, t) = ((dead >> t) & 1u) ? -INFINITY : GF_S(u, t);
+                mx = fmaxf(mx, GF_S(u, t));
             }
             float sum = 0.f;
 #pragma unroll
             for (int t = 0; t < TP; ++t) {
                 // a fully masked row gives exp(-inf - -inf) = NaN exactly like the reference's softmax
-                const float e = (t < T) ? __expf(s[u][t] - mx) : 0.f;
-                s[u][t] = e;
+                const float e = (t < T) ? __expf(GF_S(u, t) - mx) : 0.f;
+                GF_S(u, t) = e;
                 sum += e;
             }
             const float inv = 1.0f / sum;
 #pragma unroll
-            for (int t = 0; t < TP; ++t) s[u][t] *= inv;
+            for (int t = 0; t < TP; ++t) GF_S(u, t) *= inv;
         }
 #pragma unroll
         for (int t = 0; t < TP; ++t)
-            if (t < T) *reinterpret_cast<float4*>(attn + ((size_t)b * T + t) * Q + qb) = make_float4(s[0][t], s[1][t], s[2][t], s[3][t]);
+            if (t < T) *reinterpret_cast<float4*>(attn + ((size_t)b * T + t) * Q + qb) = make_float4(GF_S(0, t), GF_S(1, t), GF_S(2, t), GF_S(3, t));
     }
     float* ob = out + (size_t)b * idf * Q + qb;
 #pragma unroll 2
     for (int d = 0; d < idf; ++d) {
-        float acc[GF_PX];
+        float2 acc[GF_PX];  // (even words, odd words) partial sums
 #pragma unroll
-        for (int u = 0; u < GF_PX; ++u) acc[u] = 0.f;
+        for (int u = 0; u < GF_PX; ++u) acc[u] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < TP; t += 4) {
             const float4 v4 = *reinterpret_cast<const float4*>(vs + d * TP + t);
+            const float2 v01 = make_float2(v4.x, v4.y), v23 = make_float2(v4.z, v4.w);
 #pragma unroll
             for (int u = 0; u < GF_PX; ++u) {
-                acc[u] = fmaf(v4.x, s[u][t + 0], acc[u]);
-                acc[u] = fmaf(v4.y, s[u][t + 1], acc[u]);
-                acc[u] = fmaf(v4.z, s[u][t + 2], acc[u]);
-                acc[u] = fmaf(v4.w, s[u][t + 3], acc[u]);
+                acc[u] = __ffma2_rn(v01, s2[u][t / 2], acc[u]);
+                acc[u] = __ffma2_rn(v23, s2[u][t / 2 + 1], acc[u]);
             }
         }
-        if (ok) *reinterpret_cast<float4*>(ob + (size_t)d * Q) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (ok) *reinterpret_cast<float4*>(ob + (size_t)d * Q) = make_float4(acc[0].x + acc[0].y, acc[1].x + acc[1].y, acc[2].x + acc[2].y, acc[3].x + acc[3].y);
     }
+#undef GF_S
 }
 
 template <int TP>

@@ -465,8 +465,11 @@ def run_ours(args):
     elif world > 1 and not args.autograd:
         # N > 1: the autograd-free sharded step (same collectives and kernels, enqueued directly on static buffers);
         # --sharded-graph additionally captures it, collectives included, into one CUDA graph
-        from eegan_b200.sharded import ShardedWordsLossStep
-        sstep = ShardedWordsLossStep(B, D, HW, HW, T_MAX, dev, use_class_ids=True, words_grad=True, graph=args.sharded_graph)
+        from eegan_b200.sharded import OverlappedShardedWordsLossStep, ShardedWordsLossStep
+        if args.sharded_overlap:  # opt-in: local image block first, collectives hidden behind it (not yet measured on GPUs)
+            sstep = OverlappedShardedWordsLossStep(B, D, HW, HW, T_MAX, dev, use_class_ids=True, words_grad=True)
+        else:
+            sstep = ShardedWordsLossStep(B, D, HW, HW, T_MAX, dev, use_class_ids=True, words_grad=True, graph=args.sharded_graph)
         cls_d = cls.to(dev)
         sstep.load(img_d.detach(), words_d.detach(), lens_d, cls_d)
 
@@ -663,6 +666,8 @@ def main():
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of the CUDA-graph replay")
     ap.add_argument("--autograd", action="store_true", help="N>1: time the autograd route (sharded_words_loss + backward)")
     ap.add_argument("--sharded-graph", action="store_true", help="N>1: capture the sharded step, collectives included, into a CUDA graph")
+    ap.add_argument("--sharded-overlap", action="store_true",
+                    help="N>1: OverlappedShardedWordsLossStep (all-gather / reduce-scatter overlapped with the local image block)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -241,3 +241,163 @@ class ShardedWordsLossStep:
         self.load(img_features, words_emb, cap_lens, class_ids)
         self.run()
         return self._loss01[0], self._loss01[1], self.d_img, self.d_words
+
+
+class _CudaStepKernels:
+    """The library calls of the sharded step (C ABI on the current stream)."""
+
+    def __init__(self):
+        from . import _lib
+        self._lib = _lib
+
+    def workspace(self, Bi, Bc, D, R, Tm, device):
+        n = self._lib.lib().eegan_damsm_pair_workspace_bytes(Bi, Bc, D, R, Tm)
+        return torch.empty(n, dtype=torch.uint8, device=device)
+
+    def pair_fwd(self, img, words, lens32, Bi, Bc, D, R, Tm, m, att, ws):
+        _lib = self._lib
+        g1, g2, _ = gammas()
+        with torch.cuda.device(img.device):
+            _lib.check(_lib.lib().eegan_damsm_pair_fwd(_lib.ptr(img), _lib.ptr(words), _lib.ptr(lens32), Bi, Bc, D, R, Tm, g1, g2,
+                                                       _lib.ptr(m), _lib.ptr(att), 0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       "damsm_pair_fwd")
+
+    def pair_bwd(self, img, words, lens32, Bi, Bc, D, R, Tm, dm, d_img, d_words, ws):
+        _lib = self._lib
+        g1, g2, _ = gammas()
+        with torch.cuda.device(img.device):
+            _lib.check(_lib.lib().eegan_damsm_pair_bwd(_lib.ptr(img), _lib.ptr(words), _lib.ptr(lens32), Bi, Bc, D, R, Tm, g1, g2,
+                                                       _lib.ptr(dm), _lib.ptr(d_img), _lib.ptr(d_words), _lib.ptr(ws), ws.numel(),
+                                                       _lib.stream_ptr()), "damsm_pair_bwd")
+
+    def ce(self, m_all, cls_all, labels, gvec, Bt, sim, lse, loss01, dsim):
+        _lib = self._lib
+        L, p, st = _lib.lib(), _lib.ptr, _lib.stream_ptr()
+        _, _, g3 = gammas()
+        with torch.cuda.device(m_all.device):
+            _lib.check(L.eegan_pair_ce_fwd(p(m_all), g3, p(cls_all), p(labels), Bt, p(sim), p(loss01), p(lse), st), "pair_ce_fwd")
+            _lib.check(L.eegan_pair_ce_bwd(p(sim), p(lse), p(labels), p(gvec), g3, Bt, p(dsim), st), "pair_ce_bwd")
+
+
+class OverlappedShardedWordsLossStep:
+    """ShardedWordsLossStep with the two large collectives hidden behind the rank's LOCAL image block (opt-in; same contract:
+    ``loss0, loss1, d_img, d_words = step(img, words, cap_lens, class_ids)`` on static tensors, no autograd).
+
+    The rank's own images need no communication, so the grid is evaluated in two calls per direction:
+
+      fwd   all-gather(img) starts (async)   ||  pair grid of the LOCAL images x own captions (b x b pairs, attention maps)
+            wait                              ->  pair grid of the REMOTE images x own captions ((N-1) b x b pairs)
+            all-gather of the m blocks, two-way CE forward / backward on every rank (O(B^2), redundant)
+      bwd   backward of the REMOTE block: partial d_img for the other ranks' images, d_words part
+            reduce-scatter(d_img; own slot = zeros) starts (async)   ||  backward of the LOCAL block
+            wait -> d_img = scattered sum + local part;  d_words = remote part + local part
+
+    The gathered features live in a buffer ROTATED by the rank (slot s holds the images of rank (rank + s) % N), so that
+    the remote images are one contiguous array for the second call; rows of m / dm are permuted between rank order and
+    slot order by two small index_selects.  The collectives are the list forms of torch.distributed (NCCL on the GPU box;
+    gloo in tests/test_sharded_gloo.py, where ``kernels`` is an oracle-based stand-in for the C ABI calls).
+    The result equals the single-device full-batch result (summation order of d_words differs: two partial sums).
+    """
+
+    def __init__(self, local_batch, D, H, W, T_max, device, group=None, use_class_ids=True, words_grad=True, w0=1.0, w1=1.0,
+                 kernels=None, dtype=torch.float32):
+        self.group = group
+        self.world, self.rank = _world(group)
+        self.K = kernels if kernels is not None else _CudaStepKernels()
+        b, R, N = int(local_batch), H * W, self.world
+        Bt = b * N
+        dev = torch.device(device)
+        self.dims = (b, Bt, D, R, T_max)
+        f = dict(dtype=dtype, device=dev)
+        self.img = torch.zeros(b, D, H, W, **f)
+        self.words = torch.zeros(b, D, T_max, **f)
+        self.cap_lens32 = torch.full((b,), T_max, dtype=torch.int32, device=dev)
+        self.class_ids = torch.arange(self.rank * b, (self.rank + 1) * b, dtype=torch.int64, device=dev) if use_class_ids else None
+        self._cls_all = torch.zeros(Bt, dtype=torch.int64, device=dev) if use_class_ids else None
+        self._labels = torch.arange(Bt, dtype=torch.int64, device=dev)
+        self._img_rot = torch.zeros(Bt, D, R, **f)            # slot s = images of rank (rank + s) % N; slot 0 is not read
+        self._ws_loc = self.K.workspace(b, b, D, R, T_max, dev)
+        self._ws_rem = self.K.workspace(Bt - b, b, D, R, T_max, dev) if N > 1 else None
+        self._m_rot = torch.empty(Bt, b, **f)                 # rows in slot order
+        self._m_block = torch.empty(Bt, b, **f)               # rows in rank order
+        self._m_parts = torch.empty(N, Bt, b, **f)
+        self._m_all = torch.empty(Bt, Bt, **f)
+        self._sim = torch.empty(Bt, Bt, **f)
+        self._lse = torch.empty(2, Bt, **f)
+        self._loss01 = torch.zeros(2, **f)
+        self._gvec = torch.tensor([float(w0), float(w1)], **f)
+        self._dsim = torch.empty(Bt, Bt, **f)
+        self._dm_block = torch.empty(Bt, b, **f)
+        self._dm_rot = torch.empty(Bt, b, **f)
+        self._d_img_rot = torch.zeros(Bt, D, R, **f)          # slots 1.. = partial gradients for the other ranks' images
+        self._zero = torch.zeros(b, D, R, **f)                # the rank's own slot of the reduce-scatter
+        self._rs_out = torch.empty(b, D, R, **f)
+        self._d_img_loc = torch.empty(b, D, R, **f)
+        self._dw_loc = torch.zeros(b, D, T_max, **f) if words_grad else None
+        self._dw_rem = torch.zeros(b, D, T_max, **f) if words_grad else None
+        self.att = torch.empty(b, T_max, R, **f)
+        self.d_img = torch.zeros(b, D, H, W, **f)
+        self.d_words = torch.zeros(b, D, T_max, **f) if words_grad else None
+        # rank order <-> slot order of the Bt image rows
+        slot_of_rank = [(r - self.rank) % N for r in range(N)]
+        rows = torch.arange(b)
+        self._to_rank_order = torch.cat([slot_of_rank[r] * b + rows for r in range(N)]).to(dev)      # m_block = m_rot[idx]
+        self._to_slot_order = torch.cat([((self.rank + s) % N) * b + rows for s in range(N)]).to(dev)  # dm_rot = dm_block[idx]
+        self._slot_of_rank = slot_of_rank
+
+    def _slot(self, buf, s):
+        b = self.dims[0]
+        return buf[s * b:(s + 1) * b]
+
+    def run(self):
+        b, Bt, D, R, Tm = self.dims
+        N, rank, grp, K = self.world, self.rank, self.group, self.K
+        img_loc = self.img.view(b, D, R)
+        h = None
+        if N > 1:
+            outs = [self._slot(self._img_rot, self._slot_of_rank[r]) for r in range(N)]
+            h = dist.all_gather(outs, img_loc, group=grp, async_op=True)
+            if self._cls_all is not None:
+                dist.all_gather_into_tensor(self._cls_all, self.class_ids, group=grp)
+        elif self._cls_all is not None:
+            self._cls_all.copy_(self.class_ids)
+        K.pair_fwd(img_loc, self.words, self.cap_lens32, b, b, D, R, Tm, self._m_rot[:b], self.att, self._ws_loc)
+        if N > 1:
+            h.wait()
+            K.pair_fwd(self._img_rot[b:], self.words, self.cap_lens32, Bt - b, b, D, R, Tm, self._m_rot[b:], None, self._ws_rem)
+            torch.index_select(self._m_rot, 0, self._to_rank_order, out=self._m_block)
+            dist.all_gather_into_tensor(self._m_parts.view(N * Bt, b), self._m_block, group=grp)
+            self._m_all.view(Bt, N, b).copy_(self._m_parts.permute(1, 0, 2))
+        else:
+            self._m_all.copy_(self._m_rot)
+        K.ce(self._m_all, self._cls_all, self._labels, self._gvec, Bt, self._sim, self._lse, self._loss01, self._dsim)
+        self._dm_block.copy_(self._dsim[:, rank * b:(rank + 1) * b])
+        torch.index_select(self._dm_block, 0, self._to_slot_order, out=self._dm_rot)
+        h2 = None
+        if N > 1:
+            K.pair_bwd(self._img_rot[b:], self.words, self.cap_lens32, Bt - b, b, D, R, Tm, self._dm_rot[b:], self._d_img_rot[b:],
+                       self._dw_rem, self._ws_rem)
+            ins = [self._zero if r == rank else self._slot(self._d_img_rot, self._slot_of_rank[r]) for r in range(N)]
+            h2 = dist.reduce_scatter(self._rs_out, ins, op=dist.ReduceOp.SUM, group=grp, async_op=True)
+        K.pair_bwd(img_loc, self.words, self.cap_lens32, b, b, D, R, Tm, self._dm_rot[:b], self._d_img_loc, self._dw_loc, self._ws_loc)
+        if N > 1:
+            h2.wait()
+            torch.add(self._rs_out, self._d_img_loc, out=self.d_img.view(b, D, R))
+            if self.d_words is not None:
+                torch.add(self._dw_loc, self._dw_rem, out=self.d_words)
+        else:
+            self.d_img.view(b, D, R).copy_(self._d_img_loc)
+            if self.d_words is not None:
+                self.d_words.copy_(self._dw_loc)
+
+    def load(self, img, words, cap_lens, class_ids=None):
+        self.img.copy_(img.reshape(self.img.shape), non_blocking=True)
+        self.words.copy_(words, non_blocking=True)
+        self.cap_lens32.copy_(torch.as_tensor(cap_lens).reshape(-1), non_blocking=True)
+        if self.class_ids is not None and class_ids is not None:
+            self.class_ids.copy_(torch.as_tensor(class_ids).reshape(-1), non_blocking=True)
+
+    def __call__(self, img_features, words_emb, cap_lens, class_ids=None):
+        self.load(img_features, words_emb, cap_lens, class_ids)
+        self.run()
+        return self._loss01[0], self._loss01[1], self.d_img, self.d_words

@@ -58,6 +58,16 @@ def main():
             q0, q1, qdi, qdw = sstep(c["img"][sl].to(dev), c["words"][sl].to(dev), c["cap_lens"][sl].to(dev), c["class_ids"][sl].to(dev))
         assert abs(q0.item() - f0.item()) <= 2e-6 * max(1.0, abs(f0.item())) and abs(q1.item() - f1.item()) <= 2e-6 * max(1.0, abs(f1.item()))
         assert relmax(qdi, img.grad[sl]) <= 2e-5 and relmax(qdw, words.grad[sl]) <= 2e-5, (use_graph, relmax(qdi, img.grad[sl]))
+    if os.environ.get("EEGAN_CHECK_SHARDED_OVERLAP") == "1":  # the opt-in overlapped step (sharded.py)
+        from eegan_b200.sharded import OverlappedShardedWordsLossStep
+        ostep = OverlappedShardedWordsLossStep(b, 256, 17, 17, T, dev, w0=1.0, w1=2.0)
+        for _ in range(2):
+            q0, q1, qdi, qdw = ostep(c["img"][sl].to(dev), c["words"][sl].to(dev), c["cap_lens"][sl].to(dev), c["class_ids"][sl].to(dev))
+        assert abs(q0.item() - f0.item()) <= 2e-6 * max(1.0, abs(f0.item())) and abs(q1.item() - f1.item()) <= 2e-6 * max(1.0, abs(f1.item()))
+        assert relmax(qdi, img.grad[sl]) <= 2e-5 and relmax(qdw, words.grad[sl]) <= 2e-5, ("overlap", relmax(qdi, img.grad[sl]))
+        for i in range(b):
+            Ti = int(c["cap_lens"][sl][i])
+            assert float((ostep.att[i, :Ti].reshape(fatt[sl][i].shape) - fatt[sl][i]).abs().max()) <= 1e-7
     # sentence loss
     sc = cases.sent_case(B, seed=12)
     cnn = sc["cnn"].to(dev).requires_grad_()

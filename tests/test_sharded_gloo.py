@@ -154,3 +154,82 @@ def test_world2_sharded_equals_full_batch():
         assert r["loss"] < 1e-12 and r["dimg"] < 1e-12 and r["dwords"] < 1e-12 and r["att"] < 1e-14, r
         assert r["sent"] < 1e-12 and r["dcnn"] < 1e-12 and r["drnn"] < 1e-12, r
         assert r["bn_y"] < 1e-5 and r["bn_dx"] < 1e-4 and r["bn_rm"] < 1e-6 and r["bn_rv"] < 1e-5, r
+
+
+class OracleStepKernels:
+    """CPU stand-in for the C ABI calls of eegan_b200.sharded.OverlappedShardedWordsLossStep (float64 oracle)."""
+
+    def workspace(self, Bi, Bc, D, R, Tm, device):
+        return None
+
+    def pair_fwd(self, img, words, lens32, Bi, Bc, D, R, Tm, m, att, ws):
+        from oracle import damsm_oracle as O
+        t = O.dense_pair_terms(img, words, lens32.long())
+        m.copy_(t["m"])
+        if att is not None:
+            for i in range(Bc):
+                att[i] = t["a"][i, i]
+
+    def pair_bwd(self, img, words, lens32, Bi, Bc, D, R, Tm, dm, d_img, d_words, ws):
+        from oracle import damsm_oracle as O
+        di, dw = O.dense_words_backward(img, words, lens32.long(), dm)
+        d_img.copy_(di)
+        if d_words is not None:
+            d_words.copy_(dw)
+
+    def ce(self, m_all, cls_all, labels, gvec, Bt, sim, lse, loss01, dsim):
+        from eegan_b200.config import gammas
+        from oracle import damsm_oracle as O
+        g3 = gammas()[2]
+        s = m_all * g3
+        mask = O.class_mask(cls_all, Bt) if cls_all is not None else None
+        if mask is not None:
+            s = s.masked_fill(mask, float("-inf"))
+        l0, l1 = O._two_way_ce(s, labels)
+        loss01[0], loss01[1] = l0, l1
+        dsim.copy_(O.ce_pair_grad(s, labels, float(gvec[0]), float(gvec[1])) * g3)
+
+
+def _overlap_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    try:
+        from eegan_b200.sharded import OverlappedShardedWordsLossStep
+        from oracle import cases
+        from oracle import damsm_oracle as O
+        b, T, D, H = 3, 6, 16, 3
+        B = b * world
+        c = cases.words_case(B, T, D=D, H=H, seed=33, min_len=2)
+        sl = slice(rank * b, (rank + 1) * b)
+        step = OverlappedShardedWordsLossStep(b, D, H, H, T, "cpu", w0=1.0, w1=2.0, kernels=OracleStepKernels(), dtype=torch.float64)
+        res = {}
+        for it in range(2):  # twice: the static buffers (zero slot, rotated gradients) must survive a step
+            l0, l1, d_img, d_words = step(c["img"][sl].double(), c["words"][sl].double(), c["cap_lens"][sl], c["class_ids"][sl])
+            fi = c["img"].double().requires_grad_()
+            fw = c["words"].double().requires_grad_()
+            f0, f1, fatt, _ = O.dense_words_loss(fi, fw, c["labels"], c["cap_lens"], c["class_ids"])
+            (f0 + 2 * f1).backward()
+            lens = c["cap_lens"][sl].tolist()
+            res["it%d" % it] = dict(
+                loss=abs(float(l0 - f0.detach())) + abs(float(l1 - f1.detach())),
+                dimg=float((d_img - fi.grad[sl]).abs().max()), dwords=float((d_words - fw.grad[sl]).abs().max()),
+                att=max(float((step.att[i, :lens[i]].reshape(1, lens[i], H, H) - fatt[rank * b + i].detach()).abs().max()) for i in range(b)))
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_overlapped_sharded_step_equals_full_batch(world):
+    """Host logic of the opt-in overlapped step: rank-rotated gather buffer, local / remote image blocks, row permutations
+    of m / dm, reduce-scatter with a zero own slot, partial d_words — world 3 puts a rank in the middle of the rotation."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_overlap_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        for it in ("it0", "it1"):
+            r = out[rank][it]
+            assert r["loss"] < 1e-12 and r["dimg"] < 1e-12 and r["dwords"] < 1e-12 and r["att"] < 1e-14, (rank, it, r)

@@ -250,14 +250,15 @@ __global__ void __launch_bounds__(GAG_BT) gag_bwd_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------
-// TMA-fed forward: the x tile is streamed by the TMA engine in [16 channels][512 pixels] chunks
-// through a 4-stage mbarrier ring, so the compute threads never wait on a global load; key /
-// value stay in shared memory.  Needs Q % 4 == 0, idf % 16 == 0, 16-byte aligned x.
+// TMA-fed forward: the x tile is streamed by the TMA engine in [8 channels][512 pixels] chunks
+// (two 256-pixel boxes) through a 3-stage mbarrier ring, so the compute threads never wait on a
+// global load; key / value stay in shared memory; a thread owns four consecutive pixels and both
+// contractions run on packed fma.rn.f32x2.  Needs Q % 4 == 0, idf % 8 == 0, 16-byte aligned x / out / attn.
 // ---------------------------------------------------------------------------------------
 constexpr int GF_TILE = 512, GF_DC = 8, GF_NS = 3;
 constexpr int GF_NT = 128, GF_PX = GF_TILE / GF_NT;  // a thread owns 4 pixels: every key / value float4 (a broadcast LDS.128 holds the
                                                      // shared-memory pipe for four cycles) feeds 16 FMA instead of 8
-constexpr int GF_STAGE_BYTES = GF_DC * GF_TILE * 4;  // 32 KB
+constexpr int GF_STAGE_BYTES = GF_DC * GF_TILE * 4;  // 16 KB
 
 template <int TP>
 __global__ void __launch_bounds__(GF_NT, 3) gag_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ key,

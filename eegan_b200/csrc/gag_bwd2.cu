@@ -4,18 +4,19 @@
 // its four contractions takes one operand from shared memory, and the d_key / d_value sums over pixels need a CTA-wide
 // reduction per 8-channel chunk.  Here the work is split so that every inner loop is FMA-bound out of registers:
 //
-//   kernel 1 (thread = PX pixels)   dp[t] = sum_d d_out[d,q] v[d,t] + d_attn[t,q];  ds = p (dp - sum_t p dp)
+//   kernel 1 (thread = 4 consecutive pixels)   dp[t] = sum_d d_out[d,q] v[d,t] + d_attn[t,q];  ds = p (dp - sum_t p dp)
 //                                   d_x[d,q] = sum_t ds[t] key[d,t];  ds[t,q] -> workspace
-//                                   key / value rows are broadcast float4 reads shared by the thread's PX pixels.
+//                                   key / value rows are broadcast float4 reads shared by the thread's four pixels; every
+//                                   global access is a 16-byte one.
 //   kernel 2, launched twice        d_key[d,:] = sum_q x[d,q] ds[:,q]   and   d_value[d,:] = sum_q d_out[d,q] p[:,q]
-//   (thread = 4 channels)           over one chunk of pixels: the thread keeps its 4 x TP sums in registers for the whole
-//                                   chunk, reads its four rows 8 pixels at a time (16-byte loads) and the ds / p rows of
-//                                   those pixels as broadcast float4 from shared memory: 16 FMA per 16-byte shared load
-//                                   (a broadcast LDS.128 still occupies the shared-memory pipe for four cycles, so one
-//                                   row per thread — 4 FMA per load — ran at 14 % of the FMA pipe).
+//   (gag_bwd_rowsum_px_kernel)      over one chunk of pixels, a warp = 8 channels (4 once T > 20), lanes along the pixels:
+//                                   both operands arrive by 16-byte cp.async through a 4-deep shared-memory ring as
+//                                   contiguous 512-byte segments, the 8 x TP sums stay in registers for the whole chunk.
+//                                   (gag_bwd_rowsum_kernel, the first mapping — lanes on 32 channel groups, i.e. 32 rows
+//                                   per 16-byte load — is kept behind EEGAN_GAG_ROWSUM=0: 1.8x slower.)
 //   kernel 3                        fixed-order sum of the per-chunk partials (no atomics, nothing to zero).
 //
-// Extra HBM traffic against the one-kernel form: ds written and read once (2 T floats per pixel) and d_out read twice.
+// Extra HBM traffic against the one-kernel form: ds written and read once (2 T floats per pixel), d_out and attn read twice.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -18,6 +18,19 @@ bool pdl_enabled() {
     }();
     return on;
 }
+int num_sms_current() {
+    static std::atomic<int> cache[EEGAN_MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    if (dev < EEGAN_MAX_DEVICES) {
+        const int c = cache[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int v = 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    if (dev < EEGAN_MAX_DEVICES) cache[dev].store(v, std::memory_order_relaxed);
+    return v;
+}
 }  // namespace eegan
 
 extern "C" int eegan_abi_version(void) { return EEGAN_B200_ABI_VERSION; }

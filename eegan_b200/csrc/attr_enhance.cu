@@ -217,13 +217,9 @@ static int ae_check(int B, int D, int Tk) {
     return EEGAN_OK;
 }
 static int ae_smem_attr() {
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(ae_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(ae_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        done = true;
-    }
-    return 0;
+    static SmemGrant gf, gb;
+    if (int rc = grant_dyn_smem(ae_attn_fwd_kernel, (size_t)200 * 1024, gf, "attr_enhance fwd")) return rc;
+    return grant_dyn_smem(ae_attn_bwd_kernel, (size_t)200 * 1024, gb, "attr_enhance bwd");
 }
 
 }  // namespace eegan
@@ -245,7 +241,8 @@ extern "C" int eegan_attr_enhance_fwd(const float* sent, const float* attrs, con
     EEGAN_REQUIRE(sent && (attrs || attr_num == 0) && Wq && bq && Wk && bk && Wv && bv && out && qkv && combine,
                   "attr_enhance fwd: null pointer (qkv [3,B*Tk,D] and combine [B*Tk,D] are required scratch / stash)");
     cudaStream_t st = (cudaStream_t)stream;
-    ae_smem_attr();
+    rc = ae_smem_attr();
+    if (rc) return rc;
     const int rows = B * Tk;
     ae_pack_kernel<<<(unsigned)(((long long)rows * D + 255) / 256), 256, 0, st>>>(sent, attrs, B, D, Tk, combine);
     EEGAN_LAUNCH_CHECK("attr_enhance pack");
@@ -270,7 +267,8 @@ extern "C" int eegan_attr_enhance_bwd(const float* d_attn_sent, const float* d_a
     if (rc) return rc;
     EEGAN_REQUIRE(combine && qkv && p && Wq && Wk && Wv && g && dtok, "attr_enhance bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    ae_smem_attr();
+    rc = ae_smem_attr();
+    if (rc) return rc;
     const int rows = B * Tk;
     const size_t plane = (size_t)rows * D;
     ae_attn_bwd_kernel<<<B, 256, (size_t)(4 * Tk * D + 2 * Tk * Tk) * sizeof(float), st>>>(d_attn_sent, d_attn_attrs, qkv, p, B, D, Tk,

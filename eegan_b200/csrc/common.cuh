@@ -1,6 +1,7 @@
 // Shared helpers for libeegan_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -39,6 +40,33 @@ inline int check_launch(const char* what) {
 void prof_mark(int stage, cudaStream_t st);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (kernel, device) pair, so the
+// "largest size granted so far" is kept PER DEVICE (one zero-initialised SmemGrant per launch site): a second GPU
+// driven from the same process (nn.DataParallel's per-device threads) gets its own opt-in.  A race between two host
+// threads only repeats the idempotent call.
+constexpr int EEGAN_MAX_DEVICES = 64;
+struct SmemGrant {
+    std::atomic<size_t> per_dev[EEGAN_MAX_DEVICES];
+};
+template <typename K>
+inline int grant_dyn_smem(K kern, size_t bytes, SmemGrant& g, const char* what) {
+    if (bytes <= 48 * 1024) return EEGAN_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    const bool tracked = dev < EEGAN_MAX_DEVICES;
+    if (tracked && bytes <= g.per_dev[dev].load(std::memory_order_relaxed)) return EEGAN_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        set_error("%s: shared-memory opt-in of %zu bytes failed: %s", what, bytes, cudaGetErrorString(e));
+        return EEGAN_ERR_CUDA;
+    }
+    if (tracked) g.per_dev[dev].store(bytes, std::memory_order_relaxed);
+    return EEGAN_OK;
+}
+
+// SM count of the CURRENT device (cached per device)
+int num_sms_current();
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------
 // A kernel launched through launch_pdl() may become resident while the previous kernel of the stream is still

@@ -407,12 +407,8 @@ static int gag_fwd_tma_launch(const float* x, const float* key, const float* val
     int rc = make_tmap_2d(&tmx, x, (unsigned long long)B * idf, (unsigned long long)Q, (unsigned long long)Q, 256, GF_DC);
     if (rc) return rc;
     const size_t smem = (size_t)GF_NS * GF_STAGE_BYTES + (size_t)2 * idf * TP * sizeof(float) + 128;
-    static std::atomic<size_t> granted{48 * 1024};
-    if (smem > granted.load()) {
-        cudaError_t e = cudaFuncSetAttribute(gag_fwd_tma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("gag fwd smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-        granted.store(smem);
-    }
+    static SmemGrant grant;
+    if (int rc2 = grant_dyn_smem(gag_fwd_tma_kernel<TP>, smem, grant, "gag fwd")) return rc2;
     gag_fwd_tma_kernel<TP><<<dim3((Q + GF_TILE - 1) / GF_TILE, B), GF_NT, smem, st>>>(tmx, key, value, mask, mask_mode, B, idf, Q,
                                                                                      T, out, attn);
     return check_launch("gag fwd (tma)");
@@ -641,12 +637,8 @@ static int gag_bwd_tma_launch(const float* x, const float* key, const float* val
     rc = make_tmap_2d(&tmg, d_out, (unsigned long long)B * idf, (unsigned long long)Q, (unsigned long long)Q, 32, GB_DC, true);
     if (rc) return rc;
     const size_t smem = (size_t)GB_NS * GB_STAGE_BYTES + ((size_t)4 * idf * TP + 2 * GB_TILE * TP + 2 * 8 * 16 * TP) * sizeof(float) + 1024;
-    static std::atomic<size_t> granted{48 * 1024};
-    if (smem > granted.load()) {
-        cudaError_t e = cudaFuncSetAttribute(gag_bwd_tma_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("gag bwd smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-        granted.store(smem);
-    }
+    static SmemGrant grant;
+    if (int rc2 = grant_dyn_smem(gag_bwd_tma_kernel<TP>, smem, grant, "gag bwd")) return rc2;
     cudaMemsetAsync(d_key, 0, (size_t)B * idf * T * sizeof(float), st);
     cudaMemsetAsync(d_value, 0, (size_t)B * idf * T * sizeof(float), st);
     const int ntiles = (Q + GB_TILE - 1) / GB_TILE;

@@ -343,12 +343,8 @@ int gag_tc_fwd_launch(const float* x, const float* key, const float* value, cons
     a.xs = (int)((220 * 1024 - fixed) / TC_TILE_BYTES);
     if (a.xs > GT_XS_MAX) a.xs = GT_XS_MAX;
     const size_t smem = (size_t)a.xs * TC_TILE_BYTES + fixed;
-    static size_t granted = 0;
-    if (smem > granted) {
-        cudaError_t e = cudaFuncSetAttribute(gag_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("gag tc fwd smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-        granted = smem;
-    }
+    static SmemGrant grant;
+    if (int rc = grant_dyn_smem(gag_tc_fwd_kernel, smem, grant, "gag tc fwd")) return rc;
     const int tiles_b = (Q + GT_TILE - 1) / GT_TILE;
     int per_sample = B <= 148 ? 148 / B : 1;
     if (per_sample > tiles_b) per_sample = tiles_b;

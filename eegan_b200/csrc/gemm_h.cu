@@ -5,6 +5,14 @@
 #include "ptx.cuh"
 #include "tc_device.cuh"
 
+// Work-skipping timing switches (EEGAN_H_DBG) exist only in builds made with -DEEGAN_DEBUG_SWITCHES; the shipped
+// library compiles them out (the epilogue code below sees the constant 0) and reads no environment variable per launch.
+#ifdef EEGAN_DEBUG_SWITCHES
+#define H_DBG(p) ((p).dbg)
+#else
+#define H_DBG(p) 0
+#endif
+
 namespace eegan {
 
 // staging row pitch of the attention epilogues (floats): even, so that the read-out takes a lane's two adjacent
@@ -28,7 +36,7 @@ struct HArgs {
     const float* inv_a[2];
     const float* inv_b[2];
     HAttnEpi attn;
-    int dbg;  // timing experiments only (EEGAN_H_DBG): 1 read-out without global stores, 2 no read-out, 4 no caption phase
+    int dbg;  // timing experiments only (-DEEGAN_DEBUG_SWITCHES builds, EEGAN_H_DBG): 1 read-out without global stores, 2 no read-out, 4 no caption phase
 };
 
 template <int EPI, bool DUAL, int BN = H_BN, int NSO = 0>
@@ -275,7 +283,7 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
             const int T = __shfl_sync(0xffffffffu, myT, ci);
             if (T <= 0) continue;
             const int cl = __shfl_sync(0xffffffffu, myC, ci);
-            if (!(p.dbg & 4)) h_attn_caption<EPI>(t.tacc + (uint32_t)(64 * h + cl), T, my_row + (uint32_t)cl * 4u, t.czs + (uint32_t)cl * 4u, e.g1, inv0);
+            if (!(H_DBG(p) & 4)) h_attn_caption<EPI>(t.tacc + (uint32_t)(64 * h + cl), T, my_row + (uint32_t)cl * 4u, t.czs + (uint32_t)cl * 4u, e.g1, inv0);
         }
     }
     if (!waited) {
@@ -290,8 +298,8 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
     // read-out: region rows, coalesced; a lane owns the adjacent columns 2 lane, 2 lane + 1 of the bin: one 8-byte P store and
     // one 4-byte store per half array and row.  Padding columns of the bin hold P = 0, hence finite E' / dS' = 0 — every
     // consumer multiplies them by zero rows (GEMM4) or never reads the outputs they feed (GEMM2 / GEMM5 rows, Zpart).
-    if (p.dbg & 2) return;
-    const bool nostore = p.dbg & 1;
+    if (H_DBG(p) & 2) return;
+    const bool nostore = H_DBG(p) & 1;
     const uint32_t rd0 = t.stage + (uint32_t)(2 * lane) * 4u;
     const long long o0 = (long long)row0 * p.ldc + col0 + 2 * lane;
     uint32_t* hp = reinterpret_cast<uint32_t*>(Hz + o0);
@@ -613,24 +621,13 @@ static int h_make_map(CUtensorMap* m, const __half* ptr, const HOperand& o, bool
     return EEGAN_OK;
 }
 
-static int h_num_sms() {
-    static int n = [] {
-        int dev = 0, v = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        return v > 0 ? v : 148;
-    }();
-    return n;
-}
+static int h_num_sms() { return num_sms_current(); }
 
 template <int EPI, bool DUAL, int BN = H_BN, int NSO = 0>
 static int h_launch_t(const HMaps& maps, const HArgs& a, unsigned grid, cudaStream_t st) {
     using Cfg = HCfg<EPI, DUAL, BN, NSO>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(h_gemm_kernel<EPI, DUAL, BN, NSO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-        if (e != cudaSuccess) { set_error("h gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-        attr_set = true;
-    }
+    static SmemGrant grant;
+    if (int rc = grant_dyn_smem(h_gemm_kernel<EPI, DUAL, BN, NSO>, (size_t)Cfg::kSmem, grant, "h gemm")) return rc;
     cudaError_t e = launch_pdl(h_gemm_kernel<EPI, DUAL, BN, NSO>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmem, st, maps, a);
     if (e != cudaSuccess) { set_error("h gemm launch: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
     return check_launch("h gemm");
@@ -666,7 +663,9 @@ int h_gemm_launch(const HGemm& g, cudaStream_t st) {
     a.C = g.C; a.ldc = g.ldc; a.bC = g.bC; a.M = g.M; a.N = g.N; a.dynM = g.dynM; a.dynN = g.dynN; a.dynK = g.dynK;
     a.attn = g.attn;
     a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total; a.batch = g.batch;
+#ifdef EEGAN_DEBUG_SWITCHES
     if (const char* e = getenv("EEGAN_H_DBG")) a.dbg = atoi(e);
+#endif
     const long long tiles = (long long)((g.N + bn - 1) / bn) * ((g.M + H_BM - 1) / H_BM) * g.batch;
     const unsigned grid = (unsigned)(tiles < h_num_sms() ? tiles : h_num_sms());
     if (g.epi != TC_EPI_PLAIN) {
@@ -685,10 +684,12 @@ int h_gemm_launch(const HGemm& g, cudaStream_t st) {
     EEGAN_REQUIRE(g.C, "h gemm: no output");
     if (g.nseg == 2) return h_launch_t<TC_EPI_PLAIN, true>(maps, a, grid, st);
     if (bn == 256) return h_launch_t<TC_EPI_PLAIN, false, 256>(maps, a, grid, st);
-    static const int nso = [] { const char* e = getenv("EEGAN_H_STAGES"); return e ? atoi(e) : 0; }();  // microbenchmarks only
+#ifdef EEGAN_DEBUG_SWITCHES
+    static const int nso = [] { const char* e = getenv("EEGAN_H_STAGES"); return e ? atoi(e) : 0; }();  // stage-count probe
     if (nso == 2) return h_launch_t<TC_EPI_PLAIN, false, H_BN, 2>(maps, a, grid, st);
     if (nso == 3) return h_launch_t<TC_EPI_PLAIN, false, H_BN, 3>(maps, a, grid, st);
     if (nso == 4) return h_launch_t<TC_EPI_PLAIN, false, H_BN, 4>(maps, a, grid, st);
+#endif
     return h_launch_t<TC_EPI_PLAIN, false>(maps, a, grid, st);
 }
 

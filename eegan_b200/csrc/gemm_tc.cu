@@ -332,23 +332,12 @@ int make_tmap_2d(CUtensorMap* m, const float* ptr, unsigned long long rows, unsi
     return EEGAN_OK;
 }
 
-static int num_sms() {
-    static int n = [] {
-        int dev = 0, v = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        return v > 0 ? v : 148;
-    }();
-    return n;
-}
+static int num_sms() { return num_sms_current(); }
 
 template <bool A_K, bool B_K, int EPI>
 static int launch_t(const TcMaps& maps, const TcArgs& a, dim3 grid, cudaStream_t st) {
-    static bool attr_set = false;  // idempotent; a race only repeats the call
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<A_K, B_K, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("tc gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-        attr_set = true;
-    }
+    static SmemGrant grant;
+    if (int rc = grant_dyn_smem(tc_gemm_kernel<A_K, B_K, EPI>, (size_t)TC_SMEM_BYTES, grant, "tc gemm")) return rc;
     tc_gemm_kernel<A_K, B_K, EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, a);
     return check_launch("tc gemm");
 }
@@ -389,10 +378,12 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
     a.nseg = g.nseg; a.nred = g.nred > 0 ? g.nred : 1; a.red_total = g.red_total; a.batch = g.batch;
     a.mn_lbo = 4096 >> 4; a.mn_sbo = 512 >> 4;
     a.trunc_hi = 1;
+#ifdef EEGAN_DEBUG_SWITCHES  // descriptor / work-skipping probes: never in the shipped library
     if (const char* e = getenv("EEGAN_TS_DBG")) a.dbg = atoi(e);
     if (const char* e = getenv("EEGAN_TC_TRUNC_HI")) a.trunc_hi = atoi(e);
     if (const char* e = getenv("EEGAN_TC_MN_LBO")) a.mn_lbo = (uint32_t)atoi(e);
     if (const char* e = getenv("EEGAN_TC_MN_SBO")) a.mn_sbo = (uint32_t)atoi(e);
+#endif
     const long long tiles = (long long)((g.N + TC_BN - 1) / TC_BN) * ((g.M + TC_BM - 1) / TC_BM) * g.batch;
     dim3 grid((unsigned)(tiles < num_sms() ? tiles : num_sms()));
     const bool ak = g.A[0].kmajor, bk = g.B[0].kmajor;

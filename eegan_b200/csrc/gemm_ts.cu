@@ -20,6 +20,12 @@
 #include "ptx.cuh"
 #include "tc_device.cuh"
 
+#ifdef EEGAN_DEBUG_SWITCHES  // work-skipping timing switches: compiled out of the shipped library
+#define TS_DBG(p) ((p).dbg)
+#else
+#define TS_DBG(p) 0
+#endif
+
 namespace eegan {
 
 // The attention epilogues are the long pole of the K = D contractions (exp-heavy per-region work on a
@@ -151,7 +157,7 @@ ts_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
                         const uint64_t dbh = umma_desc(b_hi, true, ks, 0, 0), dbl = umma_desc(b_lo, true, ks, 0, 0);
                         tc_mma_tf32_ts(tmem_d, a_lo + ks * 8, dbh, idesc, (k > 0 || ks > 0) ? 1u : 0u);
-                        if (p.dbg & 1) continue;
+                        if (TS_DBG(p) & 1) continue;
                         tc_mma_tf32_ts(tmem_d, a_hi + ks * 8, dbl, idesc, 1u);
                         tc_mma_tf32_ts(tmem_d, a_hi + ks * 8, dbh, idesc, 1u);
                     }
@@ -171,7 +177,7 @@ ts_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
                 const int s = it % TS_STAGES, ph = (it / TS_STAGES) & 1;
                 mbar_wait(full(s), ph);
                 const uint32_t sA = base + s * TS_STAGE_BYTES + my_m;
-                if (p.dbg & 2) {
+                if (TS_DBG(p) & 2) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(conv(s));
                     continue;
@@ -203,7 +209,7 @@ ts_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
                 const int s = it % TS_STAGES, ph = (it / TS_STAGES) & 1;
                 const int seg = (k % kbt) >= kb0 ? 1 : 0;
                 mbar_wait(full(s), ph);
-                if (!p.b_pre[seg] && !(p.dbg & 4)) {
+                if (!p.b_pre[seg] && !(TS_DBG(p) & 4)) {
                     const uint32_t hi = base + s * TS_STAGE_BYTES + TC_TILE_BYTES, lo = hi + TC_TILE_BYTES;
                     constexpr int NF = (TC_TILE_BYTES / 16) / (32 * Cfg::kBWarps);  // float4 per thread
                     float4 v[NF];
@@ -260,12 +266,8 @@ ts_gemm_kernel(const __grid_constant__ TcMaps tm, const TcArgs p) {
 
 template <int EPI>
 static int ts_launch(const TcMaps& maps, const TcArgs& a, unsigned grid, cudaStream_t st) {
-    static bool attr_set = false;  // idempotent; a race only repeats the call
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ts_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TsCfg<EPI>::kSmem);
-        if (e != cudaSuccess) { set_error("ts gemm smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-        attr_set = true;
-    }
+    static SmemGrant grant;
+    if (int rc = grant_dyn_smem(ts_gemm_kernel<EPI>, (size_t)TsCfg<EPI>::kSmem, grant, "ts gemm")) return rc;
     ts_gemm_kernel<EPI><<<grid, TsCfg<EPI>::kThreads, TsCfg<EPI>::kSmem, st>>>(maps, a);
     return check_launch("ts gemm");
 }

@@ -44,7 +44,12 @@ __global__ void __launch_bounds__(256) pair_ce_loss_kernel(const float* __restri
     pdl_wait();
     float l0 = 0.f, l1 = 0.f;
     for (int k = threadIdx.x; k < B; k += blockDim.x) {
-        const int lab = (int)labels[k];
+        const long long lab64 = labels[k];
+        if (lab64 < 0 || lab64 >= B) {  // torch's CrossEntropyLoss raises here; a kernel cannot, so the loss is poisoned instead
+            l0 = l1 = NAN;
+            continue;
+        }
+        const int lab = (int)lab64;
         l0 += lse[k] - s[(size_t)k * B + lab];
         l1 += lse[B + k] - s[(size_t)lab * B + k];
     }

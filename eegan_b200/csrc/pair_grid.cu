@@ -539,12 +539,8 @@ static int softmax_fwd_launch(dim3 grid, cudaStream_t st, float* SP, float* A, c
                               float g1, float* att, int diag_offset, int Tm) {
     if (bulk_ok(SP, Rp) && bulk_ok(A, Rp)) {
         const size_t smem = (size_t)2 * Tm * Rp * sizeof(float);
-        static std::atomic<size_t> granted{48 * 1024};
-        if (smem > granted.load()) {
-            cudaError_t e = cudaFuncSetAttribute(pair_attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-            granted.store(smem);
-        }
+        static SmemGrant grant;
+        if (int rc = grant_dyn_smem(pair_attn_softmax_kernel, smem, grant, "pair softmax")) return rc;
         pair_attn_softmax_kernel<<<grid, 256, smem, st>>>(SP, A, col_start, NtM, R, Rp, g1, att, diag_offset, Tm);
     } else {
         EEGAN_REQUIRE(att == nullptr, "softmax: att output needs the padded pitch");
@@ -561,12 +557,8 @@ static int softmax_bwd_launch(dim3 grid, cudaStream_t st, float* DA, const float
                               int NtM, int R, int Rp, float g1, int Tm) {
     if (bulk_ok(DA, Rp) && bulk_ok(A, Rp) && bulk_ok(P, Rp)) {
         const size_t smem = (size_t)3 * Tm * Rp * sizeof(float);
-        static std::atomic<size_t> granted{48 * 1024};
-        if (smem > granted.load()) {
-            cudaError_t e = cudaFuncSetAttribute(pair_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { set_error("smem attr: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-            granted.store(smem);
-        }
+        static SmemGrant grant;
+        if (int rc = grant_dyn_smem(pair_softmax_bwd_kernel, smem, grant, "pair softmax bwd")) return rc;
         pair_softmax_bwd_kernel<<<grid, 256, smem, st>>>(DA, A, P, col_start, NtM, R, Rp, g1, Tm);
     } else {
         pair_softmax_bwd_generic_kernel<<<grid, 256, 0, st>>>(DA, A, P, col_start, NtM, R, Rp, g1);

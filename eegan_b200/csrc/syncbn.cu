@@ -383,12 +383,8 @@ extern "C" int eegan_ssa_bwd_reduce(const float* x, const float* dy, const float
     cudaMemsetAsync(dgamma, 0, (size_t)N * C * sizeof(float), st);
     cudaMemsetAsync(dbeta, 0, (size_t)N * C * sizeof(float), st);
     const size_t smem = (size_t)C * 8 * 4 * sizeof(float);
-    static std::atomic<size_t> granted{48 * 1024};
-    if (smem > granted.load()) {
-        cudaError_t e = cudaFuncSetAttribute(ssa_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("ssa bwd_reduce smem: %s", cudaGetErrorString(e)); return EEGAN_ERR_CUDA; }
-        granted.store(smem);
-    }
+    static SmemGrant grant;
+    if (int rc = grant_dyn_smem(ssa_bwd_reduce_kernel, smem, grant, "ssa bwd_reduce")) return rc;
     ssa_bwd_reduce_kernel<<<dim3((HW + BN_THREADS * 4 - 1) / (BN_THREADS * 4), N), BN_THREADS, smem, st>>>(
         x, dy, mean, inv_std, gamma, beta, mask, C, HW, red, dgamma, dbeta, dmask);
     EEGAN_LAUNCH_CHECK("ssa bwd_reduce");

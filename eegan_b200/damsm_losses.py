@@ -17,6 +17,7 @@ arithmetic step of the path runs in the CUDA library.  No CPU path exists.
 from __future__ import annotations
 
 import math
+from collections.abc import Sequence
 
 import torch
 import torch.nn as nn
@@ -28,6 +29,9 @@ __all__ = [
     "cosine_similarity", "func_attention", "GlobalAttentionGeneral", "sent_similarity",
     "words_similarity", "sent_loss", "words_loss",
 ]
+
+
+_GAG_BWD_MAX_IDF = 256  # eegan_gag_bwd's shared-memory forms (gag.cu / gag_bwd2.cu); the forward alone takes idf <= 512
 
 
 # ---------------------------------------------------------------------------------------
@@ -117,7 +121,9 @@ class _PairCEFn(torch.autograd.Function):
 
 class _ScaleMaskFn(torch.autograd.Function):
     """scores * scale with the class mask set to -inf (the *_similarity API): the forward
-    half of eegan_pair_ce_fwd; gradient = scale on unmasked cells."""
+    half of eegan_pair_ce_fwd.  The reference applies the mask through ``.data.masked_fill_``
+    (DAMSM_losses.py:163, 229), which autograd does not see: the gradient is ``g * scale`` on
+    EVERY cell, masked or not."""
 
     @staticmethod
     def forward(ctx, scores, scale, class_ids):
@@ -128,14 +134,12 @@ class _ScaleMaskFn(torch.autograd.Function):
         with torch.cuda.device(scores.device):
             _lib.check(L.eegan_pair_ce_fwd(_lib.ptr(scores), scale, _lib.ptr(class_ids), None, B, _lib.ptr(out), None,
                                            _lib.ptr(lse), _lib.stream_ptr()), "pair_ce_fwd(mask)")
-        ctx.save_for_backward(out)
         ctx.scale = scale
         return out
 
     @staticmethod
     def backward(ctx, g):
-        (out,) = ctx.saved_tensors
-        return torch.where(torch.isinf(out), torch.zeros_like(g), g * ctx.scale), None, None
+        return g * ctx.scale, None, None
 
 
 class _SentScoresFn(torch.autograd.Function):
@@ -216,39 +220,68 @@ def _device_i64(v, device, n=None):
     return t.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
 
 
-class _LazyAttMaps(list):
-    """``att_maps`` as the reference returns it — a list of [1, T_i, H, W] tensors
-    (DAMSM_losses.py:301) — but sliced out of the kernel's [B, T_max, R] buffer only when
-    first touched: slicing needs cap_lens on the host, and the reference's
-    ``cap_lens.data.tolist()`` sync (:280) is the one thing train.py never needs (it drops
-    att_maps, train.py:428)."""
+def _slice_att_maps(att, lens, hw):
+    H, W = hw
+    return [att[i:i + 1, :lens[i]].reshape(1, lens[i], H, W).contiguous() for i in range(att.shape[0])]
+
+
+class _LazyAttMaps(Sequence):
+    """``att_maps`` as the reference returns it — [1, T_i, H, W] tensors, one per caption
+    (DAMSM_losses.py:301) — sliced out of the kernel's [B, T_max, R] buffer only when first
+    touched: slicing needs cap_lens on the host, and the reference's ``cap_lens.data.tolist()``
+    sync (:280) is the one thing train.py never needs (it drops att_maps, train.py:428).
+
+    Deliberately NOT a ``list`` subclass: C-level consumers (``torch.cat``, ``list.copy``, pickling)
+    read a list's storage directly and would see an empty one before the first Python-level
+    access.  As a plain Sequence they either go through ``__getitem__`` / ``__iter__`` (and get
+    the tensors) or raise a TypeError; ``list(att_maps)`` or ``att_maps.tolist()`` gives the
+    reference's exact type.  When ``cap_lens`` is already on the host, ``_att_maps()`` returns a
+    real list straight away and this class is not used."""
 
     def __init__(self, att, cap_lens, hw):
-        super().__init__()
         self._src = (att, cap_lens, hw)
+        self._items = None
 
     def _fill(self):
-        if self._src is not None:
-            att, cap_lens, (H, W) = self._src
+        if self._items is None:
+            att, cap_lens, hw = self._src
+            self._items = _slice_att_maps(att, [int(v) for v in cap_lens.reshape(-1).tolist()], hw)
             self._src = None
-            lens = [int(v) for v in cap_lens.reshape(-1).tolist()]
-            super().extend(att[i:i + 1, :lens[i]].reshape(1, lens[i], H, W).contiguous()
-                           for i in range(att.shape[0]))
+        return self._items
+
+    def tolist(self):
+        return list(self._fill())
 
     def __len__(self):
-        return self._src[0].shape[0] if self._src is not None else super().__len__()
+        return self._src[0].shape[0] if self._items is None else len(self._items)
 
     def __getitem__(self, k):
-        self._fill()
-        return super().__getitem__(k)
+        return self._fill()[k]
 
     def __iter__(self):
-        self._fill()
-        return super().__iter__()
+        return iter(self._fill())
+
+    def __add__(self, other):
+        return self.tolist() + list(other)
+
+    def __radd__(self, other):
+        return list(other) + self.tolist()
+
+    def __reduce__(self):
+        return (list, (self.tolist(),))
 
     def __repr__(self):
-        self._fill()
-        return super().__repr__()
+        return repr(self._fill())
+
+
+def _att_maps(att, cap_lens, hw):
+    """A real list when the caption lengths are host data (no sync needed), the lazy Sequence otherwise."""
+    if att is None or att.numel() == 0:
+        return []
+    if not (torch.is_tensor(cap_lens) and cap_lens.is_cuda):
+        lens = [int(v) for v in torch.as_tensor(cap_lens).reshape(-1).tolist()]
+        return _slice_att_maps(att, lens, hw)
+    return _LazyAttMaps(att, cap_lens, hw)
 
 
 def pair_grid(img_features, words_emb, cap_lens, diag_offset=0, want_att=True):
@@ -315,6 +348,9 @@ class GlobalAttentionGeneral(nn.Module):
         mask = None
         if self.mask is not None:
             mask = self.mask.to(device=x.device).to(torch.uint8).contiguous()
+        if idf > _GAG_BWD_MAX_IDF and torch.is_grad_enabled() and (x.requires_grad or key.requires_grad or val.requires_grad):
+            raise RuntimeError("GlobalAttentionGeneral: idf=%d > %d has a forward kernel but no backward; "
+                               "run it under torch.no_grad()" % (idf, _GAG_BWD_MAX_IDF))
         out, attn = _GagFn.apply(x, key, val, mask, 0 if self.mask_mode == "reference" else 1)
         return out.view(B, -1, ih, iw), attn.view(B, -1, ih, iw)
 
@@ -353,14 +389,14 @@ def words_similarity(img_features, words_emb, cap_lens, class_ids, batch_size):
     m, att = pair_grid(img_features[:batch_size], words_emb[:batch_size], cap_lens)
     cls = _device_i64(class_ids, m.device, batch_size)
     sim = _ScaleMaskFn.apply(m, g3, cls)
-    return sim, _LazyAttMaps(att, cap_lens, _spatial(img_features))
+    return sim, _att_maps(att, cap_lens, _spatial(img_features))
 
 
 def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size):
     """DAMSM_losses.py:272-342 -> (loss0, loss1, att_maps)."""
     _, _, g3 = gammas()
     m, att = pair_grid(img_features[:batch_size], words_emb[:batch_size], cap_lens)
-    att_maps = _LazyAttMaps(att, cap_lens, _spatial(img_features))
+    att_maps = _att_maps(att, cap_lens, _spatial(img_features))
     if labels is None:
         return None, None, att_maps
     cls = _device_i64(class_ids, m.device, batch_size)

@@ -97,7 +97,7 @@ def sharded_words_loss(img_features, words_emb, labels, cap_lens, class_ids, bat
     b = batch_size
     img_all = _AllGatherRows.apply(img_features[:b].contiguous(), group, True)
     m_block, att = grid_fn(img_all, words_emb[:b], cap_lens, diag_offset=rank * b)
-    att_maps = dl._LazyAttMaps(att, cap_lens, dl._spatial(img_features))
+    att_maps = dl._att_maps(att, cap_lens, dl._spatial(img_features))
     if labels is None:
         return None, None, att_maps
     m_all = _AllGatherCols.apply(m_block, group)

@@ -112,6 +112,37 @@ class _SyncBNFn(torch.autograd.Function):
         return dx, d_w, d_b, None, None, None, None, None, None
 
 
+class _BNEvalFn(torch.autograd.Function):
+    """Eval mode (batchnorm.py:50-53 -> F.batch_norm with the running statistics), differentiable like the
+    reference's: the statistics are constants, so dx = dy * w * inv_std, d_w = sum dy * xhat, d_b = sum dy."""
+
+    @staticmethod
+    def forward(ctx, x3, weight, bias, mean, inv_std, ops):
+        y = torch.empty_like(x3)
+        ops.apply(x3, mean, inv_std, weight, bias, y)
+        ctx.save_for_backward(x3, weight, mean, inv_std)
+        ctx.ops, ctx.has_bias = ops, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x3, weight, mean, inv_std = ctx.saved_tensors
+        ops = ctx.ops
+        N, C, HW = x3.shape
+        dy = dy.contiguous()
+        d_w = d_b = dx = None
+        if (weight is not None and ctx.needs_input_grad[1]) or (ctx.has_bias and ctx.needs_input_grad[2]):
+            red = torch.empty(2 * C, dtype=torch.float32, device=x3.device)
+            ops.bwd_reduce(x3, dy, mean, inv_std, red)
+            d_w = red[C:] if weight is not None else None
+            d_b = red[:C] if ctx.has_bias else None
+        if ctx.needs_input_grad[0]:
+            zero = torch.zeros(2 * C, dtype=torch.float32, device=x3.device)  # no batch-statistics terms in eval mode
+            dx = torch.empty_like(x3)
+            ops.bwd_apply(x3, dy, mean, inv_std, weight, zero, 1, None, 0.0, 0, dx)
+        return dx, d_w, d_b, None, None, None
+
+
 class _SynchronizedBatchNorm(_BatchNorm):
     """batchnorm.py:37-125.  ``process_group`` (default: the world group) replaces the
     reference's SyncMaster / SlavePipe plumbing."""
@@ -130,8 +161,7 @@ class _SynchronizedBatchNorm(_BatchNorm):
         x3 = input.contiguous().float().reshape(shape[0], self.num_features, -1)
         if not self.training:  # batchnorm.py:50-53 eval branch: running statistics
             inv_std = torch.rsqrt(self.running_var + self.eps)
-            y = torch.empty_like(x3)
-            self._ops.apply(x3, self.running_mean.contiguous(), inv_std, self.weight, self.bias, y)
+            y = _BNEvalFn.apply(x3, self.weight, self.bias, self.running_mean.contiguous(), inv_std, self._ops)
             return y.view(shape)
         y = _SyncBNFn.apply(x3, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
                             self.momentum, self.process_group, self._ops)

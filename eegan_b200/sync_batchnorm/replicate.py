@@ -6,6 +6,18 @@ replicas from Python threads (train.py:220).  The B200 design is one process per
 (checkpoints keep their ``module.`` prefix, train.py:308-319) but runs the wrapped module on
 the rank's own device only; SynchronizedBatchNorm layers inside reduce their statistics
 across ranks over NCCL.
+
+Parameter gradients.  nn.DataParallel SUMS the replicas' parameter gradients into the one
+parameter set of the master copy.  With one process per GPU that sum has to cross processes:
+when a process group is active the wrapper registers a post-accumulate hook on every
+parameter that all-reduces (SUM) its gradient over the group, so every rank ends a backward
+with the gradient the reference's single parameter set would hold and the ranks' optimisers
+stay in lock-step.  Scale: the sharded losses (eegan_b200.sharded) already hand every rank the
+gradient of the GLOBAL-batch loss with respect to its own samples, exactly what a DataParallel
+replica receives from the scatter of the gathered outputs' gradient — hence SUM, not the MEAN of
+DistributedDataParallel.  A loss that is a per-rank mean over local samples must be divided by
+the world size by the caller (``grad_sync="mean"`` does that in the hook).  ``grad_sync=None``
+switches the hooks off (the caller then owns gradient synchronisation).
 """
 from __future__ import annotations
 
@@ -42,9 +54,36 @@ def _local_device_ids(device_ids):
     return ids
 
 
+def _register_grad_sync(module, mode, group):
+    """all-reduce every parameter's gradient over ``group`` right after autograd accumulated it."""
+    handles = []
+    if mode is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return handles
+    if mode not in ("sum", "mean"):
+        raise ValueError("grad_sync must be 'sum', 'mean' or None")
+    world = dist.get_world_size(group)
+
+    def hook(p):
+        if p.grad is not None:
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
+            if mode == "mean":
+                p.grad.div_(world)
+
+    for p in module.parameters():
+        if p.requires_grad:
+            handles.append(p.register_post_accumulate_grad_hook(hook))
+    return handles
+
+
 class DataParallelWithCallback(DataParallel):
-    def __init__(self, module, device_ids=None, output_device=None, dim=0):
+    def __init__(self, module, device_ids=None, output_device=None, dim=0, grad_sync="sum", process_group=None):
         super().__init__(module, device_ids=_local_device_ids(device_ids), output_device=output_device, dim=dim)
+        self._grad_sync_handles = _register_grad_sync(module, grad_sync, process_group)
+
+    def forward(self, *inputs, **kwargs):
+        if not torch.cuda.is_available() or not self.device_ids:
+            return self.module(*inputs, **kwargs)  # CPU (tests over gloo): DataParallel's own pass-through
+        return super().forward(*inputs, **kwargs)
 
     def replicate(self, module, device_ids):
         modules = super().replicate(module, device_ids)
@@ -52,10 +91,12 @@ class DataParallelWithCallback(DataParallel):
         return modules
 
 
-def patch_replication_callback(data_parallel):
+def patch_replication_callback(data_parallel, grad_sync="sum", process_group=None):
     """replicate.py:70-94."""
     assert isinstance(data_parallel, DataParallel)
     data_parallel.device_ids = _local_device_ids(data_parallel.device_ids)
+    if not getattr(data_parallel, "_grad_sync_handles", None):
+        data_parallel._grad_sync_handles = _register_grad_sync(data_parallel.module, grad_sync, process_group)
     old = data_parallel.replicate
 
     def new_replicate(module, device_ids):

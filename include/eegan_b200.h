@@ -17,8 +17,19 @@
  *   - return 0 on success, non-zero on error; eegan_last_error() returns a thread-local
  *     message.  No exceptions cross the boundary.
  *   - all floating point tensors are contiguous fp32.  There is no CPU fallback.
- *   - re-entrant: no global mutable state; safe from several host threads on different
- *     streams / devices (nn.DataParallel calls modules from per-device threads).
+ *   - thread safety: every compute entry point may be called concurrently from several host
+ *     threads on different streams / devices (nn.DataParallel calls modules from per-device
+ *     threads); the device is the caller's current device, the stream the one passed.
+ *     Per-call state lives in the caller's buffers.  What IS process-wide, and why:
+ *       * the engine selectors eegan_set_contraction_engine / eegan_set_gag_engine (A/B
+ *         validation knobs, atomics; the backward of a forward runs on autograd's thread,
+ *         so a thread-local selector would split one call pair over two engines),
+ *       * the bench-only stage profiler eegan_profile_* (mutex-guarded, off by default),
+ *       * caches that only memoise idempotent driver queries: the per-device shared-memory
+ *         opt-in and SM count, and a thread-local cache of encoded TMA descriptors.
+ *     Environment variables are read once per process (EEGAN_ENGINE, EEGAN_PDL, EEGAN_GAG_*
+ *     tuning knobs), never per launch; work-skipping timing switches exist only in builds
+ *     made with -DEEGAN_DEBUG_SWITCHES and are absent from the shipped library.
  */
 #ifndef EEGAN_B200_H_
 #define EEGAN_B200_H_
@@ -105,7 +116,9 @@ int eegan_cosine_rows_bwd(const float* x1, const float* x2, const float* out,
  * scores_in [B,B] row-major (row = image, col = caption/sentence); scale multiplies it
  * (gamma3 for the words grid, 1 for sentence scores that already carry gamma3).
  * class_ids [B] int64 or NULL: cell (a,b), a != b, with class_ids[a]==class_ids[b] is set
- * to -inf (:282-285,331-333).  labels [B] int64.
+ * to -inf (:282-285,331-333).  labels [B] int64; a label outside [0, B) (torch's
+ * CrossEntropyLoss raises) never reads out of bounds: it poisons loss01 with NaN and
+ * contributes no one-hot term to the backward.
  * scores_out [B,B]  OUT: scaled + masked grid (what words_similarity returns).
  * loss01 [2]        OUT: loss0 = CE(scores, labels) over rows, loss1 = CE(scores^T, labels).
  * lse [2,B]         OUT: row / column log-sum-exp, consumed by the backward.

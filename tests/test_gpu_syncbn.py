@@ -75,3 +75,14 @@ def test_module_single_replica_matches_batch_norm(cuda_lib, shape, affine):
     assert relmax(bn.running_var.cpu(), ref.running_var) <= 1e-5
     bn.eval(); ref.eval()
     assert relmax(bn(x.cuda()).cpu(), ref(x.double())) <= 1e-5
+    # eval mode is differentiable, as the reference's F.batch_norm branch is (batchnorm.py:50-53)
+    xg2, xr2 = x.cuda().requires_grad_(), x.double().requires_grad_()
+    bn.zero_grad(set_to_none=True); ref.zero_grad(set_to_none=True)
+    y2, yr2 = bn(xg2), ref(xr2)
+    assert y2.grad_fn is not None
+    (y2 * gy.cuda()).sum().backward()
+    (yr2 * gy.double()).sum().backward()
+    assert relmax(xg2.grad.cpu(), xr2.grad) <= 1e-5
+    if affine:
+        assert relmax(bn.weight.grad.cpu(), ref.weight.grad) <= 1e-4
+        assert relmax(bn.bias.grad.cpu(), ref.bias.grad) <= 1e-4

@@ -61,13 +61,23 @@ def test_cfg_follows_reference_object_when_present():
             sys.modules["miscc.config"] = saved
 
 
-def test_lazy_att_maps_is_a_list_of_reference_shapes():
+def test_att_maps_have_reference_shapes_and_type():
     att = torch.arange(3 * 4 * 9, dtype=torch.float32).reshape(3, 4, 9)
     lens = torch.tensor([4, 2, 3])
-    maps = damsm_losses._LazyAttMaps(att, lens, (3, 3))
-    assert isinstance(maps, list) and len(maps) == 3
+    # host caption lengths: the reference's exact type (a list), no laziness needed
+    maps = damsm_losses._att_maps(att, lens, (3, 3))
+    assert type(maps) is list and len(maps) == 3
     assert [tuple(m.shape) for m in maps] == [(1, 4, 3, 3), (1, 2, 3, 3), (1, 3, 3, 3)]
     assert torch.equal(maps[1].reshape(2, 9), att[1, :2])
+    # device caption lengths -> lazy Sequence: never an empty list to C-level consumers
+    lazy = damsm_losses._LazyAttMaps(att, lens, (3, 3))
+    assert not isinstance(lazy, list) and len(lazy) == 3
+    assert torch.equal(torch.cat(list(lazy), 1), torch.cat(maps, 1))
+    lazy2 = damsm_losses._LazyAttMaps(att, lens, (3, 3))
+    assert type(lazy2 + []) is list and len(lazy2 + []) == 3 and type(lazy2.tolist()) is list
+    import pickle
+    back = pickle.loads(pickle.dumps(damsm_losses._LazyAttMaps(att, lens, (3, 3))))
+    assert type(back) is list and torch.equal(back[2], maps[2])
 
 
 def test_labels_none_short_circuits_like_reference():

@@ -233,3 +233,61 @@ def test_overlapped_sharded_step_equals_full_batch(world):
         for it in ("it0", "it1"):
             r = out[rank][it]
             assert r["loss"] < 1e-12 and r["dimg"] < 1e-12 and r["dwords"] < 1e-12 and r["att"] < 1e-14, (rank, it, r)
+
+
+# ---------------------------------------------------------------------------------------
+# DataParallelWithCallback under a process group: parameter gradients are summed over ranks
+# (what nn.DataParallel does over its replicas, sync_batchnorm/replicate.py:50-67 + train.py:220)
+# ---------------------------------------------------------------------------------------
+def _tiny_net():
+    from eegan_b200.sync_batchnorm import SynchronizedBatchNorm2d
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 1), SynchronizedBatchNorm2d(8), torch.nn.ReLU(), torch.nn.Conv2d(8, 2, 1))
+    net[1]._ops = OracleBNOps
+    return net
+
+
+def _dp_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    try:
+        from eegan_b200.sync_batchnorm import DataParallelWithCallback
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(6, 3, 4, 4, generator=g)
+        gy = torch.randn(6, 2, 4, 4, generator=g)
+        sl = slice(rank * 3, (rank + 1) * 3)
+        net = DataParallelWithCallback(_tiny_net())
+        assert hasattr(net, "module")
+        (net(x[sl]) * gy[sl]).sum().backward()  # the rank's share of the global-batch loss
+        # single process, full batch, the N-replica statistics formula (batchnorm.py:113-125) in plain torch
+        ref = _tiny_net()
+        h = ref[0](x)
+        mu = h.mean(dim=(0, 2, 3), keepdim=True)
+        var = ((h - mu) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+        hn = (h - mu) * var.clamp(min=ref[1].eps) ** -0.5
+        hn = hn * ref[1].weight.view(1, -1, 1, 1) + ref[1].bias.view(1, -1, 1, 1)
+        (ref[3](torch.relu(hn)) * gy).sum().backward()
+        # (the bias of the conv in front of the batch norm has an identically-zero gradient: compare on the scale of
+        # the largest parameter gradient, not per tensor)
+        scale = max(float(q.grad.abs().max()) for q in ref.parameters())
+        err = max(float((p.grad - q.grad).abs().max()) for p, q in zip(net.module.parameters(), ref.parameters())) / scale
+        # grad_sync=None leaves the local (per-rank) gradients alone: they differ from the full-batch ones
+        net2 = DataParallelWithCallback(_tiny_net(), grad_sync=None)
+        (net2(x[sl]) * gy[sl]).sum().backward()
+        local = float((net2.module[0].weight.grad - ref[0].weight.grad).abs().max())
+        out[rank] = dict(err=err, local=local)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_data_parallel_wrapper_sums_parameter_gradients():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        assert out[rank]["err"] < 2e-5, dict(out[rank])
+        assert out[rank]["local"] > 1e-3, dict(out[rank])

@@ -23,9 +23,15 @@ from .ssa import affine_ssa, ssa_modulate  # noqa: F401
 __version__ = "0.1.0"
 
 
-def install(losses: bool = True, sync_batchnorm: bool = True) -> None:
+def install(losses: bool = True, sync_batchnorm: bool = True, distributed: bool = True) -> None:
     """Route the reference's import names to this package (drop-in boundary):
-    ``miscc.DAMSM_losses`` (train.py:24) and ``sync_batchnorm`` (models.py:8-10, train.py:25)."""
+    ``miscc.DAMSM_losses`` (train.py:24) and ``sync_batchnorm`` (models.py:8-10, train.py:25).
+
+    ``distributed=True``: under torchrun (one process per GPU, process group initialised) ``words_loss`` /
+    ``sent_loss`` called with the rank's shard return the loss of the GLOBAL batch (eegan_b200.sharded) — what
+    the reference computes on GPU 0 after nn.DataParallel gathers (train.py:195, 419-435); with a single process
+    nothing changes."""
+    damsm_losses.AUTO_SHARD = bool(distributed)
     if losses:
         sys.modules["miscc.DAMSM_losses"] = damsm_losses
         parent = sys.modules.get("miscc")

@@ -17,6 +17,7 @@ arithmetic step of the path runs in the CUDA library.  No CPU path exists.
 from __future__ import annotations
 
 import math
+import threading
 from collections.abc import Sequence
 
 import torch
@@ -31,6 +32,7 @@ __all__ = [
 ]
 
 
+_tls = threading.local()
 _GAG_BWD_MAX_IDF = 256  # eegan_gag_bwd's shared-memory forms (gag.cu / gag_bwd2.cu); the forward alone takes idf <= 512
 
 
@@ -170,6 +172,51 @@ class _SentScoresFn(torch.autograd.Function):
                                                ctx.c[0], ctx.c[1], _lib.ptr(d_cnn), _lib.ptr(d_rnn),
                                                _lib.stream_ptr()), "sent_scores_bwd")
         return d_cnn, d_rnn, None, None
+
+
+class _SentLossFn(torch.autograd.Function):
+    """sent_loss (DAMSM_losses.py:233-270) as ONE autograd node: cosine scores + class mask + two-way CE forward,
+    CE backward + score backward.  Four launches each way and a single round of autograd bookkeeping (the function
+    is called twice per training step, train.py:425, 432, and is pure launch latency)."""
+
+    @staticmethod
+    def forward(ctx, cnn, rnn, g3, eps, cls, labels):
+        L = _lib.lib()
+        B, D = cnn.shape
+        dev = cnn.device
+        scores = torch.empty(B, B, dtype=torch.float32, device=dev)
+        out = torch.empty_like(scores)
+        small = torch.empty(4 * B + 2, dtype=torch.float32, device=dev)  # norms [2,B] | lse [2,B] | loss01 [2]
+        norms, lse, loss01 = small[:2 * B], small[2 * B:4 * B], small[4 * B:]
+        p, st = _lib.ptr, _lib.stream_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(L.eegan_sent_scores_fwd(p(cnn), p(rnn), B, D, g3, eps, p(scores), p(norms), st), "sent_scores_fwd")
+            _lib.check(L.eegan_pair_ce_fwd(p(scores), 1.0, p(cls), p(labels), B, p(out), p(loss01), p(lse), st), "pair_ce_fwd")
+        ctx.save_for_backward(cnn, rnn, out, small, labels)
+        ctx.c = (g3, eps)
+        return loss01[0], loss01[1]
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        cnn, rnn, out, small, labels = ctx.saved_tensors
+        L = _lib.lib()
+        B, D = cnn.shape
+        norms, lse = small[:2 * B], small[2 * B:4 * B]
+        z = None
+        if g0 is None or g1 is None:
+            z = torch.zeros((), dtype=torch.float32, device=out.device)
+        g = torch.stack([(g0 if g0 is not None else z).float().reshape(()), (g1 if g1 is not None else z).float().reshape(())])
+        ds = torch.empty_like(out)
+        d_cnn = torch.empty_like(cnn) if ctx.needs_input_grad[0] else None
+        d_rnn = torch.empty_like(rnn) if ctx.needs_input_grad[1] else None
+        p, st = _lib.ptr, _lib.stream_ptr()
+        with torch.cuda.device(out.device):
+            _lib.check(L.eegan_pair_ce_bwd(p(out), p(lse), p(labels), p(g), 1.0, B, p(ds), st), "pair_ce_bwd")
+            tmp_c = d_cnn if d_cnn is not None else torch.empty_like(cnn)
+            tmp_r = d_rnn if d_rnn is not None else torch.empty_like(rnn)
+            _lib.check(L.eegan_sent_scores_bwd(p(cnn), p(rnn), p(norms), p(ds), B, D, ctx.c[0], ctx.c[1], p(tmp_c), p(tmp_r), st),
+                       "sent_scores_bwd")
+        return d_cnn, d_rnn, None, None, None, None
 
 
 class _GagFn(torch.autograd.Function):
@@ -368,19 +415,38 @@ def sent_similarity(cnn_code, rnn_code, class_ids, batch_size, eps=1e-8):
     return _ScaleMaskFn.apply(scores, 1.0, cls)
 
 
+# Set by ``eegan_b200.install(distributed=...)``: with one process per GPU and an initialised process group the
+# reference's call sites (train.py:425-432) hand these functions the RANK's shard, while the reference evaluates the
+# loss on the full batch gathered on GPU 0 (train.py:195).  When True, words_loss / sent_loss called under a group of
+# more than one rank evaluate the GLOBAL-batch loss from the shards (eegan_b200.sharded).
+AUTO_SHARD = False
+
+
+def _auto_shard():
+    if not AUTO_SHARD:
+        return False
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-8):
     """DAMSM_losses.py:233-270 -> (loss0, loss1)."""
     _lib.require_cuda(cnn_code, rnn_code)
+    if labels is not None and _auto_shard() and not getattr(_tls, "inside_sharded", False):
+        from . import sharded
+        _tls.inside_sharded = True
+        try:
+            return sharded.sharded_sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps)
+        finally:
+            _tls.inside_sharded = False
     if cnn_code.dim() == 3:
         cnn_code, rnn_code = cnn_code.squeeze(0), rnn_code.squeeze(0)
     if labels is None:
         return None, None
     _, _, g3 = gammas()
-    scores = _SentScoresFn.apply(_lib.f32c(cnn_code), _lib.f32c(rnn_code), g3, float(eps))
-    cls = _device_i64(class_ids, scores.device, batch_size)
-    lab = _device_i64(labels, scores.device)
-    loss0, loss1, _ = _PairCEFn.apply(scores, 1.0, cls, lab)
-    return loss0, loss1
+    cls = _device_i64(class_ids, cnn_code.device, batch_size)
+    lab = _device_i64(labels, cnn_code.device)
+    return _SentLossFn.apply(_lib.f32c(cnn_code), _lib.f32c(rnn_code), g3, float(eps), cls, lab)
 
 
 def words_similarity(img_features, words_emb, cap_lens, class_ids, batch_size):
@@ -393,7 +459,29 @@ def words_similarity(img_features, words_emb, cap_lens, class_ids, batch_size):
 
 
 def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size):
-    """DAMSM_losses.py:272-342 -> (loss0, loss1, att_maps)."""
+    """DAMSM_losses.py:272-342 -> (loss0, loss1, att_maps).
+
+    Default route: one autograd node over a per-shape plan with captured forward / backward graphs
+    (eegan_b200/fastpath.py); the two-node route below it serves labels=None, the validation engines and
+    EEGAN_WORDS_LOSS_PLAN=0."""
+    from . import fastpath
+    if _auto_shard() and not getattr(_tls, "inside_sharded", False):
+        from . import sharded
+        _tls.inside_sharded = True
+        try:
+            return sharded.sharded_words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size)
+        finally:
+            _tls.inside_sharded = False
+    if labels is not None and torch.is_tensor(img_features) and torch.is_tensor(words_emb):
+        _lib.require_cuda(img_features, words_emb)
+        img_b, words_b = img_features[:batch_size], words_emb[:batch_size]
+        if fastpath.supported(img_b, words_b):
+            Bi, D = img_b.shape[0], img_b.shape[1]
+            img3 = _lib.f32c(img_b).reshape(Bi, D, -1)
+            cls = None if class_ids is None else torch.as_tensor(class_ids)
+            loss0, loss1, att = fastpath.words_loss_planned(img3, _lib.f32c(words_b), torch.as_tensor(cap_lens), cls,
+                                                            torch.as_tensor(labels), gammas())
+            return loss0, loss1, _att_maps(att, cap_lens, _spatial(img_features))
     _, _, g3 = gammas()
     m, att = pair_grid(img_features[:batch_size], words_emb[:batch_size], cap_lens)
     att_maps = _att_maps(att, cap_lens, _spatial(img_features))

@@ -242,6 +242,15 @@ class ShardedWordsLossStep:
         self.run()
         return self._loss01[0], self._loss01[1], self.d_img, self.d_words
 
+    def release_graph(self):
+        """Drop the captured graph (it holds NCCL work on the communicator): call before
+        ``torch.distributed.destroy_process_group()`` — tearing the communicator down under a live graph that
+        captured its collectives hangs on torch 2.11 / NCCL 2.28."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.img.device)
+            self._graph = None
+            torch.cuda.synchronize(self.img.device)
+
 
 class _CudaStepKernels:
     """The library calls of the sharded step (C ABI on the current stream)."""

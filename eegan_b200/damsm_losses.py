@@ -474,13 +474,15 @@ def words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size)
             _tls.inside_sharded = False
     if labels is not None and torch.is_tensor(img_features) and torch.is_tensor(words_emb):
         _lib.require_cuda(img_features, words_emb)
-        img_b, words_b = img_features[:batch_size], words_emb[:batch_size]
+        img_b = img_features if img_features.shape[0] == batch_size else img_features[:batch_size]
+        words_b = words_emb if words_emb.shape[0] == batch_size else words_emb[:batch_size]
         if fastpath.supported(img_b, words_b):
             Bi, D = img_b.shape[0], img_b.shape[1]
-            img3 = _lib.f32c(img_b).reshape(Bi, D, -1)
-            cls = None if class_ids is None else torch.as_tensor(class_ids)
-            loss0, loss1, att = fastpath.words_loss_planned(img3, _lib.f32c(words_b), torch.as_tensor(cap_lens), cls,
-                                                            torch.as_tensor(labels), gammas())
+            img3 = _lib.f32c(img_b).view(Bi, D, -1)
+            cls = class_ids if (class_ids is None or torch.is_tensor(class_ids)) else torch.as_tensor(class_ids)
+            lens = cap_lens if torch.is_tensor(cap_lens) else torch.as_tensor(cap_lens)
+            lab = labels if torch.is_tensor(labels) else torch.as_tensor(labels)
+            loss0, loss1, att = fastpath.words_loss_planned(img3, _lib.f32c(words_b), lens, cls, lab, gammas())
             return loss0, loss1, _att_maps(att, cap_lens, _spatial(img_features))
     _, _, g3 = gammas()
     m, att = pair_grid(img_features[:batch_size], words_emb[:batch_size], cap_lens)

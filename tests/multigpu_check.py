@@ -58,6 +58,7 @@ def main():
             q0, q1, qdi, qdw = sstep(c["img"][sl].to(dev), c["words"][sl].to(dev), c["cap_lens"][sl].to(dev), c["class_ids"][sl].to(dev))
         assert abs(q0.item() - f0.item()) <= 2e-6 * max(1.0, abs(f0.item())) and abs(q1.item() - f1.item()) <= 2e-6 * max(1.0, abs(f1.item()))
         assert relmax(qdi, img.grad[sl]) <= 2e-5 and relmax(qdw, words.grad[sl]) <= 2e-5, (use_graph, relmax(qdi, img.grad[sl]))
+        sstep.release_graph()  # a live graph holding NCCL work must go before destroy_process_group (teardown hang otherwise)
     if os.environ.get("EEGAN_CHECK_SHARDED_OVERLAP") == "1":  # the opt-in overlapped step (sharded.py)
         from eegan_b200.sharded import OverlappedShardedWordsLossStep
         ostep = OverlappedShardedWordsLossStep(b, 256, 17, 17, T, dev, w0=1.0, w1=2.0)

@@ -62,7 +62,8 @@ def test_words_loss_vs_reference_fixture(cuda_lib, name):
 
 
 @pytest.mark.parametrize("kind,cls,B,T", [("realistic", "cub", 48, 18), ("stress", "unique", 16, 18),
-                                         ("realistic", "none", 7, 20), ("stress", "cub", 33, 5)])
+                                         ("realistic", "none", 7, 20), ("stress", "cub", 33, 5),
+                                         ("realistic", "unique", 64, 20)])  # the last: BASELINE config 3 (COCO shape)
 def test_words_loss_vs_oracle(cuda_lib, kind, cls, B, T):
     import eegan_b200 as E
     c = cases.words_case(B, T, kind=kind, class_mode=cls, seed=77, min_len=min(5, T))
@@ -282,6 +283,51 @@ def test_full_size_properties(cuda_lib):
         assert torch.equal(sim_j, sim)
         for a in att:
             assert float((a.sum(dim=(2, 3)) - 1).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("B,T", [(256, 20), (512, 20)])
+def test_large_batch_blocks_vs_oracle(cuda_lib, B, T):
+    """BASELINE config 5 sizes (flower sweep up to B = 512; the 31.5 GB stash of B = 512 is allocated here).  The float64
+    oracle of the whole grid would need tens of GB on the host, so VALUES are checked block-wise, which loses nothing: the
+    similarity m[j, i] depends on image j and caption i only, and with an upstream gradient G that is non-zero on a block
+    (J x I) only, d_words[i in I] and d_img[j in J] are exactly the oracle's gradients of that block."""
+    import eegan_b200 as E
+    from eegan_b200 import damsm_losses as dl
+    c = cases.words_case(B, T, seed=B, class_mode="cub")
+    gen = cases._gen(B + 1)
+    J = torch.randperm(B, generator=gen)[:6].sort().values
+    I = torch.randperm(B, generator=gen)[:5].sort().values
+    J[0], I[0] = 0, 0                 # first tile / first bin
+    J[-1], I[-1] = B - 1, B - 1       # last tile / last (partial) bin
+    G = torch.zeros(B, B)
+    Gb = torch.randn(len(J), len(I), generator=gen)
+    G[J[:, None], I[None, :]] = Gb
+    img, words = c["img"].cuda().requires_grad_(), c["words"].cuda().requires_grad_()
+    m, att = dl.pair_grid(img, words, c["cap_lens"].cuda())
+    (m * G.cuda()).sum().backward()
+    io, wo = c["img"][J].double().requires_grad_(), c["words"][I].double().requires_grad_()
+    t = O.dense_pair_terms(io, wo, c["cap_lens"][I])
+    (t["m"] * Gb.double()).sum().backward()
+    assert float((m.detach().cpu().double()[J[:, None], I[None, :]] - t["m"].detach()).abs().max()) <= TOL_SIM / 10.0  # m = sim / gamma3
+    assert relmax(words.grad[I.cuda()].cpu(), wo.grad) <= TOL_GRAD
+    assert relmax(img.grad[J.cuda()].cpu(), io.grad) <= TOL_GRAD
+    # rows / columns outside the block receive exactly nothing
+    rest_i = torch.ones(B, dtype=torch.bool); rest_i[I] = False
+    rest_j = torch.ones(B, dtype=torch.bool); rest_j[J] = False
+    assert float(words.grad[rest_i.cuda()].abs().max()) == 0.0 and float(img.grad[rest_j.cuda()].abs().max()) == 0.0
+    # the losses of the full grid: finite, and the two-way CE of the reference on the GPU's own sim (float64 on the host)
+    l0, l1, _ = E.words_loss(c["img"].cuda(), c["words"].cuda(), c["labels"].cuda(), c["cap_lens"].cuda(), c["class_ids"], B)
+    sim, _ = E.words_similarity(c["img"].cuda(), c["words"].cuda(), c["cap_lens"].cuda(), c["class_ids"], B)
+    r0, r1 = O._two_way_ce(sim.cpu().double(), c["labels"])
+    assert abs(l0.item() - float(r0)) <= 5 * TOL_LOSS * max(1.0, abs(float(r0))) and abs(l1.item() - float(r1)) <= 5 * TOL_LOSS * max(1.0, abs(float(r1)))
+    # diagonal attention maps of the sampled captions that are also sampled images
+    for i in [int(v) for v in I if int(v) in set(int(u) for u in J)]:
+        ji, ii = int((J == i).nonzero()[0]), int((I == i).nonzero()[0])
+        Ti = int(c["cap_lens"][i])
+        assert float((att[i, :Ti].cpu().double() - t["a"][ji, ii, :Ti].detach()).abs().max()) <= TOL_ATT
+    from eegan_b200 import fastpath
+    fastpath.clear_plans()
+    torch.cuda.empty_cache()
 
 
 def test_ffma_engine_still_matches(cuda_lib):

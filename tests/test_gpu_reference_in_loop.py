@@ -169,27 +169,43 @@ def test_gen_with_install_matches_reference_gen(cuda_lib):
     g = cases._gen(2)
     z, sent, attrs = torch.randn(B, 100, generator=g).cuda(), torch.randn(B, 256, generator=g).cuda(), torch.randn(B, 256, generator=g).cuda()
     go = [torch.randn(B, 3, s, s, generator=g).cuda() for s in (64, 128, 256)]
+    # The arbiter is the reference Gen in FLOAT64: a 7-stage generator with random weights and 4-sample batch statistics
+    # amplifies fp32 rounding, so "equal" means: eegan_b200's fp32 result is as close to float64 as the reference's own fp32 is.
+    import copy
+    G64 = copy.deepcopy(Gr).double()
     prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     try:
         res = []
-        for G in (Gr, Gi):
-            s = sent.clone().requires_grad_()
-            imgs = G(z, s, attrs)
-            torch.autograd.backward(imgs, go)
-            res.append((imgs, s.grad, {n: p.grad for n, p in G.named_parameters()}, {n: b for n, b in G.named_buffers()}))
+        for G, dt in ((G64, torch.float64), (Gr, torch.float32), (Gi, torch.float32)):
+            s = sent.to(dt).clone().requires_grad_()
+            imgs = G(z.to(dt), s, attrs.to(dt))
+            torch.autograd.backward(imgs, [g_.to(dt) for g_ in go])
+            res.append(([im.detach().double() for im in imgs], s.grad.double(), {n: p.grad.double() for n, p in G.named_parameters()},
+                        {n: b.double() for n, b in G.named_buffers()}))
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
-    (ri, rs, rp, rb), (ii, is_, ip, ib) = res
-    for a, b in zip(ii, ri):
-        assert float((a - b).abs().max()) <= 2e-4
-    assert relmax(is_, rs) <= 2e-3
-    scale = max(float(v.abs().max()) for v in rp.values())
-    for n in rp:
-        assert float((ip[n] - rp[n]).abs().max()) <= 2e-3 * max(scale * 1e-3, float(rp[n].abs().max())), n
-    for n in rb:
+    (di, ds, dp, db), (ri, rs, rp, rb), (ii, is_, ip, ib) = res
+
+    bad = []
+
+    def held(ours, ref32, f64, what, floor):
+        e_ref, e_ours = float((ref32 - f64).abs().max()), float((ours - f64).abs().max())
+        if not e_ours <= 4.0 * e_ref + floor * max(1e-30, float(f64.abs().max())):
+            bad.append((what, e_ours, e_ref, float(f64.abs().max())))
+
+    for k in range(3):
+        held(ii[k], ri[k], di[k], "image %d" % k, 1e-5)
+    held(is_, rs, ds, "d sent", 1e-5)
+    for n in dp:
+        # the scalar residual gates (`gamma`, models.py:103, 135) collect sum(residual * grad) over up to 8.4e6 activations with heavy
+        # cancellation, downstream of batch statistics that eegan_b200 forms as the reference's own N-replica code does
+        # (sum / square-sum, batchnorm.py:113-125) while the one-replica reference calls cuDNN's batch norm: a wider floor there
+        held(ip[n], rp[n], dp[n], n, 1e-3 if n.endswith("gamma") else 5e-5)
+    for n in db:
         if "running" in n:
-            assert relmax(ib[n], rb[n]) <= 1e-4, n
+            held(ib[n], rb[n], db[n], n, 1e-5)
+    assert not bad, bad
 
 
 # ---------------------------------------------------------------------------------------

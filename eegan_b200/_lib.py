@@ -26,6 +26,8 @@ SIGNATURES = {
                                       _p, _p, _c_int, _p, _c_size_t, _p]),
     "eegan_damsm_pair_bwd": (_c_int, [_p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,
                                       _p, _p, _p, _p, _c_size_t, _p]),
+    "eegan_damsm_pair_bwd_phased": (_c_int, [_p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,
+                                             _p, _p, _p, _c_int, _p, _c_size_t, _p]),
     "eegan_pair_ce_fwd": (_c_int, [_p, _c_float, _p, _p, _c_int, _p, _p, _p, _p]),
     "eegan_pair_ce_bwd": (_c_int, [_p, _p, _p, _p, _c_float, _c_int, _p, _p]),
     "eegan_sent_scores_fwd": (_c_int, [_p, _p, _c_int, _c_int, _c_float, _c_float, _p, _p, _p]),

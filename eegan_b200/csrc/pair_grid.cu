@@ -716,6 +716,18 @@ extern "C" int eegan_damsm_pair_fwd(const float* img, const float* words, const 
     return EEGAN_OK;
 }
 
+extern "C" int eegan_damsm_pair_bwd_phased(const float* img, const float* words, const int32_t* cap_lens, int Bi, int Bc,
+                                           int D, int R, int Tm, float g1, float g2, const float* dm, float* d_img,
+                                           float* d_words, int phases, void* workspace, size_t workspace_bytes, void* stream) {
+    EEGAN_REQUIRE(phases >= 1 && phases <= 3, "pair bwd: phases=%d (1 = image part, 2 = words part, 3 = both)", phases);
+    if (phases == 3) return eegan_damsm_pair_bwd(img, words, cap_lens, Bi, Bc, D, R, Tm, g1, g2, dm, d_img, d_words, workspace, workspace_bytes, stream);
+    int rc = validate(Bi, Bc, D, R, Tm);
+    if (rc) return rc;
+    EEGAN_REQUIRE(img && dm && workspace, "pair bwd: null pointer");
+    EEGAN_REQUIRE(g_engine.load() == 3 && fused_ok(D), "pair bwd: split phases need the default contraction engine (3) and D %% 128 == 0");
+    return pair_h_bwd(img, Bi, Bc, D, R, Tm, g1, g2, dm, d_img, d_words, workspace, workspace_bytes, (cudaStream_t)stream, phases);
+}
+
 extern "C" int eegan_damsm_pair_bwd(const float* img, const float* words, const int32_t* cap_lens, int Bi, int Bc,
                                     int D, int R, int Tm, float g1, float g2, const float* dm, float* d_img,
                                     float* d_words, void* workspace, size_t workspace_bytes, void* stream) {

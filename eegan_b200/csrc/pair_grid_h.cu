@@ -39,7 +39,7 @@ struct HWs {
     int* col_cap;
     float* scal;     // [HS_COUNT] maxima and scales
     float* pmax;     // [3][npart] per-CTA partial maxima of the prologue: |c|, column norm^2 of C, |w|
-    float* pdun;     // [Bi][maxbins] per-CTA partial maxima of the DUz row norms
+    float* pdun;     // [Bi] per-image partial maxima of the DUz row norms
     float* Wp;       // [NtP][D] packed words, fp32 (cos/lse, dU)
     float* wn;       // [NtP]
     __half* Wh;      // [NtP][D]
@@ -304,32 +304,34 @@ __global__ void __launch_bounds__(256) h_pack_kernel(const float* __restrict__ w
 // Largest row 2-norm of DUz over all (image j, packed column n'), from the per-column scalars alone:
 //   du = dcos (w / (|w||u|) - cos u / |u|^2)  =>  |du| = |dcos| sqrt(1 - cos^2) / |u|,  DUz = du / Z
 // (clamped columns, |w||u| <= 1e-8: du = dcos w / 1e-8).  The 1e-6 floor under 1 - cos^2 keeps rounding noise of
-// near-parallel columns inside the bound.  grid (bins, images), 64 threads = the bin's columns.
-__global__ void __launch_bounds__(64) h_duscale_kernel(const float* __restrict__ wn, const float* __restrict__ Z,
-                                                       const float* __restrict__ cosv, const float* __restrict__ un,
-                                                       const float* __restrict__ dm, const float* __restrict__ mst,
-                                                       const int* __restrict__ col_cap, const int* __restrict__ meta, int NtP, int Bc,
-                                                       float g2, float* __restrict__ pdun) {
+// near-parallel columns inside the bound.  One CTA per image walks that image's live columns and leaves ONE partial
+// maximum (pdun[j]): the dU kernel's CTAs each reduce the partials again, so their number must grow with B, not B^2
+// (with one partial per (image, bin) every dU CTA re-read B * bins floats: 350 KB at B = 512, 13 ms of the step).
+__global__ void __launch_bounds__(256) h_duscale_kernel(const float* __restrict__ wn, const float* __restrict__ Z,
+                                                        const float* __restrict__ cosv, const float* __restrict__ un,
+                                                        const float* __restrict__ dm, const float* __restrict__ mst,
+                                                        const int* __restrict__ col_cap, const int* __restrict__ meta, int NtP, int Bc,
+                                                        float g2, float* __restrict__ pdun) {
     __shared__ float red[32];
-    const int b = blockIdx.x, j = blockIdx.y;
+    const int j = blockIdx.x;
     pdl_trigger();
     pdl_wait();
     float nz = 0.f;
-    if (b < meta[0]) {
-        const int n = b * V3_BIN + threadIdx.x;
+    const int nlive = meta[1];
+    for (int n = threadIdx.x; n < nlive; n += blockDim.x) {
         const int i = col_cap[n];
-        if (i >= 0) {
-            const size_t idx = (size_t)j * NtP + n;
-            const float c = cosv[idx], unv = un[idx];
-            const float dcos = fabsf(dm[(size_t)j * Bc + i] * g2 * expf(g2 * c - mst[(size_t)j * Bc + i]));
-            const float nn = wn[n] * unv;
-            const float nrm = nn > 1e-8f ? dcos * sqrtf(fmaxf(1.0f - c * c, 1e-6f)) / unv : dcos * 1e8f * wn[n];
-            nz = nrm / Z[idx];
-            if (!(nz >= 0.f)) nz = INFINITY;  // NaN upstream: poison the maximum so that the scale falls back to 1
-        }
+        if (i < 0) continue;
+        const size_t idx = (size_t)j * NtP + n;
+        const float c = cosv[idx], unv = un[idx];
+        const float dcos = fabsf(dm[(size_t)j * Bc + i] * g2 * expf(g2 * c - mst[(size_t)j * Bc + i]));
+        const float nn = wn[n] * unv;
+        const float nrm = nn > 1e-8f ? dcos * sqrtf(fmaxf(1.0f - c * c, 1e-6f)) / unv : dcos * 1e8f * wn[n];
+        float v = nrm / Z[idx];
+        if (!(v >= 0.f)) v = INFINITY;  // NaN upstream: poison the maximum so that the scale falls back to 1
+        nz = fmaxf(nz, v);
     }
     nz = block_max(nz, red);
-    if (threadIdx.x == 0) pdun[(size_t)j * gridDim.x + b] = nz;  // every CTA writes (0 for dead bins): nothing to zero beforehand
+    if (threadIdx.x == 0) pdun[j] = nz;  // every CTA writes: nothing to zero beforehand
 }
 
 // One CTA per (packed column n', group of 64 images): as v3_du_kernel (pair_grid_v3.cu), with DUz written as half pairs.
@@ -546,7 +548,7 @@ int pair_h_fwd(const float* img, const float* words, const int32_t* cap_lens, in
 }
 
 int pair_h_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1, float g2, const float* dm, float* d_img,
-               float* d_words, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+               float* d_words, void* workspace, size_t workspace_bytes, cudaStream_t st, int phases) {
     (void)img;
     HWs w = h_carve(workspace, Bi, Bc, D, R, Tm);
     if (workspace_bytes < w.bytes) {
@@ -556,14 +558,17 @@ int pair_h_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1,
     const int NtP = w.NtP;
 
     prof_mark(-1, st);
-    launch_pdl(h_duscale_kernel, dim3(w.maxbins, Bi), dim3(64), 0, st, (const float*)w.wn, (const float*)w.Z, (const float*)w.cosv,
+    const HOperand opC_mn{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, R, D, w.scal + HS_IC};
+    const HOperand opC_k{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, D, R, w.scal + HS_IC};
+    if (phases & 1) {
+    launch_pdl(h_duscale_kernel, dim3(Bi), dim3(256), 0, st, (const float*)w.wn, (const float*)w.Z, (const float*)w.cosv,
                (const float*)w.un, dm, (const float*)w.mst, (const int*)w.col_cap, (const int*)w.meta, NtP, Bc, g2, w.pdun);
     {
         dim3 grid(NtP, w.ngroups);
 #define H_DU(NQ)                                                                                                                  \
     launch_pdl(h_du_kernel<NQ>, grid, dim3(256), 0, st, (const float*)w.U, (const float*)w.Wp, (const float*)w.wn, (const float*)w.Z, \
                (const float*)w.cosv, (const float*)w.un, dm, (const float*)w.mst, (const int*)w.col_cap, (const int*)w.meta, NtP, Bi, \
-               Bc, D, g1, g2, w.DUh, w.DUl, w.csz, w.dwcos, (const float*)w.pdun, Bi * w.maxbins, w.scal)
+               Bc, D, g1, g2, w.DUh, w.DUl, w.csz, w.dwcos, (const float*)w.pdun, Bi, w.scal)
         switch (D / 128) {
             case 1: H_DU(1); break;
             case 2: H_DU(2); break;
@@ -579,8 +584,6 @@ int pair_h_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1,
     EEGAN_LAUNCH_CHECK("pair dU");
     prof_mark(5, st);
 
-    const HOperand opC_mn{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, R, D, w.scal + HS_IC};
-    const HOperand opC_k{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, D, R, w.scal + HS_IC};
     {  // GEMM3 + attention backward: acc = C^T DUz^T = dA / Z -> dS^T (half pairs)
         HGemm g{};
         g.nseg = 1;
@@ -608,7 +611,8 @@ int pair_h_bwd(const float* img, int Bi, int Bc, int D, int R, int Tm, float g1,
         if (rc) return rc;
         prof_mark(8, st);
     }
-    if (d_words) {  // GEMM5: dWp[n'][d] = sum_j sum_r dS^T[j][r][n'] C[j][d][r], images split in nsplit groups
+    }  // phases & 1
+    if (d_words && (phases & 2)) {  // GEMM5: dWp[n'][d] = sum_j sum_r dS^T[j][r][n'] C[j][d][r], images split in nsplit groups
         const int nred = (Bi + w.nsplit - 1) / w.nsplit;
         HGemm g{};
         g.nseg = 1;

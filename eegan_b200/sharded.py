@@ -175,6 +175,7 @@ class ShardedWordsLossStep:
         self.d_img = torch.zeros(b, D, H, W, **f32)
         self.d_words = torch.zeros(b, D, T_max, **f32) if words_grad else None
         self._use_graph, self._graph = bool(graph), None
+        self._phased = L.eegan_get_contraction_engine() == 3 and D % 128 == 0
 
     def _enqueue(self):
         _lib = self._lib
@@ -182,10 +183,11 @@ class ShardedWordsLossStep:
         b, Bt, D, R, Tm = self.dims
         g1, g2, g3 = gammas()
         rank, grp = self.rank, self.group
+        h_cls = None
         if self.world > 1:
             dist.all_gather_into_tensor(self._img_all, self.img.view(b, D, R), group=grp)
-            if self._cls_all is not None:
-                dist.all_gather_into_tensor(self._cls_all, self.class_ids, group=grp)
+            if self._cls_all is not None:  # only the cross-entropy needs the class ids: gathered behind the pair grid
+                h_cls = dist.all_gather_into_tensor(self._cls_all, self.class_ids, group=grp, async_op=True)
         else:
             self._img_all.copy_(self.img.view(b, D, R))
             if self._cls_all is not None:
@@ -198,13 +200,26 @@ class ShardedWordsLossStep:
             self._m_all.view(Bt, self.world, b).copy_(self._m_parts.permute(1, 0, 2))
         else:
             self._m_all.copy_(self._m_block)
+        if h_cls is not None:
+            h_cls.wait()
         with torch.cuda.device(self.img.device):
             _lib.check(L.eegan_pair_ce_fwd(p(self._m_all), g3, p(self._cls_all), p(self._labels), Bt, p(self._sim), p(self._loss01),
                                            p(self._lse), st), "pair_ce_fwd")
             _lib.check(L.eegan_pair_ce_bwd(p(self._sim), p(self._lse), p(self._labels), p(self._gvec), g3, Bt, p(self._dsim), st),
                        "pair_ce_bwd")
         self._dm_block.copy_(self._dsim[:, rank * b:(rank + 1) * b])
+        split = self.world > 1 and self.d_words is not None and self._phased
         with torch.cuda.device(self.img.device):
+            if split:  # image part first: the reduce-scatter of d_img then runs behind the words part (GEMM5 + unpack)
+                _lib.check(L.eegan_damsm_pair_bwd_phased(p(self._img_all), p(self.words), p(self.cap_lens32), Bt, b, D, R, Tm, g1, g2,
+                                                         p(self._dm_block), p(self._d_img_all), None, 1, p(self._ws), self._ws.numel(), st),
+                           "damsm_pair_bwd(image part)")
+                h_rs = dist.reduce_scatter_tensor(self.d_img.view(b, D, R), self._d_img_all, op=dist.ReduceOp.SUM, group=grp, async_op=True)
+                _lib.check(L.eegan_damsm_pair_bwd_phased(p(self._img_all), p(self.words), p(self.cap_lens32), Bt, b, D, R, Tm, g1, g2,
+                                                         p(self._dm_block), None, p(self.d_words), 2, p(self._ws), self._ws.numel(), st),
+                           "damsm_pair_bwd(words part)")
+                h_rs.wait()
+                return
             _lib.check(L.eegan_damsm_pair_bwd(p(self._img_all), p(self.words), p(self.cap_lens32), Bt, b, D, R, Tm, g1, g2,
                                               p(self._dm_block), p(self._d_img_all), p(self.d_words), p(self._ws), self._ws.numel(), st),
                        "damsm_pair_bwd")

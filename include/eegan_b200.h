@@ -85,6 +85,17 @@ int eegan_damsm_pair_bwd(const float* img, const float* words, const int32_t* ca
                          const float* dm, float* d_img, float* d_words,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same backward in two calls, so that a caller can start the reduce-scatter of d_img (caption-row-sharded
+ * multi-GPU runs) while d_words is still being computed:
+ *   phases = 1  per-column scalars, dU, dS and d_img (d_words ignored);
+ *   phases = 2  d_words from the dS stash phase 1 left in the workspace (d_img ignored);
+ *   phases = 3  both = eegan_damsm_pair_bwd.   Split phases need the default contraction engine. */
+int eegan_damsm_pair_bwd_phased(const float* img, const float* words, const int32_t* cap_lens,
+                                int B_img, int B_cap, int D, int R, int T_max,
+                                float gamma1, float gamma2,
+                                const float* dm, float* d_img, float* d_words, int phases,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * func_attention — miscc/DAMSM_losses.py:25-63, as a stand-alone op (sample b's query against
  * sample b's context; the pair grid is its all-pairs form).

@@ -693,6 +693,396 @@ int h_gemm_launch(const HGemm& g, cudaStream_t st) {
     return h_launch_t<TC_EPI_PLAIN, false>(maps, a, grid, st);
 }
 
+// =======================================================================================
+// Fused forward of the pair grid: per (image j, 128-column word tile), for every 128-region slab
+//     S_slab = C[j][:, slab]^T W_tile          (tcgen05, K = D)           -> TMEM accumulator (double-buffered)
+//     P = softmax_words(S),  E' = 2^12 exp(g1 (P - 1))                    (attention epilogue, thread = region)
+//     U'[n'][d] += sum_{r in slab} E'[r][n'] C[j][d][r]   (tcgen05, K = 128 regions, N = D = 256) -> second TMEM accumulator
+// E' goes from the epilogue's registers into a shared-memory tile laid out as the MN-major SWIZZLE_128B A operand of the
+// second contraction (and, as before, to the HBM stash the backward reads) — GEMM2 no longer re-reads E from L2 / HBM, the
+// U' contraction rides behind the next slab's S contraction on the same tensor pipe, and one launch ramp disappears.
+// Roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-9 epilogue (two per TMEM lane quarter: one 64-column
+// bin of the tile each).  MMA order per item (ns slabs): M1(0); for s >= 1: M1(s), M2(s-1); M2(ns-1) — the producer issues
+// its loads in the same order through one 3-stage ring of 32 KB blocks (S: C boxes + W boxes; U': one [256 d][32 r] box pair).
+// TMEM: S0 [0,128) S1 [128,256) U' [256,512).  Needs D == 256.
+// =======================================================================================
+constexpr int HF_NS = 3;
+constexpr int HF_STAGE = 32768;
+constexpr int HF_EHALF = 32768;             // one of E hi / lo: [4 k-blocks of 32 regions][2 chunks of 64 columns][32 rows][128 B]
+constexpr int HF_EWARPS = 8;
+constexpr int HF_EPI_WARP_BYTES = 32 * H_EPI_PITCH * 4;
+constexpr int HF_THREADS = 32 * (2 + HF_EWARPS);
+constexpr int HF_SMEM = HF_NS * HF_STAGE + 2 * HF_EHALF + HF_EWARPS * HF_EPI_WARP_BYTES + 128;
+static_assert(HF_SMEM <= 232448, "fused forward: shared memory budget");
+
+struct HFMaps {
+    CUtensorMap c_mn[2];  // C as A of S:  MN-major [d][r], box [32 d][64 r]           (hi, lo)
+    CUtensorMap w_k[2];   // W as B of S:  K-major [n'][d], box [128 n'][32 d]
+    CUtensorMap c_k[2];   // C as B of U': K-major [d][r],  box [256 d][32 r]
+};
+struct HFArgs {
+    float* U;              // [Bi][NtP][D]
+    long long ldc, bC;     // stash pitch (NtP) and image stride (R * NtP) of P / E / (Zpart uses ldc)
+    int R, D, NtP, Bi;
+    const int* nlive;      // live packed columns (bins * 64)
+    const float* inv_c;
+    const float* inv_w;
+    const float* inv_e;
+    HAttnEpi attn;
+    int dbg;  // -DEEGAN_DEBUG_SWITCHES builds only (EEGAN_HF_DBG): 1 no stash stores, 2 no read-out, 4 no caption phase, 8 no U' MMAs, 16 no U' drain stores
+};
+#ifdef EEGAN_DEBUG_SWITCHES
+#define HF_DBG(p) ((p).dbg)
+#else
+#define HF_DBG(p) 0
+#endif
+
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// attention forward on one S tile (one epilogue warp: 32 regions x one 64-column bin), E' also into the shared-memory operand tile
+__device__ __forceinline__ void hf_attn_fwd_tile(const HFArgs& p, const EpiTile& t, int lane, float inv0, uint32_t e_hi, uint32_t e_lo,
+                                                 uint32_t e_free_bar, int e_free_wait, uint32_t e_free_parity, uint32_t e_ready_bar) {
+    const TcAttnEpi& e = p.attn.base;
+    const int nbins = *e.nbins;
+    const int row0 = t.m0 + t.quarter * 32;
+    const int rows_live = max(0, min(32, t.Mlive - row0));
+    const uint32_t my_row = t.stage + (uint32_t)(lane * H_EPI_PITCH) * 4u;
+    const int h = t.half;
+    const int b0 = t.n0 >> 6;
+    const int b = b0 + h;
+    if (b >= nbins) {  // no live bin for this warp in the tile: keep the hand-shakes going (in step with the live warps:
+        // an arrival for slab g may only follow the completion of slab g - 1's phase, hence the same e_free wait)
+        mbar_wait(t.full_bar, t.full_parity);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t.empty_bar);
+        if (e_free_wait) mbar_wait(e_free_bar, e_free_parity);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(e_ready_bar);
+        return;
+    }
+    const int bc_l = e.bin_cap[min(b0 + lane, nbins)];
+    const int bu_l = (lane < 2 && b0 + lane < nbins) ? e.bin_used[b0 + lane] : 0;
+    const int i0 = __shfl_sync(0xffffffffu, bc_l, h), i1 = __shfl_sync(0xffffffffu, bc_l, h + 1);
+    const int used = __shfl_sync(0xffffffffu, bu_l, h);
+    const int col0 = t.n0 + 64 * h;
+    bool waited = false;
+#pragma unroll 1
+    for (int ic = i0; ic < i1; ic += 32) {
+        const int nc = min(32, i1 - ic);
+        const int myT = lane < nc ? e.cap_len[ic + lane] : 0;
+        const int myC = lane < nc ? e.col_start[ic + lane] - col0 : 0;
+        if (!waited) {
+            mbar_wait(t.full_bar, t.full_parity);
+            tc_fence_after();
+            waited = true;
+        }
+#pragma unroll 1
+        for (int ci = 0; ci < nc; ++ci) {
+            const int T = __shfl_sync(0xffffffffu, myT, ci);
+            if (T <= 0) continue;
+            const int cl = __shfl_sync(0xffffffffu, myC, ci);
+            if (!(HF_DBG(p) & 4)) h_attn_caption<TC_EPI_ATTN_FWD>(t.tacc + (uint32_t)(64 * h + cl), T, my_row + (uint32_t)cl * 4u, 0u, e.g1, inv0);
+        }
+    }
+    if (!waited) {
+        mbar_wait(t.full_bar, t.full_parity);
+        tc_fence_after();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(t.empty_bar);
+    for (int c = used; c < 64; ++c) sts_f32(my_row + (uint32_t)c * 4u, 0.f);  // padding columns of the bin
+    __syncwarp();
+    if (e_free_wait) mbar_wait(e_free_bar, e_free_parity);  // the previous slab's U' contraction has read the operand tile
+    // read-out: region rows, coalesced; a lane owns the adjacent columns 2 lane, 2 lane + 1 of the bin
+    float* Pz = e.P + (long long)t.z * p.bC;
+    __half* Hz = p.attn.out_hi + (long long)t.z * p.bC;
+    __half* Lz = p.attn.out_lo + (long long)t.z * p.bC;
+    const uint32_t rd0 = t.stage + (uint32_t)(2 * lane) * 4u;
+    const long long o0 = (long long)row0 * p.ldc + col0 + 2 * lane;
+    uint32_t* hp = reinterpret_cast<uint32_t*>(Hz + o0);
+    uint32_t* lp = reinterpret_cast<uint32_t*>(Lz + o0);
+    float2* pp = reinterpret_cast<float2*>(Pz + o0);
+    const long long hstep = p.ldc >> 1;
+    // operand tile: k-block = lane quarter, chunk = bin h, row r of the quarter: 128-byte rows, 16-byte units XOR (r & 7)
+    const uint32_t eoff = (uint32_t)t.quarter * 8192u + (uint32_t)h * 4096u;
+    const uint32_t eunit = (uint32_t)(lane >> 2), ein = (uint32_t)(lane & 3) << 2;
+    const float a = e.g1 * 1.4426950408889634f, bb = 12.0f - a;
+    float z0 = 0.f, z1 = 0.f, em = 0.f;
+    const int rows_do = (HF_DBG(p) & 2) ? 0 : rows_live;
+#pragma unroll 4
+    for (int r = 0; r < rows_do; ++r) {
+        const float2 pv = lds_f32x2(rd0 + (uint32_t)(r * H_EPI_PITCH) * 4u);
+        float e0, e1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(pv.x, a, bb)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(pv.y, a, bb)));
+        const __half2 hh = __floats2half2_rn(e0, e1);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(e0 - hf.x, e1 - hf.y);
+        const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hh), lu = *reinterpret_cast<const uint32_t*>(&ll);
+        if (!(HF_DBG(p) & 1)) {
+            *pp = pv;
+            *hp = hu;
+            *lp = lu;
+        }
+        pp += hstep; hp += hstep; lp += hstep;
+        const uint32_t ea = eoff + (uint32_t)r * 128u + ((eunit ^ (uint32_t)(r & 7)) << 4) + ein;
+        sts_u32(e_hi + ea, hu);
+        sts_u32(e_lo + ea, lu);
+        z0 += e0;
+        z1 += e1;
+        em = fmaxf(em, fmaxf(e0, e1));
+    }
+    if (rows_live > 0) {
+        float* zp = e.Zpart + ((long long)t.z * ((p.R + 31) / 32) + (row0 >> 5)) * p.ldc + col0 + 2 * lane;
+        *reinterpret_cast<float2*>(zp) = make_float2(z0 * (1.0f / H_E_SCALE), z1 * (1.0f / H_E_SCALE));
+    }
+    em = warp_max(em) * (1.0f / H_E_SCALE);
+    if (lane == 0 && em > 0.f) atomicMax(reinterpret_cast<int*>(p.attn.emax), __float_as_int(em));
+    fence_proxy_async();  // the tensor core reads the tile through the async proxy
+    __syncwarp();
+    if (lane == 0) mbar_arrive(e_ready_bar);
+}
+
+__global__ void __launch_bounds__(HF_THREADS, 1) hf_fwd_kernel(const __grid_constant__ HFMaps tm, const HFArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = smem_u32(smem_raw);
+    const uint32_t e_hi = base + HF_NS * HF_STAGE, e_lo = e_hi + HF_EHALF;
+    const uint32_t epi_stage = e_lo + HF_EHALF;
+    const uint32_t bars = epi_stage + HF_EWARPS * HF_EPI_WARP_BYTES;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (HF_NS + s); };
+    auto s_full = [&](int a) { return bars + 8u * (2 * HF_NS + a); };
+    auto s_empty = [&](int a) { return bars + 8u * (2 * HF_NS + 2 + a); };
+    const uint32_t e_ready = bars + 8u * (2 * HF_NS + 4), e_free = e_ready + 8u, u_full = e_ready + 16u, u_empty = e_ready + 24u;
+    const uint32_t tmem_slot = e_ready + 32u;
+
+    pdl_trigger();
+    if ((base & 1023u) != 0u) __trap();  // SWIZZLE_128B tiles need the 1024-byte alignment the declaration asks for
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HF_NS; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(s_full(a), 1);
+            mbar_init(s_empty(a), HF_EWARPS);
+        }
+        mbar_init(e_ready, HF_EWARPS);
+        mbar_init(e_free, 1);
+        mbar_init(u_full, 1);
+        mbar_init(u_empty, HF_EWARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.c_mn[q]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.w_k[q]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.c_k[q]) : "memory");
+        }
+    }
+    // the operand tile starts as zeros: rows beyond the live regions of a slab are never written and must stay finite
+    for (uint32_t o = threadIdx.x * 16u; o < 2u * HF_EHALF; o += HF_THREADS * 16u)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(e_hi + o), "r"(0u) : "memory");
+    fence_proxy_async();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+    pdl_wait();  // from here on: global memory written by the previous kernels
+
+    const int nlive = min(*p.nlive, p.NtP);
+    const int ntl = (nlive + H_BN - 1) / H_BN;
+    const int nitems = ntl * p.Bi;
+    const int ns = (p.R + H_BM - 1) / H_BM;
+    const int kb1 = p.D / H_BK;
+    auto kb2_of = [&](int s) { return (min(H_BM, p.R - s * H_BM) + H_BK - 1) / H_BK; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            auto acquire = [&]() {
+                const int s = it % HF_NS, ph = (it / HF_NS) & 1;
+                mbar_wait(empty(s), ph ^ 1);
+                mbar_arrive_expect_tx(full(s), (uint32_t)HF_STAGE);
+                ++it;
+                return s;
+            };
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int j = item / ntl, n0 = (item - j * ntl) * H_BN;
+                auto load1 = [&](int sl) {
+                    for (int kb = 0; kb < kb1; ++kb) {
+                        const int s = acquire();
+                        const uint32_t sA = base + s * HF_STAGE, sB = sA + 2 * H_A_TILE;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            tma_load_3d(sA + h * H_A_TILE, &tm.c_mn[h], full(s), sl * H_BM, kb * H_BK, j);
+                            tma_load_3d(sA + h * H_A_TILE + 4096, &tm.c_mn[h], full(s), sl * H_BM + 64, kb * H_BK, j);
+                            tma_load_3d(sB + h * H_B_TILE, &tm.w_k[h], full(s), kb * H_BK, n0, 0);
+                        }
+                    }
+                };
+                auto load2 = [&](int sl) {
+                    const int nkb = kb2_of(sl);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        const int s = acquire();
+                        const uint32_t sB = base + s * HF_STAGE;
+                        tma_load_3d(sB, &tm.c_k[0], full(s), sl * H_BM + kb * H_BK, 0, j);
+                        tma_load_3d(sB + 16384, &tm.c_k[1], full(s), sl * H_BM + kb * H_BK, 0, j);
+                    }
+                };
+                load1(0);
+                for (int sl = 1; sl < ns; ++sl) {
+                    load1(sl);
+                    load2(sl - 1);
+                }
+                load2(ns - 1);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_common = (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | (1u << 15) /*A MN-major*/ |
+                                              (0u << 16) /*B K-major*/ | ((uint32_t)(H_BM >> 4) << 24);
+            constexpr uint32_t idesc1 = idesc_common | ((uint32_t)(H_BN >> 3) << 17);
+            constexpr uint32_t idesc2 = idesc_common | ((uint32_t)(256 >> 3) << 17);
+            const uint32_t tmem_u = tmem_base + 256u;
+            int it = 0, g1c = 0 /*S slabs issued*/, g2c = 0 /*U' slabs issued*/, items_done = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++items_done) {
+                auto mma1 = [&]() {
+                    const int acc = g1c & 1;
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * H_BN);
+                    mbar_wait(s_empty(acc), ((g1c >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < kb1; ++kb, ++it) {
+                        const int s = it % HF_NS, ph = (it / HF_NS) & 1;
+                        mbar_wait(full(s), ph);
+                        tc_fence_after();
+                        const uint32_t a_hi = base + s * HF_STAGE, a_lo = a_hi + H_A_TILE;
+                        const uint32_t b_hi = a_hi + 2 * H_A_TILE, b_lo = b_hi + H_B_TILE;
+#pragma unroll
+                        for (int ks = 0; ks < H_BK / 16; ++ks) {
+                            const uint64_t dah = h_desc_a(a_hi, ks), dal = h_desc_a(a_lo, ks);
+                            const uint64_t dbh = h_desc_b(b_hi, ks), dbl = h_desc_b(b_lo, ks);
+                            h_mma_f16(tmem_d, dal, dbh, idesc1, (kb > 0 || ks > 0) ? 1u : 0u);
+                            h_mma_f16(tmem_d, dah, dbl, idesc1, 1u);
+                            h_mma_f16(tmem_d, dah, dbh, idesc1, 1u);
+                        }
+                        tc_commit(empty(s));
+                    }
+                    tc_commit(s_full(acc));
+                    ++g1c;
+                };
+                auto mma2 = [&](int sl) {
+                    mbar_wait(e_ready, (uint32_t)(g2c & 1));
+                    if (sl == 0) mbar_wait(u_empty, (uint32_t)((items_done & 1) ^ 1));  // the previous item's U' has been drained
+                    tc_fence_after();
+                    const int nkb = kb2_of(sl);
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const int s = it % HF_NS, ph = (it / HF_NS) & 1;
+                        mbar_wait(full(s), ph);
+                        tc_fence_after();
+                        const uint32_t b_hi = base + s * HF_STAGE, b_lo = b_hi + 16384;
+                        const uint32_t a_hi = e_hi + (uint32_t)kb * 8192u, a_lo = e_lo + (uint32_t)kb * 8192u;
+#pragma unroll
+                        for (int ks = 0; ks < ((HF_DBG(p) & 8) ? 0 : H_BK / 16); ++ks) {
+                            const uint64_t dah = h_desc_a(a_hi, ks), dal = h_desc_a(a_lo, ks);
+                            const uint64_t dbh = h_desc_b(b_hi, ks), dbl = h_desc_b(b_lo, ks);
+                            h_mma_f16(tmem_u, dal, dbh, idesc2, (sl > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+                            h_mma_f16(tmem_u, dah, dbl, idesc2, 1u);
+                            h_mma_f16(tmem_u, dah, dbh, idesc2, 1u);
+                        }
+                        tc_commit(empty(s));
+                    }
+                    tc_commit(e_free);
+                    if (sl == ns - 1) tc_commit(u_full);
+                    ++g2c;
+                };
+                mma1();
+                for (int sl = 1; sl < ns; ++sl) {
+                    mma1();
+                    mma2(sl - 1);
+                }
+                mma2(ns - 1);
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const float inv_s = __ldg(p.inv_c) * __ldg(p.inv_w);
+        const float inv_u = __ldg(p.inv_e) * __ldg(p.inv_c);
+        HArgs pu{};  // the U' drain reuses the plain epilogue
+        pu.C = p.U; pu.ldc = p.D; pu.bC = (long long)p.NtP * p.D; pu.M = p.NtP; pu.N = p.D;
+        EpiTile et;
+        et.quarter = warp & 3;
+        et.half = ew >> 2;
+        et.stage = epi_stage + (uint32_t)ew * HF_EPI_WARP_BYTES;
+        et.czs = 0;
+        int g = 0, idone = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++idone) {
+            const int j = item / ntl, n0 = (item - j * ntl) * H_BN;
+            for (int sl = 0; sl < ns; ++sl, ++g) {
+                const int acc = g & 1;
+                et.z = j; et.m0 = sl * H_BM; et.n0 = n0; et.total = kb1; et.Mlive = p.R; et.Nlive = nlive;
+                et.tacc = tmem_base + ((uint32_t)(et.quarter * 32) << 16) + (uint32_t)(acc * H_BN);
+                et.full_bar = s_full(acc);
+                et.full_parity = (uint32_t)((g >> 1) & 1);
+                et.empty_bar = s_empty(acc);
+                hf_attn_fwd_tile(p, et, lane, inv_s, e_hi, e_lo, e_free, g > 0, (uint32_t)((g - 1) & 1), e_ready);
+            }
+            EpiTile eu = et;
+            eu.z = j; eu.m0 = n0; eu.n0 = 0; eu.total = 1; eu.Mlive = nlive; eu.Nlive = p.D;
+            eu.tacc = tmem_base + ((uint32_t)(et.quarter * 32) << 16) + 256u;
+            eu.full_bar = u_full;
+            eu.full_parity = (uint32_t)(idone & 1);
+            eu.empty_bar = u_empty;
+            h_epilogue_tile<TC_EPI_PLAIN, false, 256>(pu, eu, lane, inv_u, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+int h_fused_fwd_launch(const HFusedFwd& f, cudaStream_t st) {
+    EEGAN_REQUIRE(f.D == 256, "fused forward: D=%d (the U' accumulator takes exactly 256 tensor-memory columns)", f.D);
+    EEGAN_REQUIRE(f.NtP % 64 == 0 && f.R > 0 && f.Bi > 0, "fused forward: bad shape");
+    HFMaps maps;
+    const HOperand c_mn{f.Ch, f.Cl, f.Rp, (long long)f.D * f.Rp, f.Bi, f.R, f.D, f.inv_c};
+    const HOperand c_k{f.Ch, f.Cl, f.Rp, (long long)f.D * f.Rp, f.Bi, f.D, f.R, f.inv_c};
+    const HOperand w_k{f.Wh, f.Wl, f.D, 0, 1, f.NtP, f.D, f.inv_w};
+    int rc;
+    if ((rc = h_make_map(&maps.c_mn[0], f.Ch, c_mn, false, H_BN))) return rc;
+    if ((rc = h_make_map(&maps.c_mn[1], f.Cl, c_mn, false, H_BN))) return rc;
+    if ((rc = h_make_map(&maps.w_k[0], f.Wh, w_k, true, H_BN))) return rc;
+    if ((rc = h_make_map(&maps.w_k[1], f.Wl, w_k, true, H_BN))) return rc;
+    if ((rc = h_make_map(&maps.c_k[0], f.Ch, c_k, true, 256))) return rc;
+    if ((rc = h_make_map(&maps.c_k[1], f.Cl, c_k, true, 256))) return rc;
+    HFArgs a{};
+    a.U = f.U; a.ldc = f.NtP; a.bC = (long long)f.R * f.NtP; a.R = f.R; a.D = f.D; a.NtP = f.NtP; a.Bi = f.Bi;
+    a.nlive = f.nlive; a.inv_c = f.inv_c; a.inv_w = f.inv_w; a.inv_e = f.inv_e; a.attn = f.attn;
+#ifdef EEGAN_DEBUG_SWITCHES
+    if (const char* e = getenv("EEGAN_HF_DBG")) a.dbg = atoi(e);
+#endif
+    const TcAttnEpi& e = f.attn.base;
+    EEGAN_REQUIRE(e.nbins && e.bin_cap && e.bin_used && e.col_start && e.cap_len && e.P && e.Zpart && f.attn.out_hi && f.attn.out_lo &&
+                      f.attn.emax && f.U && f.nlive, "fused forward: arguments missing");
+    static SmemGrant grant;
+    if ((rc = grant_dyn_smem(hf_fwd_kernel, (size_t)HF_SMEM, grant, "fused forward"))) return rc;
+    const long long items = (long long)(f.NtP / H_BN + (f.NtP % H_BN ? 1 : 0)) * f.Bi;
+    const unsigned grid = (unsigned)(items < h_num_sms() ? items : h_num_sms());
+    cudaError_t err = launch_pdl(hf_fwd_kernel, dim3(grid), dim3(HF_THREADS), (size_t)HF_SMEM, st, maps, a);
+    if (err != cudaSuccess) { set_error("fused forward launch: %s", cudaGetErrorString(err)); return EEGAN_ERR_CUDA; }
+    return check_launch("fused forward");
+}
+
 // elementwise split of an fp32 array into the half pair of x * s (test entry point below)
 __global__ void h_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, long long n, float s) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {

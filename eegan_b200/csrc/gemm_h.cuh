@@ -78,6 +78,22 @@ struct HGemm {
 
 int h_gemm_launch(const HGemm& g, cudaStream_t st);
 
+// Fused forward of the pair grid (gemm_h.cu, hf_fwd_kernel): S = C^T W -> attention -> U' = E^T C in one persistent launch.
+struct HFusedFwd {
+    const __half* Ch;        // [Bi][D][Rp] image features (hi, lo)
+    const __half* Cl;
+    const __half* Wh;        // [NtP][D] packed words
+    const __half* Wl;
+    int Bi, D, R, Rp, NtP;
+    const int* nlive;        // device: live packed columns
+    const float* inv_c;      // device: 2^-e of C, W, E
+    const float* inv_w;
+    const float* inv_e;
+    float* U;                // [Bi][NtP][D] OUT: un-normalised word contexts U' = E C^T
+    HAttnEpi attn;           // packing metadata + P / E' (hi, lo) / Zpart / emax outputs, g1
+};
+int h_fused_fwd_launch(const HFusedFwd& f, cudaStream_t st);
+
 // x -> (hi, lo) halves of x * s, clamped to the fp16 range
 __device__ __forceinline__ void h_split(float xs, __half& hi, __half& lo) {
     xs = xs > H_CLAMP ? H_CLAMP : (xs < -H_CLAMP ? -H_CLAMP : xs);  // comparisons, not fminf/fmaxf: a NaN stays a NaN, as in the reference

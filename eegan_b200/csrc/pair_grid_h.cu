@@ -470,6 +470,14 @@ __global__ void __launch_bounds__(256) h_du_kernel(const float* __restrict__ U, 
 // ---------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------
+// EEGAN_FUSED_FWD=1 (read once) selects the one-launch forward (hf_fwd_kernel, gemm_h.cu: S + attention + U' per (image, word
+// tile)).  Parity-green (the whole GPU suite passes on it) and 35 MB less DRAM traffic per step at B = 48, but not faster yet
+// (68.9 us against 39.4 + 30.6 us for the two launches; profiles/README.md "r2 fused forward" has the ablation): off by default.
+static bool h_fused_fwd_on() {
+    static const bool on = [] { const char* e = getenv("EEGAN_FUSED_FWD"); return e ? atoi(e) != 0 : false; }();
+    return on;
+}
+
 static HAttnEpi h_attn_args(const HWs& w, float g1) {
     HAttnEpi a{};
     a.base.nbins = w.meta;
@@ -510,6 +518,19 @@ int pair_h_fwd(const float* img, const float* words, const int32_t* cap_lens, in
 
     const HOperand opC_mn{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, R, D, w.scal + HS_IC};  // A: rows = regions, K = channels
     const HOperand opC_k{w.Ch, w.Cl, w.Rp, (long long)D * w.Rp, Bi, D, R, w.scal + HS_IC};   // B: rows = channels, K = regions
+    if (h_fused_fwd_on() && D == 256) {  // one launch: S + attention forward + U' per (image, word tile)
+        HFusedFwd f{};
+        f.Ch = w.Ch; f.Cl = w.Cl; f.Wh = w.Wh; f.Wl = w.Wl;
+        f.Bi = Bi; f.D = D; f.R = R; f.Rp = w.Rp; f.NtP = NtP;
+        f.nlive = w.meta + 1;
+        f.inv_c = w.scal + HS_IC; f.inv_w = w.scal + HS_IW; f.inv_e = w.scal + HS_IE;
+        f.U = w.U;
+        f.attn = h_attn_args(w, g1);
+        f.attn.out_hi = w.Eh; f.attn.out_lo = w.El; f.attn.emax = w.scal + HS_EMAX;
+        int rc = h_fused_fwd_launch(f, st);
+        if (rc) return rc;
+        prof_mark(1, st);
+    } else {
     {  // GEMM1 + attention forward: S^T[j][r][n'] -> P^T, E^T (half pairs), Zpart
         HGemm g{};
         g.nseg = 1;
@@ -535,6 +556,7 @@ int pair_h_fwd(const float* img, const float* words, const int32_t* cap_lens, in
         if (rc) return rc;
     }
     prof_mark(3, st);
+    }
 
     launch_pdl(v3_cos_lse_kernel, dim3(w.maxbins, Bi), dim3(256), 0, st, (const float*)w.U, (const float*)w.Wp, (const float*)w.wn,
                (const float*)w.Zpart, (const int*)w.col_start, (const int*)w.cap_len, (const int*)w.bin_cap, (const int*)w.bin_used,

@@ -902,9 +902,10 @@ def _c4_build(ns, dev, seed, fuse):
     for p in enc.parameters():
         p.requires_grad = False
     enc.eval()
-    if fuse:
+    if fuse:  # the opt-in one-liners of INTEGRATION.md: same parameter tensors, fused kernels
         import eegan_b200 as E
         E.fuse_emb_features(enc)
+        E.fuse_affine_ssa(netG)
     return netG.to(dev).train(), attr.to(dev).train(), enc.to(dev)
 
 
@@ -1004,7 +1005,8 @@ def run_full_step(args):
     sampler = ClockSampler(cx.local) if rank == 0 else None
     t0 = time.time()
     ours = build_and_time(inst, True, "reference Gen / ATTR_Enhance / Trainer.DAMSM_loss imported with eegan_b200.install(): 24 eegan_b200 SyncBN "
-                                      "layers, eegan_b200 words_loss / sent_loss (global-batch losses over NCCL when N > 1), fused emb_features")
+                                      "layers (14 of them inside fused affine_ssa, eegan_b200.fuse_affine_ssa), eegan_b200 words_loss / sent_loss "
+                                      "(global-batch losses over NCCL when N > 1), fused emb_features")
     refarm = None
     if world == 1:
         refarm = build_and_time(ref, False, "the unmodified reference modules and losses, eager on the same GPU (cfg.CUDA=True)")

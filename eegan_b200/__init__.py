@@ -18,7 +18,7 @@ from .damsm_losses import (GlobalAttentionGeneral, cosine_similarity, func_atten
 from .attr_enhance import ATTR_Enhance, attr_enhance  # noqa: F401
 from .encoder import EmbFeatures, conv1x1_features, fuse_emb_features  # noqa: F401
 from .evaluation import r_precision  # noqa: F401
-from .ssa import affine_ssa, ssa_modulate  # noqa: F401
+from .ssa import affine_ssa, fuse_affine_ssa, ssa_modulate  # noqa: F401
 
 __version__ = "0.1.0"
 

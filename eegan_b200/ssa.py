@@ -156,3 +156,36 @@ class affine_ssa(nn.Module):
         weight = self.fc_gamma(cond)
         bias = self.fc_beta(cond)
         return ssa_modulate(feat, weight, bias, semi_mask, self.norm2d)
+
+
+def fuse_affine_ssa(root: nn.Module) -> int:
+    """Swap every reference ``affine_ssa`` (models.py:43-86) inside ``root`` — ``Gen`` holds 14 — for the fused module above,
+    in place.  The new module ADOPTS the old one's sub-modules (``norm2d``, ``fc_gamma``, ``fc_beta``): same parameter and buffer
+    tensors, same ``state_dict`` keys, optimiser state stays valid.  A ``norm2d`` that is the reference's own SyncBN (no
+    ``eegan_b200.install()``) is re-housed in eegan_b200's class on the same running-statistics buffers.  Returns the count.
+
+        netG = models.Gen(ngf, nz)           # the reference's generator, unchanged
+        eegan_b200.fuse_affine_ssa(netG)     # 14 x (SyncBN + 6 elementwise passes) -> 14 x (stats pass + 1 apply pass)
+    """
+    n = 0
+    for name, child in list(root.named_children()):
+        if type(child).__name__ == "affine_ssa" and not isinstance(child, affine_ssa):
+            new = affine_ssa.__new__(affine_ssa)
+            nn.Module.__init__(new)
+            norm = child.norm2d
+            if not isinstance(norm, SynchronizedBatchNorm2d):
+                if getattr(norm, "affine", False) or not hasattr(norm, "running_mean"):
+                    raise TypeError("fuse_affine_ssa: %s.norm2d is not an affine-free batch norm" % name)
+                mine = SynchronizedBatchNorm2d(norm.num_features, eps=norm.eps, momentum=norm.momentum, affine=False)
+                mine._buffers["running_mean"] = norm.running_mean
+                mine._buffers["running_var"] = norm.running_var
+                if getattr(norm, "num_batches_tracked", None) is not None:
+                    mine._buffers["num_batches_tracked"] = norm.num_batches_tracked
+                norm = mine
+            new.norm2d, new.fc_gamma, new.fc_beta = norm, child.fc_gamma, child.fc_beta
+            new.train(child.training)
+            setattr(root, name, new)
+            n += 1
+        else:
+            n += fuse_affine_ssa(child)
+    return n

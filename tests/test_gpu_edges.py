@@ -208,3 +208,28 @@ def test_r_precision_matches_reference_arithmetic(cuda_lib, B, Rv, D):
         assert s1[2] == s1[3]
     if B > 2:
         assert int(best[2]) == 0 and bool(hits[2])
+
+
+def test_phased_backward_equals_one_call(cuda_lib):
+    """eegan_damsm_pair_bwd_phased: phase 1 (d_img) then phase 2 (d_words) on the same stash == eegan_damsm_pair_bwd."""
+    from eegan_b200 import _lib
+    L = cuda_lib
+    B, T, D, R = 20, 14, 256, 289
+    c = cases.words_case(B, T, seed=8)
+    img = c["img"].cuda().reshape(B, D, R).contiguous()
+    words = c["words"].cuda().contiguous()
+    lens = c["cap_lens"].cuda().to(torch.int32)
+    need = L.eegan_damsm_pair_workspace_bytes(B, B, D, R, T)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    m, att = torch.empty(B, B, device="cuda"), torch.empty(B, T, R, device="cuda")
+    p, st = _lib.ptr, _lib.stream_ptr()
+    _lib.check(L.eegan_damsm_pair_fwd(p(img), p(words), p(lens), B, B, D, R, T, 5.0, 5.0, p(m), p(att), 0, p(ws), need, st))
+    dm = torch.randn(B, B, generator=cases._gen(9)).cuda() * 0.01
+    di0, dw0 = torch.empty_like(img), torch.empty_like(words)
+    _lib.check(L.eegan_damsm_pair_bwd(p(img), p(words), p(lens), B, B, D, R, T, 5.0, 5.0, p(dm), p(di0), p(dw0), p(ws), need, st))
+    di1, dw1 = torch.zeros_like(img), torch.zeros_like(words)
+    _lib.check(L.eegan_damsm_pair_bwd_phased(p(img), p(words), p(lens), B, B, D, R, T, 5.0, 5.0, p(dm), p(di1), None, 1, p(ws), need, st))
+    assert float(dw1.abs().max()) == 0.0
+    _lib.check(L.eegan_damsm_pair_bwd_phased(p(img), p(words), p(lens), B, B, D, R, T, 5.0, 5.0, p(dm), None, p(dw1), 2, p(ws), need, st))
+    assert torch.equal(di0, di1) and torch.equal(dw0, dw1)
+    assert L.eegan_damsm_pair_bwd_phased(p(img), p(words), p(lens), B, B, D, R, T, 5.0, 5.0, p(dm), p(di1), p(dw1), 7, p(ws), need, st) != 0

@@ -956,10 +956,8 @@ def run_full_step(args):
     def build_and_time(ns, fuse, tag):
         nets = _c4_build(ns, dev, 7, fuse)
         if world > 1:  # train.py:220: DataParallelWithCallback(netG); here one process per GPU, gradients all-reduced by the wrapper
-            wrapped = (ns.sync_batchnorm.DataParallelWithCallback(nets[0]), nets[1], nets[2])
+            wrapped = (ns.sync_batchnorm.DataParallelWithCallback(nets[0]), ns.sync_batchnorm.DataParallelWithCallback(nets[1]), nets[2])
             params = list(nets[0].parameters()) + list(nets[1].parameters())
-            for p in nets[1].parameters():
-                p.register_post_accumulate_grad_hook(lambda q: dist.all_reduce(q.grad))
         else:
             wrapped = nets
             params = list(nets[0].parameters()) + list(nets[1].parameters())

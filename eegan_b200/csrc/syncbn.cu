@@ -172,6 +172,23 @@ extern "C" int eegan_syncbn_stats(const float* x, int N, int C, int HW, float* s
     return EEGAN_OK;
 }
 
+__global__ void bn_count_kernel(float* __restrict__ cnt, float hi, float lo) {
+    cnt[0] = hi;
+    cnt[1] = lo;
+}
+
+// stats [2*C + 2]: the statistics of eegan_syncbn_stats followed by the local element count N*HW as the exact pair
+// {count / 4096, count % 4096} — the whole buffer is then ONE all-reduce and eegan_syncbn_finalize reads the total from
+// its tail (count_dev = stats + 2*C): no host-side scalar writes per layer.
+extern "C" int eegan_syncbn_stats_counted(const float* x, int N, int C, int HW, float* stats, void* stream) {
+    int rc = eegan_syncbn_stats(x, N, C, HW, stats, stream);
+    if (rc) return rc;
+    const long long local = (long long)N * HW;
+    bn_count_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(stats + 2 * (size_t)C, (float)(local / 4096), (float)(local % 4096));
+    EEGAN_LAUNCH_CHECK("syncbn stats (count)");
+    return EEGAN_OK;
+}
+
 extern "C" int eegan_syncbn_finalize(const float* stats, int C, double count, const float* count_dev, float eps, float momentum,
                                      int clamp_mode, float* mean, float* inv_std, float* running_mean,
                                      float* running_var, void* stream) {

@@ -22,6 +22,21 @@ import torch.distributed as dist
 from .config import gammas
 
 
+class _no_auto_shard:
+    """Marks the calling thread as being inside a sharded evaluation, so that damsm_losses' AUTO_SHARD dispatch
+    (``eegan_b200.install(distributed=True)``) does not shard an already-gathered batch a second time."""
+
+    def __init__(self, dl):
+        self._tls = dl._tls
+
+    def __enter__(self):
+        self._prev = getattr(self._tls, "inside_sharded", False)
+        self._tls.inside_sharded = True
+
+    def __exit__(self, *a):
+        self._tls.inside_sharded = self._prev
+
+
 def _world(group):
     if not (dist.is_available() and dist.is_initialized()):
         return 1, 0
@@ -93,7 +108,8 @@ def sharded_words_loss(img_features, words_emb, labels, cap_lens, class_ids, bat
     grid_fn = grid_fn or dl.pair_grid
     world, rank = _world(group)
     if world == 1:
-        return dl.words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size)
+        with _no_auto_shard(dl):
+            return dl.words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size)
     b = batch_size
     img_all = _AllGatherRows.apply(img_features[:b].contiguous(), group, True)
     m_block, att = grid_fn(img_all, words_emb[:b], cap_lens, diag_offset=rank * b)
@@ -118,7 +134,8 @@ def sharded_sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-
     from . import damsm_losses as dl
     world, _ = _world(group)
     if world == 1:
-        return (loss_fn or dl.sent_loss)(cnn_code, rnn_code, labels, class_ids, batch_size, eps)
+        with _no_auto_shard(dl):
+            return (loss_fn or dl.sent_loss)(cnn_code, rnn_code, labels, class_ids, batch_size, eps)
     if labels is None:
         return None, None
     b = batch_size
@@ -126,7 +143,8 @@ def sharded_sent_loss(cnn_code, rnn_code, labels, class_ids, batch_size, eps=1e-
     rnn_all = _AllGatherRows.apply(rnn_code[:b].contiguous(), group, False)
     cls_all = _gather_ids(class_ids, cnn_all.device, group)
     lab_all = torch.arange(world * b, device=cnn_all.device, dtype=torch.int64)
-    return (loss_fn or dl.sent_loss)(cnn_all, rnn_all, lab_all, cls_all, world * b, eps)
+    with _no_auto_shard(dl):  # the gathered codes are the full batch: evaluate it as such, even under install(distributed=True)
+        return (loss_fn or dl.sent_loss)(cnn_all, rnn_all, lab_all, cls_all, world * b, eps)
 
 
 class ShardedWordsLossStep:

@@ -19,7 +19,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import _lib
-from .sync_batchnorm.batchnorm import _COUNT_SPLIT, CudaBNOps, SynchronizedBatchNorm2d, _group_size
+from .sync_batchnorm.batchnorm import CudaBNOps, SynchronizedBatchNorm2d, _group_size, _stats_with_count
 
 
 class CudaSSAOps:
@@ -59,14 +59,13 @@ class _SSAFn(torch.autograd.Function):
         world = _group_size(group) if training else 1
         if training:
             buf = torch.empty(2 * C + 2, dtype=torch.float32, device=x3.device)
-            bn_ops.stats(x3, buf)
             local = N * HW
             if world > 1:
-                buf[2 * C] = float(local // _COUNT_SPLIT)
-                buf[2 * C + 1] = float(local % _COUNT_SPLIT)
+                _stats_with_count(bn_ops, x3, buf, local)
                 dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
                 count, count_dev = 0, buf[2 * C:]
             else:
+                bn_ops.stats(x3, buf)
                 count, count_dev = local, None
             clamp_mode = 1 if world > 1 else 0  # batchnorm.py:125 vs :50-53
             mean = torch.empty(C, dtype=torch.float32, device=x3.device)

@@ -32,6 +32,13 @@ class CudaBNOps:
             _lib.check(_lib.lib().eegan_syncbn_stats(_lib.ptr(x3), N, C, HW, _lib.ptr(out), _lib.stream_ptr()), "syncbn_stats")
 
     @staticmethod
+    def stats_counted(x3, out):
+        """stats + the local element count as the exact pair {n // 4096, n % 4096} in out[2C:2C+2] (one launch more, no host writes)."""
+        N, C, HW = x3.shape
+        with torch.cuda.device(x3.device):
+            _lib.check(_lib.lib().eegan_syncbn_stats_counted(_lib.ptr(x3), N, C, HW, _lib.ptr(out), _lib.stream_ptr()), "syncbn_stats_counted")
+
+    @staticmethod
     def finalize(stats, C, count, count_dev, eps, momentum, clamp_mode, mean, inv_std, rm, rv):
         with torch.cuda.device(stats.device):
             _lib.check(_lib.lib().eegan_syncbn_finalize(_lib.ptr(stats), C, float(count), _lib.ptr(count_dev), eps,
@@ -63,6 +70,17 @@ class CudaBNOps:
                                                          N, C, HW, _lib.ptr(dx), _lib.stream_ptr()), "syncbn_bwd_apply")
 
 
+def _stats_with_count(ops, x3, buf, local):
+    """[sum, square-sum] into buf[:2C] and the exact count pair into buf[2C:] (device-side when the ops provide it)."""
+    if hasattr(ops, "stats_counted"):
+        ops.stats_counted(x3, buf)
+    else:  # CPU stand-ins of the tests
+        C = x3.shape[1]
+        ops.stats(x3, buf)
+        buf[2 * C] = float(local // _COUNT_SPLIT)
+        buf[2 * C + 1] = float(local % _COUNT_SPLIT)
+
+
 def _group_size(group):
     if not (dist.is_available() and dist.is_initialized()):
         return 1
@@ -75,14 +93,13 @@ class _SyncBNFn(torch.autograd.Function):
         N, C, HW = x3.shape
         world = _group_size(group)
         buf = torch.empty(2 * C + 2, dtype=torch.float32, device=x3.device)
-        ops.stats(x3, buf)  # fills [0, 2C)
         local = N * HW
         if world > 1:
-            buf[2 * C] = float(local // _COUNT_SPLIT)
-            buf[2 * C + 1] = float(local % _COUNT_SPLIT)
+            _stats_with_count(ops, x3, buf, local)
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)  # batchnorm.py:102 (ReduceAddCoalesced)
             count, count_dev = 0, buf[2 * C:]  # the total stays on the device: no host sync per layer
         else:
+            ops.stats(x3, buf)  # fills [0, 2C)
             count, count_dev = local, None
         clamp_mode = 1 if world > 1 else 0  # batchnorm.py:125 vs :50-53
         mean = torch.empty(C, dtype=torch.float32, device=x3.device)

@@ -17,7 +17,10 @@ gradient of the GLOBAL-batch loss with respect to its own samples, exactly what 
 replica receives from the scatter of the gathered outputs' gradient — hence SUM, not the MEAN of
 DistributedDataParallel.  A loss that is a per-rank mean over local samples must be divided by
 the world size by the caller (``grad_sync="mean"`` does that in the hook).  ``grad_sync=None``
-switches the hooks off (the caller then owns gradient synchronisation).
+switches the hooks off (the caller then owns gradient synchronisation).  The reduction is ONE
+all-reduce of the flattened gradients at the end of each backward pass, applied to ``p.grad`` as it
+stands then: zero the gradients before every backward (train.py:499 does), as a gradient carried
+over from an earlier pass would be summed over the ranks a second time.
 """
 from __future__ import annotations
 
@@ -62,16 +65,29 @@ def _register_grad_sync(module, mode, group):
     if mode not in ("sum", "mean"):
         raise ValueError("grad_sync must be 'sum', 'mean' or None")
     world = dist.get_world_size(group)
+    params = [p for p in module.parameters() if p.requires_grad]
+    state = {"queued": False}
+
+    def flush():
+        # end of the backward pass: ONE all-reduce over the flattened gradients (a generator has ~100 parameter tensors; a
+        # collective per tensor costs the host more than the whole reduction costs the links)
+        state["queued"] = False
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if mode == "mean":
+            flat.div_(world)
+        torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
 
     def hook(p):
-        if p.grad is not None:
-            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
-            if mode == "mean":
-                p.grad.div_(world)
+        if not state["queued"]:  # first gradient of this backward pass: run flush() once the pass is complete
+            state["queued"] = True
+            torch.autograd.Variable._execution_engine.queue_callback(flush)
 
-    for p in module.parameters():
-        if p.requires_grad:
-            handles.append(p.register_post_accumulate_grad_hook(hook))
+    for p in params:
+        handles.append(p.register_post_accumulate_grad_hook(hook))
     return handles
 
 

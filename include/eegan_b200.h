@@ -216,6 +216,11 @@ int eegan_gag_bwd_ws(const float* x, const float* key, const float* value, const
  *   whose variance was clamped (inv_std == eps^-1/2) has no variance term.
  * ---------------------------------------------------------------------------------- */
 int eegan_syncbn_stats(const float* x, int N, int C, int HW, float* stats, void* stream);
+/* stats [2*C + 2]: as above, followed by the local element count N*HW as the exact fp32 pair
+ * {count / 4096, count % 4096}: statistics and count cross the replicas in ONE all-reduce
+ * (batchnorm.py:102 reduces sum, ssum and sum_size together) and finalize takes
+ * count_dev = stats + 2*C. */
+int eegan_syncbn_stats_counted(const float* x, int N, int C, int HW, float* stats, void* stream);
 int eegan_syncbn_finalize(const float* stats, int C, double count, const float* count_dev,
                           float eps, float momentum,
                           int clamp_mode, float* mean, float* inv_std,

@@ -38,6 +38,9 @@ SIGNATURES = {
     "eegan_gag_bwd_ws": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p, _c_size_t, _p]),
     "eegan_syncbn_stats": (_c_int, [_p, _c_int, _c_int, _c_int, _p, _p]),
     "eegan_syncbn_stats_counted": (_c_int, [_p, _c_int, _c_int, _c_int, _p, _p]),
+    "eegan_syncbn_fwd_fused": (_c_int, [_p, _p, _p, _c_int, _c_int, _c_int, _c_float, _c_float, _p, _p, _p, _p, _p]),
+    "eegan_syncbn_bwd_fused": (_c_int, [_p, _p, _p, _p, _c_int, _c_int, _c_int, _c_float, _p, _p, _p]),
+    "eegan_ssa_fwd_fused": (_c_int, [_p, _p, _p, _p, _c_int, _c_int, _c_int, _c_float, _c_float, _p, _p, _p, _p, _p]),
     "eegan_syncbn_finalize": (_c_int, [_p, _c_int, _c_double, _p, _c_float, _c_float, _c_int, _p, _p, _p, _p, _p]),
     "eegan_syncbn_apply": (_c_int, [_p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p]),
     "eegan_syncbn_bwd_reduce": (_c_int, [_p, _p, _p, _p, _c_int, _c_int, _c_int, _p, _p]),

@@ -141,6 +141,148 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Single-replica, small-map forms: ONE launch per direction, one CTA per channel.
+// 14 of the 24 SyncBN layers of Gen work on maps of 32 x 32 or less: a few MB that a multi-launch
+// sequence (memset + reduce + finalize + apply) spends in launch latency.  Here a CTA makes the channel's statistics pass and
+// the normalising pass itself; the second pass re-reads the channel from L2 (<= 64K elements = 256 KB per channel).
+//   KIND 0: y = (x - mean) * inv_std * w + b              (SynchronizedBatchNorm2d, batchnorm.py:50-53 single replica)
+//   KIND 1: y = (g m + 1) xhat + b m                      (affine_ssa, models.py:69-86)
+// ---------------------------------------------------------------------------------------
+constexpr int BN_SMALL_THREADS = 512;
+constexpr long long BN_SMALL_MAX = 65536;  // elements per channel
+
+template <typename F>
+__device__ __forceinline__ void bn_small_foreach(int N, int C, int HW, int c, bool vec, F f) {
+    if (vec) {
+        const int hw4 = HW >> 2;
+        const int total = N * hw4;
+        for (int e = threadIdx.x; e < total; e += BN_SMALL_THREADS) {
+            const int n = e / hw4, k = e - n * hw4;
+            f(n, ((size_t)n * C + c) * HW + (size_t)k * 4, k * 4, 4);
+        }
+    } else {
+        const int total = N * HW;
+        for (int e = threadIdx.x; e < total; e += BN_SMALL_THREADS) {
+            const int n = e / HW, k = e - n * HW;
+            f(n, ((size_t)n * C + c) * HW + k, k, 1);
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BN_SMALL_THREADS) bn_fwd_small_kernel(const float* __restrict__ x, const float* __restrict__ weight,
+                                                                        const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta, const float* __restrict__ mask,
+                                                                        int N, int C, int HW, float eps, float momentum,
+                                                                        float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                        float* __restrict__ y, float* __restrict__ mean,
+                                                                        float* __restrict__ inv_std) {
+    __shared__ float red[32];
+    const int c = blockIdx.x;
+    const bool vec = (HW % 4 == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                                         (KIND == 1 ? reinterpret_cast<uintptr_t>(mask) : 0)) & 15) == 0);
+    float a = 0.f, b = 0.f;
+    bn_small_foreach(N, C, HW, c, vec, [&](int, size_t off, int, int w) {
+        if (w == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(x + off);
+            a += (v.x + v.y) + (v.z + v.w);
+            b = fmaf(v.x, v.x, b); b = fmaf(v.y, v.y, b); b = fmaf(v.z, v.z, b); b = fmaf(v.w, v.w, b);
+        } else {
+            const float v = x[off];
+            a += v;
+            b = fmaf(v, v, b);
+        }
+    });
+    a = block_sum(a, red);
+    b = block_sum(b, red);
+    const float size = (float)N * (float)HW;
+    const float mu = a / size, sumvar = b - a * mu;  // batchnorm.py:116-117
+    const float is = 1.0f / sqrtf(sumvar / size + eps);
+    if (threadIdx.x == 0) {
+        mean[c] = mu;
+        inv_std[c] = is;
+        if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+        if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (sumvar / (size - 1.f));
+    }
+    const float wv = (KIND == 0 && weight) ? weight[c] : 1.f, bv = (KIND == 0 && bias) ? bias[c] : 0.f;
+    const float scale = is * wv;
+    bn_small_foreach(N, C, HW, c, vec, [&](int n, size_t off, int k, int w) {
+        float g = 0.f, bt = 0.f;
+        if (KIND == 1) {
+            g = gamma[(size_t)n * C + c];
+            bt = beta[(size_t)n * C + c];
+        }
+        if (w == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(x + off);
+            float4 o;
+            if (KIND == 0) {
+                o.x = (v.x - mu) * scale + bv; o.y = (v.y - mu) * scale + bv; o.z = (v.z - mu) * scale + bv; o.w = (v.w - mu) * scale + bv;
+            } else {
+                const float4 m = *reinterpret_cast<const float4*>(mask + (size_t)n * HW + k);
+                o.x = fmaf(fmaf(g, m.x, 1.f), (v.x - mu) * is, bt * m.x); o.y = fmaf(fmaf(g, m.y, 1.f), (v.y - mu) * is, bt * m.y);
+                o.z = fmaf(fmaf(g, m.z, 1.f), (v.z - mu) * is, bt * m.z); o.w = fmaf(fmaf(g, m.w, 1.f), (v.w - mu) * is, bt * m.w);
+            }
+            *reinterpret_cast<float4*>(y + off) = o;
+        } else {
+            const float v = x[off];
+            if (KIND == 0) {
+                y[off] = (v - mu) * scale + bv;
+            } else {
+                const float m = mask[(size_t)n * HW + k];
+                y[off] = fmaf(fmaf(g, m, 1.f), (v - mu) * is, bt * m);
+            }
+        }
+    });
+}
+
+// dx = w inv_std (dy - S0 / n - xhat S1 / n),  S0 = sum dy, S1 = sum dy xhat;  red[c] = S0, red[C + c] = S1 (d_bias, d_weight)
+__global__ void __launch_bounds__(BN_SMALL_THREADS) bn_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                        const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                                                        const float* __restrict__ weight, int N, int C, int HW,
+                                                                        float* __restrict__ dx, float* __restrict__ red_out) {
+    __shared__ float red[32];
+    const int c = blockIdx.x;
+    const bool vec = (HW % 4 == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0);
+    const float mu = mean[c], is = inv_std[c];
+    float a = 0.f, b = 0.f;
+    bn_small_foreach(N, C, HW, c, vec, [&](int, size_t off, int, int w) {
+        if (w == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(x + off);
+            const float4 g = *reinterpret_cast<const float4*>(dy + off);
+            a += (g.x + g.y) + (g.z + g.w);
+            b = fmaf(g.x, (v.x - mu) * is, b); b = fmaf(g.y, (v.y - mu) * is, b);
+            b = fmaf(g.z, (v.z - mu) * is, b); b = fmaf(g.w, (v.w - mu) * is, b);
+        } else {
+            a += dy[off];
+            b = fmaf(dy[off], (x[off] - mu) * is, b);
+        }
+    });
+    a = block_sum(a, red);
+    b = block_sum(b, red);
+    if (threadIdx.x == 0) {
+        red_out[c] = a;
+        red_out[C + c] = b;
+    }
+    const float inv_count = 1.0f / ((float)N * (float)HW);
+    const float r0 = a * inv_count, r1 = b * inv_count;
+    const float scale = is * (weight ? weight[c] : 1.f);
+    bn_small_foreach(N, C, HW, c, vec, [&](int, size_t off, int, int w) {
+        if (w == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(x + off);
+            const float4 g = *reinterpret_cast<const float4*>(dy + off);
+            float4 o;
+            o.x = scale * (g.x - r0 - (v.x - mu) * is * r1); o.y = scale * (g.y - r0 - (v.y - mu) * is * r1);
+            o.z = scale * (g.z - r0 - (v.z - mu) * is * r1); o.w = scale * (g.w - r0 - (v.w - mu) * is * r1);
+            *reinterpret_cast<float4*>(dx + off) = o;
+        } else {
+            dx[off] = scale * (dy[off] - r0 - (x[off] - mu) * is * r1);
+        }
+    });
+}
+
+static bool bn_small_ok(int N, int C, int HW) { return (long long)N * HW <= BN_SMALL_MAX && C >= 32; }
+
 static int reduce_splits(int N, int C, int HW) {
     const long long per_c = (long long)N * HW;
     long long want = (4LL * 148 + C - 1) / C;             // ~4 CTAs per SM in total
@@ -241,6 +383,41 @@ extern "C" int eegan_syncbn_bwd_apply(const float* x, const float* dy, const flo
         x, dy, mean, inv_std, weight, nullptr, red, (float)count, count_dev, clamp_mode, 1.0f / sqrtf(eps), C, HW, dx);
     EEGAN_LAUNCH_CHECK("syncbn bwd_apply");
     return EEGAN_OK;
+}
+
+// Single-replica forward / backward in ONE call each (the caller passes work [4*C]: statistics scratch [2C], then the
+// mean [C] and inv_std [C] the backward needs).  Small maps take the one-launch kernels above, the rest the same
+// stats -> finalize -> apply sequence as the separate entry points.
+extern "C" int eegan_syncbn_fwd_fused(const float* x, const float* weight, const float* bias, int N, int C, int HW, float eps,
+                                      float momentum, float* running_mean, float* running_var, float* y, float* work, void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && y && work, "syncbn fwd_fused: null pointer");
+    EEGAN_REQUIRE((long long)N * HW > 1, "BatchNorm computes unbiased standard-deviation, which requires size > 1.");
+    float *mean = work + 2 * (size_t)C, *inv_std = work + 3 * (size_t)C;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn_small_ok(N, C, HW)) {
+        bn_fwd_small_kernel<0><<<C, BN_SMALL_THREADS, 0, st>>>(x, weight, bias, nullptr, nullptr, nullptr, N, C, HW, eps, momentum,
+                                                              running_mean, running_var, y, mean, inv_std);
+        return check_launch("syncbn fwd (one launch)");
+    }
+    if ((rc = eegan_syncbn_stats(x, N, C, HW, work, stream))) return rc;
+    if ((rc = eegan_syncbn_finalize(work, C, (double)N * HW, nullptr, eps, momentum, 0, mean, inv_std, running_mean, running_var, stream))) return rc;
+    return eegan_syncbn_apply(x, mean, inv_std, weight, bias, N, C, HW, y, stream);
+}
+
+extern "C" int eegan_syncbn_bwd_fused(const float* x, const float* dy, const float* work, const float* weight, int N, int C, int HW,
+                                      float eps, float* dx, float* red, void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && dy && work && dx && red, "syncbn bwd_fused: null pointer");
+    const float *mean = work + 2 * (size_t)C, *inv_std = work + 3 * (size_t)C;
+    if (bn_small_ok(N, C, HW)) {
+        bn_bwd_small_kernel<<<C, BN_SMALL_THREADS, 0, (cudaStream_t)stream>>>(x, dy, mean, inv_std, weight, N, C, HW, dx, red);
+        return check_launch("syncbn bwd (one launch)");
+    }
+    if ((rc = eegan_syncbn_bwd_reduce(x, dy, mean, inv_std, N, C, HW, red, stream))) return rc;
+    return eegan_syncbn_bwd_apply(x, dy, mean, inv_std, weight, red, (double)N * HW, nullptr, eps, 0, N, C, HW, dx, stream);
 }
 
 // =======================================================================================
@@ -419,4 +596,23 @@ extern "C" int eegan_ssa_bwd_apply(const float* x, const float* dy, const float*
         x, dy, mean, inv_std, gamma, nullptr, mask, red, (float)count, count_dev, clamp_mode, 1.0f / sqrtf(eps), C, HW, dx);
     EEGAN_LAUNCH_CHECK("ssa bwd_apply");
     return EEGAN_OK;
+}
+
+// Single-replica forward of affine_ssa in one call (work [4*C] as for eegan_syncbn_fwd_fused).
+extern "C" int eegan_ssa_fwd_fused(const float* x, const float* gamma, const float* beta, const float* mask, int N, int C, int HW,
+                                   float eps, float momentum, float* running_mean, float* running_var, float* y, float* work,
+                                   void* stream) {
+    int rc = validate_bn(N, C, HW);
+    if (rc) return rc;
+    EEGAN_REQUIRE(x && gamma && beta && mask && y && work, "ssa fwd_fused: null pointer");
+    EEGAN_REQUIRE((long long)N * HW > 1, "BatchNorm computes unbiased standard-deviation, which requires size > 1.");
+    float *mean = work + 2 * (size_t)C, *inv_std = work + 3 * (size_t)C;
+    if (bn_small_ok(N, C, HW)) {
+        bn_fwd_small_kernel<1><<<C, BN_SMALL_THREADS, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, gamma, beta, mask, N, C, HW, eps,
+                                                                                momentum, running_mean, running_var, y, mean, inv_std);
+        return check_launch("ssa fwd (one launch)");
+    }
+    if ((rc = eegan_syncbn_stats(x, N, C, HW, work, stream))) return rc;
+    if ((rc = eegan_syncbn_finalize(work, C, (double)N * HW, nullptr, eps, momentum, 0, mean, inv_std, running_mean, running_var, stream))) return rc;
+    return eegan_ssa_apply(x, mean, inv_std, gamma, beta, mask, N, C, HW, y, stream);
 }

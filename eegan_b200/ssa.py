@@ -33,6 +33,15 @@ class CudaSSAOps:
                                                   _lib.ptr(mask2), N, C, HW, _lib.ptr(y), _lib.stream_ptr()), "ssa_apply")
 
     @staticmethod
+    def fwd_fused(x3, gamma, beta, mask2, eps, momentum, rm, rv, y, work):
+        """single replica: statistics + modulate in one library call (one launch for small maps); work [4C] keeps mean / inv_std"""
+        N, C, HW = x3.shape
+        with torch.cuda.device(x3.device):
+            _lib.check(_lib.lib().eegan_ssa_fwd_fused(_lib.ptr(x3), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(mask2), N, C, HW, eps,
+                                                      momentum, _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(y), _lib.ptr(work),
+                                                      _lib.stream_ptr()), "ssa_fwd_fused")
+
+    @staticmethod
     def bwd_reduce(x3, dy3, mean, inv_std, gamma, beta, mask2, red, dgamma, dbeta, dmask):
         N, C, HW = x3.shape
         with torch.cuda.device(x3.device):
@@ -57,6 +66,14 @@ class _SSAFn(torch.autograd.Function):
     def forward(ctx, x3, gamma, beta, mask2, running_mean, running_var, eps, momentum, group, training, bn_ops, ops):
         N, C, HW = x3.shape
         world = _group_size(group) if training else 1
+        if training and world == 1 and hasattr(ops, "fwd_fused") and bn_ops is CudaBNOps:
+            work = torch.empty(4 * C, dtype=torch.float32, device=x3.device)
+            y = torch.empty_like(x3)
+            ops.fwd_fused(x3, gamma, beta, mask2, eps, momentum, running_mean, running_var, y, work)
+            ctx.save_for_backward(x3, gamma, beta, mask2, work[2 * C:3 * C], work[3 * C:])
+            ctx.count_dev = None
+            ctx.cfg = (N * HW, eps, 0, group, ops, 1, training)
+            return y
         if training:
             buf = torch.empty(2 * C + 2, dtype=torch.float32, device=x3.device)
             local = N * HW

@@ -39,6 +39,21 @@ class CudaBNOps:
             _lib.check(_lib.lib().eegan_syncbn_stats_counted(_lib.ptr(x3), N, C, HW, _lib.ptr(out), _lib.stream_ptr()), "syncbn_stats_counted")
 
     @staticmethod
+    def fwd_fused(x3, w, b, eps, momentum, rm, rv, y, work):
+        """single replica: statistics + normalise in one library call (one launch for small maps); work [4C] keeps mean / inv_std"""
+        N, C, HW = x3.shape
+        with torch.cuda.device(x3.device):
+            _lib.check(_lib.lib().eegan_syncbn_fwd_fused(_lib.ptr(x3), _lib.ptr(w), _lib.ptr(b), N, C, HW, eps, momentum, _lib.ptr(rm),
+                                                         _lib.ptr(rv), _lib.ptr(y), _lib.ptr(work), _lib.stream_ptr()), "syncbn_fwd_fused")
+
+    @staticmethod
+    def bwd_fused(x3, dy3, work, w, eps, dx, red):
+        N, C, HW = x3.shape
+        with torch.cuda.device(x3.device):
+            _lib.check(_lib.lib().eegan_syncbn_bwd_fused(_lib.ptr(x3), _lib.ptr(dy3), _lib.ptr(work), _lib.ptr(w), N, C, HW, eps,
+                                                         _lib.ptr(dx), _lib.ptr(red), _lib.stream_ptr()), "syncbn_bwd_fused")
+
+    @staticmethod
     def finalize(stats, C, count, count_dev, eps, momentum, clamp_mode, mean, inv_std, rm, rv):
         with torch.cuda.device(stats.device):
             _lib.check(_lib.lib().eegan_syncbn_finalize(_lib.ptr(stats), C, float(count), _lib.ptr(count_dev), eps,
@@ -92,6 +107,15 @@ class _SyncBNFn(torch.autograd.Function):
     def forward(ctx, x3, weight, bias, running_mean, running_var, eps, momentum, group, ops):
         N, C, HW = x3.shape
         world = _group_size(group)
+        if world == 1 and hasattr(ops, "fwd_fused"):  # one replica: nothing to wait for between statistics and normalisation
+            work = torch.empty(4 * C, dtype=torch.float32, device=x3.device)
+            y = torch.empty_like(x3)
+            ops.fwd_fused(x3, weight, bias, eps, momentum, running_mean, running_var, y, work)
+            ctx.save_for_backward(x3, weight, work)
+            ctx.fused = True
+            ctx.cfg = (N * HW, eps, 0, group, ops, 1, bias is not None)
+            return y
+        ctx.fused = False
         buf = torch.empty(2 * C + 2, dtype=torch.float32, device=x3.device)
         local = N * HW
         if world > 1:
@@ -114,6 +138,14 @@ class _SyncBNFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        if ctx.fused:
+            x3, weight, work = ctx.saved_tensors
+            count, eps, _, _, ops, _, has_bias = ctx.cfg
+            C = x3.shape[1]
+            red = torch.empty(2 * C, dtype=torch.float32, device=x3.device)
+            dx = torch.empty_like(x3)
+            ops.bwd_fused(x3, dy.contiguous(), work, weight, eps, dx, red)
+            return dx, (red[C:] if weight is not None else None), (red[:C] if has_bias else None), None, None, None, None, None, None
         x3, weight, mean, inv_std = ctx.saved_tensors
         count, eps, clamp_mode, group, ops, world, has_bias = ctx.cfg
         N, C, HW = x3.shape

@@ -237,6 +237,20 @@ int eegan_syncbn_bwd_apply(const float* x, const float* dy, const float* mean,
                            int N, int C, int HW,
                            float* dx, void* stream);
 
+/* One replica (no cross-rank reduction to wait for): forward / backward as ONE call each.  work [4*C] floats: statistics
+ * scratch [2C], then mean [C] and inv_std [C] (kept by the caller for the backward).  Maps of at most 64K elements per
+ * channel run as a single launch (one CTA per channel; 14 of Gen's 24 layers are 32x32 or smaller), larger ones as the
+ * stats / finalize / apply sequence above.  F.batch_norm arithmetic (batchnorm.py:50-53).  red [2*C] OUT: sum dy (d_bias),
+ * sum dy * xhat (d_weight). */
+int eegan_syncbn_fwd_fused(const float* x, const float* weight, const float* bias, int N, int C, int HW,
+                           float eps, float momentum, float* running_mean, float* running_var,
+                           float* y, float* work, void* stream);
+int eegan_syncbn_bwd_fused(const float* x, const float* dy, const float* work, const float* weight,
+                           int N, int C, int HW, float eps, float* dx, float* red, void* stream);
+int eegan_ssa_fwd_fused(const float* x, const float* gamma, const float* beta, const float* mask,
+                        int N, int C, int HW, float eps, float momentum, float* running_mean,
+                        float* running_var, float* y, float* work, void* stream);
+
 /* Contraction engine of the pair grid's GEMM-shaped stages (process-wide setting; all are sm_100a
  * kernels of this library):
  *   3 = tcgen05 "3xFP16": operands stored pre-split as fp16 hi/lo pairs with per-tensor power-of-two

@@ -86,3 +86,32 @@ def test_module_single_replica_matches_batch_norm(cuda_lib, shape, affine):
     if affine:
         assert relmax(bn.weight.grad.cpu(), ref.weight.grad) <= 1e-4
         assert relmax(bn.bias.grad.cpu(), ref.bias.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("shape", [(32, 256, 16, 16), (8, 64, 32, 32), (3, 32, 5, 7), (2, 40, 128, 128)])
+def test_single_replica_fused_calls_match_the_separate_steps(cuda_lib, shape):
+    """eegan_syncbn_fwd_fused / _bwd_fused (one launch per direction on small maps, the stats/finalize/apply sequence on
+    large ones) against the separate entry points on the same data: same arithmetic, different launch structure."""
+    from eegan_b200.sync_batchnorm.batchnorm import CudaBNOps as K
+    N, C, H, W = shape
+    g = cases._gen(N * C + H)
+    x = (torch.randn(N, C, H * W, generator=g) * 1.3 + 0.2).cuda()
+    dy = torch.randn(N, C, H * W, generator=g).cuda()
+    w, b = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    # separate steps
+    buf = torch.empty(2 * C, device="cuda"); K.stats(x, buf)
+    mean, inv = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    K.finalize(buf, C, N * H * W, None, 1e-5, 0.1, 0, mean, inv, rm, rv)
+    y = torch.empty_like(x); K.apply(x, mean, inv, w, b, y)
+    red = torch.empty(2 * C, device="cuda"); K.bwd_reduce(x, dy, mean, inv, red)
+    dx = torch.empty_like(x); K.bwd_apply(x, dy, mean, inv, w, red, N * H * W, None, 1e-5, 0, dx)
+    # fused
+    work = torch.empty(4 * C, device="cuda")
+    rm2, rv2 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    y2 = torch.empty_like(x); K.fwd_fused(x, w, b, 1e-5, 0.1, rm2, rv2, y2, work)
+    red2 = torch.empty(2 * C, device="cuda"); dx2 = torch.empty_like(x)
+    K.bwd_fused(x, dy, work, w, 1e-5, dx2, red2)
+    assert relmax(work[2 * C:3 * C], mean) <= 1e-5 and relmax(work[3 * C:], inv) <= 1e-5
+    assert float((y2 - y).abs().max()) <= 1e-5 and relmax(dx2, dx) <= 1e-4
+    assert relmax(red2, red) <= 1e-4 and relmax(rm2, rm) <= 1e-5 and relmax(rv2, rv) <= 1e-5

@@ -230,23 +230,17 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
     const int b0 = t.n0 >> 6;
     const int bc_l = e.bin_cap[min(b0 + lane, nbins)];
     const int bu_l = (lane < 2 && b0 + lane < nbins) ? e.bin_used[b0 + lane] : 0;
+    // P rows of this warp's (32 regions x 64 columns) block -> staging, as 8-byte asynchronous copies (global -> shared without
+    // a register stop-over): all 32 rows are in flight at once and nothing waits until cp.async.wait_all in front of the caption
+    // phase.  (The register form — 8 rows of loads, then their shared stores — stalled the epilogue on the L2 latency four
+    // times per tile: 17 % of this kernel's stall samples sat on those stores, profiles/README.md "r2".)
     auto load_p_bin = [&](int col0) {
-#pragma unroll 1
-        for (int r8 = 0; r8 < rows_live; r8 += 8) {
-            float a0[8], a1[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int rr = min(r8 + q, rows_live - 1);
-                const float* src = Pz + (long long)(row0 + rr) * p.ldc + col0 + lane;
-                a0[q] = __ldg(src);
-                a1[q] = __ldg(src + 32);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                sts_f32(t.stage + (uint32_t)((r8 + q) * H_EPI_PITCH + lane) * 4u, a0[q]);
-                sts_f32(t.stage + (uint32_t)((r8 + q) * H_EPI_PITCH + lane + 32) * 4u, a1[q]);
-            }
-        }
+        const float* src = Pz + (long long)row0 * p.ldc + col0 + 2 * lane;
+        const uint32_t dst = t.stage + (uint32_t)(2 * lane) * 4u;
+#pragma unroll 4
+        for (int r = 0; r < rows_live; ++r)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)(r * H_EPI_PITCH) * 4u), "l"(src + (long long)r * p.ldc) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     __syncwarp();
     const int h = t.half;  // the 64-column bin of the tile this warp handles
@@ -276,6 +270,10 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
         if (!waited) {
             mbar_wait(t.full_bar, t.full_parity);
             tc_fence_after();
+            if (EPI == TC_EPI_ATTN_BWD) {  // the P rows copied asynchronously into staging have landed, for every lane of the warp
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+            }
             waited = true;
         }
 #pragma unroll 1
@@ -289,6 +287,7 @@ __device__ __forceinline__ void h_epilogue_tile(const HArgs& p, const EpiTile& t
     if (!waited) {
         mbar_wait(t.full_bar, t.full_parity);
         tc_fence_after();
+        if (EPI == TC_EPI_ATTN_BWD) asm volatile("cp.async.wait_all;" ::: "memory");
     }
     tc_fence_before();
     __syncwarp();

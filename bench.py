@@ -59,7 +59,7 @@ WORKLOADS = {
 LAUNCHES_PER_STEP = {3: 15, 2: 14}
 # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, averaged over the five launches of one step at B = 48.  NOT measured by
 # this run: a constant copied from the committed ncu --set full capture named in `traffic_source`.
-NCU_TRAFFIC = {3: (66.1e6, "profiles/r1_h_gemm_ncu_full_summary.csv (30.6 / 53.2 / 88.6 / 107.9 / 50.3 MB for the five GEMM launches, B=48)"),
+NCU_TRAFFIC = {3: (66.4e6, "profiles/r2_h_gemm_ncu_full_summary.csv (31.1 / 52.8 / 88.7 / 107.3 / 50.4 MB for the five GEMM launches, B=48; round 1: 30.6 / 53.2 / 88.6 / 107.9 / 50.3)"),
                2: (66.4e6, "profiles/r1_v3_fused_step_ncu_full_summary.csv")}
 ENGINE_NOTE = {
     3: ("h_gemm_kernel (tcgen05.mma.kind::f16 on operands stored as fp16 hi/lo pairs with power-of-two scales; TMA -> MMA, no "

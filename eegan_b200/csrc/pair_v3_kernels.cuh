@@ -102,16 +102,16 @@ static __global__ void __launch_bounds__(256) v3_cos_lse_kernel(const float* __r
     const int used = bin_used[b];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int d4 = D >> 2;
-#pragma unroll 1
-    for (int c4 = 0; c4 < 8; c4 += 4) {  // four packed columns in flight per warp
-        const int c0 = w * 8 + c4;
-        if (c0 >= used) break;
-        float dot[4], uu[4], zz[4];
-        size_t nn[4];
-        const float4* up[4];
-        const float4* wp[4];
+    constexpr int NCW = 8;  // packed columns per warp, all in flight at once (one round of loads per warp)
+    {
+        const int c0 = w * 8;
+        if (c0 < used) {
+        float dot[NCW], uu[NCW], zz[NCW];
+        size_t nn[NCW];
+        const float4* up[NCW];
+        const float4* wp[NCW];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NCW; ++k) {
             nn[k] = (size_t)b * V3_BIN + min(c0 + k, used - 1);
             up[k] = reinterpret_cast<const float4*>(U + ((size_t)j * NtP + nn[k]) * D);
             wp[k] = reinterpret_cast<const float4*>(Wp + nn[k] * D);
@@ -120,11 +120,11 @@ static __global__ void __launch_bounds__(256) v3_cos_lse_kernel(const float* __r
             uu[k] = 0.f;
         }
         for (int q = lane; q < d4; q += 32) {
-            float4 a[4], bw[4];
+            float4 a[NCW], bw[NCW];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { a[k] = up[k][q]; bw[k] = __ldg(wp[k] + q); }
+            for (int k = 0; k < NCW; ++k) { a[k] = up[k][q]; bw[k] = __ldg(wp[k] + q); }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < NCW; ++k) {
                 dot[k] = fmaf(a[k].x, bw[k].x, dot[k]); dot[k] = fmaf(a[k].y, bw[k].y, dot[k]);
                 dot[k] = fmaf(a[k].z, bw[k].z, dot[k]); dot[k] = fmaf(a[k].w, bw[k].w, dot[k]);
                 uu[k] = fmaf(a[k].x, a[k].x, uu[k]); uu[k] = fmaf(a[k].y, a[k].y, uu[k]);
@@ -132,12 +132,12 @@ static __global__ void __launch_bounds__(256) v3_cos_lse_kernel(const float* __r
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { dot[k] = warp_sum(dot[k]); uu[k] = warp_sum(uu[k]); zz[k] = warp_sum(zz[k]); }
-        if (lane < 4 && c0 + lane < used) {
+        for (int k = 0; k < NCW; ++k) { dot[k] = warp_sum(dot[k]); uu[k] = warp_sum(uu[k]); zz[k] = warp_sum(zz[k]); }
+        if (lane < NCW && c0 + lane < used) {
             float z = zz[0], d = dot[0], u2 = uu[0];
             size_t n = nn[0];
 #pragma unroll
-            for (int k = 1; k < 4; ++k)
+            for (int k = 1; k < NCW; ++k)
                 if (lane == k) { z = zz[k]; d = dot[k]; u2 = uu[k]; n = nn[k]; }
             const float unv = sqrtf(u2) / z;  // |u|, u = U' / Z
             const float c = (d / z) / fmaxf(wn[n] * unv, 1e-8f);
@@ -145,6 +145,7 @@ static __global__ void __launch_bounds__(256) v3_cos_lse_kernel(const float* __r
             cosv[(size_t)j * NtP + n] = c;
             un[(size_t)j * NtP + n] = unv;
             s_cos[c0 + lane] = c;
+        }
         }
     }
     __syncthreads();
@@ -210,8 +211,17 @@ static __global__ void __launch_bounds__(256) v3_unpack_dw_kernel(const float* _
         float v = 0.f;
         if (t < T && d0 + dd < D) {
             const size_t k = (size_t)(cs + t) * D + d0 + dd, plane = (size_t)NtP * D;
-            for (int s = 0; s < ngroups; ++s) v += dwcos[(size_t)s * plane + k];
-            for (int s0 = 0; s0 < nsplit; s0 += 8) {  // eight partials in flight per round
+            // the cosine part and the first sixteen split partials leave in ONE batch of loads (one memory round trip for the
+            // usual nsplit <= 16 instead of three); the summation order stays fixed
+            float c0 = ngroups > 0 ? dwcos[k] : 0.f;
+            float p16[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) p16[q] = (q < nsplit) ? dWpart[(size_t)q * plane + k] : 0.f;
+            for (int s = 1; s < ngroups; ++s) c0 += dwcos[(size_t)s * plane + k];
+            v = c0;
+            v += ((p16[0] + p16[1]) + (p16[2] + p16[3])) + ((p16[4] + p16[5]) + (p16[6] + p16[7]));
+            v += ((p16[8] + p16[9]) + (p16[10] + p16[11])) + ((p16[12] + p16[13]) + (p16[14] + p16[15]));
+            for (int s0 = 16; s0 < nsplit; s0 += 8) {  // eight partials in flight per further round
                 float p8[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) p8[q] = (s0 + q < nsplit) ? dWpart[(size_t)(s0 + q) * plane + k] : 0.f;

@@ -66,6 +66,8 @@ SIGNATURES = {
     "eegan_ssa_bwd_apply": (_c_int, [_p] * 7 + [_c_double, _p, _c_float, _c_int, _c_int, _c_int, _c_int, _p, _p]),
     "eegan_set_gag_engine": (_c_int, [_c_int]),
     "eegan_get_gag_engine": (_c_int, []),
+    "eegan_set_gag_bwd_engine": (_c_int, [_c_int]),
+    "eegan_get_gag_bwd_engine": (_c_int, []),
     "eegan_set_contraction_engine": (_c_int, [_c_int]),
     "eegan_get_contraction_engine": (_c_int, []),
     "eegan_profile_enable": (_c_int, [_c_int]),

@@ -19,6 +19,8 @@
 // Extra HBM traffic against the one-kernel form: ds written and read once (2 T floats per pixel), d_out and attn read twice.
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace eegan {
@@ -474,10 +476,37 @@ static int g2_launch(const G2Plan& pl, const float* x, const float* key, const f
 
 using namespace eegan;
 
+// gag_tc_bwd.cu: the one-pass tensor-core backward (idf = 32 / 64 / 128)
+namespace eegan {
+int gag_tc_bwd_chunks(int B, int Q);
+bool gag_tc_bwd_supported(const float* x, const float* attn, const float* d_out, const float* d_attn, const float* d_x, int B, int idf, int Q, int T);
+size_t gag_tc_bwd_part_floats(int B, int idf, int Q);
+int gag_tc_bwd_launch(const float* x, const float* key, const float* value, const float* attn, const float* d_out, const float* d_attn,
+                      int B, int idf, int Q, int T, float* d_x, float* part_k, float* part_v, int* chunks, cudaStream_t st);
+}  // namespace eegan
+
+// backward engine of eegan_gag_bwd_ws: 1 = tcgen05 one-pass kernel where the shape allows (default), 0 = CUDA-core kernels
+static std::atomic<int> g_gag_bwd_engine{[] {
+    const char* e = getenv("EEGAN_GAG_TC_BWD");
+    return e ? atoi(e) : 1;
+}()};
+extern "C" int eegan_set_gag_bwd_engine(int engine) {
+    EEGAN_REQUIRE(engine == 0 || engine == 1, "gag backward engine must be 0 (CUDA cores) or 1 (tensor cores)");
+    g_gag_bwd_engine.store(engine);
+    return EEGAN_OK;
+}
+extern "C" int eegan_get_gag_bwd_engine(void) { return g_gag_bwd_engine.load(); }
+
+static size_t g2_tc_bytes(int B, int idf, int Q, int T) {
+    if (!(idf == 32 || idf == 64 || idf == 128) || T > 32 || Q % 4 != 0) return 0;
+    return 2 * align_up(gag_tc_bwd_part_floats(B, idf, Q) * sizeof(float), 256);
+}
+
 extern "C" size_t eegan_gag_bwd_workspace_bytes(int B, int idf, int Q, int T) {
     G2Plan pl;
     if (B <= 0 || idf <= 0 || Q <= 0 || T <= 0 || !g2_plan(B, idf, Q, T, &pl)) return 0;
-    return pl.ds_bytes + 2 * pl.part_bytes;
+    const size_t cc = pl.ds_bytes + 2 * pl.part_bytes, tc = g2_tc_bytes(B, idf, Q, T);
+    return cc > tc ? cc : tc;
 }
 
 extern "C" int eegan_gag_bwd(const float* x, const float* key, const float* value, const float* attn, const float* d_out,
@@ -496,12 +525,23 @@ extern "C" int eegan_gag_bwd_ws(const float* x, const float* key, const float* v
                                          reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(d_attn) | reinterpret_cast<uintptr_t>(d_x)) & 15) == 0;
     if (!workspace || !aligned || !g2_plan(B, idf, Q, T, &pl) || B > 65535)
         return eegan_gag_bwd(x, key, value, attn, d_out, d_attn, B, idf, Q, T, d_x, d_key, d_value, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_gag_bwd_engine.load() == 1 && gag_tc_bwd_supported(x, attn, d_out, d_attn, d_x, B, idf, Q, T)) {
+        const size_t half = g2_tc_bytes(B, idf, Q, T) / 2;
+        EEGAN_REQUIRE(workspace_bytes >= 2 * half, "gag bwd: workspace %zu < %zu bytes", workspace_bytes, 2 * half);
+        float* tk = (float*)workspace;
+        float* tv = (float*)((char*)workspace + half);
+        int S = 0;
+        if (int rc = gag_tc_bwd_launch(x, key, value, attn, d_out, d_attn, B, idf, Q, T, d_x, tk, tv, &S, st)) return rc;
+        const long long n = (long long)B * idf * T;
+        gag_bwd_kv_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tk, tv, B, idf, T, 32, S, d_key, d_value);
+        return check_launch("gag tc bwd (reduce)");
+    }
     EEGAN_REQUIRE(workspace_bytes >= pl.ds_bytes + 2 * pl.part_bytes, "gag bwd: workspace %zu < %zu bytes", workspace_bytes,
                   pl.ds_bytes + 2 * pl.part_bytes);
     float* dsw = (float*)workspace;
     float* pk = (float*)((char*)workspace + pl.ds_bytes);
     float* pv = (float*)((char*)workspace + pl.ds_bytes + pl.part_bytes);
-    cudaStream_t st = (cudaStream_t)stream;
 #define G2_CALL(TPV) g2_launch<TPV>(pl, x, key, value, attn, d_out, d_attn, B, idf, Q, T, d_x, d_key, d_value, dsw, pk, pv, st)
     switch (pl.TP) {
         case 8: return G2_CALL(8);

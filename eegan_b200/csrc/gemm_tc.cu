@@ -332,6 +332,23 @@ int make_tmap_2d(CUtensorMap* m, const float* ptr, unsigned long long rows, unsi
     return EEGAN_OK;
 }
 
+int make_tmap_3d(CUtensorMap* m, const float* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                 unsigned long long pitch1, unsigned long long pitch2, unsigned box0, unsigned box1) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("tmap3d: cuTensorMapEncodeTiled unavailable"); return EEGAN_ERR_CUDA; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch1 % 4) || (pitch2 % 4)) {
+        set_error("tmap3d: base/pitches must be 16-byte aligned");
+        return EEGAN_ERR_INVALID;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2}, strides[2] = {pitch1 * 4, pitch2 * 4};
+    cuuint32_t box[3] = {box0, box1, 1}, estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tmap3d: cuTensorMapEncodeTiled failed (%d)", (int)r); return EEGAN_ERR_CUDA; }
+    return EEGAN_OK;
+}
+
 static int num_sms() { return num_sms_current(); }
 
 template <bool A_K, bool B_K, int EPI>

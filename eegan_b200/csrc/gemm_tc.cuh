@@ -86,6 +86,11 @@ struct TcGemm {
 int make_tmap_2d(CUtensorMap* m, const float* ptr, unsigned long long rows, unsigned long long cols, unsigned long long pitch,
                  unsigned box_cols, unsigned box_rows, bool swizzle128 = false);
 
+// Plain (un-swizzled) 3-D fp32 tensor map over [d2][d1][d0] (d0 contiguous; pitches in elements, multiples of 4) with a
+// [1][box1][box0] box (gag_tc_bwd.cu: [channels][pixels] units of x / d_out); TMA zero-fills out of bounds.
+int make_tmap_3d(CUtensorMap* m, const float* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                 unsigned long long pitch1, unsigned long long pitch2, unsigned box0, unsigned box1);
+
 // Un-swizzled 3-D map of an MN-major operand ([K][rows], rows contiguous): box [32 k][128 rows] (gemm_ts.cu, gag_tc.cu)
 int tc_make_map_plain(CUtensorMap* m, const TcOperand& o);
 

@@ -233,6 +233,7 @@ class _GagFn(torch.autograd.Function):
             _lib.check(L.eegan_gag_fwd(_lib.ptr(x), _lib.ptr(key), _lib.ptr(value), _lib.ptr(mask_u8), mask_mode,
                                        B, idf, Q, T, _lib.ptr(out), _lib.ptr(attn), _lib.stream_ptr()), "gag_fwd")
         ctx.save_for_backward(x, key, value, attn)
+        ctx.set_materialize_grads(False)  # an unused output arrives as None (the kernels take NULL), not as a zero tensor to read
         return out, attn
 
     @staticmethod

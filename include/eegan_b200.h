@@ -159,6 +159,11 @@ int eegan_sent_scores_bwd(const float* cnn, const float* rnn, const float* norms
  * softmax in the accumulator's threads, P written back to TMEM for out = P value^T); process-wide. */
 int eegan_set_gag_engine(int engine);
 int eegan_get_gag_engine(void);
+/* Backward engine of eegan_gag_bwd_ws: 1 = one-pass tcgen05 kernel (gag_tc_bwd.cu: all four contractions of the backward
+ * of miscc/DAMSM_losses.py:96-132 on the tensor cores, bf16 hi/lo operand pairs, d_out / x / attn read once; idf = 32 / 64 /
+ * 128, d_out given; default), 0 = CUDA-core kernels (gag_bwd2.cu); process-wide, for A/B validation. */
+int eegan_set_gag_bwd_engine(int engine);
+int eegan_get_gag_bwd_engine(void);
 
 /* ------------------------------------------------------------------------------------
  * R-precision scoring — test.py:306-336 (Tester.cal_sim_one_by_one), the evaluation-side consumer of

@@ -119,6 +119,18 @@ __device__ __forceinline__ uint16_t lds_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
     return v;
 }
+// the two halves of a packed pair to two addresses
+__device__ __forceinline__ void sts_u16x2(uint32_t addr_lo, uint32_t addr_hi, uint32_t packed) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b16 l, h;\n\t"
+        "mov.b32 {l, h}, %2;\n\t"
+        "st.shared.u16 [%0], l;\n\t"
+        "st.shared.u16 [%1], h;\n\t"
+        "}" ::"r"(addr_lo),
+        "r"(addr_hi), "r"(packed)
+        : "memory");
+}
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
@@ -364,138 +376,146 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(conv(s));
         }
-    } else if (warp < 10) {
-        // ===== pixel warps =====
+    } else {
+        // ===== pixel warps (6-9) and p / output warps (10-13): a thread owns pixel pl of the tile = TMEM lane pl =====
         const int quarter = warp & 3;
-        const int pl = quarter * 32 + lane;  // pixel of the tile = TMEM lane
+        const int pl = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t tile_off = (uint32_t)(pl >> 6) * 4096u + (uint32_t)(pl & 7) * 2u;  // + t * 128 + ((j ^ (t & 7)) << 4)
-        const uint32_t jq = (uint32_t)(pl & 63) >> 3;
-        const float* attn_b = p.attn + (size_t)b * T * p.Q;
-        const float* dattn_b = p.d_attn ? p.d_attn + (size_t)b * T * p.Q : nullptr;
+        // byte offset of (row t, pixel pl) in a [32 t][128 q] bf16 tile = offs[t & 7] + t * 128 (the 128-byte swizzle XORs the
+        // 16-byte chunk index with t & 7): eight registers, every store / load below takes t * 128 as an immediate
+        uint32_t offs[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) offs[k] = (uint32_t)(pl >> 6) * 4096u + (uint32_t)(pl & 7) * 2u + ((((uint32_t)(pl & 63) >> 3) ^ (uint32_t)k) << 4);
+        // val[0..TP) -> the tile's hi / lo panels (rows >= T carry zeros: val is zero there)
         auto write_tile = [&](uint32_t hi_base, uint32_t lo_base, const float (&val)[TP]) {
 #pragma unroll
-            for (int t = 0; t < TP; ++t)
-                if (t < T) {
-                    uint16_t h, l;
-                    gb_split1(val[t], h, l);
-                    const uint32_t off = tile_off + (uint32_t)t * 128u + ((jq ^ (uint32_t)(t & 7)) << 4);
-                    sts_u16(hi_base + off, h);
-                    sts_u16(lo_base + off, l);
-                }
+            for (int t = 0; t < TP; t += 2) {
+                uint32_t h2, l2;
+                gb_split2(val[t], val[t + 1], h2, l2);
+                const uint32_t o0 = offs[t & 7] + (uint32_t)t * 128u, o1 = offs[(t + 1) & 7] + (uint32_t)(t + 1) * 128u;
+                sts_u16x2(hi_base + o0, hi_base + o1, h2);
+                sts_u16x2(lo_base + o0, lo_base + o1, l2);
+            }
             fence_proxy_async();
             __syncwarp();
         };
-        // p(i+1) is written into the OTHER p buffer at the top of iteration i, from registers loaded one iteration earlier, so
-        // neither the load latency nor the softmax backward of tile i sits between two tiles' d_out contractions; the fp32
-        // p of tile i is not kept: ds re-reads it as hi + lo from the thread's own column of the p panels (2^-17 relative).
-        float pn[TP], da[TP];
-        auto load_p = [&](int i, float (&dst)[TP]) {
+        // rows of a [B][T][Q] array at this thread's pixel of tile i: clamped addresses, zeros beyond T / Q (no NaN from a neighbour)
+        auto load_rows = [&](const float* arr_b, int i, float (&dst)[TP]) {
             const int q = tile_q0(i) + pl;
+            const bool ok = q < p.Q;
+            const float* src = arr_b + (ok ? q : p.Q - 1);
 #pragma unroll
-            for (int t = 0; t < TP; ++t) dst[t] = (t < T && q < p.Q) ? __ldg(attn_b + (size_t)t * p.Q + q) : 0.f;
-        };
-        load_p(0, pn);
-        write_tile(p_hi, p_lo, pn);
-        if (lane == 0) mbar_arrive(p_full(0));
-        if (my_tiles > 1) load_p(1, pn);
-        int g = 0, g_end = gr0(1);
-        for (int i = 0; i < my_tiles; ++i) {
-            const int a = i & 1, k = i >> 1;
-            const int q = tile_q0(i) + pl;
-            if (i + 1 < my_tiles) {
-                // the contractions (2) of tile i-1 are done with buffer (i+1) & 1: its completion number (i-1) >> 1
-                mbar_wait(p_empty(a ^ 1), (((i + 1) >> 1) & 1) ^ 1);
-                const uint32_t nb = (uint32_t)(a ^ 1) * 2u * GB_PT;
-                write_tile(p_hi + nb, p_lo + nb, pn);
-                if (lane == 0) mbar_arrive(p_full(a ^ 1));
-                if (i + 2 < my_tiles) load_p(i + 2, pn);
+            for (int t = 0; t < TP; ++t) {
+                const float v = __ldg(src + (size_t)(t < T ? t : T - 1) * p.Q);
+                dst[t] = (ok && t < T) ? v : 0.f;
             }
+        };
+        if (warp < 10) {
+            // ---- pixel warps: dP -> ds = p (dp - sum p dp) -> ds panels; at the end of a group dV / dK -> partials.
+            // The fp32 p of the tile is re-read as hi + lo from the thread's own column of the p panels (2^-17 relative).
+            const float* dattn_b = p.d_attn ? p.d_attn + (size_t)b * T * p.Q : nullptr;
+            float da[TP], dn[TP];
 #pragma unroll
-            for (int t = 0; t < TP; ++t) da[t] = (dattn_b && t < T && q < p.Q) ? __ldg(dattn_b + (size_t)t * p.Q + q) : 0.f;
-            mbar_wait(dp_full(a), k & 1);
-            tc_fence_after();
-            uint32_t v[32];
-            tmem_ld32(lane_base + COL_DP + (uint32_t)a * 32u, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dp_empty(a));
-            float pc[TP];
-            {
+            for (int t = 0; t < TP; ++t) dn[t] = 0.f;
+            if (dattn_b) load_rows(dattn_b, 0, dn);
+            int g = 0, g_end = gr0(1);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int a = i & 1, k = i >> 1;
+#pragma unroll
+                for (int t = 0; t < TP; ++t) da[t] = dn[t];
+                if (dattn_b && i + 1 < my_tiles) load_rows(dattn_b, i + 1, dn);  // one tile ahead: the latency hides behind this tile
+                mbar_wait(dp_full(a), k & 1);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(lane_base + COL_DP + (uint32_t)a * 32u, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dp_empty(a));
+                float pc[TP];
                 const uint32_t cb = (uint32_t)a * 2u * GB_PT;
 #pragma unroll
                 for (int t = 0; t < TP; ++t) {
-                    pc[t] = 0.f;
-                    if (t < T) {
-                        const uint32_t off = cb + tile_off + (uint32_t)t * 128u + ((jq ^ (uint32_t)(t & 7)) << 4);
-                        pc[t] = __uint_as_float((uint32_t)lds_u16(p_hi + off) << 16) + __uint_as_float((uint32_t)lds_u16(p_lo + off) << 16);
-                    }
+                    const uint32_t off = cb + offs[t & 7] + (uint32_t)t * 128u;
+                    pc[t] = __uint_as_float((uint32_t)lds_u16(p_hi + off) << 16) + __uint_as_float((uint32_t)lds_u16(p_lo + off) << 16);
                 }
-            }
-            float dot = 0.f;
+                float dot = 0.f;
 #pragma unroll
-            for (int t = 0; t < TP; ++t) {
-                da[t] += __uint_as_float(v[t]);  // dp = dP + d_attn
-                dot = fmaf(pc[t], da[t], dot);
-            }
+                for (int t = 0; t < TP; ++t) {
+                    da[t] += __uint_as_float(v[t]);  // dp = dP + d_attn
+                    dot = fmaf(pc[t], da[t], dot);
+                }
 #pragma unroll
-            for (int t = 0; t < TP; ++t) da[t] = pc[t] * (da[t] - dot);  // ds
-            mbar_wait(ds_empty, (i & 1) ^ 1);
-            write_tile(ds_hi, ds_lo, da);
-            if (lane == 0) mbar_arrive(ds_full);
-            if (i + 1 == g_end) {
-                // ---- end of a group: dV / dK accumulators (M = 64: row m sits in lane (m % 16) + 32 (m / 16)) -> the group's partial.
-                // The tensor core accumulates with truncation, so a long chain of accumulations drifts (measured: 6e-5 of the
-                // maximum after 170 tiles); a group is at most GB_GROUP tiles and the partials are summed in fp32 by the reduce kernel.
-                mbar_wait(acc_full, g & 1);
-                tc_fence_after();
-                const int cl = quarter * 16 + lane;  // channel of the unit held by this lane (lanes 0-15)
-                const size_t pbase = (((size_t)b * gridDim.x + blockIdx.x) * NGR + g) * idf;
-                for (int u = 0; u < NU; ++u) {
-                    uint32_t vk[32], vv[32];
-                    tmem_ld32(lane_base + COL_DK + (uint32_t)u * 32u, vk);
-                    tmem_ld32(lane_base + COL_DV + (uint32_t)u * 32u, vv);
-                    tmem_ld_wait();
-                    if (lane < 16 && cl < UC) {
-                        float4* ok = reinterpret_cast<float4*>(p.part_k + (pbase + (size_t)u * UC + cl) * 32);
-                        float4* ov = reinterpret_cast<float4*>(p.part_v + (pbase + (size_t)u * UC + cl) * 32);
+                for (int t = 0; t < TP; ++t) da[t] = pc[t] * (da[t] - dot);  // ds
+                mbar_wait(ds_empty, (i & 1) ^ 1);
+                write_tile(ds_hi, ds_lo, da);
+                if (lane == 0) mbar_arrive(ds_full);
+                if (i + 1 == g_end) {
+                    // ---- end of a group: dV / dK accumulators (M = 64: row m sits in lane (m % 16) + 32 (m / 16)) -> the group's partial.
+                    // The tensor core accumulates with truncation, so a long chain of accumulations drifts (measured: 6e-5 of the
+                    // maximum after 170 tiles); a group is at most GB_GROUP tiles and the partials are summed in fp32 by the reduce kernel.
+                    mbar_wait(acc_full, g & 1);
+                    tc_fence_after();
+                    const int cl = quarter * 16 + lane;  // channel of the unit held by this lane (lanes 0-15)
+                    const size_t pbase = (((size_t)b * gridDim.x + blockIdx.x) * NGR + g) * idf;
+                    for (int u = 0; u < NU; ++u) {
+                        uint32_t vk[32], vv[32];
+                        tmem_ld32(lane_base + COL_DK + (uint32_t)u * 32u, vk);
+                        tmem_ld32(lane_base + COL_DV + (uint32_t)u * 32u, vv);
+                        tmem_ld_wait();
+                        if (lane < 16 && cl < UC) {
+                            float4* ok = reinterpret_cast<float4*>(p.part_k + (pbase + (size_t)u * UC + cl) * 32);
+                            float4* ov = reinterpret_cast<float4*>(p.part_v + (pbase + (size_t)u * UC + cl) * 32);
 #pragma unroll
-                        for (int t = 0; t < 32; t += 4) {
-                            ok[t >> 2] = make_float4(__uint_as_float(vk[t]), __uint_as_float(vk[t + 1]), __uint_as_float(vk[t + 2]), __uint_as_float(vk[t + 3]));
-                            ov[t >> 2] = make_float4(__uint_as_float(vv[t]), __uint_as_float(vv[t + 1]), __uint_as_float(vv[t + 2]), __uint_as_float(vv[t + 3]));
+                            for (int t = 0; t < 32; t += 4) {
+                                ok[t >> 2] = make_float4(__uint_as_float(vk[t]), __uint_as_float(vk[t + 1]), __uint_as_float(vk[t + 2]), __uint_as_float(vk[t + 3]));
+                                ov[t >> 2] = make_float4(__uint_as_float(vv[t]), __uint_as_float(vv[t + 1]), __uint_as_float(vv[t + 2]), __uint_as_float(vv[t + 3]));
+                            }
                         }
                     }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);
-                ++g;
-                g_end = gr0(g + 1);
-            }
-        }
-    } else {
-        // ===== output warps: dX[q][c] -> d_x[b][c][q] =====
-        const int quarter = warp & 3;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + COL_DX;
-        for (int j = 0; j < my_tiles; ++j) {
-            const int a = j & 1, k = j >> 1;
-            const int q = tile_q0(j) + quarter * 32 + lane;
-            mbar_wait(dx_full(a), k & 1);
-            tc_fence_after();
-            float* orow = p.d_x + (size_t)b * idf * p.Q + q;
-            for (int c = 0; c < idf; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + (uint32_t)a * 128u + (uint32_t)c, v);
-                tmem_ld_wait();
-                if (c + 32 >= idf) {  // accumulator fully read
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(dx_empty(a));
+                    if (lane == 0) mbar_arrive(acc_empty);
+                    ++g;
+                    g_end = gr0(g + 1);
                 }
-                if (q < p.Q) {
+            }
+        } else {
+            // ---- p / output warps: the p panels of tile i+1 (two buffers) at the top of iteration i, from registers loaded one
+            // iteration earlier, then dX[q][c] of tile i -> d_x[b][c][q] (coalesced 128-byte rows per channel)
+            const float* attn_b = p.attn + (size_t)b * T * p.Q;
+            float pn[TP];
+            load_rows(attn_b, 0, pn);
+            write_tile(p_hi, p_lo, pn);
+            if (lane == 0) mbar_arrive(p_full(0));
+            if (my_tiles > 1) load_rows(attn_b, 1, pn);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int a = i & 1, k = i >> 1;
+                if (i + 1 < my_tiles) {
+                    // the contractions (2) of tile i-1 are done with buffer (i+1) & 1: its completion number (i-1) >> 1
+                    mbar_wait(p_empty(a ^ 1), (((i + 1) >> 1) & 1) ^ 1);
+                    const uint32_t nb = (uint32_t)(a ^ 1) * 2u * GB_PT;
+                    write_tile(p_hi + nb, p_lo + nb, pn);
+                    if (lane == 0) mbar_arrive(p_full(a ^ 1));
+                    if (i + 2 < my_tiles) load_rows(attn_b, i + 2, pn);
+                }
+                const int q = tile_q0(i) + pl;
+                mbar_wait(dx_full(a), k & 1);
+                tc_fence_after();
+                float* orow = p.d_x + (size_t)b * idf * p.Q + q;
+                for (int c = 0; c < idf; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + COL_DX + (uint32_t)a * 128u + (uint32_t)c, v);
+                    tmem_ld_wait();
+                    if (c + 32 >= idf) {  // accumulator fully read
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(dx_empty(a));
+                    }
+                    if (q < p.Q) {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) orow[(size_t)(c + jj) * p.Q] = __uint_as_float(v[jj]);
+                        for (int jj = 0; jj < 32; ++jj) orow[(size_t)(c + jj) * p.Q] = __uint_as_float(v[jj]);
+                    }
                 }
             }
         }

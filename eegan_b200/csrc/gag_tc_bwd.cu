@@ -119,6 +119,21 @@ __device__ __forceinline__ uint16_t lds_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
     return v;
 }
+// predicated read-only load, zero when off: nothing is executed on the loaded value afterwards, so the loads of a whole tile
+// stay in flight until their first real use (a select after the load would make the warp wait for each of them at once)
+__device__ __forceinline__ float ldg_pred(const float* ptr, bool pred) {
+    float v;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\t"
+        "@p ld.global.nc.f32 %0, [%1];\n\t"
+        "}"
+        : "=f"(v)
+        : "l"(ptr), "r"((int)pred));
+    return v;
+}
 // the two halves of a packed pair to two addresses
 __device__ __forceinline__ void sts_u16x2(uint32_t addr_lo, uint32_t addr_hi, uint32_t packed) {
     asm volatile(
@@ -140,7 +155,7 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     return v;
 }
 
-template <int TP>
+template <int TP, int UC>
 __global__ void __launch_bounds__(GB_THREADS, 1)
 gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_x, const GagTcBwdArgs p) {
     extern __shared__ uint8_t smem_raw[];
@@ -150,7 +165,7 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
     const int b = blockIdx.y;
     const int tiles_b = (p.Q + GB_TILE - 1) / GB_TILE;
     const int my_tiles = (tiles_b - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // >= 1: the launch keeps gridDim.x <= tiles_b
-    const int UC = p.uc, NU = p.nu, NS = p.ns, T = p.T, idf = p.idf, NGR = p.ngr;
+    const int NU = p.nu, NS = p.ns, T = p.T, idf = p.idf, NGR = p.ngr;
     // the CTA's tiles in NGR groups (all non-empty: my_tiles >= NGR, see gag_tc_bwd_groups); group g = local tiles [gr0(g), gr0(g+1))
     auto gr0 = [&](int g) { return (int)(((long long)g * my_tiles) / NGR); };
 
@@ -349,20 +364,19 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
     } else if (warp < 6) {
         // ===== converters: fp32 unit [UC][128 q] -> bf16 hi / lo, two [UC][64 q] panels each, in place =====
         const int ctid = threadIdx.x - 64;
-        const int nchunk = UC / 4;  // 16-byte chunks per thread
+        constexpr int nchunk = UC / 4;  // 16-byte chunks per thread
         const int units = 2 * NU * my_tiles;
         for (int it = 0; it < units; ++it) {
             const int s = it % NS, ph = (it / NS) & 1;
             mbar_wait(full(s), ph);
             const uint32_t sb = base + (uint32_t)s * slot_bytes;
-            float4 v[16];
+            float4 v[nchunk];
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < nchunk) v[k] = lds_v4(sb + (uint32_t)(ctid + 128 * k) * 16u);
+            for (int k = 0; k < nchunk; ++k) v[k] = lds_v4(sb + (uint32_t)(ctid + 128 * k) * 16u);
             asm volatile("bar.sync 1, 128;" ::: "memory");  // the whole unit is in registers: the slot may be overwritten
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < nchunk) {
+            for (int k = 0; k < nchunk; ++k) {
+                {
                     const int idx = ctid + 128 * k, row = idx >> 5, ch = idx & 31;
                     uint32_t h0, l0, h1, l1;
                     gb_split2(v[k].x, v[k].y, h0, l0);
@@ -372,6 +386,7 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
                     sts_v2(sb + off, h0, h1);
                     sts_v2(sb + half_bytes + off, l0, l1);
                 }
+            }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(conv(s));
@@ -399,16 +414,13 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
             fence_proxy_async();
             __syncwarp();
         };
-        // rows of a [B][T][Q] array at this thread's pixel of tile i: clamped addresses, zeros beyond T / Q (no NaN from a neighbour)
+        // rows of a [B][T][Q] array at this thread's pixel of tile i: predicated loads, zeros beyond T / Q
         auto load_rows = [&](const float* arr_b, int i, float (&dst)[TP]) {
             const int q = tile_q0(i) + pl;
             const bool ok = q < p.Q;
-            const float* src = arr_b + (ok ? q : p.Q - 1);
+            const float* src = arr_b + q;
 #pragma unroll
-            for (int t = 0; t < TP; ++t) {
-                const float v = __ldg(src + (size_t)(t < T ? t : T - 1) * p.Q);
-                dst[t] = (ok && t < T) ? v : 0.f;
-            }
+            for (int t = 0; t < TP; ++t) dst[t] = ldg_pred(src + (size_t)t * p.Q, ok && t < T);
         };
         if (warp < 10) {
             // ---- pixel warps: dP -> ds = p (dp - sum p dp) -> ds panels; at the end of a group dV / dK -> partials.
@@ -581,15 +593,15 @@ int gag_tc_bwd_launch(const float* x, const float* key, const float* value, cons
     const size_t smem = (size_t)a.ns * slot + fixed;
     const int S = gag_tc_bwd_chunks(B, Q);
     *chunks = S * a.ngr;
-    if (T <= 20) {
-        static SmemGrant grant;
-        if ((rc = grant_dyn_smem(gag_tc_bwd_kernel<20>, smem, grant, "gag tc bwd"))) return rc;
-        gag_tc_bwd_kernel<20><<<dim3(S, B), GB_THREADS, smem, st>>>(tm_do, tm_x, a);
-    } else {
-        static SmemGrant grant;
-        if ((rc = grant_dyn_smem(gag_tc_bwd_kernel<32>, smem, grant, "gag tc bwd"))) return rc;
-        gag_tc_bwd_kernel<32><<<dim3(S, B), GB_THREADS, smem, st>>>(tm_do, tm_x, a);
-    }
+    auto run = [&](auto kern, SmemGrant& grant) -> int {
+        if (int r = grant_dyn_smem(kern, smem, grant, "gag tc bwd")) return r;
+        kern<<<dim3(S, B), GB_THREADS, smem, st>>>(tm_do, tm_x, a);
+        return EEGAN_OK;
+    };
+    static SmemGrant g0, g1, g2, g3;
+    if (T <= 20) rc = UC == 64 ? run(gag_tc_bwd_kernel<20, 64>, g0) : run(gag_tc_bwd_kernel<20, 32>, g1);
+    else rc = UC == 64 ? run(gag_tc_bwd_kernel<32, 64>, g2) : run(gag_tc_bwd_kernel<32, 32>, g3);
+    if (rc) return rc;
     return check_launch("gag tc bwd");
 }
 

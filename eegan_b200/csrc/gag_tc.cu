@@ -42,6 +42,18 @@ struct GagTcArgs {
     int a_col0;          // first TMEM column of the x stages
 };
 
+__device__ __forceinline__ bool gt_elect() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // byte offset of element (row, k) in a K-major SWIZZLE_128B tile of 32-float rows
 __device__ __forceinline__ uint32_t sw128_off(int row, int k) { return (uint32_t)(row * 128 + ((((k >> 2) ^ (row & 7))) << 4) + ((k & 3) << 2)); }
 
@@ -49,7 +61,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
 gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t s_maskbits[1024];  // per mask row: bit t set = word t is padding
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle is provably warp-uniform: the role branches become uniform branches and the issuer's
+    // operands live in uniform registers (otherwise every MMA is wrapped in an elect / broadcast loop)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int tiles_b = (p.Q + GT_TILE - 1) / GT_TILE;
     const int my_tiles = ((int)blockIdx.x < tiles_b) ? (tiles_b - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -150,8 +164,9 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp walks the loop, one elected lane issues =====
+        const bool leader = gt_elect();
+        {
             const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GT_TP >> 3) << 17) | ((uint32_t)(GT_TILE >> 4) << 24);
             const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.idf_pad >> 3) << 17) | ((uint32_t)(GT_TILE >> 4) << 24);
             int it = 0;
@@ -169,13 +184,13 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t dbh = umma_desc(b_hi, true, ks, 0, 0), dbl = umma_desc(b_lo, true, ks, 0, 0);
-                        tc_mma_tf32_ts(d_s, a_lo + ks * 8, dbh, idesc_s, (kb > 0 || ks > 0) ? 1u : 0u);
-                        tc_mma_tf32_ts(d_s, a_hi + ks * 8, dbl, idesc_s, 1u);
-                        tc_mma_tf32_ts(d_s, a_hi + ks * 8, dbh, idesc_s, 1u);
+                        if (leader) tc_mma_tf32_ts(d_s, a_lo + ks * 8, dbh, idesc_s, (kb > 0 || ks > 0) ? 1u : 0u);
+                        if (leader) tc_mma_tf32_ts(d_s, a_hi + ks * 8, dbl, idesc_s, 1u);
+                        if (leader) tc_mma_tf32_ts(d_s, a_hi + ks * 8, dbh, idesc_s, 1u);
                     }
-                    tc_commit(empty(s));
+                    if (leader) tc_commit(empty(s));
                 }
-                tc_commit(s_full(sb));
+                if (leader) tc_commit(s_full(sb));
             };
             issue_s(0);
             for (int i = 0; i < my_tiles; ++i) {
@@ -187,12 +202,12 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint64_t dbh = umma_desc(vt_hi, true, ks, 0, 0), dbl = umma_desc(vt_lo, true, ks, 0, 0);
-                    tc_mma_tf32_ts(d_o, p_lo + ks * 8, dbh, idesc_o, ks > 0 ? 1u : 0u);
-                    tc_mma_tf32_ts(d_o, p_hi + ks * 8, dbl, idesc_o, 1u);
-                    tc_mma_tf32_ts(d_o, p_hi + ks * 8, dbh, idesc_o, 1u);
+                    if (leader) tc_mma_tf32_ts(d_o, p_lo + ks * 8, dbh, idesc_o, ks > 0 ? 1u : 0u);
+                    if (leader) tc_mma_tf32_ts(d_o, p_hi + ks * 8, dbl, idesc_o, 1u);
+                    if (leader) tc_mma_tf32_ts(d_o, p_hi + ks * 8, dbh, idesc_o, 1u);
                 }
-                tc_commit(o_full);
-                tc_commit(p_empty);
+                if (leader) tc_commit(o_full);
+                if (leader) tc_commit(p_empty);
             }
         }
     } else if (warp < 6) {

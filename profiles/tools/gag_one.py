@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only-bwd-engine", type=int, default=-1)
+    ap.add_argument("--fwd-engine", type=int, default=-1)
     ap.add_argument("--no-dattn", action="store_true")
     ap.add_argument("--no-mask", action="store_true")
     a = ap.parse_args()
@@ -109,9 +110,24 @@ def main():
         ms = time(graph(fwd_bwd), a.iters)
         print("bwd engine %d: fwd+bwd %.1f us  %.1f%% of 6549 GB/s (algorithmic %.0f MB)" % (eng, ms * 1e3, by / (ms / 1e3) / 1e9 / 6549 * 100, by / 1e6),
               flush=True)
-    with torch.no_grad():
-        ms_f = time(graph(lambda: mod(x, key, val)), a.iters)
-    print("fwd only: %.1f us  %.1f%%" % (ms_f * 1e3, by_f / (ms_f / 1e3) / 1e9 / 6549 * 100))
+    fwd_engines = (0, 1) if a.fwd_engine < 0 else (a.fwd_engine,)
+    for fe in fwd_engines:
+        assert L.eegan_set_gag_engine(fe) == 0
+        with torch.no_grad():
+            ms_f = time(graph(lambda: mod(x, key, val)), a.iters)
+            o, at = mod(x, key, val)
+        msg = ""
+        if a.check:
+            xd, kd, vd = x.detach().double().view(B, idf, -1), key.detach().double(), val.detach().double()
+            sc = torch.bmm(xd.transpose(1, 2), kd)
+            if mask is not None:
+                sc = sc.masked_fill(mask[:, None, :], float("-inf"))
+            pr = torch.softmax(sc, dim=2)
+            ro = torch.bmm(vd, pr.transpose(1, 2))
+            msg = "  attn abs err %.2e  out rel err %.2e" % (float((at.double().view(B, T, -1) - pr.transpose(1, 2)).abs().max()),
+                                                          float((o.double().view(B, idf, -1) - ro).abs().max() / ro.abs().max()))
+        print("fwd engine %d: %.1f us  %.1f%%%s" % (fe, ms_f * 1e3, by_f / (ms_f / 1e3) / 1e9 / 6549 * 100, msg), flush=True)
+    L.eegan_set_gag_engine(0)
     if a.check:
         rx, rk, rv = ref64(x, key, val, mask, go, ga)
         rel = lambda u, v: float((u.double() - v).abs().max() / v.abs().max())

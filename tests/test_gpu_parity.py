@@ -188,15 +188,27 @@ def test_gag_tensor_core_forward_shapes(cuda_lib, B, idf, H, T):
         assert float((out.cpu().double()[okr] - oo[okr]).abs().max()) <= 1e-5 * float(oo[okr].abs().max()), eng
 
 
+@pytest.fixture(params=[1, 0], ids=["gag-bwd-tcgen05", "gag-bwd-cuda-cores"])
+def gag_bwd_engine(request, cuda_lib):
+    """Both backward engines of GlobalAttentionGeneral: the one-pass tcgen05 kernel (gag_tc_bwd.cu; default where the shape
+    allows: idf = 32 / 64 / 128 with a gradient on `out`) and the CUDA-core kernels (gag_bwd2.cu / gag.cu)."""
+    assert cuda_lib.eegan_set_gag_bwd_engine(request.param) == 0
+    yield request.param
+    cuda_lib.eegan_set_gag_bwd_engine(1)
+
+
 @pytest.mark.parametrize("B,idf,H,T,grads", [(3, 128, 16, 18, "both"), (2, 64, 20, 18, "both"), (4, 32, 24, 5, "both"),
                                               (2, 96, 12, 20, "both"), (2, 256, 8, 32, "both"), (3, 64, 16, 18, "out"),
-                                              (3, 64, 16, 18, "attn"), (2, 48, 12, 7, "both"), (2, 32, 23, 18, "both")])
-def test_gag_backward_shapes(cuda_lib, B, idf, H, T, grads):
+                                              (3, 64, 16, 18, "attn"), (2, 48, 12, 7, "both"), (2, 32, 23, 18, "both"),
+                                              (2, 64, 12, 32, "both"), (5, 128, 10, 21, "out")])
+def test_gag_backward_shapes(cuda_lib, gag_bwd_engine, B, idf, H, T, grads):
     """The two-kernel backward (gag_bwd2.cu: per-pixel-quad pass + key/value row sums with the lanes along the pixels) at its
     shape edges — idf = 32 / 64 / 96 / 128 / 256 (1 … 8 channel sets of 8 channels per warp; 4 per warp once T > 20),
     T = 5 … 32 (every TP instantiation), Q = 144 … 576 (partial 128-pixel rounds, several pixel chunks), a gradient on only
     one of the two outputs — and the one-kernel fallback it hands idf = 48 and Q % 4 != 0 to, against the float64
-    oracle's autograd."""
+    oracle's autograd.  With the tcgen05 engine selected the same cases run through gag_tc_bwd.cu where it takes the shape
+    (idf = 32 / 64 / 128, a gradient on `out`; partial last tile at Q = 144 / 400 / 576, T <= 20 and T > 20 instantiations, one
+    and two 64-channel units) and through the CUDA-core kernels elsewhere."""
     import eegan_b200 as E
     c = cases.gag_case(B, idf, H, T, seed=B * 7 + idf + T, masked=False)
     gen = cases._gen(5)
@@ -220,6 +232,61 @@ def test_gag_backward_shapes(cuda_lib, B, idf, H, T, grads):
         assert relmax(v.grad.cpu(), vo.grad) <= TOL_GRAD
     else:  # value only feeds `out`
         assert float(v.grad.abs().max()) == 0.0
+
+
+def _gag_ref64_gpu(x, key, val, mask, go, ga):
+    """float64 autograd of miscc/DAMSM_losses.py:96-132 (intended mask mode) on the GPU: the checker for shapes where the CPU
+    oracle would take minutes."""
+    x, key, val = (t.detach().double().requires_grad_() for t in (x, key, val))
+    B, idf, H, W = x.shape
+    s = torch.bmm(x.view(B, idf, H * W).transpose(1, 2), key)
+    if mask is not None:
+        s = s.masked_fill(mask[:, None, :], float("-inf"))
+    p = torch.softmax(s, dim=2)
+    out = torch.bmm(val, p.transpose(1, 2)).view(B, idf, H, W)
+    attn = p.transpose(1, 2).reshape(B, -1, H, W)
+    ((out * go.double()).sum() + ((attn * ga.double()).sum() if ga is not None else 0.0)).backward()
+    return out.detach(), attn.detach(), x.grad, key.grad, val.grad
+
+
+@pytest.mark.parametrize("B,idf,H,T,dattn", [(40, 64, 128, 18, True), (48, 128, 64, 18, True), (37, 32, 100, 12, False),
+                                              (150, 32, 72, 18, True)])
+def test_gag_tensor_core_backward_long_chains(cuda_lib, B, idf, H, T, dattn):
+    """gag_tc_bwd.cu where a CTA walks many tiles: several tiles per CTA (the unit ring wraps, every barrier changes phase many
+    times), more than one accumulation group (43 tiles per CTA at B = 40, 128^2: two groups; B = 150: one CTA per sample, 41
+    tiles), a benchmarked shape (B = 48, 64^2 x 128), a partial last tile (Q = 10000) and no gradient on attn — against float64
+    autograd of the same math on the GPU.  The d_key / d_value bound also holds the accumulation-drift fix (one group per 32
+    tiles) in place: without it the error grows with the number of tiles a CTA accumulates."""
+    import eegan_b200 as E
+    gen = torch.Generator(device="cpu").manual_seed(B + idf + H)
+    lens = torch.randint(3, T + 1, (B,), generator=gen)
+    mask = (torch.arange(T)[None, :] >= lens[:, None]).cuda()
+    x = torch.randn(B, idf, H, H, generator=gen).cuda().requires_grad_()
+    key = (torch.randn(B, idf, T, generator=gen) * idf ** -0.5).cuda().requires_grad_()
+    val = torch.randn(B, idf, T, generator=gen).cuda().requires_grad_()
+    go = torch.randn(B, idf, H, H, generator=gen).cuda()
+    ga = torch.randn(B, T, H, H, generator=gen).cuda() if dattn else None
+    mod = E.GlobalAttentionGeneral(idf, 256, mask_mode="intended")
+    mod.applyMask(mask)
+    assert cuda_lib.eegan_get_gag_bwd_engine() == 1
+    out, attn = mod(x, key, val)
+    torch.autograd.backward([out, attn] if dattn else [out], [go, ga] if dattn else [go])
+    ro, ra, rx, rk, rv = _gag_ref64_gpu(x, key, val, mask, go, ga)
+    assert float((attn.double() - ra).abs().max()) <= TOL_ATT_STRESS
+    assert relmax(out.detach().cpu(), ro.cpu()) <= 1e-5
+    assert relmax(x.grad.cpu(), rx.cpu()) <= TOL_GRAD
+    assert relmax(key.grad.cpu(), rk.cpu()) <= TOL_GRAD
+    assert relmax(val.grad.cpu(), rv.cpu()) <= TOL_GRAD
+    # the two engines agree far inside the tolerance (same math, bf16-pair operands against fp32 FMA)
+    gx, gk, gv = x.grad.clone(), key.grad.clone(), val.grad.clone()
+    x.grad = key.grad = val.grad = None
+    try:
+        cuda_lib.eegan_set_gag_bwd_engine(0)
+        out, attn = mod(x, key, val)
+        torch.autograd.backward([out, attn] if dattn else [out], [go, ga] if dattn else [go])
+    finally:
+        cuda_lib.eegan_set_gag_bwd_engine(1)
+    assert relmax(gx.cpu(), x.grad.cpu()) <= 5e-5 and relmax(gk.cpu(), key.grad.cpu()) <= 5e-5 and relmax(gv.cpu(), val.grad.cpu()) <= 5e-5
 
 
 @pytest.mark.parametrize("name", golden_names("words_")[:3])

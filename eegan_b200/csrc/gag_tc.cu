@@ -57,6 +57,7 @@ __device__ __forceinline__ bool gt_elect() {
 // byte offset of element (row, k) in a K-major SWIZZLE_128B tile of 32-float rows
 __device__ __forceinline__ uint32_t sw128_off(int row, int k) { return (uint32_t)(row * 128 + ((((k >> 2) ^ (row & 7))) << 4) + ((k & 3) << 2)); }
 
+template <int TP>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
@@ -245,12 +246,19 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
             }
         }
     } else if (warp < 10) {
-        // ===== softmax warps =====
+        // ===== softmax warps =====  (lean on purpose: at idf = 32 a tile is ~1000 cycles of HBM time, and this loop is what
+        // every pixel pays — one mask word, exp2 on the shifted score, pointer-increment stores, no per-element range checks)
         const int quarter = warp & 3;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t padbits = p.T >= 32 ? 0u : (0xffffffffu << p.T);  // words >= T count as masked: exp(-inf) = 0
+        const int qstep = (int)gridDim.x * GT_TILE;
+        int q = tile_q0(0) + quarter * 32 + lane;
+        // mask quirk (:114-118): row (b, q) takes mask[(b Q + q) mod B]; mode 1 = mask[b].  The residue is carried
+        // from tile to tile instead of a 64-bit modulo per tile.
+        int rq = p.mask_mode ? b : (int)(((long long)b * p.Q + q) % p.B);
+        const int rstep = qstep % p.B;
         for (int i = 0; i < my_tiles; ++i) {
             const int sb = i & 1;
-            const int q = tile_q0(i) + quarter * 32 + lane;
             mbar_wait(s_full(sb), (i >> 1) & 1);
             tc_fence_after();
             uint32_t v[32];
@@ -259,36 +267,37 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty(sb));
-            // mask quirk (:114-118): row (b, q) takes mask[(b Q + q) mod B]; mode 1 = mask[b]
-            uint32_t mbits = 0;
-            if (p.mask) mbits = s_maskbits[p.mask_mode ? b : (int)(((long long)b * p.Q + q) % p.B)];
+            const uint32_t mbits = padbits | (p.mask ? s_maskbits[rq] : 0u);
             float mx = -INFINITY;
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const bool on = t < p.T && !((mbits >> t) & 1u);
-                const float sv = on ? __uint_as_float(v[t]) : -INFINITY;
+            for (int t = 0; t < TP; ++t) {
+                const float sv = ((mbits >> t) & 1u) ? -INFINITY : __uint_as_float(v[t]);
                 v[t] = __float_as_uint(sv);
                 mx = fmaxf(mx, sv);
             }
             float sum = 0.f;
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const float e = __expf(__uint_as_float(v[t]) - mx);  // all words masked: -inf - -inf = NaN, as in the reference
+            for (int t = 0; t < TP; ++t) {
+                float e;  // exp(s - max): all words masked gives -inf - -inf = NaN, as in the reference
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((__uint_as_float(v[t]) - mx) * 1.4426950408889634f));
                 v[t] = __float_as_uint(e);
                 sum += e;
             }
             const float inv = 1.0f / sum;
             uint32_t lo[32];
-            float* arow = p.attn + (size_t)b * p.T * p.Q + q;
+            float* ap = p.attn + (size_t)b * p.T * p.Q + q;
+            const int nst = q < p.Q ? p.T : 0;  // rows this thread stores
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const float pv = __uint_as_float(v[t]) * inv;
-                if (t < p.T && q < p.Q) arow[(size_t)t * p.Q] = pv;
-                const float pz = t < p.T ? pv : 0.f;  // padded words must not reach the second contraction (NaN * 0)
-                const float h = trunc_tf32(pz);
+            for (int t = 0; t < TP; ++t) {
+                const float pv = __uint_as_float(v[t]) * inv;  // masked / padded words: exactly 0 (NaN rows stay NaN, as in the reference)
+                if (t < nst) *ap = pv;
+                ap += p.Q;
+                const float h = trunc_tf32(pv);
                 v[t] = __float_as_uint(h);
-                lo[t] = __float_as_uint(to_tf32(pz - h));
+                lo[t] = __float_as_uint(pv - h);  // exact; the tensor core truncates it to tf32 itself
             }
+#pragma unroll
+            for (int t = TP; t < 32; ++t) v[t] = lo[t] = 0u;
             mbar_wait(p_empty, (i & 1) ^ 1);  // the previous tile's P has been consumed by its MMAs
             tc_fence_after();
             tmem_st32(lane_base + 64u, v);
@@ -297,6 +306,9 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
+            q += qstep;
+            rq += rstep;
+            if (rq >= p.B) rq -= p.B;
         }
     } else {
         // ===== output warps: O[q][d] -> out[b][d][q] =====
@@ -306,9 +318,11 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
             const int q = tile_q0(i) + quarter * 32 + lane;
             mbar_wait(o_full, i & 1);
             tc_fence_after();
-            float* orow = p.out + (size_t)b * p.idf * p.Q + q;
+            float* op = p.out + (size_t)b * p.idf * p.Q + q;
+            const bool okq = q < p.Q;
             for (int c = 0; c < p.idf_pad; c += 32) {
                 uint32_t v[32];
+                const bool whole = p.idf - c >= 32;
                 if (p.idf_pad - c >= 32) tmem_ld32(lane_base + (uint32_t)c, v);
                 else tmem_ld16(lane_base + (uint32_t)c, v);
                 tmem_ld_wait();
@@ -317,10 +331,16 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(o_empty);
                 }
-                if (q < p.Q) {
+                if (whole) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (okq) *op = __uint_as_float(v[j]);
+                        op += p.Q;
+                    }
+                } else if (okq) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c + j < p.idf) orow[(size_t)(c + j) * p.Q] = __uint_as_float(v[j]);
+                        if (c + j < p.idf) op[(size_t)j * p.Q] = __uint_as_float(v[j]);
                 }
             }
         }
@@ -358,14 +378,17 @@ int gag_tc_fwd_launch(const float* x, const float* key, const float* value, cons
     a.xs = (int)((220 * 1024 - fixed) / TC_TILE_BYTES);
     if (a.xs > GT_XS_MAX) a.xs = GT_XS_MAX;
     const size_t smem = (size_t)a.xs * TC_TILE_BYTES + fixed;
-    static SmemGrant grant;
-    if (int rc = grant_dyn_smem(gag_tc_fwd_kernel, smem, grant, "gag tc fwd")) return rc;
     const int tiles_b = (Q + GT_TILE - 1) / GT_TILE;
     int per_sample = B <= 148 ? 148 / B : 1;
     if (per_sample > tiles_b) per_sample = tiles_b;
     if (per_sample < 1) per_sample = 1;
-    gag_tc_fwd_kernel<<<dim3(per_sample, B), GT_THREADS, smem, st>>>(tmx, a);
-    return check_launch("gag tc fwd");
+    auto run = [&](auto kern, SmemGrant& grant) -> int {
+        if (int r = grant_dyn_smem(kern, smem, grant, "gag tc fwd")) return r;
+        kern<<<dim3(per_sample, B), GT_THREADS, smem, st>>>(tmx, a);
+        return check_launch("gag tc fwd");
+    };
+    static SmemGrant g20, g32;  // words padded to 20 or 32 in the softmax loops
+    return T <= 20 ? run(gag_tc_fwd_kernel<20>, g20) : run(gag_tc_fwd_kernel<32>, g32);
 }
 
 }  // namespace eegan

@@ -16,7 +16,7 @@
 //   warps 2-5   x splitters: shared memory -> hi / lo in TMEM (lane = pixel)
 //   warps 6-9   softmax warps: S -> p -> attn, p hi / lo -> TMEM
 //   warps 10-13 output warps: O accumulator -> out
-// TMEM columns: S0 0-31, S1 32-63, P hi 64-95, P lo 96-127, O 128.., x stages after O (64 columns each).
+// TMEM columns: S0 0-31, S1 32-63, P hi 64-95, P lo 96-127, O 128.., [cross-term accumulators of S, 2 x 32, idf <= 128], x stages (64 columns each).
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 #include "tc_device.cuh"
@@ -40,6 +40,9 @@ struct GagTcArgs {
     int ns;              // TMEM x stages (4, or 2 when idf_pad > 128: the O accumulator takes 256 columns)
     int xs;              // shared-memory x stages (TMA ring; deeper than the TMEM ring to keep enough HBM reads in flight)
     int a_col0;          // first TMEM column of the x stages
+    int sx_col0;         // >= 0: the cross terms (lo hi, hi lo) of S accumulate in their own two 32-column buffers from this column
+                         // (the tensor core adds with truncation: 48 small additions into one large sum cost ~1e-6 in a
+                         // probability; apart, the large sum sees a third of the additions); -1: one accumulator (idf > 128)
 };
 
 __device__ __forceinline__ bool gt_elect() {
@@ -107,15 +110,29 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
         uint8_t* g_vt_lo = gbase + (vt_lo - base);
         const float* kb_ = p.key + (size_t)b * p.idf * p.T;
         const float* vb_ = p.value + (size_t)b * p.idf * p.T;
-        for (int idx = threadIdx.x; idx < p.idf * p.T; idx += blockDim.x) {
-            const int d = idx / p.T, t = idx - d * p.T;
-            const float kv = __ldg(kb_ + idx), vv = __ldg(vb_ + idx);
-            const uint32_t ko = (uint32_t)(d >> 5) * 4096u + sw128_off(t, d & 31);  // key^T: row = word, k = channel
-            *reinterpret_cast<float*>(g_kt_hi + ko) = kv;
-            *reinterpret_cast<float*>(g_kt_lo + ko) = to_tf32(kv - trunc_tf32(kv));
-            const uint32_t vo = sw128_off(d, t);                                    // value: row = channel, k = word
-            *reinterpret_cast<float*>(g_vt_hi + vo) = vv;
-            *reinterpret_cast<float*>(g_vt_lo + vo) = to_tf32(vv - trunc_tf32(vv));
+        // all loads of a thread first (idf T <= 256 x 32 elements over 448 threads), then the scatter: one load latency
+        constexpr int PER = (256 * 32 + GT_THREADS - 1) / GT_THREADS;
+        float kr[PER], vr[PER];
+        const int n = p.idf * p.T;
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int idx = (int)threadIdx.x + r * GT_THREADS;
+            kr[r] = idx < n ? __ldg(kb_ + idx) : 0.f;
+            vr[r] = idx < n ? __ldg(vb_ + idx) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int idx = (int)threadIdx.x + r * GT_THREADS;
+            if (idx < n) {
+                const int d = idx / p.T, t = idx - d * p.T;
+                const float kv = kr[r], vv = vr[r];
+                const uint32_t ko = (uint32_t)(d >> 5) * 4096u + sw128_off(t, d & 31);  // key^T: row = word, k = channel
+                *reinterpret_cast<float*>(g_kt_hi + ko) = kv;
+                *reinterpret_cast<float*>(g_kt_lo + ko) = to_tf32(kv - trunc_tf32(kv));
+                const uint32_t vo = sw128_off(d, t);                                    // value: row = channel, k = word
+                *reinterpret_cast<float*>(g_vt_hi + vo) = vv;
+                *reinterpret_cast<float*>(g_vt_lo + vo) = to_tf32(vv - trunc_tf32(vv));
+            }
         }
     }
     if (threadIdx.x == 0) {
@@ -176,6 +193,8 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
                 mbar_wait(s_empty(sb), ((i >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_s = tmem_base + (uint32_t)(sb * GT_TP);
+                const uint32_t d_x = p.sx_col0 >= 0 ? tmem_base + (uint32_t)(p.sx_col0 + sb * GT_TP) : d_s;
+                const bool split = p.sx_col0 >= 0;
                 for (int kb = 0; kb < p.nkb; ++kb, ++it) {
                     const int s = it % NS, ph = (it / NS) & 1;
                     mbar_wait(conv(s), ph);
@@ -185,9 +204,9 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t dbh = umma_desc(b_hi, true, ks, 0, 0), dbl = umma_desc(b_lo, true, ks, 0, 0);
-                        if (leader) tc_mma_tf32_ts(d_s, a_lo + ks * 8, dbh, idesc_s, (kb > 0 || ks > 0) ? 1u : 0u);
-                        if (leader) tc_mma_tf32_ts(d_s, a_hi + ks * 8, dbl, idesc_s, 1u);
-                        if (leader) tc_mma_tf32_ts(d_s, a_hi + ks * 8, dbh, idesc_s, 1u);
+                        if (leader) tc_mma_tf32_ts(d_x, a_lo + ks * 8, dbh, idesc_s, (kb > 0 || ks > 0) ? 1u : 0u);
+                        if (leader) tc_mma_tf32_ts(d_x, a_hi + ks * 8, dbl, idesc_s, 1u);
+                        if (leader) tc_mma_tf32_ts(d_s, a_hi + ks * 8, dbh, idesc_s, (!split || kb > 0 || ks > 0) ? 1u : 0u);
                     }
                     if (leader) tc_commit(empty(s));
                 }
@@ -263,7 +282,15 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
             tc_fence_after();
             uint32_t v[32];
             tmem_ld32(lane_base + (uint32_t)(sb * GT_TP), v);
-            tmem_ld_wait();
+            if (p.sx_col0 >= 0) {
+                uint32_t vx[32];
+                tmem_ld32(lane_base + (uint32_t)(p.sx_col0 + sb * GT_TP), vx);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < TP; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) + __uint_as_float(vx[t]));
+            } else {
+                tmem_ld_wait();
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty(sb));
@@ -371,7 +398,8 @@ int gag_tc_fwd_launch(const float* x, const float* key, const float* value, cons
     a.nkb = (idf + 31) / 32;
     a.idf_pad = (idf + 15) / 16 * 16;
     const int o_cols = a.idf_pad <= 128 ? 128 : 256;
-    a.a_col0 = 128 + o_cols;
+    a.sx_col0 = o_cols == 128 ? 128 + o_cols : -1;
+    a.a_col0 = 128 + o_cols + (a.sx_col0 >= 0 ? 64 : 0);
     a.ns = (TC_TMEM_COLS - a.a_col0) / 64;  // 4 or 2
     const size_t vt = (size_t)((a.idf_pad + 7) / 8 * 8) * 128;
     const size_t fixed = 2 * (size_t)a.nkb * 4096 + 2 * (vt + 1024) + 1024 + 1024 + 512;

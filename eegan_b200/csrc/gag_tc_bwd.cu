@@ -200,20 +200,34 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
         __syncthreads();
         const float* kb_ = p.key + (size_t)b * idf * T;
         const float* vb_ = p.value + (size_t)b * idf * T;
-        for (int idx = threadIdx.x; idx < idf * T; idx += blockDim.x) {
-            const int c = idx / T, t = idx - c * T;
-            uint16_t h, l;
-            // value^T: per unit a K-major tile [32 t rows][64 c] of 128-byte rows, SWIZZLE_128B
-            gb_split1(__ldg(vb_ + idx), h, l);
-            const int u = c / UC, cc = c - u * UC;
-            const uint32_t vo = (uint32_t)u * 4096u + (uint32_t)t * 128u + (uint32_t)(((cc >> 3) ^ (t & 7)) << 4) + (uint32_t)(cc & 7) * 2u;
-            sts_u16(vt_hi + vo, h);
-            sts_u16(vt_lo + vo, l);
-            // key: K-major [idf rows][32 t] of 64-byte rows, SWIZZLE_64B (16-byte chunk ^= bits 7-8 of the offset)
-            gb_split1(__ldg(kb_ + idx), h, l);
-            const uint32_t ko = (uint32_t)c * 64u + (uint32_t)(((t >> 3) ^ ((c >> 1) & 3)) << 4) + (uint32_t)(t & 7) * 2u;
-            sts_u16(key_hi + ko, h);
-            sts_u16(key_lo + ko, l);
+        // all loads of a thread first (idf T <= 128 x 32 elements over 448 threads), then the conversions: one load latency
+        constexpr int PER = (128 * 32 + GB_THREADS - 1) / GB_THREADS;
+        float kr[PER], vr[PER];
+        const int n = idf * T;
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int idx = (int)threadIdx.x + r * GB_THREADS;
+            kr[r] = idx < n ? __ldg(kb_ + idx) : 0.f;
+            vr[r] = idx < n ? __ldg(vb_ + idx) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int idx = (int)threadIdx.x + r * GB_THREADS;
+            if (idx < n) {
+                const int c = idx / T, t = idx - c * T;
+                uint16_t h, l;
+                // value^T: per unit a K-major tile [32 t rows][64 c] of 128-byte rows, SWIZZLE_128B
+                gb_split1(vr[r], h, l);
+                const int u = c / UC, cc = c - u * UC;
+                const uint32_t vo = (uint32_t)u * 4096u + (uint32_t)t * 128u + (uint32_t)(((cc >> 3) ^ (t & 7)) << 4) + (uint32_t)(cc & 7) * 2u;
+                sts_u16(vt_hi + vo, h);
+                sts_u16(vt_lo + vo, l);
+                // key: K-major [idf rows][32 t] of 64-byte rows, SWIZZLE_64B (16-byte chunk ^= bits 7-8 of the offset)
+                gb_split1(kr[r], h, l);
+                const uint32_t ko = (uint32_t)c * 64u + (uint32_t)(((t >> 3) ^ ((c >> 1) & 3)) << 4) + (uint32_t)(t & 7) * 2u;
+                sts_u16(key_hi + ko, h);
+                sts_u16(key_lo + ko, l);
+            }
         }
     }
     if (threadIdx.x == 0) {

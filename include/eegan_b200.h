@@ -155,8 +155,9 @@ int eegan_sent_scores_bwd(const float* cnn, const float* rnn, const float* norms
                           const float* dscores, int B, int D, float gamma3, float eps,
                           float* d_cnn, float* d_rnn, void* stream);
 
-/* Forward engine of eegan_gag_fwd: 0 = CUDA-core kernels (default), 1 = tcgen05 kernel (x staged in tensor memory,
- * softmax in the accumulator's threads, P written back to TMEM for out = P value^T); process-wide. */
+/* Forward engine of eegan_gag_fwd: 1 = tcgen05 kernel (x staged in tensor memory, softmax in the accumulator's threads, P
+ * written back to TMEM for out = P value^T; 3xTF32, default where the shape allows: Q % 4 == 0, idf % 16 == 0, idf <= 256),
+ * 0 = CUDA-core kernels; process-wide. */
 int eegan_set_gag_engine(int engine);
 int eegan_get_gag_engine(void);
 /* Backward engine of eegan_gag_bwd_ws: 1 = one-pass tcgen05 kernel (gag_tc_bwd.cu: all four contractions of the backward

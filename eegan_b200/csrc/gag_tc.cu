@@ -275,7 +275,7 @@ gag_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const GagTcArgs p) {
         // mask quirk (:114-118): row (b, q) takes mask[(b Q + q) mod B]; mode 1 = mask[b].  The residue is carried
         // from tile to tile instead of a 64-bit modulo per tile.
         int rq = p.mask_mode ? b : (int)(((long long)b * p.Q + q) % p.B);
-        const int rstep = qstep % p.B;
+        const int rstep = p.mask_mode ? 0 : qstep % p.B;
         for (int i = 0; i < my_tiles; ++i) {
             const int sb = i & 1;
             mbar_wait(s_full(sb), (i >> 1) & 1);

@@ -39,7 +39,7 @@
 
 namespace eegan {
 
-constexpr int GB_THREADS = 32 * 14;
+constexpr int GB_THREADS = 32 * 16;
 constexpr int GB_TILE = 128;       // pixels per tile
 constexpr int GB_NS_MAX = 10;      // most ring slots
 constexpr uint32_t GB_PT = 8192;   // bytes of one [32 t][128 q] bf16 tile: 2 panels x 32 rows x 128 B
@@ -242,7 +242,7 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
         }
         mbar_init(ds_full, 4);
         mbar_init(ds_empty, 1);
-        mbar_init(acc_full, 1);
+        mbar_init(acc_full, 2);
         mbar_init(acc_empty, 4);
         for (int a = 0; a < 2; ++a) {
             mbar_init(dp_full(a), 1);
@@ -265,16 +265,27 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
     auto tile_q0 = [&](int i) { return ((int)blockIdx.x + i * (int)gridDim.x) * GB_TILE; };
     constexpr uint32_t COL_DP = 0, COL_DV = 64, COL_DK = 128, COL_DX = 192;
 
+    // position of a unit in the ring, carried along instead of a division per unit
+    struct Ring {
+        int s = 0, ph = 0;
+    };
+    auto ring_adv = [&](Ring& r, int n) {  // n <= NU <= 2 <= NS
+        r.s += n;
+        if (r.s >= NS) {
+            r.s -= NS;
+            r.ph ^= 1;
+        }
+    };
+
     if (warp == 0) {
         // ===== TMA producer: per group  d_out(t0) | d_out(t0+1) x(t0) | ... | x(t1-1) =====
         if (lane == 0) {
-            int it = 0;
+            Ring r;
             auto load = [&](const CUtensorMap* map, int q0, int u) {
-                const int s = it % NS, ph = (it / NS) & 1;
-                mbar_wait(sfree(s), ph ^ 1);
-                mbar_arrive_expect_tx(full(s), slot_bytes);
-                tma_load_3d(base + (uint32_t)s * slot_bytes, map, full(s), q0, u * UC, b);
-                ++it;
+                mbar_wait(sfree(r.s), r.ph ^ 1);
+                mbar_arrive_expect_tx(full(r.s), slot_bytes);
+                tma_load_3d(base + (uint32_t)r.s * slot_bytes, map, full(r.s), q0, u * UC, b);
+                ring_adv(r, 1);
             };
             for (int g = 0; g < NGR; ++g) {
                 const int t0 = gr0(g), t1 = gr0(g + 1);
@@ -286,53 +297,56 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
+    } else if (warp == 1 || warp == 2) {
+        // ===== MMA issuers: warp 1 takes the d_out units ((1) + (2)), warp 2 the ds / x side ((3) + (4)); each walks the whole
+        // unit sequence (uniform control flow, one elected lane issues) and skips the other's units.  One issuer for all four
+        // contractions was the bottleneck at idf = 32 (60 MMAs and their waits per 2 us tile in one instruction stream).
         const bool leader = gb_elect();
-        {
-            constexpr uint32_t ID_BF16 = (1u << 4) /*D = f32*/ | (1u << 7) /*A = bf16*/ | (1u << 10) /*B = bf16*/;
-            const uint32_t idesc1 = ID_BF16 | (1u << 15) /*A MN-major*/ | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t idesc24 = ID_BF16 | ((32u >> 3) << 17) | ((64u >> 4) << 24);
-            const uint32_t idesc3 = ID_BF16 | (1u << 15) | (((uint32_t)idf >> 3) << 17) | ((128u >> 4) << 24);
-            const int ks1 = UC / 16;  // K-steps of (1) per unit
-            const uint32_t pan16 = panel_bytes >> 4, half16 = half_bytes >> 4;
-            const uint32_t ph_k = gb_lo_k(p_hi), pl_k = gb_lo_k(p_lo), dsh_k = gb_lo_k(ds_hi), dsl_k = gb_lo_k(ds_lo);
-            const uint32_t dsh_mn = gb_lo_mn(ds_hi, 4096u), dsl_mn = gb_lo_mn(ds_lo, 4096u);
-            const uint32_t kh_k = gb_lo_k(key_hi), kl_k = gb_lo_k(key_lo);
-            // (2) / (4): acc[c][t] (+)= sum_q unit[c][q] w[t][q] : A = unit, K-major (M = 64 channels), B = p / ds panels
-            auto rowsum = [&](uint32_t d_acc, uint32_t a_k, uint32_t wh, uint32_t wl, bool fresh) {
+        const bool side_a = warp == 1;
+        constexpr uint32_t ID_BF16 = (1u << 4) /*D = f32*/ | (1u << 7) /*A = bf16*/ | (1u << 10) /*B = bf16*/;
+        const uint32_t idesc1 = ID_BF16 | (1u << 15) /*A MN-major*/ | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc24 = ID_BF16 | ((32u >> 3) << 17) | ((64u >> 4) << 24);
+        const uint32_t idesc3 = ID_BF16 | (1u << 15) | (((uint32_t)idf >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr int ks1 = UC / 16;  // K-steps of (1) per unit
+        const uint32_t pan16 = panel_bytes >> 4, half16 = half_bytes >> 4;
+        const uint32_t ph_k = gb_lo_k(p_hi), pl_k = gb_lo_k(p_lo), dsh_k = gb_lo_k(ds_hi), dsl_k = gb_lo_k(ds_lo);
+        const uint32_t dsh_mn = gb_lo_mn(ds_hi, 4096u), dsl_mn = gb_lo_mn(ds_lo, 4096u);
+        const uint32_t kh_k = gb_lo_k(key_hi), kl_k = gb_lo_k(key_lo);
+        // (2) / (4): acc[c][t] (+)= sum_q unit[c][q] w[t][q] : A = unit, K-major (M = 64 channels), B = p / ds panels
+        auto rowsum = [&](uint32_t d_acc, uint32_t a_k, uint32_t wh, uint32_t wl, bool fresh) {
 #pragma unroll
-                for (int pp = 0; pp < 2; ++pp)
+            for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t ao = (uint32_t)pp * pan16 + (uint32_t)ks * 2u, bo = (uint32_t)pp * 256u + (uint32_t)ks * 2u;
-                        gb_mma(leader, d_acc, a_k + half16 + ao, GB_HI128, wh + bo, GB_HI128, idesc24, (!fresh || pp > 0 || ks > 0) ? 1u : 0u);
-                        gb_mma(leader, d_acc, a_k + ao, GB_HI128, wl + bo, GB_HI128, idesc24, 1u);
-                        gb_mma(leader, d_acc, a_k + ao, GB_HI128, wh + bo, GB_HI128, idesc24, 1u);
-                    }
-            };
-            int it = 0;
-            for (int g = 0; g < NGR; ++g) {
-                const int t0 = gr0(g), t1 = gr0(g + 1);
-                if (g > 0) {  // the pixel warps have read the dV / dK accumulators of the previous group
-                    mbar_wait(acc_empty, (g - 1) & 1);
-                    tc_fence_after();
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ao = (uint32_t)pp * pan16 + (uint32_t)ks * 2u, bo = (uint32_t)pp * 256u + (uint32_t)ks * 2u;
+                    gb_mma(leader, d_acc, a_k + half16 + ao, GB_HI128, wh + bo, GB_HI128, idesc24, (!fresh || pp > 0 || ks > 0) ? 1u : 0u);
+                    gb_mma(leader, d_acc, a_k + ao, GB_HI128, wl + bo, GB_HI128, idesc24, 1u);
+                    gb_mma(leader, d_acc, a_k + ao, GB_HI128, wh + bo, GB_HI128, idesc24, 1u);
                 }
-                for (int i = t0; i <= t1; ++i) {
-                    if (i < t1) {
+        };
+        Ring r;
+        for (int g = 0; g < NGR; ++g) {
+            const int t0 = gr0(g), t1 = gr0(g + 1);
+            if (g > 0) {  // the pixel warps have read the dV / dK accumulators of the previous group
+                mbar_wait(acc_empty, (g - 1) & 1);
+                tc_fence_after();
+            }
+            for (int i = t0; i <= t1; ++i) {
+                if (i < t1) {
+                    if (side_a) {
                         const int a = i & 1, k = i >> 1;
                         mbar_wait(p_full(a), k & 1);
                         mbar_wait(dp_empty(a), (k & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t d_dp = tmem_base + COL_DP + (uint32_t)a * 32u;
-                        for (int u = 0; u < NU; ++u, ++it) {
-                            const int s = it % NS, ph = (it / NS) & 1;
-                            mbar_wait(conv(s), ph);
+                        for (int u = 0; u < NU; ++u) {
+                            mbar_wait(conv(r.s), r.ph);
                             tc_fence_after();
-                            const uint32_t sa = base + (uint32_t)s * slot_bytes;
+                            const uint32_t sa = base + (uint32_t)r.s * slot_bytes;
                             const uint32_t a_k = gb_lo_k(sa), a_mn = gb_lo_mn(sa, panel_bytes);
                             const uint32_t vh = gb_lo_k(vt_hi + (uint32_t)u * 4096u), vl = gb_lo_k(vt_lo + (uint32_t)u * 4096u);
                             // (1) dP += d_out^T value : A = unit, MN-major (M = pixels), B = value^T chunk u
+#pragma unroll
                             for (int ks = 0; ks < ks1; ++ks) {
                                 const uint32_t ao = (uint32_t)ks * 128u, bo = (uint32_t)ks * 2u;
                                 gb_mma(leader, d_dp, a_mn + half16 + ao, GB_HI128, vh + bo, GB_HI128, idesc1, (u > 0 || ks > 0) ? 1u : 0u);
@@ -341,12 +355,17 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
                             }
                             // (2) dV_u += d_out p^T
                             rowsum(tmem_base + COL_DV + (uint32_t)u * 32u, a_k, ph_k + (uint32_t)a * (2 * GB_PT >> 4), pl_k + (uint32_t)a * (2 * GB_PT >> 4), i == t0);
-                            gb_commit(leader, sfree(s));
+                            gb_commit(leader, sfree(r.s));
+                            ring_adv(r, 1);
                         }
                         gb_commit(leader, dp_full(a));
                         gb_commit(leader, p_empty(a));
+                    } else {
+                        ring_adv(r, NU);
                     }
-                    if (i > t0) {
+                }
+                if (i > t0) {
+                    if (!side_a) {
                         const int j = i - 1, a = j & 1, k = j >> 1;
                         mbar_wait(ds_full, j & 1);
                         mbar_wait(dx_empty(a), (k & 1) ^ 1);
@@ -362,26 +381,31 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
                         }
                         gb_commit(leader, dx_full(a));
                         // (4) dK_u += x ds^T
-                        for (int u = 0; u < NU; ++u, ++it) {
-                            const int s = it % NS, ph = (it / NS) & 1;
-                            mbar_wait(conv(s), ph);
+                        for (int u = 0; u < NU; ++u) {
+                            mbar_wait(conv(r.s), r.ph);
                             tc_fence_after();
-                            rowsum(tmem_base + COL_DK + (uint32_t)u * 32u, gb_lo_k(base + (uint32_t)s * slot_bytes), dsh_k, dsl_k, j == t0);
-                            gb_commit(leader, sfree(s));
+                            rowsum(tmem_base + COL_DK + (uint32_t)u * 32u, gb_lo_k(base + (uint32_t)r.s * slot_bytes), dsh_k, dsl_k, j == t0);
+                            gb_commit(leader, sfree(r.s));
+                            ring_adv(r, 1);
                         }
                         gb_commit(leader, ds_empty);
+                    } else {
+                        ring_adv(r, NU);
                     }
                 }
-                gb_commit(leader, acc_full);
             }
+            gb_commit(leader, acc_full);  // one arrival per issuer
         }
-    } else if (warp < 6) {
+    } else if (warp == 3) {
+        // spare warp (the register file is allocated in units of four warps: 16 warps cost what 14 did)
+    } else if (warp < 8) {
         // ===== converters: fp32 unit [UC][128 q] -> bf16 hi / lo, two [UC][64 q] panels each, in place =====
-        const int ctid = threadIdx.x - 64;
+        const int ctid = threadIdx.x - 128;
         constexpr int nchunk = UC / 4;  // 16-byte chunks per thread
         const int units = 2 * NU * my_tiles;
-        for (int it = 0; it < units; ++it) {
-            const int s = it % NS, ph = (it / NS) & 1;
+        Ring r;
+        for (int it = 0; it < units; ++it, ring_adv(r, 1)) {
+            const int s = r.s, ph = r.ph;
             mbar_wait(full(s), ph);
             const uint32_t sb = base + (uint32_t)s * slot_bytes;
             float4 v[nchunk];
@@ -406,7 +430,7 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
             if (lane == 0) mbar_arrive(conv(s));
         }
     } else {
-        // ===== pixel warps (6-9) and p / output warps (10-13): a thread owns pixel pl of the tile = TMEM lane pl =====
+        // ===== pixel warps (8-11) and p / output warps (12-15): a thread owns pixel pl of the tile = TMEM lane pl =====
         const int quarter = warp & 3;
         const int pl = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -436,7 +460,7 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
 #pragma unroll
             for (int t = 0; t < TP; ++t) dst[t] = ldg_pred(src + (size_t)t * p.Q, ok && t < T);
         };
-        if (warp < 10) {
+        if (warp < 12) {
             // ---- pixel warps: dP -> ds = p (dp - sum p dp) -> ds panels; at the end of a group dV / dK -> partials.
             // The fp32 p of the tile is re-read as hi + lo from the thread's own column of the p panels (2^-17 relative).
             const float* dattn_b = p.d_attn ? p.d_attn + (size_t)b * T * p.Q : nullptr;

@@ -395,7 +395,9 @@ class GlobalAttentionGeneral(nn.Module):
         key, val = _lib.f32c(context_key), _lib.f32c(content_value)
         mask = None
         if self.mask is not None:
-            mask = self.mask.to(device=x.device).to(torch.uint8).contiguous()
+            mask = self.mask.to(device=x.device).contiguous()
+            # a bool mask IS one byte of 0 / 1 per word: reinterpret it (no conversion kernel per call)
+            mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
         if idf > _GAG_BWD_MAX_IDF and torch.is_grad_enabled() and (x.requires_grad or key.requires_grad or val.requires_grad):
             raise RuntimeError("GlobalAttentionGeneral: idf=%d > %d has a forward kernel but no backward; "
                                "run it under torch.no_grad()" % (idf, _GAG_BWD_MAX_IDF))

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only-bwd-engine", type=int, default=-1)
     ap.add_argument("--fwd-engine", type=int, default=-1)
+    ap.add_argument("--flush", default="write", choices=["write", "read", "both"])
     ap.add_argument("--no-dattn", action="store_true")
     ap.add_argument("--no-mask", action="store_true")
     a = ap.parse_args()
@@ -85,10 +86,15 @@ def main():
             fn()
         return g.replay
 
+    sweep = torch.empty(256 * 1024 * 1024 // 4, device=dev) if a.flush != "write" else None
+
     def time(fn, iters):
         ms = 0.0
         for _ in range(iters):
-            flush.fill_(1.0)
+            if a.flush != "read":
+                flush.fill_(1.0)
+            if sweep is not None:
+                sweep.sum()  # a read sweep larger than L2: the cache is cold AND holds no dirty lines to write back in the timed span
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()

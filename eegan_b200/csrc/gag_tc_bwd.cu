@@ -22,14 +22,21 @@
 // for (1).  p and ds are written by the threads that own the pixels as [32 t][64 q] panels: K-major B operand of
 // (2)/(4), MN-major A operand of (3).  value^T and key are converted once per CTA.
 //
-//   warp 0       TMA producer: unit order  d_out(0) | d_out(1) x(0) | d_out(2) x(1) | ... | x(last)
-//   warp 1       TMEM allocator + MMA issuer: (1)+(2) of tile i are issued before (3)+(4) of tile i-1, so the softmax
-//                backward of tile i-1 runs behind the d_out contractions of tile i (dP is double-buffered)
-//   warps 2-5    converters (fp32 unit -> bf16 hi/lo panels, in place)
-//   warps 6-9    pixel warps: p / d_attn from global, p panels, dP -> ds, ds panels; at the end dV / dK -> partials
-//   warps 10-13  output warps: dX accumulator (double-buffered) -> d_x, coalesced 128-byte rows
+//   warp 0       TMA producer: unit order  d_out(0) | d_out(1) x(0) | d_out(2) x(1) | ... | x(last)   (per accumulation group)
+//   warp 1       TMEM allocator + MMA issuer of the d_out side: (1) + (2) of tile i, issued while the pixel warps still work on
+//                tile i-1 (dP and the p panels are double-buffered)
+//   warp 2       MMA issuer of the ds / x side: (3) + (4) of tile i-1.  Both issuers walk the whole unit sequence and skip the
+//                other's units; each is warp-uniform with one elected lane (uniform-register descriptors, no broadcast loops)
+//   warp 3       spare (registers are allocated per four warps)
+//   warps 4-7    converters (fp32 unit -> bf16 hi/lo panels, in place)
+//   warps 8-11   pixel warps: d_attn from global one tile ahead, dP -> ds (p re-read from the panels), ds panels; at the end of a
+//                group dV / dK -> partials
+//   warps 12-15  p / output warps: attn from global -> p panels of tile i+1 (loaded one iteration earlier), then the dX
+//                accumulator (double-buffered) -> d_x, coalesced 128-byte rows
 // TMEM columns: dP 0-63 (2 x 32), dV 64-127 (2 x 32), dK 128-191, dX 192-447 (2 x 128).
-// d_key / d_value: per-CTA partials [b][chunk][c][32], summed in a fixed order by gag_bwd_kv_reduce_kernel (gag_bwd2.cu).
+// d_key / d_value: the tensor core adds into its fp32 accumulator with truncation, so a long accumulation chain drifts; every CTA
+// writes its accumulators out as a partial [b][chunk][c][32] at most every GB_GROUP tiles, and gag_bwd_kv_reduce_kernel
+// (gag_bwd2.cu) sums the partials in fp32 in a fixed order.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 

@@ -534,16 +534,20 @@ def time_pair_workload(args, cx, cfg_name, B, T, cls_mode, full=True):
         graphed = GraphedWordsLoss(B, D, HW, HW, T, dev, use_class_ids=True, words_grad=True)
         graphed(img_d.detach(), words_d.detach(), lens_d, cls_d)  # capture
         run_step = graphed.graph.replay
+        shard_by = None
         launch = "one CUDA graph per step (eegan_b200.graphed.GraphedWordsLoss)"
     else:
         from eegan_b200.sharded import OverlappedShardedWordsLossStep, ShardedWordsLossStep
         if args.sharded_mode == "overlap":
             sstep = OverlappedShardedWordsLossStep(B, D, HW, HW, T, dev, use_class_ids=True, words_grad=True)
+            shard_by = "captions"
         else:
-            sstep = ShardedWordsLossStep(B, D, HW, HW, T, dev, use_class_ids=True, words_grad=True, graph=args.sharded_mode == "graph")
+            sstep = ShardedWordsLossStep(B, D, HW, HW, T, dev, use_class_ids=True, words_grad=True, graph=args.sharded_mode == "graph",
+                                         shard=args.shard)
+            shard_by = sstep.shard
         sstep.load(img_d.detach(), words_d.detach(), lens_d, cls_d)
         run_step = sstep.run
-        launch = "sharded step, mode=%s (eegan_b200.sharded.%s)" % (args.sharded_mode, type(sstep).__name__)
+        launch = "sharded step, mode=%s, grid partitioned by %s (eegan_b200.sharded.%s)" % (args.sharded_mode, shard_by, type(sstep).__name__)
 
     # ---- device-resident timing ---------------------------------------------------
     for _ in range(args.warmup):
@@ -567,7 +571,7 @@ def time_pair_workload(args, cx, cfg_name, B, T, cls_mode, full=True):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     pairs_per_step = float(Btot) * Btot
-    res = dict(B_local=B, B_total=Btot, T=T, lens_sum=int(lens_sum.item()), ms_per_step=ms_step, value=pairs_per_step / (ms_step / 1e3),
+    res = dict(shard_by=shard_by, B_local=B, B_total=Btot, T=T, lens_sum=int(lens_sum.item()), ms_per_step=ms_step, value=pairs_per_step / (ms_step / 1e3),
                pairs_per_step=pairs_per_step, launch=launch, engine=engine, wall=(t_wall0, t_wall1))
 
     # ---- the drop-in API, device-resident (words_loss + backward through the reference's signature) ----
@@ -620,19 +624,21 @@ def time_pair_workload(args, cx, cfg_name, B, T, cls_mode, full=True):
     # ---- N > 1: the same-shape block without any collective, and the collectives alone ----
     if world > 1:
         p = _lib.ptr
-        ws = torch.empty(L.eegan_damsm_pair_workspace_bytes(Btot, B, D, R, T), dtype=torch.uint8, device=dev)
-        img_all = img_d.detach().reshape(B, D, R).repeat(world, 1, 1).contiguous()
-        m_blk, dm_blk = torch.empty(Btot, B, device=dev), torch.full((Btot, B), 1e-3, device=dev)
-        att = torch.empty(B, T, R, device=dev)
-        d_img_all, d_words = torch.empty(Btot, D, R, device=dev), torch.empty(B, D, T, device=dev)
-        lens32 = lens_d.to(torch.int32)
-        wd = words_d.detach()
+        by_img = res.get("shard_by") == "images"
+        Bi_blk, Bc_blk = (B, Btot) if by_img else (Btot, B)  # the rank's block: own images x all captions, or all images x own captions
+        ws = torch.empty(L.eegan_damsm_pair_workspace_bytes(Bi_blk, Bc_blk, D, R, T), dtype=torch.uint8, device=dev)
+        img_all = img_d.detach().reshape(B, D, R).repeat(1 if by_img else world, 1, 1).contiguous()
+        wd = words_d.detach().repeat(world if by_img else 1, 1, 1).contiguous()
+        lens32 = lens_d.to(torch.int32).repeat(world if by_img else 1).contiguous()
+        m_blk, dm_blk = torch.empty(Bi_blk, Bc_blk, device=dev), torch.full((Bi_blk, Bc_blk), 1e-3, device=dev)
+        att = torch.empty(Bc_blk, T, R, device=dev)
+        d_img_all, d_words = torch.empty(Bi_blk, D, R, device=dev), torch.empty(Bc_blk, D, T, device=dev)
 
         def comm_free():
             st = _lib.stream_ptr()
-            _lib.check(L.eegan_damsm_pair_fwd(p(img_all), p(wd), p(lens32), Btot, B, D, R, T, 5.0, 5.0, p(m_blk), p(att), rank * B,
-                                              p(ws), ws.numel(), st), "pair_fwd")
-            _lib.check(L.eegan_damsm_pair_bwd(p(img_all), p(wd), p(lens32), Btot, B, D, R, T, 5.0, 5.0, p(dm_blk), p(d_img_all),
+            _lib.check(L.eegan_damsm_pair_fwd(p(img_all), p(wd), p(lens32), Bi_blk, Bc_blk, D, R, T, 5.0, 5.0, p(m_blk), p(att),
+                                              -rank * B if by_img else rank * B, p(ws), ws.numel(), st), "pair_fwd")
+            _lib.check(L.eegan_damsm_pair_bwd(p(img_all), p(wd), p(lens32), Bi_blk, Bc_blk, D, R, T, 5.0, 5.0, p(dm_blk), p(d_img_all),
                                               p(d_words), p(ws), ws.numel(), st), "pair_bwd")
 
         cf = _graph_replay(comm_free, dev)
@@ -641,20 +647,38 @@ def time_pair_workload(args, cx, cfg_name, B, T, cls_mode, full=True):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         cf_ms = float(t.item())
         res["comm_free_same_shape"] = {
-            "what": "pair grid fwd + bwd of this rank's (%d x %d) block, no collective, no CE (O(B^2), ~10 us), one CUDA graph, max over ranks" % (Btot, B),
+            "what": "pair grid fwd + bwd of this rank's (%d images x %d captions) block, no collective, no CE (O(B^2), ~10 us), one CUDA graph, "
+                    "max over ranks" % (Bi_blk, Bc_blk),
             "ms_per_step": cf_ms, "per_gpu_pairs_per_s": Btot * B / (cf_ms / 1e3),
             "sharded_step_over_comm_free": ms_step / cf_ms}
         del ws
-        # the four collectives of one step, alone, back to back
-        img_loc = img_d.detach().reshape(B, D, R)
-        g_img, g_m, g_mp = torch.empty(Btot, D, R, device=dev), torch.empty(Btot, B, device=dev), torch.empty(world * Btot, B, device=dev)
-        g_cls, rs_out = torch.empty(Btot, dtype=torch.int64, device=dev), torch.empty(B, D, R, device=dev)
+        # the collectives of one step, alone, back to back
+        g_cls = torch.empty(Btot, dtype=torch.int64, device=dev)
+        if by_img:
+            w_loc = words_d.detach().contiguous()
+            g_w, g_l, g_m = torch.empty(Btot, D, T, device=dev), torch.empty(Btot, dtype=torch.int32, device=dev), torch.empty(Btot, Btot, device=dev)
+            l_loc, rs_out = lens_d.to(torch.int32), torch.empty(B, D, T, device=dev)
 
-        def colls():
-            dist.all_gather_into_tensor(g_img, img_loc)
-            dist.all_gather_into_tensor(g_cls, cls_d)
-            dist.all_gather_into_tensor(g_mp, g_m)
-            dist.reduce_scatter_tensor(rs_out, d_img_all)
+            def colls():
+                dist.all_gather_into_tensor(g_w, w_loc)
+                dist.all_gather_into_tensor(g_l, l_loc)
+                dist.all_gather_into_tensor(g_cls, cls_d)
+                dist.all_gather_into_tensor(g_m, m_blk)
+                dist.reduce_scatter_tensor(rs_out, d_words)
+
+            nbytes = {"all_gather_words": Btot * D * T * 4, "reduce_scatter_d_words": Btot * D * T * 4, "all_gather_m": Btot * Btot * 4}
+        else:
+            img_loc = img_d.detach().reshape(B, D, R)
+            g_img, g_m, g_mp = torch.empty(Btot, D, R, device=dev), torch.empty(Btot, B, device=dev), torch.empty(world * Btot, B, device=dev)
+            rs_out = torch.empty(B, D, R, device=dev)
+
+            def colls():
+                dist.all_gather_into_tensor(g_img, img_loc)
+                dist.all_gather_into_tensor(g_cls, cls_d)
+                dist.all_gather_into_tensor(g_mp, g_m)
+                dist.reduce_scatter_tensor(rs_out, d_img_all)
+
+            nbytes = {"all_gather_img": Btot * D * R * 4, "reduce_scatter_d_img": Btot * D * R * 4, "all_gather_m": world * Btot * B * 4}
 
         for _ in range(3):
             colls()
@@ -662,9 +686,8 @@ def time_pair_workload(args, cx, cfg_name, B, T, cls_mode, full=True):
         t = torch.tensor([_time_cuda(colls, max(5, args.steps // 2), None)], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res["nccl_ms_per_step"] = float(t.item())
-        res["nccl_bytes_per_step"] = {"all_gather_img": Btot * D * R * 4, "reduce_scatter_d_img": Btot * D * R * 4,
-                                      "all_gather_m": world * Btot * B * 4}
-        del img_all, d_img_all, g_img
+        res["nccl_bytes_per_step"] = nbytes
+        del img_all, d_img_all
 
     # ---- end to end from pinned host buffers, through the reference-facing API ----
     h2d = img_h.numel() * 4 + words_h.numel() * 4 + lens_h.numel() * 8
@@ -807,7 +830,7 @@ def setup_ours(args):
 def parity_block(cx, args):
     from oracle import parity
     try:
-        return parity.run(cx.world, cx.rank, cx.dev, mode=args.sharded_mode if cx.world > 1 else "serial")
+        return parity.run(cx.world, cx.rank, cx.dev, mode=args.sharded_mode if cx.world > 1 else "serial", shard=args.shard)
     except Exception as e:  # a parity block that cannot run is a failed one, and says why
         return {"ok": False, "error": "%s: %s" % (type(e).__name__, e)}
 
@@ -1093,6 +1116,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--no-extra", action="store_true", help="skip the GlobalAttentionGeneral / SyncBN / reference-eager side measurements")
+    ap.add_argument("--shard", default=None, choices=["images", "captions"],
+                    help="N > 1: partition of the pair grid (default: eegan_b200.sharded.SHARD_BY = images: own images x all captions, the word "
+                         "features travel; captions: own captions x all images, the region features travel)")
     ap.add_argument("--sharded-mode", default=os.environ.get("EEGAN_SHARDED_MODE", "serial"), choices=["serial", "overlap", "graph"],
                     help="N>1: ShardedWordsLossStep with direct launches (serial), the same captured into one CUDA graph, collectives "
                          "included (graph), or OverlappedShardedWordsLossStep (collectives hidden behind the local image block)")

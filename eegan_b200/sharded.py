@@ -1,8 +1,17 @@
-"""Caption-row-sharded DAMSM losses for one process per GPU.
+"""Sharded DAMSM losses for one process per GPU.
 
-The reference computes the full-batch B x B grid on GPU 0 after nn.DataParallel gathers the
-generator's output (train.py:195, 419-435).  Here rank g owns captions [g*b, (g+1)*b) and
-the same slice of images:
+The reference computes the full-batch B x B grid m[image j][caption i] on GPU 0 after nn.DataParallel gathers the
+generator's output (train.py:195, 419-435).  Here rank g owns samples [g*b, (g+1)*b) and evaluates one block of the grid.
+Two partitions of the same grid, same kernels, same result (``shard=`` / ``EEGAN_SHARD_BY``):
+
+``"images"`` (default): the rank's IMAGES against all captions — the block m[imgs_g, :] (b x B pairs).
+  fwd: all-gather the WORD features and caption lengths (B x D x T: 18 KB per caption); block; all-gather of the row blocks ->
+       the full grid everywhere; the O(B^2) cross-entropy tail redundantly on every rank.
+  bwd: d_img of the own images is complete locally; the rank holds a partial d_words [B, D, T] -> reduce-scatter(sum).
+  Per step and rank this moves 2 x B x 18 KB; the caption partition below moves 2 x B x 296 KB (the region features are 16x
+  the word features): 7 MB against 114 MB per collective at B = 384.
+
+``"captions"`` (the partition BASELINE.json's north_star describes): the rank's CAPTIONS against all images, m[:, caps_g]:
 
   fwd: all-gather region features -> every rank holds [B, D, R]; the rank computes its column
        block m[:, caps_g] (B x b pairs); all-gather of the blocks -> the full grid everywhere;
@@ -19,7 +28,18 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+import os
+
 from .config import gammas
+
+SHARD_BY = os.environ.get("EEGAN_SHARD_BY", "images")  # "images" | "captions": default partition of the pair grid (read once)
+
+
+def _shard_mode(shard):
+    mode = SHARD_BY if shard is None else shard
+    if mode not in ("images", "captions"):
+        raise ValueError("shard must be 'images' or 'captions', got %r" % (mode,))
+    return mode
 
 
 class _no_auto_shard:
@@ -97,7 +117,7 @@ def _gather_ids(ids, device, group):
 
 
 def sharded_words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size, group=None,
-                       grid_fn=None, ce_fn=None):
+                       grid_fn=None, ce_fn=None, shard=None):
     """words_loss (DAMSM_losses.py:272-342) over the GLOBAL batch, from per-rank shards.
 
     Arguments are the rank's local shard with the reference's meaning (``batch_size`` is the
@@ -111,12 +131,24 @@ def sharded_words_loss(img_features, words_emb, labels, cap_lens, class_ids, bat
         with _no_auto_shard(dl):
             return dl.words_loss(img_features, words_emb, labels, cap_lens, class_ids, batch_size)
     b = batch_size
-    img_all = _AllGatherRows.apply(img_features[:b].contiguous(), group, True)
-    m_block, att = grid_fn(img_all, words_emb[:b], cap_lens, diag_offset=rank * b)
-    att_maps = dl._att_maps(att, cap_lens, dl._spatial(img_features))
-    if labels is None:
-        return None, None, att_maps
-    m_all = _AllGatherCols.apply(m_block, group)
+    if _shard_mode(shard) == "images":
+        # own images x all captions: the word features travel (partial d_words comes back through the reduce-scatter of the
+        # gather's backward), d_img is complete locally
+        words_all = _AllGatherRows.apply(words_emb[:b].contiguous(), group, True)
+        lens_all = _gather_ids(torch.as_tensor(cap_lens).reshape(-1)[:b], words_all.device, group)
+        m_block, att_all = grid_fn(img_features[:b], words_all, lens_all, diag_offset=-rank * b)  # [b, B], [B, T, R]
+        att = att_all[rank * b:(rank + 1) * b] if att_all is not None else None
+        att_maps = dl._att_maps(att, cap_lens, dl._spatial(img_features))
+        if labels is None:
+            return None, None, att_maps
+        m_all = _AllGatherRows.apply(m_block, group, False)  # row blocks; every rank gets the complete gradient, keeps its rows
+    else:
+        img_all = _AllGatherRows.apply(img_features[:b].contiguous(), group, True)
+        m_block, att = grid_fn(img_all, words_emb[:b], cap_lens, diag_offset=rank * b)
+        att_maps = dl._att_maps(att, cap_lens, dl._spatial(img_features))
+        if labels is None:
+            return None, None, att_maps
+        m_all = _AllGatherCols.apply(m_block, group)
     cls_all = _gather_ids(class_ids, m_all.device, group)
     lab_all = torch.arange(world * b, device=m_all.device, dtype=torch.int64)
     _, _, g3 = gammas()
@@ -160,12 +192,16 @@ class ShardedWordsLossStep:
     ``graph=True`` captures the step (collectives included) into one CUDA graph."""
 
     def __init__(self, local_batch, D, H, W, T_max, device, group=None, use_class_ids=True, words_grad=True, w0=1.0, w1=1.0,
-                 graph=False):
+                 graph=False, shard=None):
         from . import _lib
         self._lib = _lib
         L = _lib.lib()
         self.group = group
         self.world, self.rank = _world(group)
+        self.shard = _shard_mode(shard)
+        if self.shard == "images":
+            self._init_images(L, int(local_batch), D, H, W, T_max, torch.device(device), use_class_ids, words_grad, w0, w1, graph)
+            return
         b, R = int(local_batch), H * W
         Bt = b * self.world
         dev = torch.device(device)
@@ -195,7 +231,81 @@ class ShardedWordsLossStep:
         self._use_graph, self._graph = bool(graph), None
         self._phased = L.eegan_get_contraction_engine() == 3 and D % 128 == 0
 
+    def _init_images(self, L, b, D, H, W, T_max, dev, use_class_ids, words_grad, w0, w1, graph):
+        """Static buffers of the image-row partition: own images x all captions."""
+        R = H * W
+        Bt = b * self.world
+        self.dims = (b, Bt, D, R, T_max)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.img = torch.zeros(b, D, H, W, **f32)
+        self.words = torch.zeros(b, D, T_max, **f32)
+        self.cap_lens32 = torch.full((b,), T_max, dtype=torch.int32, device=dev)
+        self.class_ids = torch.arange(self.rank * b, (self.rank + 1) * b, dtype=torch.int64, device=dev) if use_class_ids else None
+        self._cls_all = torch.zeros(Bt, dtype=torch.int64, device=dev) if use_class_ids else None
+        self._labels = torch.arange(Bt, dtype=torch.int64, device=dev)
+        self._words_all = torch.empty(Bt, D, T_max, **f32)
+        self._lens_all = torch.empty(Bt, dtype=torch.int32, device=dev)
+        self._ws = torch.empty(L.eegan_damsm_pair_workspace_bytes(b, Bt, D, R, T_max), dtype=torch.uint8, device=dev)
+        self._m_block = torch.empty(b, Bt, **f32)
+        self._m_all = torch.empty(Bt, Bt, **f32)
+        self._sim = torch.empty(Bt, Bt, **f32)
+        self._lse = torch.empty(2, Bt, **f32)
+        self._loss01 = torch.zeros(2, **f32)
+        self._gvec = torch.tensor([float(w0), float(w1)], **f32)
+        self._dsim = torch.empty(Bt, Bt, **f32)
+        self._att_all = torch.empty(Bt, T_max, R, **f32)
+        self.att = self._att_all[self.rank * b:(self.rank + 1) * b]
+        self.d_img = torch.zeros(b, D, H, W, **f32)
+        self._d_words_all = torch.empty(Bt, D, T_max, **f32) if words_grad else None
+        self.d_words = torch.zeros(b, D, T_max, **f32) if words_grad else None
+        self._use_graph, self._graph = bool(graph), None
+        self._phased = False
+
+    def _enqueue_images(self):
+        _lib = self._lib
+        L, p, st = _lib.lib(), _lib.ptr, _lib.stream_ptr()
+        b, Bt, D, R, Tm = self.dims
+        g1, g2, g3 = gammas()
+        rank, grp = self.rank, self.group
+        h_cls = None
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._words_all, self.words, group=grp)
+            dist.all_gather_into_tensor(self._lens_all, self.cap_lens32, group=grp)
+            if self._cls_all is not None:  # only the cross-entropy needs the class ids: gathered behind the pair grid
+                h_cls = dist.all_gather_into_tensor(self._cls_all, self.class_ids, group=grp, async_op=True)
+        else:
+            self._words_all.copy_(self.words)
+            self._lens_all.copy_(self.cap_lens32)
+            if self._cls_all is not None:
+                self._cls_all.copy_(self.class_ids)
+        dev = self.img.device
+        with torch.cuda.device(dev):
+            _lib.check(L.eegan_damsm_pair_fwd(p(self.img), p(self._words_all), p(self._lens_all), b, Bt, D, R, Tm, g1, g2,
+                                              p(self._m_block), p(self._att_all), -rank * b, p(self._ws), self._ws.numel(), st), "damsm_pair_fwd")
+        if self.world > 1:  # row blocks: the gathered tensor IS the grid
+            dist.all_gather_into_tensor(self._m_all, self._m_block, group=grp)
+        else:
+            self._m_all.copy_(self._m_block)
+        if h_cls is not None:
+            h_cls.wait()
+        with torch.cuda.device(dev):
+            _lib.check(L.eegan_pair_ce_fwd(p(self._m_all), g3, p(self._cls_all), p(self._labels), Bt, p(self._sim), p(self._loss01),
+                                           p(self._lse), st), "pair_ce_fwd")
+            _lib.check(L.eegan_pair_ce_bwd(p(self._sim), p(self._lse), p(self._labels), p(self._gvec), g3, Bt, p(self._dsim), st),
+                       "pair_ce_bwd")
+            dm_block = self._dsim[rank * b:(rank + 1) * b]  # the rank's rows: contiguous, no copy
+            _lib.check(L.eegan_damsm_pair_bwd(p(self.img), p(self._words_all), p(self._lens_all), b, Bt, D, R, Tm, g1, g2,
+                                              p(dm_block), p(self.d_img), p(self._d_words_all), p(self._ws), self._ws.numel(), st),
+                       "damsm_pair_bwd")
+        if self.d_words is not None:
+            if self.world > 1:
+                dist.reduce_scatter_tensor(self.d_words, self._d_words_all, op=dist.ReduceOp.SUM, group=grp)
+            else:
+                self.d_words.copy_(self._d_words_all)
+
     def _enqueue(self):
+        if self.shard == "images":
+            return self._enqueue_images()
         _lib = self._lib
         L, p, st = _lib.lib(), _lib.ptr, _lib.stream_ptr()
         b, Bt, D, R, Tm = self.dims

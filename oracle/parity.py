@@ -30,7 +30,7 @@ def _relmax(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
 
 
-def run(world: int, rank: int, dev, b: int = None, T: int = 12, mode: str = "serial"):
+def run(world: int, rank: int, dev, b: int = None, T: int = 12, mode: str = "serial", shard: str = None):
     """Returns the parity dict (identical on every rank).  `mode` selects the sharded step class under test."""
     import eegan_b200 as E
     from eegan_b200 import sharded
@@ -59,6 +59,8 @@ def run(world: int, rank: int, dev, b: int = None, T: int = 12, mode: str = "ser
         kw = dict(w0=w0, w1=w1)
         if mode == "graph":
             kw["graph"] = True
+        if mode != "overlap":
+            kw["shard"] = shard  # None = the package default (eegan_b200.sharded.SHARD_BY)
         step = cls_map[mode](b, c["img"].shape[1], c["img"].shape[2], c["img"].shape[3], T, dev, **kw)
         for _ in range(2):
             l0, l1, d_img, d_words = step(c["img"][sl].to(dev), c["words"][sl].to(dev), c["cap_lens"][sl].to(dev),
@@ -67,7 +69,7 @@ def run(world: int, rank: int, dev, b: int = None, T: int = 12, mode: str = "ser
         for i in range(b):
             Ti = int(c["cap_lens"][sl][i])
             att_err = max(att_err, float((step.att[i, :Ti].cpu().double().reshape(-1) - oatt[rank * b + i].detach().reshape(-1)).abs().max()))
-        what = "eegan_b200.sharded.%s (%s)" % (type(step).__name__, mode)
+        what = "eegan_b200.sharded.%s (%s, grid partitioned by %s)" % (type(step).__name__, mode, getattr(step, "shard", "captions"))
         if mode == "graph":
             step.release_graph()
     err["loss0_rel"] = abs(float(l0) - float(o0)) / max(1.0, abs(float(o0)))

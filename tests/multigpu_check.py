@@ -38,27 +38,32 @@ def main():
     words = c["words"].to(dev).requires_grad_()
     f0, f1, fatt = E.words_loss(img, words, c["labels"].to(dev), c["cap_lens"].to(dev), c["class_ids"], B)
     (f0 + 2.0 * f1).backward()
-    # sharded
-    img_s = c["img"][sl].to(dev).requires_grad_()
-    words_s = c["words"][sl].to(dev).requires_grad_()
-    s0, s1, satt = sharded_words_loss(img_s, words_s, torch.arange(b, device=dev), c["cap_lens"][sl].to(dev),
-                                      c["class_ids"][sl], b)
-    (s0 + 2.0 * s1).backward()
-    assert abs(s0.item() - f0.item()) <= 2e-6 * max(1.0, abs(f0.item())), (s0.item(), f0.item())
-    assert abs(s1.item() - f1.item()) <= 2e-6 * max(1.0, abs(f1.item())), (s1.item(), f1.item())
-    assert relmax(img_s.grad, img.grad[sl]) <= 2e-5, relmax(img_s.grad, img.grad[sl])
-    assert relmax(words_s.grad, words.grad[sl]) <= 2e-5, relmax(words_s.grad, words.grad[sl])
-    for a, r in zip(satt, fatt[sl]):
-        assert float((a - r).abs().max()) <= 1e-7
-    # the autograd-free step API (static buffers, direct launches; EEGAN_CHECK_SHARDED_GRAPH=1: also as one CUDA graph)
+    # sharded, both partitions of the grid (own images x all captions: the default; own captions x all images)
     from eegan_b200.sharded import ShardedWordsLossStep
-    for use_graph in ([False, True] if os.environ.get("EEGAN_CHECK_SHARDED_GRAPH") == "1" else [False]):
-        sstep = ShardedWordsLossStep(b, 256, 17, 17, T, dev, w0=1.0, w1=2.0, graph=use_graph)
-        for _ in range(2):  # second call: replay on the same buffers
-            q0, q1, qdi, qdw = sstep(c["img"][sl].to(dev), c["words"][sl].to(dev), c["cap_lens"][sl].to(dev), c["class_ids"][sl].to(dev))
-        assert abs(q0.item() - f0.item()) <= 2e-6 * max(1.0, abs(f0.item())) and abs(q1.item() - f1.item()) <= 2e-6 * max(1.0, abs(f1.item()))
-        assert relmax(qdi, img.grad[sl]) <= 2e-5 and relmax(qdw, words.grad[sl]) <= 2e-5, (use_graph, relmax(qdi, img.grad[sl]))
-        sstep.release_graph()  # a live graph holding NCCL work must go before destroy_process_group (teardown hang otherwise)
+    for shard in ("images", "captions"):
+        img_s = c["img"][sl].to(dev).requires_grad_()
+        words_s = c["words"][sl].to(dev).requires_grad_()
+        s0, s1, satt = sharded_words_loss(img_s, words_s, torch.arange(b, device=dev), c["cap_lens"][sl].to(dev),
+                                          c["class_ids"][sl], b, shard=shard)
+        (s0 + 2.0 * s1).backward()
+        assert abs(s0.item() - f0.item()) <= 2e-6 * max(1.0, abs(f0.item())), (shard, s0.item(), f0.item())
+        assert abs(s1.item() - f1.item()) <= 2e-6 * max(1.0, abs(f1.item())), (shard, s1.item(), f1.item())
+        assert relmax(img_s.grad, img.grad[sl]) <= 2e-5, (shard, relmax(img_s.grad, img.grad[sl]))
+        assert relmax(words_s.grad, words.grad[sl]) <= 2e-5, (shard, relmax(words_s.grad, words.grad[sl]))
+        assert len(satt) == b
+        for a, r in zip(satt, fatt[sl]):
+            assert float((a - r).abs().max()) <= 1e-7, shard
+        # the autograd-free step API (static buffers, direct launches; EEGAN_CHECK_SHARDED_GRAPH=1: also as one CUDA graph)
+        for use_graph in ([False, True] if os.environ.get("EEGAN_CHECK_SHARDED_GRAPH") == "1" else [False]):
+            sstep = ShardedWordsLossStep(b, 256, 17, 17, T, dev, w0=1.0, w1=2.0, graph=use_graph, shard=shard)
+            for _ in range(2):  # second call: replay on the same buffers
+                q0, q1, qdi, qdw = sstep(c["img"][sl].to(dev), c["words"][sl].to(dev), c["cap_lens"][sl].to(dev), c["class_ids"][sl].to(dev))
+            assert abs(q0.item() - f0.item()) <= 2e-6 * max(1.0, abs(f0.item())) and abs(q1.item() - f1.item()) <= 2e-6 * max(1.0, abs(f1.item())), shard
+            assert relmax(qdi, img.grad[sl]) <= 2e-5 and relmax(qdw, words.grad[sl]) <= 2e-5, (shard, use_graph, relmax(qdi, img.grad[sl]), relmax(qdw, words.grad[sl]))
+            for i in range(b):
+                Ti = int(c["cap_lens"][sl][i])
+                assert float((sstep.att[i, :Ti].reshape(Ti, -1) - fatt[rank * b + i].reshape(Ti, -1)).abs().max()) <= 1e-7, (shard, "att")
+            sstep.release_graph()  # a live graph holding NCCL work must go before destroy_process_group (teardown hang otherwise)
     if os.environ.get("EEGAN_CHECK_SHARDED_OVERLAP") == "1":  # the opt-in overlapped step (sharded.py)
         from eegan_b200.sharded import OverlappedShardedWordsLossStep
         ostep = OverlappedShardedWordsLossStep(b, 256, 17, 17, T, dev, w0=1.0, w1=2.0)

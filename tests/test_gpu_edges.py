@@ -181,6 +181,37 @@ def test_sharded_block_equals_columns_of_full_grid(cuda_lib):
         assert float((att - att_full[sl]).abs().max()) <= 1e-7
 
 
+@pytest.mark.parametrize("B,b,T", [(12, 4, 18), (384, 48, 18), (96, 32, 20)])
+def test_sharded_block_equals_rows_of_full_grid(cuda_lib, B, b, T):
+    """The image-row partition (the default of eegan_b200.sharded) on ONE GPU: a rank's block = its b images against ALL B captions
+    with a negative diag_offset.  Forward: the rows of the full grid, attention maps only for the rank's own captions (zeros
+    elsewhere).  Backward with the rank's rows of dm: d_img of the own images is complete, the partial d_words of the blocks add up
+    to the full-batch d_words (what the reduce-scatter does).  (384, 48) is the block of the 8-GPU CUB run: B_img = 48, B_cap = 384."""
+    from eegan_b200.damsm_losses import pair_grid
+    c = cases.words_case(B, T, seed=B + b)
+    img, words, lens = c["img"].cuda().requires_grad_(), c["words"].cuda().requires_grad_(), c["cap_lens"].cuda()
+    full, att_full = pair_grid(img, words, lens)
+    dm = torch.randn(B, B, generator=cases._gen(3)).cuda() * 0.1
+    (full * dm).sum().backward()
+    d_img_full, d_words_full = img.grad.clone(), words.grad.clone()
+    d_words_sum = torch.zeros_like(d_words_full)
+    ranks = range(B // b) if B <= 96 else (0, 3, B // b - 1)  # the large case: three of the eight blocks (no d_words sum check)
+    for rank in ranks:
+        sl = slice(rank * b, (rank + 1) * b)
+        ib, wb = img.detach()[sl].clone().requires_grad_(), words.detach().clone().requires_grad_()
+        blk, att = pair_grid(ib, wb, lens, diag_offset=-rank * b)
+        assert tuple(blk.shape) == (b, B) and float((blk - full[sl]).abs().max()) <= 2e-6
+        assert float((att[sl] - att_full[sl]).abs().max()) <= 1e-7
+        rest = torch.ones(B, dtype=torch.bool)
+        rest[sl] = False
+        assert float(att[rest.cuda()].abs().max()) == 0.0
+        (blk * dm[sl]).sum().backward()
+        assert relmax(ib.grad.cpu(), d_img_full[sl].cpu()) <= 2e-5
+        d_words_sum += wb.grad
+    if B <= 96:
+        assert relmax(d_words_sum.cpu(), d_words_full.cpu()) <= 2e-5
+
+
 @pytest.mark.parametrize("B,Rv,D", [(10, 100, 256), (3, 7, 64), (1, 1, 256)])
 def test_r_precision_matches_reference_arithmetic(cuda_lib, B, Rv, D):
     """eegan_b200.r_precision vs the restated loop body of Tester.cal_sim_one_by_one (test.py:323-330):

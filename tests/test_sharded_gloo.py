@@ -23,10 +23,13 @@ def _free_port():
 
 
 def _oracle_grid(img_all, words, cap_lens, diag_offset=0, want_att=True):
+    """(m [B_img, B_cap], diagonal attention [B_cap, T, R]) as the library returns them: caption i's own image is
+    j = i + diag_offset; captions whose image is not in the block get zeros (eegan_damsm_pair_fwd)."""
     from oracle import damsm_oracle as O
     t = O.dense_pair_terms(img_all, words, cap_lens)
-    b = words.shape[0]
-    att = torch.stack([t["a"][diag_offset + i, i] for i in range(b)])  # [b, T, R]
+    Bi, Bc = img_all.shape[0], words.shape[0]
+    zero = torch.zeros_like(t["a"][0, 0])
+    att = torch.stack([t["a"][diag_offset + i, i] if 0 <= diag_offset + i < Bi else zero for i in range(Bc)])  # [Bc, T, R]
     return t["m"], att.detach()
 
 
@@ -96,9 +99,20 @@ def _worker(rank, world, port, out):
         sl = slice(rank * b, (rank + 1) * b)
         img = c["img"][sl].double().requires_grad_()
         words = c["words"][sl].double().requires_grad_()
+        # the caption partition first (own captions x all images), checked on its own; then the default image partition
+        # (own images x all captions), which the result dict below carries
         l0, l1, att = sharded.sharded_words_loss(img, words, torch.arange(b), c["cap_lens"][sl], c["class_ids"][sl], b,
-                                                 grid_fn=_oracle_grid, ce_fn=_oracle_ce)
+                                                 grid_fn=_oracle_grid, ce_fn=_oracle_ce, shard="captions")
         (l0 + 2 * l1).backward()
+        cap_part = (l0.detach().clone(), l1.detach().clone(), img.grad.clone(), words.grad.clone(), [a.clone() for a in att])
+        img.grad = words.grad = None
+        l0, l1, att = sharded.sharded_words_loss(img, words, torch.arange(b), c["cap_lens"][sl], c["class_ids"][sl], b,
+                                                 grid_fn=_oracle_grid, ce_fn=_oracle_ce, shard="images")
+        (l0 + 2 * l1).backward()
+        assert sharded.SHARD_BY == "images"
+        assert float((cap_part[0] - l0.detach()).abs() + (cap_part[1] - l1.detach()).abs()) < 1e-12
+        assert float((cap_part[2] - img.grad).abs().max()) < 1e-12 and float((cap_part[3] - words.grad).abs().max()) < 1e-12
+        assert len(att) == len(cap_part[4]) == b and all(float((a - q).abs().max()) < 1e-12 for a, q in zip(att, cap_part[4]))
         # single-process full batch
         fi = c["img"].double().requires_grad_()
         fw = c["words"].double().requires_grad_()

@@ -9,7 +9,9 @@ aggregation and the two cross-entropies.  Metric: attention pairs/s (one pair = 
 
 Workloads (BASELINE.json `configs`):
   c2 (default; the metric's config)  CUB cfg/bird.yml shape: B = 48 per GPU, T <= 18 ragged, CUB-like class ids.  N > 1: the
-      grid is caption-row-sharded (eegan_b200/sharded.py), per-GPU caption rows fixed -> pairs = (48 N)^2, "weak".
+      grid is sharded over the ranks (eegan_b200/sharded.py; --shard images (default): own images x all captions, the word
+      features travel; --shard captions: own captions x all images, the region features travel), per-GPU samples fixed ->
+      pairs = (48 N)^2, "weak".
   c3  COCO cfg/coco.yml shape: GLOBAL B = 64, T <= 20, unique class ids, split over the N GPUs ("strong").
   c5  flower cfg/flower.yml shape: GLOBAL B in {32, 64, 128, 256, 512} split over the N GPUs, one sub-line per B.
   c4  the generator step: the reference's own models.Gen (24 SyncBN layers) + Trainer.DAMSM_loss, B = 32 per GPU, imported
@@ -22,7 +24,7 @@ Every line carries:
   parity     BEFORE timing: the sharded step / drop-in API, sent_loss and one SyncBN layer against the float64 oracle (oracle/parity.py)
   roofline   the dominant kernels' algorithmic FLOP/s from stage events recorded inside warmed steps, against MEASURED_PEAKS.json
   cpu_baseline  the UNMODIFIED reference (baseline/_ref, kind "reference"; the validated port when it is not staged) on this host's cores
-  N > 1 also: comm_free_same_shape (the rank's (B_total x b) block timed without any collective) and nccl_ms_per_step.
+  N > 1 also: comm_free_same_shape (the rank's block of the grid timed without any collective) and nccl_ms_per_step.
 `--impl reference` prints the CPU arm as its own line (rank 0 only).
 """
 from __future__ import annotations
@@ -870,7 +872,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_string(args.config, res["B_total"], res["T"]),
                        "config_id": args.config, "sum_cap_lens": res["lens_sum"], "per_gpu_B": res["B_local"],
-                       "sharding": ("caption rows over %d GPUs (eegan_b200/sharded.py)" % world) if world > 1 else "none",
+                       "sharding": ("%s rows of the grid over %d GPUs (eegan_b200/sharded.py)" % ({"images": "image", "captions": "caption"}.get(
+                           res.get("shard_by"), "caption"), world)) if world > 1 else "none",
                        "l2": "256 MB write, then a 256 MB read sweep, between timed steps (outside the timed spans): cold cache, no dirty lines left to write back inside a span",
                        "pairs_per_step": res["pairs_per_step"], "launch": res["launch"], "contraction_engine": engine,
                        "eager_ms_per_step": res.get("eager_ms_per_step")},

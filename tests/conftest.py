@@ -24,6 +24,19 @@ def golden_names(prefix):
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith(prefix) and f.endswith(".npz"))
 
 
+@pytest.fixture(autouse=True)
+def _seed_global_rng(request):
+    """Every test starts from its own fixed seed of torch's GLOBAL generator.  Inputs come from explicit generators
+    (oracle/cases.py), but module parameters (nn.Linear in ATTR_Enhance / affine_ssa) are drawn from the global one: unseeded, a
+    case near its tolerance passes or fails by the process's random seed (test_attr_enhance_cuda_vs_float64_oracle[2-512-1]: one
+    run in twelve)."""
+    import zlib
+
+    import torch
+    torch.manual_seed(zlib.crc32(request.node.nodeid.encode()) & 0x7FFFFFFF)
+    yield
+
+
 @pytest.fixture(scope="session")
 def cuda_lib():
     """The product library on a GPU box: fails (does not skip) when it cannot be used."""

@@ -91,3 +91,14 @@ def test_device_ids_helper():
     t = damsm_losses._device_i64([3, 1, 2, 9], "cpu", 3)
     assert t.dtype == torch.int64 and t.tolist() == [3, 1, 2]
     assert damsm_losses._device_i64(None, "cpu") is None
+
+
+def test_shard_mode_selection():
+    """The grid partition of the N > 1 path: package default (images), explicit choice, and a loud error for anything else."""
+    from eegan_b200 import sharded
+    assert sharded.SHARD_BY in ("images", "captions")
+    assert sharded._shard_mode(None) == sharded.SHARD_BY
+    assert sharded._shard_mode("captions") == "captions" and sharded._shard_mode("images") == "images"
+    import pytest
+    with pytest.raises(ValueError):
+        sharded._shard_mode("rows")

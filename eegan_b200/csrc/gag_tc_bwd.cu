@@ -632,8 +632,6 @@ int gag_tc_bwd_launch(const float* x, const float* key, const float* value, cons
     const size_t slot = (size_t)UC * 512;
     a.ns = (int)((232448 - fixed) / slot);
     if (a.ns > GB_NS_MAX) a.ns = GB_NS_MAX;
-    static const int ns_env = [] { const char* e = getenv("EEGAN_GAGTC_NS"); return e ? atoi(e) : 0; }();
-    if (ns_env >= 2 && ns_env < a.ns) a.ns = ns_env;
     EEGAN_REQUIRE(a.ns >= 2, "gag tc bwd: no room for the unit ring");
     const size_t smem = (size_t)a.ns * slot + fixed;
     const int S = gag_tc_bwd_chunks(B, Q);

@@ -194,11 +194,13 @@ int eegan_gag_fwd(const float* x, const float* key, const float* value, const ui
 int eegan_gag_bwd(const float* x, const float* key, const float* value, const float* attn,
                   const float* d_out, const float* d_attn, int B, int idf, int Q, int T,
                   float* d_x, float* d_key, float* d_value, void* stream);
-/* Backward with a caller-owned workspace (eegan_gag_bwd_workspace_bytes, 0 = shape not covered): the
- * register-tiled two-kernel form (gag_bwd2.cu: per-pixel pass writing d_x and ds, then d_key / d_value as
- * per-channel sums over pixel chunks, partials added in a fixed order: deterministic, no atomics, ~4x the
- * speed of eegan_gag_bwd).  Falls back to eegan_gag_bwd when workspace is NULL or the shape is not covered
- * (idf % 32 != 0, Q % 4 != 0, unaligned rows). */
+/* Backward with a caller-owned workspace (eegan_gag_bwd_workspace_bytes, 0 = shape not covered).  Default
+ * (eegan_set_gag_bwd_engine(1)) for idf = 32 / 64 / 128 with d_out given: the one-pass tcgen05 kernel of gag_tc_bwd.cu
+ * (all four contractions on the tensor cores, bf16 hi/lo operand pairs: gradients ~1e-5 of their maximum from float64;
+ * d_out, x, attn, d_attn read once).  Otherwise the register-tiled CUDA-core form (gag_bwd2.cu: per-pixel pass writing
+ * d_x and ds, then d_key / d_value as per-channel sums over pixel chunks).  Either way the d_key / d_value partials are
+ * added in a fixed order: deterministic, no atomics.  Falls back to eegan_gag_bwd when workspace is NULL or the shape is
+ * not covered (idf % 32 != 0, Q % 4 != 0, unaligned rows). */
 size_t eegan_gag_bwd_workspace_bytes(int B, int idf, int Q, int T);
 int eegan_gag_bwd_ws(const float* x, const float* key, const float* value, const float* attn,
                      const float* d_out, const float* d_attn, int B, int idf, int Q, int T, float* d_x,

@@ -186,9 +186,13 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
     const uint32_t key_hi = vt_lo + (uint32_t)NU * 4096u, key_lo = key_hi + (uint32_t)idf * 64u;
     const uint32_t bars = key_lo + (uint32_t)idf * 64u;
     auto full = [&](int s) { return bars + 8u * s; };                       // TMA landed
-    auto conv = [&](int s) { return bars + 8u * (GB_NS_MAX + s); };         // bf16 panels written
-    auto sfree = [&](int s) { return bars + 8u * (2 * GB_NS_MAX + s); };    // MMAs done with the slot
-    const uint32_t b0 = bars + 8u * (3 * GB_NS_MAX);
+    // "bf16 panels written": one barrier array PER ISSUER (d_out units / x units).  With one array an issuer would see only every
+    // other completion of a slot's barrier — the other issuer's units pass it by — and a parity wait tells completion n from
+    // completion n - 1 only (tests/test_gag_tc_bwd_protocol.py: wrong unit contracted on a two-slot ring).
+    auto conv_do = [&](int s) { return bars + 8u * (GB_NS_MAX + s); };
+    auto conv_x = [&](int s) { return bars + 8u * (2 * GB_NS_MAX + s); };
+    auto sfree = [&](int s) { return bars + 8u * (3 * GB_NS_MAX + s); };    // MMAs done with the slot
+    const uint32_t b0 = bars + 8u * (4 * GB_NS_MAX);
     const uint32_t ds_full = b0 + 16, ds_empty = b0 + 24, acc_full = b0 + 32, acc_empty = b0 + 40;
     // one barrier pair PER p buffer: with a single pair a waiter could be lapped by two completions (the phase parity aliases)
     auto p_full = [&](int a) { return b0 + 112u + 8u * a; };
@@ -240,7 +244,8 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < GB_NS_MAX; ++s) {
             mbar_init(full(s), 1);
-            mbar_init(conv(s), 4);
+            mbar_init(conv_do(s), 4);
+            mbar_init(conv_x(s), 4);
             mbar_init(sfree(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -332,6 +337,11 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
                 }
         };
         Ring r;
+        uint32_t used = 0;  // bit s: parity of THIS issuer's units that went through slot s = the phase of its barrier of the slot
+        auto wait_converted = [&]() {
+            mbar_wait(side_a ? conv_do(r.s) : conv_x(r.s), (used >> r.s) & 1u);
+            used ^= 1u << r.s;
+        };
         for (int g = 0; g < NGR; ++g) {
             const int t0 = gr0(g), t1 = gr0(g + 1);
             if (g > 0) {  // the pixel warps have read the dV / dK accumulators of the previous group
@@ -347,7 +357,7 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
                         tc_fence_after();
                         const uint32_t d_dp = tmem_base + COL_DP + (uint32_t)a * 32u;
                         for (int u = 0; u < NU; ++u) {
-                            mbar_wait(conv(r.s), r.ph);
+                            wait_converted();
                             tc_fence_after();
                             const uint32_t sa = base + (uint32_t)r.s * slot_bytes;
                             const uint32_t a_k = gb_lo_k(sa), a_mn = gb_lo_mn(sa, panel_bytes);
@@ -389,7 +399,7 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
                         gb_commit(leader, dx_full(a));
                         // (4) dK_u += x ds^T
                         for (int u = 0; u < NU; ++u) {
-                            mbar_wait(conv(r.s), r.ph);
+                            wait_converted();
                             tc_fence_after();
                             rowsum(tmem_base + COL_DK + (uint32_t)u * 32u, gb_lo_k(base + (uint32_t)r.s * slot_bytes), dsh_k, dsl_k, j == t0);
                             gb_commit(leader, sfree(r.s));
@@ -409,10 +419,27 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
         // ===== converters: fp32 unit [UC][128 q] -> bf16 hi / lo, two [UC][64 q] panels each, in place =====
         const int ctid = threadIdx.x - 128;
         constexpr int nchunk = UC / 4;  // 16-byte chunks per thread
-        const int units = 2 * NU * my_tiles;
         Ring r;
-        for (int it = 0; it < units; ++it, ring_adv(r, 1)) {
+        // the same unit sequence as the producer's, to know whose unit a slot holds (which issuer's barrier to arrive on)
+        int g = 0, i = gr0(0), t0 = gr0(0), t1 = gr0(1), sub = 0;  // sub: 0 .. NU-1 d_out units of tile i, NU .. 2NU-1 x units of tile i-1
+        auto next_unit = [&](bool& is_x) -> bool {
+            for (;;) {
+                if (g >= NGR) return false;
+                const bool has_do = i < t1, has_x = i > t0;
+                if (sub < NU && has_do) { is_x = false; ++sub; return true; }
+                if (sub < NU) sub = NU;
+                if (sub < 2 * NU && has_x) { is_x = true; ++sub; return true; }
+                sub = 0;
+                if (++i > t1) {
+                    ++g;
+                    if (g < NGR) { t0 = gr0(g); t1 = gr0(g + 1); i = t0; }
+                }
+            }
+        };
+        bool is_x = false;
+        while (next_unit(is_x)) {
             const int s = r.s, ph = r.ph;
+            ring_adv(r, 1);
             mbar_wait(full(s), ph);
             const uint32_t sb = base + (uint32_t)s * slot_bytes;
             float4 v[nchunk];
@@ -434,7 +461,7 @@ gag_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_consta
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(conv(s));
+            if (lane == 0) mbar_arrive(is_x ? conv_x(s) : conv_do(s));
         }
     } else {
         // ===== pixel warps (8-11) and p / output warps (12-15): a thread owns pixel pl of the tile = TMEM lane pl =====
@@ -628,7 +655,7 @@ int gag_tc_bwd_launch(const float* x, const float* key, const float* value, cons
     a.B = B; a.idf = idf; a.Q = Q; a.T = T;
     a.uc = UC; a.nu = idf / UC;
     a.ngr = gag_tc_bwd_groups(B, Q);
-    const size_t fixed = 6 * (size_t)GB_PT + 2 * (size_t)a.nu * 4096 + 2 * (size_t)idf * 64 + 512 /*barriers*/ + 1024 /*align*/;
+    const size_t fixed = 6 * (size_t)GB_PT + 2 * (size_t)a.nu * 4096 + 2 * (size_t)idf * 64 + 640 /*barriers*/ + 1024 /*align*/;
     const size_t slot = (size_t)UC * 512;
     a.ns = (int)((232448 - fixed) / slot);
     if (a.ns > GB_NS_MAX) a.ns = GB_NS_MAX;

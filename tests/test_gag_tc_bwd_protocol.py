@@ -1,6 +1,6 @@
 """CPU model of the mbarrier protocol of eegan_b200/csrc/gag_tc_bwd.cu (the one-pass tcgen05 backward of GlobalAttentionGeneral).
 
-The kernel is six roles — TMA producer, two MMA issuers, converters, pixel warps, p / output warps — that talk through ~45
+The kernel is six roles — TMA producer, two MMA issuers, converters, pixel warps, p / output warps — that talk through ~55
 mbarriers, a ring of operand slots, two p-panel buffers, one ds-panel buffer and double-buffered dP / dX accumulators.  Nothing
 of that can be unit-tested on a CPU, but its PROTOCOL can: this file restates every role's loop (same barriers, same parities,
 same order; keep it in step with the kernel) as a coroutine over a model of mbarrier phase parity, runs the roles under many
@@ -212,7 +212,6 @@ class Model:
                 self.ds_full.arrive()
             if i + 1 == g_end:
                 yield ("wait", self.acc_full, g & 1)
-                assert not self.A.queue or all(kind != "mma" for kind, _ in self.A.queue[:0]), "unreachable"
                 self.flushed = g
                 for _ in range(4):
                     self.acc_empty.arrive()
